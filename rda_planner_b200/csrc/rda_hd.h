@@ -1,0 +1,66 @@
+// rda_hd.h — host/device portability shims.  The numerical cores (cell_solver.cuh,
+// su_solver.cuh) are plain templates that compile both with nvcc for sm_100a (the
+// product) and with g++ (tests/host_shim, CPU-only checks of the same arithmetic).
+#pragma once
+#include <math.h>
+#include <stdint.h>
+#include "../../include/rda_b200.h"
+
+#if defined(__CUDACC__)
+#define RDA_HD __host__ __device__ __forceinline__
+#define RDA_HD_NOINLINE __host__ __device__ __noinline__
+#else
+#define RDA_HD inline
+#define RDA_HD_NOINLINE
+#endif
+
+namespace rda {
+
+template <typename T> RDA_HD T rmin(T a, T b) { return a < b ? a : b; }
+template <typename T> RDA_HD T rmax(T a, T b) { return a > b ? a : b; }
+template <typename T> RDA_HD T rclamp(T x, T lo, T hi) { return x < lo ? lo : (x > hi ? hi : x); }
+RDA_HD float rsqrt_(float x) { return 1.0f / sqrtf(x); }
+RDA_HD double rsqrt_(double x) { return 1.0 / sqrt(x); }
+RDA_HD float sqrt_(float x) { return sqrtf(x); }
+RDA_HD double sqrt_(double x) { return sqrt(x); }
+RDA_HD float abs_(float x) { return fabsf(x); }
+RDA_HD double abs_(double x) { return fabs(x); }
+RDA_HD bool finite_(float x) { return isfinite(x); }
+RDA_HD bool finite_(double x) { return isfinite(x); }
+
+// Robot body (convex polygon, car_tuple.G/h with Rpositive cone), prepared once at
+// rda_create: vertices y_j (vertex j joins rows j-1 and j, rda mpc.py:476-510 ordering),
+// unit outward normals and row norms.
+struct RobotGeom {
+  int R;
+  float yx[RDA_MAX_ROBOT_EDGE], yy[RDA_MAX_ROBOT_EDGE];
+  float nx[RDA_MAX_ROBOT_EDGE], ny[RDA_MAX_ROBOT_EDGE], gnorm[RDA_MAX_ROBOT_EDGE];
+  float h[RDA_MAX_ROBOT_EDGE];
+};
+
+// Fill RobotGeom from (G, h); returns 0 or RDA_E_UNSUPPORTED when the rows do not describe a
+// closed convex polygon listed counter-clockwise.
+inline int robot_geom_from_halfspaces(const float* G, const float* h, int R, RobotGeom* out) {
+  if (R < 3 || R > RDA_MAX_ROBOT_EDGE) return RDA_E_UNSUPPORTED;
+  out->R = R;
+  for (int j = 0; j < R; ++j) {
+    double gx = G[2 * j], gy = G[2 * j + 1];
+    double n = sqrt(gx * gx + gy * gy);
+    if (!(n > 0)) return RDA_E_UNSUPPORTED;
+    out->nx[j] = (float)(gx / n);
+    out->ny[j] = (float)(gy / n);
+    out->gnorm[j] = (float)n;
+    out->h[j] = h[j];
+  }
+  for (int j = 0; j < R; ++j) {
+    int a = (j + R - 1) % R;
+    double ax = G[2 * a], ay = G[2 * a + 1], bx = G[2 * j], by = G[2 * j + 1];
+    double det = ax * by - ay * bx;
+    if (!(det > 1e-12)) return RDA_E_UNSUPPORTED;  // CCW rows => positive turn
+    out->yx[j] = (float)((h[a] * by - h[j] * ay) / det);
+    out->yy[j] = (float)((ax * h[j] - bx * h[a]) / det);
+  }
+  return 0;
+}
+
+}  // namespace rda

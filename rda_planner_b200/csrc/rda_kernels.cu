@@ -1,0 +1,581 @@
+// rda_kernels.cu — sm_100a kernels and the C ABI (include/rda_b200.h) of the RDA ADMM hot path.
+//
+// One ADMM iteration (rda_solver.py:612-637) is three launches on the caller's stream:
+//   k_su      one warp per planning instance: su-QP (su_solver.cuh), state staged in shared memory
+//   k_cells   one thread per (instance, obstacle, stage) cell: (lam, mu, z) + xi/zeta update +
+//             residual partial sums + the next su-QP's hinge inputs (cell_solver.cuh)
+//   k_finalize per instance: residuals, early-stop flag (:594-596)
+// No host synchronisation, no allocation, CUDA-graph capturable.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+#include <new>
+#include "rda_hd.h"
+#include "cell_solver.cuh"
+#include "su_solver.cuh"
+
+using namespace rda;
+
+struct rda_handle {
+  rda_config cfg;
+  rda_tunables tun;
+  RobotGeom rb;
+  int B, T, N, E, R;
+  float *lam, *mu, *z, *xi, *zeta, *dis, *coef, *pref, *cur_s, *cur_u, *ref_s, *ref_speed;
+  float *resi_acc, *resi_pri, *resi_dual;
+  int *status, *iters, *done, *counters;
+  const float *obs_A, *obs_b;
+  const int *obs_kind, *obs_count;
+  int obs_tv;
+  float iter_threshold;
+  int launches;
+  size_t su_smem;
+  int began;
+};
+
+#define RDA_CUDA(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return (int)e_; } while (0)
+
+namespace {
+
+struct WarpCtx {
+  __device__ __forceinline__ int lane() const { return threadIdx.x & 31; }
+  __device__ __forceinline__ int nlanes() const { return 32; }
+  __device__ __forceinline__ void sync() const { __syncwarp(); }
+  template <typename R> __device__ __forceinline__ R sum(R x) const {
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    return x;
+  }
+  template <typename R> __device__ __forceinline__ R min(R x) const {
+    for (int o = 16; o > 0; o >>= 1) { R y = __shfl_xor_sync(0xffffffffu, x, o); x = y < x ? y : x; }
+    return x;
+  }
+  template <typename R> __device__ __forceinline__ R max(R x) const {
+    for (int o = 16; o > 0; o >>= 1) { R y = __shfl_xor_sync(0xffffffffu, x, o); x = y > x ? y : x; }
+    return x;
+  }
+};
+
+struct DevPtrs {
+  float *lam, *mu, *z, *xi, *zeta, *dis, *coef, *pref, *cur_s, *cur_u, *ref_s, *ref_speed;
+  float *resi_acc, *resi_pri, *resi_dual;
+  int *status, *iters, *done, *counters;
+  const float *obs_A, *obs_b;
+  const int *obs_kind, *obs_count;
+  int obs_tv;
+  int B, T, N, E, R;
+};
+
+__global__ void k_begin(DevPtrs d, const float* nom_s, const float* nom_u, const float* ref_s,
+                        const float* ref_speed) {
+  const int T = d.T;
+  const int per = 3 * (T + 1);
+  const int total = d.B * per;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    d.cur_s[i] = nom_s[i];
+    d.ref_s[i] = ref_s[i];
+    int b = i / per, r = i - b * per;
+    if (r < 2 * T) d.cur_u[b * 2 * T + r] = nom_u[b * 2 * T + r];
+    if (r == 0) {
+      d.ref_speed[b] = ref_speed[b];
+      d.done[b] = 0; d.iters[b] = 0; d.status[b] = 0;
+      d.resi_acc[2 * b] = 0; d.resi_acc[2 * b + 1] = 0;
+      d.resi_pri[b] = 0; d.resi_dual[b] = 0;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1: su-QP, one warp per instance.
+// ------------------------------------------------------------------------------------------------
+template <typename Real>
+__global__ void __launch_bounds__(32) k_su(DevPtrs d, SuParams P) {
+  extern __shared__ __align__(16) char smem[];
+  const int b = blockIdx.x;
+  if (b >= d.B) return;
+  if (d.done[b]) return;
+  const int T = P.T, N = P.N, NT = N * T;
+  const int lane = threadIdx.x;
+  SuWork<Real> W;
+  su_work_layout<Real>(T, N, &W, smem);
+  const float* cs = d.cur_s + (size_t)b * 3 * (T + 1);   // [3][T+1]
+  const float* cu = d.cur_u + (size_t)b * 2 * T;         // [2][T]
+  const float* rf = d.ref_s + (size_t)b * 3 * (T + 1);
+  for (int i = lane; i < 3 * (T + 1); i += 32) {
+    int r = i / (T + 1), t = i - r * (T + 1);
+    W.lins[3 * t + r] = cs[i];
+    W.ref[3 * t + r] = rf[i];
+  }
+  for (int i = lane; i < 2 * T; i += 32) {
+    int r = i / T, t = i - r * T;
+    W.linu[2 * t + r] = cu[i];
+    W.pref[2 * t + r] = d.pref[(size_t)b * 2 * T + i];
+  }
+  for (int t = lane; t < T; t += 32) W.d[t] = d.dis[(size_t)b * T + t];
+  const float* cf = d.coef + (size_t)b * 5 * NT;
+  for (int i = lane; i < NT; i += 32) {
+    W.hx[i] = cf[i];
+    W.hy[i] = cf[NT + i];
+    W.hc[i] = cf[2 * NT + i];
+  }
+  W.vref = d.ref_speed[b];
+  __syncwarp();
+  WarpCtx ctx;
+  int iters = 0;
+  int st = su_solve<Real, WarpCtx>(P, W, ctx, cf + 3 * NT, cf + 4 * NT, &iters);
+  __syncwarp();
+  // accept OPTIMAL and OPTIMAL_INACCURATE (iteration cap), else keep the previous nominal
+  // ("No update of state and control vector", rda_solver.py:696-700)
+  bool ok = st != 2;
+  if (ok) {
+    for (int i = lane; i < 3 * (T + 1); i += 32) {
+      int r = i / (T + 1), t = i - r * (T + 1);
+      float v = (float)W.s[3 * t + r];
+      if (!isfinite(v)) ok = false;
+    }
+    for (int i = lane; i < 2 * T; i += 32) {
+      int r = i / T, t = i - r * T;
+      if (!isfinite((float)W.u[2 * t + r])) ok = false;
+    }
+    ok = __all_sync(0xffffffffu, ok);
+  }
+  if (ok) {
+    float* ws = d.cur_s + (size_t)b * 3 * (T + 1);
+    float* wu = d.cur_u + (size_t)b * 2 * T;
+    for (int i = lane; i < 3 * (T + 1); i += 32) {
+      int r = i / (T + 1), t = i - r * (T + 1);
+      ws[i] = (float)W.s[3 * t + r];
+    }
+    for (int i = lane; i < 2 * T; i += 32) {
+      int r = i / T, t = i - r * T;
+      wu[i] = (float)W.u[2 * t + r];
+    }
+    for (int t = lane; t < T; t += 32) d.dis[(size_t)b * T + t] = (float)W.d[t];
+  }
+  if (lane == 0) {
+    d.iters[b] += 1;
+    int flag = 0;
+    if (st == 1) flag |= RDA_ST_SU_NOT_CONVERGED;
+    if (!ok) flag |= RDA_ST_SU_NONFINITE;
+    if (flag) d.status[b] |= flag;
+    atomicAdd(&d.counters[3], iters);
+    atomicAdd(&d.counters[4], 1);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2: (lam, mu, z) cells + multiplier update, one thread per cell.
+// ------------------------------------------------------------------------------------------------
+template <typename Real>
+__global__ void __launch_bounds__(128) k_cells(DevPtrs d, RobotGeom rb, float ro2, float theta) {
+  const int T = d.T, N = d.N, E = d.E, R = d.R;
+  const int NT = N * T;
+  const long long total = (long long)d.B * NT;
+  const int lane = threadIdx.x & 31;
+  for (long long base = (long long)blockIdx.x * blockDim.x; base < total; base += (long long)gridDim.x * blockDim.x) {
+    long long idx = base + threadIdx.x;
+    bool live = idx < total;
+    int b = live ? (int)(idx / NT) : -1;
+    float hm2 = 0.f, dual = 0.f;
+    int path = -1;
+    if (live && (d.done[b] || d.obs_count[b] == 0)) live = false;
+    if (live) {
+      int rem = (int)(idx - (long long)b * NT);
+      int o = rem / T, t = rem - o * T;
+      const float* cs = d.cur_s + (size_t)b * 3 * (T + 1);
+      Real px = cs[t + 1], py = cs[(T + 1) + t + 1];
+      Real phib = cs[2 * (T + 1) + t];                 // NB column t (rda_solver.py:457-460)
+      float spf, cpf;
+      sincosf((float)phib, &spf, &cpf);
+      Real sp = spf, cp = cpf;
+      Real dbar = d.dis[(size_t)b * T + t];
+      size_t cell = (size_t)b * NT + (size_t)o * T + t;
+      Real zeta = d.zeta[cell];
+      float* xi = d.xi + (size_t)b * 2 * NT;
+      Real xi0 = xi[(size_t)o * T + t], xi1 = xi[NT + (size_t)o * T + t];
+      int tc = d.obs_tv ? (t + 1) : 0;
+      int Tc = d.obs_tv ? (T + 1) : 1;
+      size_t ob = ((size_t)b * N + o) * Tc + tc;
+      const float* A = d.obs_A + ob * E * 2;
+      const float* bb = d.obs_b + ob * E;
+      int kind = d.obs_kind[(size_t)b * N + o];
+      CellOut<Real> out;
+      cell_solve<Real>(rb, kind, E, A, bb, px, py, cp, sp, dbar, zeta, xi0, xi1, (Real)ro2, (Real)theta, out);
+      path = out.path;
+      if (out.path != CELL_FAILED) {
+        // dual residual |lam - lam_prev|^2 + |mu - mu_prev|^2 + |z - z_prev|^2 (:783-787)
+        float* lam = d.lam + ((size_t)b * N + o) * E * T + t;
+        float acc = 0.f;
+        for (int i = 0; i < E; ++i) {
+          float nv = (float)out.lam[i];
+          float df = nv - lam[(size_t)i * T];
+          acc += df * df;
+          lam[(size_t)i * T] = nv;
+        }
+        float* mu = d.mu + ((size_t)b * N + o) * R * T + t;
+        for (int j = 0; j < R; ++j) {
+          float nv = (float)out.mu[j];
+          float df = nv - mu[(size_t)j * T];
+          acc += df * df;
+          mu[(size_t)j * T] = nv;
+        }
+        float zn = (float)out.z;
+        float dz = zn - d.z[cell];
+        acc += dz * dz;
+        d.z[cell] = zn;
+        dual = acc;
+        d.zeta[cell] = (float)out.zeta_new;
+        xi[(size_t)o * T + t] = (float)out.xi0_new;
+        xi[NT + (size_t)o * T + t] = (float)out.xi1_new;
+        hm2 = (float)(out.hm0 * out.hm0 + out.hm1 * out.hm1);
+        float* cf = d.coef + (size_t)b * 5 * NT + (size_t)o * T + t;
+        cf[0] = (float)out.ax;
+        cf[NT] = (float)out.ay;
+        cf[2 * NT] = (float)out.c0;
+        cf[3 * NT] = (float)out.gx;
+        cf[4 * NT] = (float)out.gy;
+        if (o == 0) {
+          d.pref[(size_t)b * 2 * T + t] = (float)px;
+          d.pref[(size_t)b * 2 * T + T + t] = (float)py;
+        }
+      } else {
+        // "Update Lam Mu Fail": previous duals kept, residual inf (:791-793)
+        dual = INFINITY;
+        atomicOr(&d.status[b], RDA_ST_CELL_FALLBACK);
+      }
+    }
+    // residual partial sums: a warp spans at most two instances when N*T >= 32
+    int b0 = __shfl_sync(0xffffffffu, b, 0);
+    for (int pass = 0; pass < 2; ++pass) {
+      bool mine = live && ((pass == 0) ? (b == b0) : (b != b0));
+      unsigned m = __ballot_sync(0xffffffffu, mine);
+      if (m == 0) continue;
+      float h = mine ? hm2 : 0.f, q = mine ? dual : 0.f;
+      // general case (N*T < 32): fall back to per-thread atomics for the second group
+      int leader = __ffs(m) - 1;
+      int bl = __shfl_sync(0xffffffffu, b, leader);
+      bool uniform = __all_sync(0xffffffffu, !mine || b == bl);
+      if (uniform) {
+        for (int o2 = 16; o2 > 0; o2 >>= 1) {
+          h += __shfl_xor_sync(0xffffffffu, h, o2);
+          q += __shfl_xor_sync(0xffffffffu, q, o2);
+        }
+        if (lane == leader) {
+          atomicAdd(&d.resi_acc[2 * bl], h);
+          atomicAdd(&d.resi_acc[2 * bl + 1], q);
+        }
+      } else if (mine) {
+        atomicAdd(&d.resi_acc[2 * b], h);
+        atomicAdd(&d.resi_acc[2 * b + 1], q);
+      }
+    }
+    // path statistics
+    unsigned fast = __ballot_sync(0xffffffffu, path == CELL_FAST_INACTIVE || path == CELL_FAST_VERTEX || path == CELL_OVERLAP_FREE);
+    unsigned slow = __ballot_sync(0xffffffffu, path == CELL_SLOW_A || path == CELL_SLOW_B);
+    unsigned fail = __ballot_sync(0xffffffffu, path == CELL_FAILED);
+    if (lane == 0) {
+      if (fast) atomicAdd(&d.counters[0], __popc(fast));
+      if (slow) atomicAdd(&d.counters[1], __popc(slow));
+      if (fail) atomicAdd(&d.counters[2], __popc(fail));
+    }
+  }
+}
+
+// per instance: residuals (:688, :735-739), early stop (:594-596), empty-list quirk (:564-568)
+__global__ void k_finalize(DevPtrs d, RobotGeom rb, float thr) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= d.B) return;
+  if (d.done[b]) return;
+  const int T = d.T, N = d.N, NT = N * T, R = d.R;
+  float pri = 0.f, dual = 0.f;
+  if (d.obs_count[b] != 0 && N > 0) {
+    pri = sqrtf(d.resi_acc[2 * b]);
+    dual = d.resi_acc[2 * b + 1] / (float)N;
+  } else if (N > 0) {
+    // obstacle list empty: only the LAST slot's lam'A and lam'b are cleared (loop-variable leak)
+    int o = N - 1;
+    float* cf = d.coef + (size_t)b * 5 * NT + (size_t)o * T;
+    for (int t = 0; t < T; ++t) {
+      const float* mu = d.mu + ((size_t)b * N + o) * R * T + t;
+      float muh = 0.f;
+      for (int j = 0; j < R; ++j) muh += mu[(size_t)j * T] * rb.h[j];
+      size_t cell = (size_t)b * NT + (size_t)o * T + t;
+      cf[t] = 0.f; cf[NT + t] = 0.f;
+      cf[2 * NT + t] = -muh - d.z[cell] + d.zeta[cell];
+    }
+  }
+  d.resi_acc[2 * b] = 0.f; d.resi_acc[2 * b + 1] = 0.f;
+  d.resi_pri[b] = pri; d.resi_dual[b] = dual;
+  if (dual < thr && pri < thr) { d.done[b] = 1; d.status[b] |= RDA_ST_EARLY_STOP; }
+}
+
+__global__ void k_finish(DevPtrs d, rda_outputs o) {
+  const int T = d.T;
+  const int per = 3 * (T + 1);
+  const int total = d.B * per;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    o.s_opt[i] = d.cur_s[i];
+    int b = i / per, r = i - b * per;
+    if (r < 2 * T) o.u_opt[b * 2 * T + r] = d.cur_u[b * 2 * T + r];
+    if (r == 0) {
+      o.resi_pri[b] = d.resi_pri[b]; o.resi_dual[b] = d.resi_dual[b];
+      o.status[b] = d.status[b]; o.iters[b] = d.iters[b];
+    }
+  }
+}
+
+// RDA_solver.reset (:1060-1068): lam'A = 0, lam'b = 0; mu, z, zeta, xi are NOT cleared.
+__global__ void k_reset(DevPtrs d, RobotGeom rb) {
+  const int T = d.T, N = d.N, NT = N * T, R = d.R;
+  const long long total = (long long)d.B * NT;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    int b = (int)(idx / NT);
+    int rem = (int)(idx - (long long)b * NT);
+    int o = rem / T, t = rem - o * T;
+    const float* mu = d.mu + ((size_t)b * N + o) * R * T + t;
+    float muh = 0.f;
+    for (int j = 0; j < R; ++j) muh += mu[(size_t)j * T] * rb.h[j];
+    float* cf = d.coef + (size_t)b * 5 * NT + rem;
+    cf[0] = 0.f; cf[NT] = 0.f;
+    cf[2 * NT] = -muh - d.z[idx] + d.zeta[idx];
+  }
+}
+
+__global__ void k_fill(float* p, float v, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+DevPtrs dev_ptrs(const rda_handle* h) {
+  DevPtrs d;
+  d.lam = h->lam; d.mu = h->mu; d.z = h->z; d.xi = h->xi; d.zeta = h->zeta; d.dis = h->dis;
+  d.coef = h->coef; d.pref = h->pref; d.cur_s = h->cur_s; d.cur_u = h->cur_u; d.ref_s = h->ref_s;
+  d.ref_speed = h->ref_speed; d.resi_acc = h->resi_acc; d.resi_pri = h->resi_pri; d.resi_dual = h->resi_dual;
+  d.status = h->status; d.iters = h->iters; d.done = h->done; d.counters = h->counters;
+  d.obs_A = h->obs_A; d.obs_b = h->obs_b; d.obs_kind = h->obs_kind; d.obs_count = h->obs_count;
+  d.obs_tv = h->obs_tv;
+  d.B = h->B; d.T = h->T; d.N = h->N; d.E = h->E; d.R = h->R;
+  return d;
+}
+
+SuParams su_params(const rda_handle* h) {
+  SuParams P;
+  P.T = h->T; P.N = h->N; P.dynamics = h->cfg.dynamics; P.accelerated = h->cfg.accelerated;
+  P.dt = h->cfg.step_time; P.L = h->cfg.wheelbase;
+  P.umax[0] = h->cfg.max_speed[0]; P.umax[1] = h->cfg.max_speed[1];
+  P.ab[0] = h->cfg.acce_bound[0]; P.ab[1] = h->cfg.acce_bound[1];
+  P.ws = h->cfg.ws; P.wu = h->cfg.wu;
+  P.slack_gain = h->tun.slack_gain; P.dmin = h->tun.min_sd; P.dmax = h->tun.max_sd;
+  P.ro1 = h->tun.ro1; P.ro2 = h->tun.ro2;
+  P.max_iter = 40;
+  return P;
+}
+
+int grid_for(long long n, int block) {
+  long long g = (n + block - 1) / block;
+  const long long cap = 148LL * 16;      // a few waves of the 148 SMs; kernels grid-stride
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* rda_version(void) { return "rda_b200 0.1 (sm_100a)"; }
+
+int rda_create(const rda_config* cfg, const rda_tunables* tun, rda_handle** out) {
+  if (!cfg || !tun || !out) return RDA_E_ARG;
+  if (cfg->batch < 1 || cfg->receding < 1 || cfg->max_obs_num < 0) return RDA_E_ARG;
+  if (cfg->max_edge_num < 3 || cfg->max_edge_num > RDA_MAX_EDGE) return RDA_E_UNSUPPORTED;
+  if (cfg->dynamics < 0 || cfg->dynamics > 2) return RDA_E_ARG;
+  rda_handle* h = new (std::nothrow) rda_handle();
+  if (!h) return RDA_E_NOMEM;
+  memset(h, 0, sizeof(*h));
+  h->cfg = *cfg; h->tun = *tun;
+  int rc = robot_geom_from_halfspaces(cfg->G, cfg->h, cfg->robot_edges, &h->rb);
+  if (rc) { delete h; return rc; }
+  h->B = cfg->batch; h->T = cfg->receding; h->N = cfg->max_obs_num; h->E = cfg->max_edge_num;
+  h->R = cfg->robot_edges;
+  const size_t B = h->B, T = h->T, N = h->N, E = h->E, R = h->R, NT = N * T;
+  h->su_smem = cfg->su_fp64 ? su_work_layout<double>((int)T, (int)N, nullptr, nullptr)
+                            : su_work_layout<float>((int)T, (int)N, nullptr, nullptr);
+  if (h->su_smem > 227 * 1024) { delete h; return RDA_E_UNSUPPORTED; }
+  cudaError_t e = cudaSuccess;
+  auto alloc = [&](float** p, size_t n) { if (e == cudaSuccess) e = cudaMalloc((void**)p, (n ? n : 1) * sizeof(float)); };
+  alloc(&h->lam, B * N * E * T); alloc(&h->mu, B * N * R * T); alloc(&h->z, B * NT);
+  alloc(&h->xi, B * 2 * NT); alloc(&h->zeta, B * NT); alloc(&h->dis, B * T);
+  alloc(&h->coef, B * 5 * NT); alloc(&h->pref, B * 2 * T); alloc(&h->cur_s, B * 3 * (T + 1));
+  alloc(&h->cur_u, B * 2 * T); alloc(&h->ref_s, B * 3 * (T + 1)); alloc(&h->ref_speed, B);
+  alloc(&h->resi_acc, B * 2); alloc(&h->resi_pri, B); alloc(&h->resi_dual, B);
+  alloc((float**)&h->status, B); alloc((float**)&h->iters, B); alloc((float**)&h->done, B);
+  alloc((float**)&h->counters, 8);
+  if (e != cudaSuccess) { rda_destroy(h); return (int)e; }
+  if (cfg->su_fp64) e = cudaFuncSetAttribute(k_su<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->su_smem);
+  else e = cudaFuncSetAttribute(k_su<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->su_smem);
+  if (e != cudaSuccess) { rda_destroy(h); return (int)e; }
+  rc = rda_cold_start(h, nullptr);
+  if (rc) { rda_destroy(h); return rc; }
+  e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { rda_destroy(h); return (int)e; }
+  *out = h;
+  return 0;
+}
+
+int rda_destroy(rda_handle* h) {
+  if (!h) return RDA_E_ARG;
+  float* bufs[] = {h->lam, h->mu, h->z, h->xi, h->zeta, h->dis, h->coef, h->pref, h->cur_s, h->cur_u,
+                   h->ref_s, h->ref_speed, h->resi_acc, h->resi_pri, h->resi_dual, (float*)h->status,
+                   (float*)h->iters, (float*)h->done, (float*)h->counters};
+  for (float* p : bufs) if (p) cudaFree(p);
+  delete h;
+  return 0;
+}
+
+int rda_set_tunables(rda_handle* h, const rda_tunables* tun) {
+  if (!h || !tun) return RDA_E_ARG;
+  h->tun = *tun;
+  return 0;
+}
+
+int rda_get_tunables(const rda_handle* h, rda_tunables* tun) {
+  if (!h || !tun) return RDA_E_ARG;
+  *tun = h->tun;
+  return 0;
+}
+
+int rda_cold_start(rda_handle* h, void* stream) {
+  if (!h) return RDA_E_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t B = h->B, T = h->T, N = h->N, E = h->E, R = h->R, NT = N * T;
+  RDA_CUDA(cudaMemsetAsync(h->lam, 0, B * N * E * T * 4, s));
+  RDA_CUDA(cudaMemsetAsync(h->mu, 0, B * N * R * T * 4, s));
+  RDA_CUDA(cudaMemsetAsync(h->z, 0, B * NT * 4, s));
+  RDA_CUDA(cudaMemsetAsync(h->xi, 0, B * 2 * NT * 4, s));
+  RDA_CUDA(cudaMemsetAsync(h->zeta, 0, B * NT * 4, s));
+  RDA_CUDA(cudaMemsetAsync(h->coef, 0, B * 5 * NT * 4, s));
+  RDA_CUDA(cudaMemsetAsync(h->pref, 0, B * 2 * T * 4, s));
+  RDA_CUDA(cudaMemsetAsync(h->cur_s, 0, B * 3 * (T + 1) * 4, s));
+  RDA_CUDA(cudaMemsetAsync(h->cur_u, 0, B * 2 * T * 4, s));
+  RDA_CUDA(cudaMemsetAsync(h->resi_acc, 0, B * 2 * 4, s));
+  RDA_CUDA(cudaMemsetAsync(h->resi_pri, 0, B * 4, s));
+  RDA_CUDA(cudaMemsetAsync(h->resi_dual, 0, B * 4, s));
+  RDA_CUDA(cudaMemsetAsync(h->status, 0, B * 4, s));
+  RDA_CUDA(cudaMemsetAsync(h->iters, 0, B * 4, s));
+  RDA_CUDA(cudaMemsetAsync(h->done, 0, B * 4, s));
+  RDA_CUDA(cudaMemsetAsync(h->counters, 0, 8 * 4, s));
+  k_fill<<<grid_for((long long)(B * T), 256), 256, 0, s>>>(h->dis, 1.0f, B * T);   // para_dis = 1 (:119)
+  RDA_CUDA(cudaGetLastError());
+  h->launches = 1;
+  return 0;
+}
+
+int rda_reset(rda_handle* h, void* stream) {
+  if (!h) return RDA_E_ARG;
+  if (h->N == 0) return 0;
+  DevPtrs d = dev_ptrs(h);
+  k_reset<<<grid_for((long long)h->B * h->N * h->T, 256), 256, 0, (cudaStream_t)stream>>>(d, h->rb);
+  RDA_CUDA(cudaGetLastError());
+  h->launches = 1;
+  return 0;
+}
+
+int rda_begin(rda_handle* h, const rda_inputs* in, float iter_threshold, void* stream) {
+  if (!h || !in || !in->nom_s || !in->nom_u || !in->ref_s || !in->ref_speed) return RDA_E_ARG;
+  if (h->N > 0 && (!in->obs_A || !in->obs_b || !in->obs_kind || !in->obs_count)) return RDA_E_ARG;
+  h->obs_A = in->obs_A; h->obs_b = in->obs_b; h->obs_kind = in->obs_kind; h->obs_count = in->obs_count;
+  h->obs_tv = in->obs_time_varying;
+  h->iter_threshold = iter_threshold;
+  DevPtrs d = dev_ptrs(h);
+  k_begin<<<grid_for((long long)h->B * 3 * (h->T + 1), 256), 256, 0, (cudaStream_t)stream>>>(
+      d, in->nom_s, in->nom_u, in->ref_s, in->ref_speed);
+  RDA_CUDA(cudaGetLastError());
+  h->began = 1;
+  h->launches = 1;
+  return 0;
+}
+
+int rda_step_su(rda_handle* h, void* stream) {
+  if (!h || !h->began) return RDA_E_ARG;
+  DevPtrs d = dev_ptrs(h);
+  SuParams P = su_params(h);
+  if (h->cfg.su_fp64) k_su<double><<<h->B, 32, h->su_smem, (cudaStream_t)stream>>>(d, P);
+  else k_su<float><<<h->B, 32, h->su_smem, (cudaStream_t)stream>>>(d, P);
+  RDA_CUDA(cudaGetLastError());
+  h->launches += 1;
+  return 0;
+}
+
+int rda_step_lammuz(rda_handle* h, void* stream) {
+  if (!h || !h->began) return RDA_E_ARG;
+  DevPtrs d = dev_ptrs(h);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (h->N > 0) {
+    k_cells<float><<<grid_for((long long)h->B * h->N * h->T, 128), 128, 0, s>>>(d, h->rb, h->tun.ro2,
+        h->cfg.accelerated ? h->tun.z_theta : 1.0f);
+    RDA_CUDA(cudaGetLastError());
+    h->launches += 1;
+  }
+  k_finalize<<<(h->B + 127) / 128, 128, 0, s>>>(d, h->rb, h->iter_threshold);
+  RDA_CUDA(cudaGetLastError());
+  h->launches += 1;
+  return 0;
+}
+
+int rda_finish(rda_handle* h, const rda_outputs* out, void* stream) {
+  if (!h || !out || !out->u_opt || !out->s_opt || !out->resi_pri || !out->resi_dual || !out->status || !out->iters)
+    return RDA_E_ARG;
+  DevPtrs d = dev_ptrs(h);
+  k_finish<<<grid_for((long long)h->B * 3 * (h->T + 1), 256), 256, 0, (cudaStream_t)stream>>>(d, *out);
+  RDA_CUDA(cudaGetLastError());
+  h->launches += 1;
+  return 0;
+}
+
+int rda_solve(rda_handle* h, const rda_inputs* in, const rda_outputs* out, int iter_num,
+              float iter_threshold, void* stream) {
+  if (iter_num < 1) return RDA_E_ARG;
+  int rc = rda_begin(h, in, iter_threshold, stream);
+  if (rc) return rc;
+  for (int i = 0; i < iter_num; ++i) {
+    rc = rda_step_su(h, stream);
+    if (rc) return rc;
+    rc = rda_step_lammuz(h, stream);
+    if (rc) return rc;
+  }
+  return rda_finish(h, out, stream);
+}
+
+int rda_get_buffer(rda_handle* h, int id, void** dev_ptr, size_t* count) {
+  if (!h || !dev_ptr || !count) return RDA_E_ARG;
+  const size_t B = h->B, T = h->T, N = h->N, E = h->E, R = h->R, NT = N * T;
+  switch (id) {
+    case RDA_BUF_LAM: *dev_ptr = h->lam; *count = B * N * E * T; break;
+    case RDA_BUF_MU: *dev_ptr = h->mu; *count = B * N * R * T; break;
+    case RDA_BUF_Z: *dev_ptr = h->z; *count = B * NT; break;
+    case RDA_BUF_XI: *dev_ptr = h->xi; *count = B * 2 * NT; break;
+    case RDA_BUF_ZETA: *dev_ptr = h->zeta; *count = B * NT; break;
+    case RDA_BUF_DIS: *dev_ptr = h->dis; *count = B * T; break;
+    case RDA_BUF_COEF: *dev_ptr = h->coef; *count = B * 5 * NT; break;
+    case RDA_BUF_PREF: *dev_ptr = h->pref; *count = B * 2 * T; break;
+    case RDA_BUF_CUR_S: *dev_ptr = h->cur_s; *count = B * 3 * (T + 1); break;
+    case RDA_BUF_CUR_U: *dev_ptr = h->cur_u; *count = B * 2 * T; break;
+    case RDA_BUF_COUNTERS: *dev_ptr = h->counters; *count = 8; break;
+    default: return RDA_E_ARG;
+  }
+  return 0;
+}
+
+int rda_copy_buffer(rda_handle* h, int id, void* user, int to_handle, void* stream) {
+  void* p = nullptr;
+  size_t n = 0;
+  int rc = rda_get_buffer(h, id, &p, &n);
+  if (rc) return rc;
+  if (!user) return RDA_E_ARG;
+  RDA_CUDA(cudaMemcpyAsync(to_handle ? p : user, to_handle ? user : p, n * 4, cudaMemcpyDeviceToDevice,
+                           (cudaStream_t)stream));
+  return 0;
+}
+
+int rda_last_launch_count(const rda_handle* h) { return h ? h->launches : RDA_E_ARG; }
+
+}  // extern "C"

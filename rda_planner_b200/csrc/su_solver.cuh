@@ -1,0 +1,535 @@
+// su_solver.cuh — the state/control "su" QP of one planning instance.
+//
+// Replaces rda_solver.py: su_prob_solve :692-700 (cvxpy -> ECOS) for the problem defined by
+// construct_su_prob :216-231, nav_cost_cons :313-328, update_su_cost_cons :330-387,
+// Im_su :831-851, Hm_su :853-872, dynamics_constraint :911-928, bound_su_constraints :930-938,
+// bound_dis_constraints :940-947, C0_cost :1011-1029, C1_cost :1031-1032, and the
+// re-linearisation assign_state_parameter :436-460 / linear_*_model :949-994.
+//
+// Method: Mehrotra predictor-corrector primal-dual interior point method.
+//  * decision variables (u_t, d_t); states follow the linearised dynamics exactly, so every Newton
+//    step is an equality-constrained LQ problem solved by a Riccati recursion over the horizon
+//    with state (s_t, u_{t-1}) in R^5 and control (u_t, d_t) in R^3 (the banded KKT system);
+//  * inequality constraints: |u| <= max_speed, |u_t - u_{t-1}| <= max_acce*dt, min_sd <= d <= max_sd;
+//  * every hinge term ro1/2 neg(Im)^2 is the exact partial minimum over a slack w of
+//    ro1/2 w^2 s.t. Im + w >= 0; w is eliminated analytically (w = nu/ro1), leaving one
+//    (slack, multiplier) pair per hinge and a rank-one term in the stage Hessian.
+// The code is written against a "cooperative group" context Ctx (lane(), nlanes(), sync(),
+// min/sum reductions): one warp per instance on the GPU (lanes = horizon stages), one lane on the
+// host (tests/host_shim).
+#pragma once
+#include "rda_hd.h"
+
+namespace rda {
+
+struct SuParams {
+  int T, N, dynamics, accelerated;
+  float dt, L, umax[2], ab[2], ws, wu;
+  float slack_gain, dmin, dmax, ro1, ro2;
+  int max_iter;
+};
+
+// Per-instance workspace (shared memory on the GPU).  All arrays indexed by stage t (0..T-1)
+// unless noted; hinge arrays indexed [o*T + t].
+template <typename Real>
+struct SuWork {
+  Real *s, *u, *d;            // iterate: 3(T+1), 2T, T
+  Real *ref;                  // 3(T+1)
+  Real *lins, *linu;          // linearisation point 3(T+1), 2T
+  Real *cph, *sph;            // cos/sin of nominal heading (column t)
+  Real *Aj, *Bj, *Cj;         // 2T (A02, A12), 6T, 3T
+  Real *Skk, *Sgk;            // aggregated rotation-consensus terms
+  Real *pref;                 // 2T positions the hinge offsets refer to
+  float *hx, *hy, *hc;        // hinge rows: lam'A (2) and offset
+  Real *hs, *hnu;             // hinge slack / multiplier
+  Real *bs, *bnu;             // 10T box/rate slack / multiplier
+  Real *Wm;                   // 6T hinge Hessian (xx, xy, xd, yy, yd, dd)
+  Real *gw;                   // 8T gradient in stage coordinates
+  Real *wb;                   // 5T barrier weights (u0, u1, d, rate0, rate1)
+  Real *K, *Lc, *kf;          // 15T, 6T, 3T Riccati gains / Cholesky of Hvv / feed-forward
+  Real *dz, *dv;              // 5(T+1), 3T Newton step
+  Real *dza, *dva;            // affine (predictor) step
+  Real vref;
+};
+
+template <typename Real>
+RDA_HD size_t su_work_layout(int T, int N, SuWork<Real>* w, char* base) {
+  // returns bytes used; if base != nullptr the pointers are set
+  size_t off = 0;
+  auto take = [&](size_t n, size_t elt) {
+    off = (off + 15) & ~(size_t)15;
+    char* p = base ? base + off : nullptr;
+    off += n * elt;
+    return p;
+  };
+#define RDA_TAKE(field, n, type) { char* p_ = take((size_t)(n), sizeof(type)); if (w) w->field = (type*)p_; }
+  RDA_TAKE(s, 3 * (T + 1), Real) RDA_TAKE(u, 2 * T, Real) RDA_TAKE(d, T, Real)
+  RDA_TAKE(ref, 3 * (T + 1), Real) RDA_TAKE(lins, 3 * (T + 1), Real) RDA_TAKE(linu, 2 * T, Real)
+  RDA_TAKE(cph, T, Real) RDA_TAKE(sph, T, Real)
+  RDA_TAKE(Aj, 2 * T, Real) RDA_TAKE(Bj, 6 * T, Real) RDA_TAKE(Cj, 3 * T, Real)
+  RDA_TAKE(Skk, T, Real) RDA_TAKE(Sgk, T, Real) RDA_TAKE(pref, 2 * T, Real)
+  RDA_TAKE(hx, N * T, float) RDA_TAKE(hy, N * T, float) RDA_TAKE(hc, N * T, float)
+  RDA_TAKE(hs, N * T, Real) RDA_TAKE(hnu, N * T, Real)
+  RDA_TAKE(bs, 10 * T, Real) RDA_TAKE(bnu, 10 * T, Real)
+  RDA_TAKE(Wm, 6 * T, Real) RDA_TAKE(gw, 8 * T, Real) RDA_TAKE(wb, 5 * T, Real)
+  RDA_TAKE(K, 15 * T, Real) RDA_TAKE(Lc, 6 * T, Real) RDA_TAKE(kf, 3 * T, Real)
+  RDA_TAKE(dz, 5 * (T + 1), Real) RDA_TAKE(dv, 3 * T, Real)
+  RDA_TAKE(dza, 5 * (T + 1), Real) RDA_TAKE(dva, 3 * T, Real)
+#undef RDA_TAKE
+  return (off + 15) & ~(size_t)15;
+}
+
+// Single-lane context (host tests; also valid on the device for a thread-per-instance launch).
+struct SeqCtx {
+  RDA_HD int lane() const { return 0; }
+  RDA_HD int nlanes() const { return 1; }
+  RDA_HD void sync() const {}
+  template <typename R> RDA_HD R sum(R x) const { return x; }
+  template <typename R> RDA_HD R min(R x) const { return x; }
+  template <typename R> RDA_HD R max(R x) const { return x; }
+};
+
+// Jacobians of the discrete model about (s, u): linear_ackermann_model :949-963,
+// linear_diff_model :966-979, linear_omni_model :982-994.
+template <typename Real>
+RDA_HD void su_linearise(const SuParams& P, const Real* st, const Real* ut, Real* Aj, Real* Bj, Real* Cj) {
+  const Real dt = P.dt;
+  if (P.dynamics == RDA_DYN_OMNI) {
+    Real phi = ut[1], v = ut[0];
+    Real c = cos(phi), s = sin(phi);
+    Aj[0] = 0; Aj[1] = 0;
+    Bj[0] = c * dt; Bj[1] = -v * s * dt; Bj[2] = s * dt; Bj[3] = v * c * dt; Bj[4] = 0; Bj[5] = 0;
+    Cj[0] = phi * v * s * dt; Cj[1] = -phi * v * c * dt; Cj[2] = 0;
+    return;
+  }
+  Real phi = st[2], v = ut[0];
+  Real c = cos(phi), s = sin(phi);
+  Aj[0] = -v * dt * s; Aj[1] = v * dt * c;
+  Bj[0] = c * dt; Bj[1] = 0; Bj[2] = s * dt; Bj[3] = 0;
+  Cj[0] = phi * v * s * dt; Cj[1] = -phi * v * c * dt;
+  if (P.dynamics == RDA_DYN_ACKER) {
+    Real psi = ut[1];
+    Real cp = cos(psi);
+    Real k = v * dt / ((Real)P.L * cp * cp);
+    Bj[4] = tan(psi) * dt / (Real)P.L; Bj[5] = k;
+    Cj[2] = -psi * k;
+  } else {
+    Bj[4] = 0; Bj[5] = dt;
+    Cj[2] = 0;
+  }
+}
+
+// One inequality row of stage t.  c in 0..9: (u0 hi, u0 lo, u1 hi, u1 lo, d hi, d lo,
+// rate0 hi, rate0 lo, rate1 hi, rate1 lo).  value g >= 0, gradient = sgn on component `comp`
+// (3: u0, 4: u1, 5: d) and -sgn on the previous control for rate rows.
+template <typename Real>
+struct Row { Real g; Real sgn; int comp; bool rate; bool live; };
+
+template <typename Real>
+RDA_HD Row<Real> su_row(const SuParams& P, const SuWork<Real>& W, int t, int c) {
+  Row<Real> r;
+  r.rate = c >= 6;
+  r.live = true;
+  const bool hi = (c & 1) == 0;
+  r.sgn = hi ? (Real)-1 : (Real)1;
+  if (c < 4) {
+    int k = c >> 1;
+    r.comp = 3 + k;
+    Real uv = W.u[2 * t + k], m = P.umax[k];
+    r.g = hi ? m - uv : uv + m;
+  } else if (c < 6) {
+    r.comp = 5;
+    Real dv = W.d[t];
+    Real lo = P.dmin > 0 ? P.dmin : 0;
+    r.g = hi ? (Real)P.dmax - dv : dv - lo;
+    r.live = P.N > 0;
+  } else {
+    int k = (c - 6) >> 1;
+    r.comp = 3 + k;
+    r.live = t >= 1;
+    Real du = r.live ? W.u[2 * t + k] - W.u[2 * (t - 1) + k] : (Real)0;
+    r.g = hi ? (Real)P.ab[k] - du : (Real)P.ab[k] + du;
+  }
+  return r;
+}
+
+// directional derivative of row (t, c) along the Newton step held in (dz, dv)
+template <typename Real>
+RDA_HD Real su_row_dir(const Row<Real>& r, const Real* dz_t, const Real* dv_t) {
+  Real x = dv_t[r.comp - 3];
+  if (r.rate) x -= dz_t[3 + (r.comp - 3)];
+  return r.sgn * x;
+}
+
+template <typename Real, typename Ctx>
+RDA_HD void su_riccati(const SuParams& P, SuWork<Real>& W, Ctx& ctx, bool factor, Real* dz, Real* dv) {
+  // Backward sweep (all lanes execute the same recursion; lane 0 stores), then forward sweep.
+  const int T = P.T;
+  const Real reg = (Real)1e-9;
+  Real Pm[5][5], pv[5];
+  for (int a = 0; a < 5; ++a) { pv[a] = 0; for (int b = 0; b < 5; ++b) Pm[a][b] = 0; }
+  const bool writer = ctx.lane() == 0;
+  for (int t = T - 1; t >= 0; --t) {
+    Real E[8][8];
+    for (int a = 0; a < 8; ++a) for (int b = 0; b < 8; ++b) E[a][b] = 0;
+    E[0][0] = 1; E[1][1] = 1; E[2][2] = 1;
+    E[0][2] = W.Aj[2 * t]; E[1][2] = W.Aj[2 * t + 1];
+    for (int r = 0; r < 3; ++r) { E[r][5] = W.Bj[6 * t + 2 * r]; E[r][6] = W.Bj[6 * t + 2 * r + 1]; }
+    E[3][5] = 1; E[4][6] = 1; E[5][7] = 1; E[6][3] = 1; E[7][4] = 1;
+    Real gy[8];
+    for (int a = 0; a < 8; ++a) gy[a] = W.gw[8 * t + a];
+    for (int a = 0; a < 5; ++a) gy[a] += pv[a];
+    Real g[8];
+    for (int c = 0; c < 8; ++c) { Real sacc = 0; for (int r = 0; r < 8; ++r) sacc += E[r][c] * gy[r]; g[c] = sacc; }
+    Real L00, L10, L11, L20, L21, L22;
+    Real Kt[3][5];
+    if (factor) {
+      Real Wt[8][8];
+      for (int a = 0; a < 8; ++a) for (int b = 0; b < 8; ++b) Wt[a][b] = 0;
+      for (int a = 0; a < 5; ++a) for (int b = 0; b < 5; ++b) Wt[a][b] = Pm[a][b];
+      const Real tw = 2 * (Real)P.ws;
+      Wt[0][0] += tw; Wt[1][1] += tw;
+      Wt[2][2] += (P.dynamics == RDA_DYN_OMNI ? (Real)0 : tw) + (Real)P.ro2 * W.Skk[t];
+      const Real* M = W.Wm + 6 * t;
+      Wt[0][0] += M[0]; Wt[0][1] += M[1]; Wt[1][0] += M[1]; Wt[0][5] += M[2]; Wt[5][0] += M[2];
+      Wt[1][1] += M[3]; Wt[1][5] += M[4]; Wt[5][1] += M[4]; Wt[5][5] += M[5];
+      const Real* wb = W.wb + 5 * t;
+      Wt[3][3] += 2 * (Real)P.wu + reg + wb[0] + wb[3];
+      Wt[4][4] += reg + wb[1] + wb[4];
+      Wt[5][5] += (P.N > 0 ? reg + wb[2] : (Real)1);
+      Wt[6][6] += wb[3]; Wt[3][6] -= wb[3]; Wt[6][3] -= wb[3];
+      Wt[7][7] += wb[4]; Wt[4][7] -= wb[4]; Wt[7][4] -= wb[4];
+      Real T1[8][8];
+      for (int a = 0; a < 8; ++a)
+        for (int c = 0; c < 8; ++c) { Real sacc = 0; for (int r = 0; r < 8; ++r) sacc += Wt[a][r] * E[r][c]; T1[a][c] = sacc; }
+      Real H[8][8];
+      for (int a = 0; a < 8; ++a)
+        for (int c = a; c < 8; ++c) { Real sacc = 0; for (int r = 0; r < 8; ++r) sacc += E[r][a] * T1[r][c]; H[a][c] = sacc; H[c][a] = sacc; }
+      // Cholesky of Hvv (indices 5..7)
+      L00 = sqrt_(H[5][5]);
+      L10 = H[6][5] / L00;
+      L11 = sqrt_(H[6][6] - L10 * L10);
+      L20 = H[7][5] / L00;
+      L21 = (H[7][6] - L20 * L10) / L11;
+      L22 = sqrt_(H[7][7] - L20 * L20 - L21 * L21);
+      for (int b = 0; b < 5; ++b) {
+        Real r0 = -H[5][b], r1 = -H[6][b], r2 = -H[7][b];
+        Real y0 = r0 / L00, y1 = (r1 - L10 * y0) / L11, y2 = (r2 - L20 * y0 - L21 * y1) / L22;
+        Real x2 = y2 / L22, x1 = (y1 - L21 * x2) / L11, x0 = (y0 - L10 * x1 - L20 * x2) / L00;
+        Kt[0][b] = x0; Kt[1][b] = x1; Kt[2][b] = x2;
+      }
+      for (int a = 0; a < 5; ++a)
+        for (int b = a; b < 5; ++b) {
+          Real v = H[a][b] + H[5][a] * Kt[0][b] + H[6][a] * Kt[1][b] + H[7][a] * Kt[2][b];
+          Pm[a][b] = v; Pm[b][a] = v;
+        }
+      if (writer) {
+        Real* Ls = W.Lc + 6 * t;
+        Ls[0] = L00; Ls[1] = L10; Ls[2] = L11; Ls[3] = L20; Ls[4] = L21; Ls[5] = L22;
+        for (int k = 0; k < 3; ++k) for (int b = 0; b < 5; ++b) W.K[15 * t + 5 * k + b] = Kt[k][b];
+      }
+    } else {
+      const Real* Ls = W.Lc + 6 * t;
+      L00 = Ls[0]; L10 = Ls[1]; L11 = Ls[2]; L20 = Ls[3]; L21 = Ls[4]; L22 = Ls[5];
+      for (int k = 0; k < 3; ++k) for (int b = 0; b < 5; ++b) Kt[k][b] = W.K[15 * t + 5 * k + b];
+    }
+    {
+      Real r0 = -g[5], r1 = -g[6], r2 = -g[7];
+      Real y0 = r0 / L00, y1 = (r1 - L10 * y0) / L11, y2 = (r2 - L20 * y0 - L21 * y1) / L22;
+      Real x2 = y2 / L22, x1 = (y1 - L21 * x2) / L11, x0 = (y0 - L10 * x1 - L20 * x2) / L00;
+      if (writer) { W.kf[3 * t] = x0; W.kf[3 * t + 1] = x1; W.kf[3 * t + 2] = x2; }
+      for (int a = 0; a < 5; ++a) pv[a] = g[a] + Kt[0][a] * g[5] + Kt[1][a] * g[6] + Kt[2][a] * g[7];
+    }
+  }
+  ctx.sync();
+  // forward sweep
+  Real z[5] = {0, 0, 0, 0, 0};
+  for (int t = 0; t < T; ++t) {
+    Real v[3];
+    for (int k = 0; k < 3; ++k) {
+      Real sacc = W.kf[3 * t + k];
+      for (int b = 0; b < 5; ++b) sacc += W.K[15 * t + 5 * k + b] * z[b];
+      v[k] = sacc;
+    }
+    if (writer) {
+      for (int a = 0; a < 5; ++a) dz[5 * t + a] = z[a];
+      for (int k = 0; k < 3; ++k) dv[3 * t + k] = v[k];
+    }
+    Real n0 = z[0] + W.Aj[2 * t] * z[2] + W.Bj[6 * t] * v[0] + W.Bj[6 * t + 1] * v[1];
+    Real n1 = z[1] + W.Aj[2 * t + 1] * z[2] + W.Bj[6 * t + 2] * v[0] + W.Bj[6 * t + 3] * v[1];
+    Real n2 = z[2] + W.Bj[6 * t + 4] * v[0] + W.Bj[6 * t + 5] * v[1];
+    z[0] = n0; z[1] = n1; z[2] = n2; z[3] = v[0]; z[4] = v[1];
+  }
+  if (writer) for (int a = 0; a < 5; ++a) dz[5 * T + a] = z[a];
+  ctx.sync();
+}
+
+// Solve the su-QP.  Inputs already staged in W: lins, linu, ref, vref, hx/hy/hc, pref, Skk/Sgk
+// are computed here from (gx, gy) planes passed as pointers (global or shared memory, [o*T+t]).
+// On entry W.d holds para_dis (initial guess of d).  Returns 0 (converged), 1 (iteration cap),
+// 2 (non-finite).  On return W.s, W.u, W.d hold the solution.
+template <typename Real, typename Ctx>
+RDA_HD int su_solve(const SuParams& P, SuWork<Real>& W, Ctx& ctx, const float* gx, const float* gy,
+                    int* iters_out) {
+  const int T = P.T, N = P.N;
+  const int lane = ctx.lane(), nl = ctx.nlanes();
+  const Real ro1 = P.ro1, ro2 = P.ro2;
+  const bool acc = P.accelerated != 0;
+  // ---- linearisation and aggregated rotation terms (lane-parallel over stages) ----
+  for (int t = lane; t < T; t += nl) {
+    su_linearise<Real>(P, W.lins + 3 * t, W.linu + 2 * t, W.Aj + 2 * t, W.Bj + 6 * t, W.Cj + 3 * t);
+    Real phib = W.lins[3 * t + 2];
+    Real c = cos(phib), s = sin(phib);
+    W.cph[t] = c; W.sph[t] = s;
+    Real skk = 0, sgk = 0;
+    for (int o = 0; o < N; ++o) {
+      Real ax = W.hx[o * T + t], ay = W.hy[o * T + t];
+      Real k0 = -ax * s + ay * c, k1 = -ax * c - ay * s;          // a R'
+      Real g0 = (Real)gx[o * T + t] + ax * c + ay * s;            // mu'G + xi + a R
+      Real g1 = (Real)gy[o * T + t] - ax * s + ay * c;
+      skk += k0 * k0 + k1 * k1;
+      sgk += g0 * k0 + g1 * k1;
+    }
+    W.Skk[t] = skk; W.Sgk[t] = sgk;
+    W.u[2 * t] = W.linu[2 * t]; W.u[2 * t + 1] = W.linu[2 * t + 1];
+  }
+  ctx.sync();
+  // ---- initial iterate: roll the linearised model out from s_0 ----
+  if (lane == 0) {
+    W.s[0] = W.lins[0]; W.s[1] = W.lins[1]; W.s[2] = W.lins[2];
+    for (int t = 0; t < T; ++t) {
+      const Real* s0 = W.s + 3 * t;
+      Real u0 = W.u[2 * t], u1 = W.u[2 * t + 1];
+      W.s[3 * t + 3] = s0[0] + W.Aj[2 * t] * s0[2] + W.Bj[6 * t] * u0 + W.Bj[6 * t + 1] * u1 + W.Cj[3 * t];
+      W.s[3 * t + 4] = s0[1] + W.Aj[2 * t + 1] * s0[2] + W.Bj[6 * t + 2] * u0 + W.Bj[6 * t + 3] * u1 + W.Cj[3 * t + 1];
+      W.s[3 * t + 5] = s0[2] + W.Bj[6 * t + 4] * u0 + W.Bj[6 * t + 5] * u1 + W.Cj[3 * t + 2];
+    }
+  }
+  ctx.sync();
+  const Real mu0 = 1;
+  int nrows = 0;
+  for (int t = lane; t < T; t += nl) {
+    for (int c = 0; c < 10; ++c) {
+      Row<Real> r = su_row<Real>(P, W, t, c);
+      Real sv = r.live ? rmax(r.g, (Real)1e-2) : (Real)1;
+      W.bs[10 * t + c] = sv;
+      W.bnu[10 * t + c] = r.live ? mu0 / sv : (Real)0;
+      if (r.live) ++nrows;
+    }
+    if (acc) {
+      Real dx = W.s[3 * t + 3] - W.pref[2 * t], dy = W.s[3 * t + 4] - W.pref[2 * t + 1];
+      for (int o = 0; o < N; ++o) {
+        Real l = (Real)W.hx[o * T + t] * dx + (Real)W.hy[o * T + t] * dy + (Real)W.hc[o * T + t] - W.d[t];
+        Real sv = (l + sqrt_(l * l + 4 * mu0 / ro1)) / 2;
+        W.hs[o * T + t] = sv;
+        W.hnu[o * T + t] = mu0 / sv;
+        ++nrows;
+      }
+    }
+  }
+  const Real Mrows = ctx.sum((Real)nrows);
+  ctx.sync();
+  const Real tol_mu = sizeof(Real) == 4 ? (Real)1e-6 : (Real)1e-10;
+  const Real tol_r = sizeof(Real) == 4 ? (Real)1e-5 : (Real)1e-9;
+  const Real reg = (Real)1e-9;
+  int status = 1, it = 0;
+  for (it = 0; it < P.max_iter; ++it) {
+    Real sigma_mu = 0;
+    Real mu = 0;
+    for (int phase = 0; phase < 2; ++phase) {
+      // ---- assemble stage gradients (and, in phase 0, Hessian weights) ----
+      Real acc_mu = 0, acc_r = 0;
+      for (int t = lane; t < T; t += nl) {
+        Real* gw = W.gw + 8 * t;
+        const Real* sn = W.s + 3 * t + 3;
+        const Real tw = 2 * (Real)P.ws;
+        gw[0] = tw * (sn[0] - W.ref[3 * t + 3]);
+        gw[1] = tw * (sn[1] - W.ref[3 * t + 4]);
+        gw[2] = (P.dynamics == RDA_DYN_OMNI ? (Real)0 : tw * (sn[2] - W.ref[3 * t + 5]))
+                + ro2 * (W.Skk[t] * (sn[2] - W.lins[3 * t + 2]) + W.Sgk[t]);
+        gw[3] = 2 * (Real)P.wu * (W.u[2 * t] - W.vref) + reg * W.u[2 * t];
+        gw[4] = reg * W.u[2 * t + 1];
+        gw[5] = N > 0 ? -(Real)P.slack_gain + reg * W.d[t] : (Real)0;
+        gw[6] = 0; gw[7] = 0;
+        Real wb[5] = {0, 0, 0, 0, 0};
+        for (int c = 0; c < 10; ++c) {
+          Row<Real> r = su_row<Real>(P, W, t, c);
+          if (!r.live) continue;
+          Real sv = W.bs[10 * t + c], nu = W.bnu[10 * t + c];
+          Real res = r.g - sv;
+          Real om = nu / sv;
+          Real term;
+          if (phase == 0) {
+            term = -om * res;
+            acc_mu += sv * nu;
+            acc_r = rmax(acc_r, abs_(res));
+          } else {
+            Real dir = su_row_dir<Real>(r, W.dza + 5 * t, W.dva + 3 * t);
+            Real dsa = dir + res;
+            Real dna = (-sv * nu - nu * dsa) / sv;
+            term = (sigma_mu - dsa * dna) / sv - om * res;
+          }
+          // g -= grad * term
+          gw[r.comp] -= r.sgn * term;
+          if (r.rate) gw[r.comp + 3] += r.sgn * term;
+          if (phase == 0) wb[(r.rate ? 3 : 0) + (r.comp - 3)] += om;
+        }
+        if (phase == 0) for (int k = 0; k < 5; ++k) W.wb[5 * t + k] = wb[k];
+        Real m0 = 0, m1 = 0, m2 = 0, m3 = 0, m4 = 0, m5 = 0;
+        Real dx = sn[0] - W.pref[2 * t], dy = sn[1] - W.pref[2 * t + 1];
+        Real dd = W.d[t];
+        for (int o = 0; o < N; ++o) {
+          Real ax = W.hx[o * T + t], ay = W.hy[o * T + t];
+          Real l = ax * dx + ay * dy + (Real)W.hc[o * T + t] - dd;
+          Real tk, om;
+          if (acc) {
+            Real sv = W.hs[o * T + t], nu = W.hnu[o * T + t];
+            Real res = l + nu / ro1 - sv;
+            Real den = sv + nu / ro1;
+            om = nu / den;
+            if (phase == 0) {
+              tk = om * (nu / ro1 - res);
+              acc_mu += sv * nu;
+              acc_r = rmax(acc_r, abs_(res));
+            } else {
+              Real dir = ax * W.dza[5 * t + 5] + ay * W.dza[5 * t + 6] - W.dva[3 * t + 2];
+              Real dna = -(sv * nu + nu * res + nu * dir) / den;
+              Real dsa = dir + dna / ro1 + res;
+              Real cc = sv * nu - sigma_mu + dsa * dna;
+              tk = nu - (cc + nu * res) / den;
+            }
+          } else {
+            om = ro1;               // plain quadratic 1/2 ro1 Im^2  (rda_solver.py:378-379)
+            tk = -ro1 * l;
+          }
+          gw[0] -= ax * tk; gw[1] -= ay * tk; gw[5] += tk;
+          if (phase == 0) {
+            m0 += om * ax * ax; m1 += om * ax * ay; m2 -= om * ax;
+            m3 += om * ay * ay; m4 -= om * ay; m5 += om;
+          }
+        }
+        if (phase == 0) {
+          Real* M = W.Wm + 6 * t;
+          M[0] = m0; M[1] = m1; M[2] = m2; M[3] = m3; M[4] = m4; M[5] = m5;
+        }
+      }
+      if (phase == 0) {
+        mu = ctx.sum(acc_mu) / Mrows;
+        Real rmx = ctx.max(acc_r);
+        if (!finite_(mu)) { status = 2; break; }
+        if (mu < tol_mu && rmx < tol_r && it > 0) { status = 0; break; }
+      }
+      ctx.sync();
+      su_riccati<Real, Ctx>(P, W, ctx, phase == 0, phase == 0 ? W.dza : W.dz, phase == 0 ? W.dva : W.dv);
+      // ---- step lengths ----
+      const Real* dz = phase == 0 ? W.dza : W.dz;
+      const Real* dv = phase == 0 ? W.dva : W.dv;
+      Real amax = 1e30f, s0 = 0, s1 = 0, s2 = 0;
+      for (int t = lane; t < T; t += nl) {
+        for (int c = 0; c < 10; ++c) {
+          Row<Real> r = su_row<Real>(P, W, t, c);
+          if (!r.live) continue;
+          Real sv = W.bs[10 * t + c], nu = W.bnu[10 * t + c];
+          Real res = r.g - sv;
+          Real dir = su_row_dir<Real>(r, dz + 5 * t, dv + 3 * t);
+          Real ds = dir + res, dn;
+          if (phase == 0) dn = (-sv * nu - nu * ds) / sv;
+          else {
+            Real dira = su_row_dir<Real>(r, W.dza + 5 * t, W.dva + 3 * t);
+            Real dsa = dira + res;
+            Real dna = (-sv * nu - nu * dsa) / sv;
+            dn = (-(sv * nu - sigma_mu + dsa * dna) - nu * ds) / sv;
+          }
+          if (ds < 0) amax = rmin(amax, -sv / ds);
+          if (dn < 0) amax = rmin(amax, -nu / dn);
+          s0 += sv * nu; s1 += sv * dn + nu * ds; s2 += ds * dn;
+        }
+        if (acc) {
+          Real dx = W.s[3 * t + 3] - W.pref[2 * t], dy = W.s[3 * t + 4] - W.pref[2 * t + 1];
+          for (int o = 0; o < N; ++o) {
+            Real ax = W.hx[o * T + t], ay = W.hy[o * T + t];
+            Real l = ax * dx + ay * dy + (Real)W.hc[o * T + t] - W.d[t];
+            Real sv = W.hs[o * T + t], nu = W.hnu[o * T + t];
+            Real res = l + nu / ro1 - sv, den = sv + nu / ro1;
+            Real dir = ax * dz[5 * t + 5] + ay * dz[5 * t + 6] - dv[3 * t + 2];
+            Real cc = sv * nu;
+            if (phase == 1) {
+              Real dira = ax * W.dza[5 * t + 5] + ay * W.dza[5 * t + 6] - W.dva[3 * t + 2];
+              Real dna = -(sv * nu + nu * res + nu * dira) / den;
+              Real dsa = dira + dna / ro1 + res;
+              cc = sv * nu - sigma_mu + dsa * dna;
+            }
+            Real dn = -(cc + nu * res + nu * dir) / den;
+            Real ds = dir + dn / ro1 + res;
+            if (ds < 0) amax = rmin(amax, -sv / ds);
+            if (dn < 0) amax = rmin(amax, -nu / dn);
+            s0 += sv * nu; s1 += sv * dn + nu * ds; s2 += ds * dn;
+          }
+        }
+      }
+      amax = ctx.min(amax);
+      if (phase == 0) {
+        Real a = rmin((Real)1, amax);
+        Real mua = (ctx.sum(s0) + a * ctx.sum(s1) + a * a * ctx.sum(s2)) / Mrows;
+        Real sg = mua / mu;
+        sg = sg * sg * sg;
+        sigma_mu = rmin(sg, (Real)1) * mu;
+      } else {
+        Real a = rmin((Real)1, (Real)0.995 * amax);
+        // ---- update (needs the corrector quantities once more) ----
+        for (int t = lane; t < T; t += nl) {
+          // rows first: they read the OLD iterate through su_row
+          Real gsave[10], lsave[RDA_MAX_EDGE > 0 ? 1 : 1];
+          (void)lsave;
+          for (int c = 0; c < 10; ++c) { Row<Real> r = su_row<Real>(P, W, t, c); gsave[c] = r.g; }
+          for (int c = 0; c < 10; ++c) {
+            Row<Real> r = su_row<Real>(P, W, t, c);
+            if (!r.live) continue;
+            Real sv = W.bs[10 * t + c], nu = W.bnu[10 * t + c];
+            Real res = gsave[c] - sv;
+            Real dir = su_row_dir<Real>(r, W.dz + 5 * t, W.dv + 3 * t);
+            Real ds = dir + res;
+            Real dira = su_row_dir<Real>(r, W.dza + 5 * t, W.dva + 3 * t);
+            Real dsa = dira + res;
+            Real dna = (-sv * nu - nu * dsa) / sv;
+            Real dn = (-(sv * nu - sigma_mu + dsa * dna) - nu * ds) / sv;
+            W.bs[10 * t + c] = sv + a * ds;
+            W.bnu[10 * t + c] = nu + a * dn;
+          }
+          if (acc) {
+            Real dx = W.s[3 * t + 3] - W.pref[2 * t], dy = W.s[3 * t + 4] - W.pref[2 * t + 1];
+            for (int o = 0; o < N; ++o) {
+              Real ax = W.hx[o * T + t], ay = W.hy[o * T + t];
+              Real l = ax * dx + ay * dy + (Real)W.hc[o * T + t] - W.d[t];
+              Real sv = W.hs[o * T + t], nu = W.hnu[o * T + t];
+              Real res = l + nu / ro1 - sv, den = sv + nu / ro1;
+              Real dir = ax * W.dz[5 * t + 5] + ay * W.dz[5 * t + 6] - W.dv[3 * t + 2];
+              Real dira = ax * W.dza[5 * t + 5] + ay * W.dza[5 * t + 6] - W.dva[3 * t + 2];
+              Real dna = -(sv * nu + nu * res + nu * dira) / den;
+              Real dsa = dira + dna / ro1 + res;
+              Real cc = sv * nu - sigma_mu + dsa * dna;
+              Real dn = -(cc + nu * res + nu * dir) / den;
+              Real ds = dir + dn / ro1 + res;
+              W.hs[o * T + t] = sv + a * ds;
+              W.hnu[o * T + t] = nu + a * dn;
+            }
+          }
+        }
+        ctx.sync();   // every lane has finished reading the old (s, u, d) of its neighbours
+        for (int t = lane; t < T; t += nl) {
+          W.u[2 * t] += a * W.dv[3 * t]; W.u[2 * t + 1] += a * W.dv[3 * t + 1];
+          if (N > 0) W.d[t] += a * W.dv[3 * t + 2];
+          W.s[3 * t + 3] += a * W.dz[5 * t + 5];
+          W.s[3 * t + 4] += a * W.dz[5 * t + 6];
+          W.s[3 * t + 5] += a * W.dz[5 * t + 7];
+        }
+        ctx.sync();
+      }
+    }
+    if (status != 1) break;
+  }
+  if (iters_out) *iters_out = it;
+  return status;
+}
+
+}  // namespace rda

@@ -1,0 +1,279 @@
+"""RDA_solver — the drop-in for RDA_planner.rda_solver.RDA_solver, backed by sm_100a kernels.
+
+Mirror of /root/reference/RDA_planner/rda_solver.py (class RDA_solver): constructor :18-22
+(+ tunables :185-201, ws/wu :218-219), iterative_solve :573-610, assign_adjust_parameter
+:426-434, get_adjust_parameter :1055-1056, reset :1060-1068.  numpy in / numpy out at this
+level, exactly like the reference; all arithmetic runs in librda_b200.so (include/rda_b200.h)
+on the current CUDA device, with PyTorch used only for device memory and streams.
+
+New surface (absent in the reference, required by BASELINE.json): `batch` > 1 and
+`iterative_solve_batch` on CUDA tensors — B independent planning instances that share
+(T, N, E, robot, dynamics) and keep their own warm-start state on the device.
+"""
+import ctypes as C
+import time
+
+import numpy as np
+import torch
+
+from . import _cabi
+
+
+def _as_cuda_f32(x, device):
+    return torch.as_tensor(x, dtype=torch.float32, device=device).contiguous()
+
+
+def canonical_polygon_rows(A, b):
+    """Order the rows of a closed convex polygon {x: Ax <= b} counter-clockwise by normal
+    angle (a no-op for the output of mpc.py:476-510) so that vertex i joins rows i-1 and i."""
+    A = np.asarray(A, float)
+    b = np.asarray(b, float).reshape(-1)
+    n = A.shape[0]
+    det = A[np.arange(n) - 1, 0] * A[:, 1] - A[np.arange(n) - 1, 1] * A[:, 0]
+    if n >= 3 and np.all(det > 0):
+        return A, b
+    ang = np.arctan2(A[:, 1], A[:, 0])
+    order = np.argsort(ang)
+    A, b = A[order], b[order]
+    det = A[np.arange(n) - 1, 0] * A[:, 1] - A[np.arange(n) - 1, 1] * A[:, 0]
+    if n < 3 or not np.all(det > 0):
+        raise ValueError('obstacle half-spaces must describe a closed convex polygon '
+                         '(unbounded polyhedra are not supported by rda_planner_b200)')
+    return A, b
+
+
+def pack_obstacles(obstacle_list, T, N, E):
+    """assign_obstacle_parameter (rda_solver.py:483-526): pad a short list by repeating its
+    last element (mutating the caller's list, as the reference does), truncate a long one,
+    zero-pad rows to E.  Returns (A [N,Tc,E,2], b [N,Tc,E], kind [N], count, time_varying)."""
+    count = len(obstacle_list)
+    if 0 < count < N:
+        obstacle_list += [obstacle_list[-1]] * (N - count)
+    number = min(len(obstacle_list), N)
+    tv = any(isinstance(o.A, list) for o in obstacle_list[:number])
+    Tc = T + 1 if tv else 1
+    A = np.zeros((N, Tc, E, 2), np.float32)
+    b = np.zeros((N, Tc, E), np.float32)
+    kind = np.zeros(N, np.int32)
+    for i in range(number):
+        o = obstacle_list[i]
+        circle = o.cone_type != 'Rpositive'
+        kind[i] = _cabi.OBS_CIRCLE if circle else _cabi.OBS_POLYGON
+        for t in range(Tc):
+            At = o.A[t] if isinstance(o.A, list) else o.A
+            bt = o.b[t] if isinstance(o.b, list) else o.b
+            At = np.asarray(At, float)
+            bt = np.asarray(bt, float).reshape(-1)
+            if not circle:
+                At, bt = canonical_polygon_rows(At, bt)
+            en = At.shape[0]
+            if en > E:
+                raise ValueError(f'obstacle with {en} edges exceeds max_edge_num={E}')
+            A[i, t, :en] = At
+            b[i, t, :en] = bt
+    return A, b, kind, count, tv
+
+
+class RDA_solver:
+    def __init__(self, receding, car_tuple, max_edge_num=5, max_obs_num=5, iter_num=2, step_time=0.1,
+                 iter_threshold=0.2, process_num=4, accelerated=True, time_print=True, batch=1,
+                 device=None, su_fp64=True, z_theta=0.5, **kwargs):
+        """kwargs: slack_gain (8), max_sd (1.0), min_sd (0.1), ro1 (200), ro2 (1), ws (1), wu (1)
+        — rda_solver.py:24-31.  `process_num` is accepted for compatibility and ignored."""
+        if not torch.cuda.is_available():
+            raise RuntimeError('rda_planner_b200 needs a CUDA device (B200); there is no CPU fallback')
+        self.lib = _cabi.load()
+        self.device = torch.device(device if device is not None else f'cuda:{torch.cuda.current_device()}')
+        self.T = receding
+        self.car_tuple = car_tuple
+        self.L = car_tuple.wheelbase
+        self.max_obs_num = max_obs_num
+        self.max_edge_num = max(max_edge_num, 3)
+        self.dynamics = car_tuple.dynamics
+        self.iter_num = iter_num
+        self.dt = step_time
+        self.iter_threshold = iter_threshold
+        self.accelerated = accelerated
+        self.process_num = process_num
+        self.time_print = time_print
+        self.batch = batch
+        self.ws = kwargs.get('ws', 1)
+        self.wu = kwargs.get('wu', 1)
+        if car_tuple.cone_type != 'Rpositive':
+            raise NotImplementedError('rda_planner_b200 supports polygon (Rpositive) robots')
+        G = np.asarray(car_tuple.G, float)
+        h = np.asarray(car_tuple.h, float).reshape(-1)
+        G, h = canonical_polygon_rows(G, h)
+        R = G.shape[0]
+        if R > _cabi.MAX_ROBOT_EDGE or self.max_edge_num > _cabi.MAX_EDGE:
+            raise ValueError('at most 8 robot edges / obstacle edges are supported')
+        cfg = _cabi.Config()
+        cfg.batch, cfg.receding, cfg.max_obs_num = batch, receding, max_obs_num
+        cfg.max_edge_num, cfg.robot_edges = self.max_edge_num, R
+        cfg.dynamics = _cabi.DYNAMICS[self.dynamics]
+        cfg.accelerated = int(bool(accelerated))
+        cfg.su_fp64 = int(bool(su_fp64))
+        cfg.step_time, cfg.wheelbase = step_time, float(self.L)
+        ms = np.asarray(car_tuple.max_speed, float).reshape(-1)
+        ma = np.asarray(car_tuple.max_acce, float).reshape(-1)
+        for k in range(2):
+            cfg.max_speed[k] = ms[k]
+            cfg.acce_bound[k] = ma[k] * step_time                      # :44
+        cfg.ws, cfg.wu = self.ws, self.wu
+        for j in range(R):
+            cfg.G[2 * j], cfg.G[2 * j + 1], cfg.h[j] = G[j, 0], G[j, 1], h[j]
+        self._tun = _cabi.Tunables(kwargs.get('slack_gain', 8), kwargs.get('max_sd', 1.0),
+                                   kwargs.get('min_sd', 0.1), kwargs.get('ro1', 200),
+                                   kwargs.get('ro2', 1), z_theta)
+        self._cfg = cfg
+        self._h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.rda_create(C.byref(cfg), C.byref(self._tun), C.byref(self._h)), 'rda_create')
+        B, T = batch, receding
+        dev = self.device
+        self._out = {
+            'u': torch.empty((B, 2, T), dtype=torch.float32, device=dev),
+            's': torch.empty((B, 3, T + 1), dtype=torch.float32, device=dev),
+            'resi_pri': torch.empty(B, dtype=torch.float32, device=dev),
+            'resi_dual': torch.empty(B, dtype=torch.float32, device=dev),
+            'status': torch.empty(B, dtype=torch.int32, device=dev),
+            'iters': torch.empty(B, dtype=torch.int32, device=dev),
+        }
+        self._keep = None
+        self.obstacle_num = 0
+
+    def __del__(self):
+        try:
+            if getattr(self, '_h', None) is not None and self._h.value:
+                self.lib.rda_destroy(self._h)
+                self._h = C.c_void_p()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ tunables
+    def assign_adjust_parameter(self, **kwargs):
+        """slack_gain, max_sd, min_sd, ro1, ro2 (ws/wu silently ignored, as in :426-434)."""
+        t = self._tun
+        t.slack_gain = kwargs.get('slack_gain', t.slack_gain)
+        t.max_sd = kwargs.get('max_sd', t.max_sd)
+        t.min_sd = kwargs.get('min_sd', t.min_sd)
+        t.ro1 = kwargs.get('ro1', t.ro1)
+        t.ro2 = kwargs.get('ro2', t.ro2)
+        _cabi.check(self.lib.rda_set_tunables(self._h, C.byref(t)), 'rda_set_tunables')
+
+    def get_adjust_parameter(self):
+        t = _cabi.Tunables()
+        _cabi.check(self.lib.rda_get_tunables(self._h, C.byref(t)), 'rda_get_tunables')
+        return {'slack_gain': t.slack_gain, 'max_sd': t.max_sd, 'min_sd': t.min_sd, 'ro1': t.ro1,
+                'ro2': t.ro2, 'ws': self.ws, 'wu': self.wu}
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def reset(self):
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.rda_reset(self._h, self._stream()), 'rda_reset')
+
+    def cold_start(self):
+        """Extension: forget every warm-start quantity (constructor state)."""
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.rda_cold_start(self._h, self._stream()), 'rda_cold_start')
+
+    def buffer_count(self, buf_id):
+        ptr, cnt = C.c_void_p(), C.c_size_t()
+        _cabi.check(self.lib.rda_get_buffer(self._h, buf_id, C.byref(ptr), C.byref(cnt)), 'rda_get_buffer')
+        return cnt.value
+
+    def state_buffer(self, buf_id, shape=None):
+        """Copy of a persistent device buffer (checkpointing / tests)."""
+        dtype = torch.int32 if buf_id == _cabi.BUF_COUNTERS else torch.float32
+        out = torch.empty(self.buffer_count(buf_id), dtype=dtype, device=self.device)
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.rda_copy_buffer(self._h, buf_id, out.data_ptr(), 0, self._stream()),
+                        'rda_copy_buffer')
+        return out if shape is None else out.reshape(shape)
+
+    def load_state_buffer(self, buf_id, values):
+        """Overwrite a persistent device buffer (resume / tests)."""
+        dtype = torch.int32 if buf_id == _cabi.BUF_COUNTERS else torch.float32
+        src = torch.as_tensor(values, dtype=dtype, device=self.device).contiguous().reshape(-1)
+        if src.numel() != self.buffer_count(buf_id):
+            raise ValueError('wrong element count')
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.rda_copy_buffer(self._h, buf_id, src.data_ptr(), 1, self._stream()),
+                        'rda_copy_buffer')
+        self._keep_state = src
+
+    # ------------------------------------------------------------------ solve
+    def _inputs(self, nom_s, nom_u, ref_s, ref_speed, obs_A, obs_b, obs_kind, obs_count, time_varying):
+        B, T, N, E = self.batch, self.T, self.max_obs_num, self.max_edge_num
+        dev = self.device
+        t = {
+            'nom_s': _as_cuda_f32(nom_s, dev).reshape(B, 3, T + 1),
+            'nom_u': _as_cuda_f32(nom_u, dev).reshape(B, 2, T),
+            'ref_s': _as_cuda_f32(ref_s, dev).reshape(B, 3, T + 1),
+            'ref_speed': _as_cuda_f32(ref_speed, dev).reshape(B),
+        }
+        Tc = T + 1 if time_varying else 1
+        if N > 0:
+            t['obs_A'] = _as_cuda_f32(obs_A, dev).reshape(B, N, Tc, E, 2)
+            t['obs_b'] = _as_cuda_f32(obs_b, dev).reshape(B, N, Tc, E)
+            t['obs_kind'] = torch.as_tensor(obs_kind, dtype=torch.int32, device=dev).reshape(B, N).contiguous()
+            t['obs_count'] = torch.as_tensor(obs_count, dtype=torch.int32, device=dev).reshape(B).contiguous()
+        inp = _cabi.Inputs()
+        for k in ('nom_s', 'nom_u', 'ref_s', 'ref_speed', 'obs_A', 'obs_b', 'obs_kind', 'obs_count'):
+            setattr(inp, k, t[k].data_ptr() if k in t else None)
+        inp.obs_time_varying = int(bool(time_varying))
+        self._keep = t          # the kernels read these buffers asynchronously
+        return inp
+
+    def _outputs(self):
+        o = _cabi.Outputs()
+        o.u_opt, o.s_opt = self._out['u'].data_ptr(), self._out['s'].data_ptr()
+        o.resi_pri, o.resi_dual = self._out['resi_pri'].data_ptr(), self._out['resi_dual'].data_ptr()
+        o.status, o.iters = self._out['status'].data_ptr(), self._out['iters'].data_ptr()
+        return o
+
+    def iterative_solve_batch(self, nom_s, nom_u, ref_s, ref_speed, obs_A=None, obs_b=None, obs_kind=None,
+                              obs_count=None, time_varying=False, iter_num=None, iter_threshold=None):
+        """B instances at once.  Arguments are array-likes or CUDA tensors with the layouts of
+        include/rda_b200.h; returns a dict of CUDA tensors (u [B,2,T], s [B,3,T+1], resi_pri,
+        resi_dual, status, iters) valid on the current stream.  No host synchronisation."""
+        inp = self._inputs(nom_s, nom_u, ref_s, ref_speed, obs_A, obs_b, obs_kind, obs_count, time_varying)
+        out = self._outputs()
+        it = self.iter_num if iter_num is None else iter_num
+        thr = self.iter_threshold if iter_threshold is None else iter_threshold
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.rda_solve(self._h, C.byref(inp), C.byref(out), int(it), float(thr),
+                                           self._stream()), 'rda_solve')
+        return self._out
+
+    def launch_count(self):
+        return self.lib.rda_last_launch_count(self._h)
+
+    def iterative_solve(self, nom_s, nom_u, ref_states, ref_speed, obstacle_list, **kwargs):
+        """Reference signature (:573): numpy in, (u (2,T) ndarray, info dict) out."""
+        if self.batch != 1:
+            raise RuntimeError('iterative_solve is the single-instance API; use iterative_solve_batch')
+        T, N, E = self.T, self.max_obs_num, self.max_edge_num
+        start = time.time()
+        ref = np.hstack(ref_states)[0:3, :]                                     # :580
+        if N > 0:
+            A, b, kind, count, tv = pack_obstacles(obstacle_list, T, N, E)
+        else:
+            A = b = kind = None
+            count, tv = len(obstacle_list), False
+        self.obstacle_num = len(obstacle_list)
+        res = self.iterative_solve_batch(np.asarray(nom_s, float)[None], np.asarray(nom_u, float)[None],
+                                         ref[None], np.array([ref_speed], float),
+                                         None if A is None else A[None], None if b is None else b[None],
+                                         None if kind is None else kind[None], np.array([count]), tv)
+        u = res['u'][0].double().cpu().numpy()
+        s = res['s'][0].double().cpu().numpy()
+        info = {'ref_traj_list': ref_states, 'opt_state_list': [s[:, t:t + 1] for t in range(T + 1)],
+                'iteration_time': time.time() - start,
+                'resi_dual': float(res['resi_dual'][0]), 'resi_pri': float(res['resi_pri'][0]),
+                'status': int(res['status'][0]), 'iterations': int(res['iters'][0])}
+        if self.time_print:
+            print('iterations:', info['iterations'], ' time:', info['iteration_time'])
+        return u, info

@@ -1,0 +1,121 @@
+"""Seeded synthetic planning instances shared by bench.py and the tests.
+
+Everything here is plain numpy on the host; it only produces the inputs of
+RDA_solver.iterative_solve / iterative_solve_batch (nominal states and controls,
+reference points, obstacle half-spaces)."""
+from collections import namedtuple
+from math import cos, sin, tan
+
+import numpy as np
+
+from .mpc import polygon_halfspaces, rdaobs
+
+car = namedtuple('car', 'G h cone_type wheelbase max_speed max_acce dynamics')
+
+
+def rectangle_robot(length=4.6, width=1.6, wheelbase=3.0, dynamics='acker',
+                    max_speed=(10, 1), max_acce=(10, 0.5)):
+    """Car tuple for a rectangular body whose reference point is the rear axle centre
+    (ir-sim convention): x in [-(length-wheelbase)/2, (length+wheelbase)/2]."""
+    x0 = -(length - wheelbase) / 2
+    x1 = (length + wheelbase) / 2
+    y1 = width / 2
+    vert = np.array([[x0, x1, x1, x0], [-y1, -y1, y1, y1]])
+    G, h = polygon_halfspaces(vert)
+    return car(G, h, 'Rpositive', wheelbase, list(max_speed), list(max_acce), dynamics)
+
+
+def rollout(state, u, dt, L, dynamics):
+    """Nominal trajectory of the nonlinear model (mpc.py:293-336) for controls u (2,T)."""
+    T = u.shape[1]
+    s = np.zeros((3, T + 1))
+    s[:, 0] = np.asarray(state, float).reshape(3)
+    for t in range(T):
+        v, w = u[0, t], u[1, t]
+        th = s[2, t]
+        if dynamics == 'acker':
+            ds = np.array([v * cos(th), v * sin(th), v * tan(w) / L])
+        elif dynamics == 'diff':
+            ds = np.array([v * cos(th), v * sin(th), w])
+        else:
+            ds = np.array([v * cos(w), v * sin(w), 0.0])
+        s[:, t + 1] = s[:, t] + ds * dt
+    return s
+
+
+def rect_vertices(cx, cy, length, width, yaw):
+    c, s = cos(yaw), sin(yaw)
+    loc = np.array([[-length / 2, length / 2, length / 2, -length / 2],
+                    [-width / 2, -width / 2, width / 2, width / 2]])
+    return np.array([[c, -s], [s, c]]) @ loc + np.array([[cx], [cy]])
+
+
+def random_convex_polygon(rng, cx, cy, radius, k):
+    ang = np.sort(rng.uniform(0, 2 * np.pi, k))
+    # keep it well-conditioned: spread the angles
+    ang = np.linspace(0, 2 * np.pi, k, endpoint=False) + rng.uniform(-0.3, 0.3, k) * (2 * np.pi / k)
+    return np.array([cx + radius * np.cos(ang), cy + radius * np.sin(ang)])
+
+
+def make_instance(seed, T=30, N=20, E=4, dynamics='acker', dt=0.1, ref_speed=4.0,
+                  kind='polygon', moving=False, lateral=(1.8, 6.0), v_nom=None):
+    """One planning instance along a straight reference line (corridor geometry).
+
+    Returns dict(nom_s (3,T+1), nom_u (2,T), ref (3,T+1), ref_speed, obstacles [rdaobs]*N).
+    Obstacles are boxes / convex k-gons / discs scattered beside and on the path ahead of
+    the robot so that a few of them constrain the motion."""
+    rng = np.random.default_rng(seed)
+    L = 3.0
+    heading = rng.uniform(-np.pi, np.pi)
+    start = np.array([rng.uniform(5, 55), rng.uniform(5, 55)])
+    dirv = np.array([cos(heading), sin(heading)])
+    nrm = np.array([-dirv[1], dirv[0]])
+    state = np.array([start[0] + rng.normal(0, 0.3) * nrm[0], start[1] + rng.normal(0, 0.3) * nrm[1],
+                      heading + rng.normal(0, 0.1)])
+    v0 = ref_speed if v_nom is None else v_nom
+    nom_u = np.vstack([np.full(T, v0), np.zeros(T)])
+    if dynamics == 'omni':
+        nom_u[1] = heading
+    nom_s = rollout(state, nom_u, dt, L, dynamics)
+    ref = np.zeros((3, T + 1))
+    for t in range(T + 1):
+        ref[0:2, t] = start + dirv * (ref_speed * dt * t)
+        ref[2, t] = heading
+    reach = ref_speed * dt * T
+    obstacles = []
+    for o in range(N):
+        along = rng.uniform(2.0, reach + 6.0)
+        side = rng.choice([-1.0, 1.0])
+        lat = side * rng.uniform(*lateral)
+        c = start + dirv * along + nrm * lat
+        vel = np.zeros((2, 1))
+        if moving:
+            sp = rng.uniform(0, 1.0)
+            hd = rng.uniform(-np.pi, np.pi)
+            vel = np.array([[sp * cos(hd)], [sp * sin(hd)]])
+        if kind == 'circle':
+            r = rng.uniform(0.5, 1.0)
+            A0 = np.array([[1.0, 0], [0, 1.0], [0, 0]])
+            if moving and np.linalg.norm(vel) > 0.01:
+                A = [A0.copy() for _ in range(T + 1)]
+                b = [np.vstack((c.reshape(2, 1) + vel * (t * dt), [[-r]])) for t in range(T + 1)]
+            else:
+                A, b = A0, np.vstack((c.reshape(2, 1), [[-r]]))
+            obstacles.append(rdaobs(A, b, 'norm2', c.reshape(2, 1), None))
+        else:
+            if E == 4:
+                vert = rect_vertices(c[0], c[1], rng.uniform(1.5, 5.0), rng.uniform(1.0, 2.5),
+                                     rng.uniform(0, np.pi))
+            else:
+                k = int(rng.integers(3, E + 1))
+                vert = random_convex_polygon(rng, c[0], c[1], rng.uniform(0.5, 2.0), k)
+            if moving and np.linalg.norm(vel) > 0.01:
+                A, b = [], []
+                for t in range(T + 1):
+                    At, bt = polygon_halfspaces(vert + vel * (t * dt))
+                    A.append(At); b.append(bt)
+            else:
+                A, b = polygon_halfspaces(vert)
+            obstacles.append(rdaobs(A, b, 'Rpositive', None, vert))
+    return {'nom_s': nom_s, 'nom_u': nom_u, 'ref': ref, 'ref_speed': ref_speed,
+            'obstacles': obstacles, 'state': state}

@@ -1,0 +1,82 @@
+"""ctypes access to tests/_build/libhost_shim.so (g++ build of the CUDA kernels' numerical
+cores) — test infrastructure only."""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO = os.path.join(HERE, '_build', 'libhost_shim.so')
+SRC = os.path.join(HERE, 'host_shim', 'host_shim.cpp')
+
+
+class SuParams(C.Structure):
+    _fields_ = [('T', C.c_int), ('N', C.c_int), ('dynamics', C.c_int), ('accelerated', C.c_int),
+                ('dt', C.c_float), ('L', C.c_float), ('umax', C.c_float * 2), ('ab', C.c_float * 2),
+                ('ws', C.c_float), ('wu', C.c_float), ('slack_gain', C.c_float), ('dmin', C.c_float),
+                ('dmax', C.c_float), ('ro1', C.c_float), ('ro2', C.c_float), ('max_iter', C.c_int)]
+
+
+def build(force=False):
+    csrc = os.path.join(HERE, '..', 'rda_planner_b200', 'csrc')
+    deps = [SRC] + [os.path.join(csrc, f) for f in os.listdir(csrc)]
+    if (not force) and os.path.exists(SO) and all(os.path.getmtime(SO) >= os.path.getmtime(d) for d in deps):
+        return SO
+    os.makedirs(os.path.dirname(SO), exist_ok=True)
+    subprocess.check_call(['g++', '-O2', '-std=c++17', '-shared', '-fPIC', '-o', SO, SRC])
+    return SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(build())
+    return _lib
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+DYN = {'acker': 0, 'diff': 1, 'omni': 2}
+
+
+def cell(G, h, kind, A, b, p, phi, dbar, zeta, xi, ro2, theta=0.5, prec='d'):
+    G = _f32(G); h = _f32(np.ravel(h)); A = _f32(A); b = _f32(np.ravel(b))
+    out = np.zeros(28)
+    fn = getattr(lib(), 'shim_cell_' + prec)
+    fn.restype = C.c_int
+    rc = fn(_p(G), _p(h), C.c_int(G.shape[0]), C.c_int(kind), C.c_int(A.shape[0]), _p(A), _p(b),
+            C.c_double(p[0]), C.c_double(p[1]), C.c_double(phi), C.c_double(dbar), C.c_double(zeta),
+            C.c_double(xi[0]), C.c_double(xi[1]), C.c_double(ro2), C.c_double(theta), _p(out))
+    assert rc == 0, rc
+    E, R = A.shape[0], G.shape[0]
+    keys = ['z', 'zeta_new', 'xi0', 'xi1', 'ax', 'ay', 'c0', 'gx', 'gy', 'hm0', 'hm1', 'path']
+    r = {k: out[16 + i] for i, k in enumerate(keys)}
+    r['lam'] = out[:E].copy(); r['mu'] = out[8:8 + R].copy(); r['path'] = int(r['path'])
+    return r
+
+
+def su(params, lins, linu, ref, vref, dis, hx, hy, hc, gx, gy, pref, prec='d'):
+    T, N = params.T, params.N
+    lins = _f64(np.asarray(lins).T); linu = _f64(np.asarray(linu).T); ref = _f64(np.asarray(ref).T)
+    pref = _f64(np.asarray(pref).T); dis = _f64(np.ravel(dis))
+    hx, hy, hc, gx, gy = (_f32(np.asarray(a).reshape(N, T)) for a in (hx, hy, hc, gx, gy))
+    s = np.zeros((T + 1, 3)); u = np.zeros((T, 2)); d = np.zeros(T)
+    it = C.c_int(0)
+    fn = getattr(lib(), 'shim_su_' + prec)
+    fn.restype = C.c_int
+    st = fn(C.byref(params), _p(lins), _p(linu), _p(ref), C.c_double(vref), _p(dis), _p(hx), _p(hy), _p(hc),
+            _p(gx), _p(gy), _p(pref), _p(s), _p(u), _p(d), C.byref(it))
+    return s.T.copy(), u.T.copy(), d, st, it.value
