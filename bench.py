@@ -1,0 +1,303 @@
+#!/usr/bin/env python
+"""bench.py — MPC solves/s of the ADMM hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # own arm (B200 kernels)
+    python bench.py --impl reference --gpus N --steps K ...   # CPU arm (compiled port of the path)
+
+Workload ("step" = one batched solve of B instances per GPU, cold warm-start state, inputs resident
+in HBM): metric row of SURVEY.md §8d — Ackermann robot 4.6 x 1.6 m, horizon T=30, N=20 static
+polygon obstacles (E=4), 50 ADMM iterations with early stop disabled (iter_threshold = 0), seeded
+synthetic instances (rda_planner_b200/scenarios.py).  One JSON line on stdout (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+T, N, E, R, ITERS = 30, 20, 4, 4, 50
+METRIC = 'MPC solves/sec (T=30, 20 obs, 50 ADMM iters)'
+WORKLOAD = 'metric row: acker, T=30, N=20 static polygons (E=4), 50 ADMM iterations, iter_threshold=0, cold start'
+
+
+def algorithmic_bytes():
+    """SURVEY.md §8d, float32: compulsory HBM bytes per instance-iteration of K2 (cells) and K1 (su)."""
+    w = 4
+    k2 = w * (N * T * (2 * E + 2 * R + 2 + 4 + 2 + 5) + 3 * N * E * 1 + 4 * T)
+    k1 = w * (5 * N * T + 3 * (T + 1) + 2 * (3 * (T + 1) + 3 * T))
+    return k2, k1
+
+
+def build_inputs(batch, seed0):
+    from rda_planner_b200.scenarios import make_instance
+    from rda_planner_b200.rda_solver import pack_obstacles
+    uniq = min(batch, 1024)
+    insts = [make_instance(seed0 + i, T=T, N=N, E=E) for i in range(uniq)]
+    packs = [pack_obstacles(list(i['obstacles']), T, N, E) for i in insts]
+    rep = -(-batch // uniq)
+
+    def tile(a):
+        return np.concatenate([a] * rep, 0)[:batch]
+    return {
+        'nom_s': tile(np.stack([i['nom_s'] for i in insts]).astype(np.float32)),
+        'nom_u': tile(np.stack([i['nom_u'] for i in insts]).astype(np.float32)),
+        'ref_s': tile(np.stack([i['ref'] for i in insts]).astype(np.float32)),
+        'ref_speed': tile(np.array([i['ref_speed'] for i in insts], np.float32)),
+        'obs_A': tile(np.stack([p[0] for p in packs])),
+        'obs_b': tile(np.stack([p[1] for p in packs])),
+        'obs_kind': tile(np.stack([p[2] for p in packs])),
+        'obs_count': tile(np.array([p[3] for p in packs], np.int32)),
+    }
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
+                                          '-i', str(self.idx), '-lms', '100'], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(',')]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[5:9]):
+                if val.lower().startswith('active'):
+                    reasons.add(nm)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def cpu_port_rate(inputs, sample, threads, iters=ITERS):
+    """Compiled CPU port (oracle/cpu_port) on `sample` instances; returns (solves/s, seconds)."""
+    from oracle import cpu_port
+    from rda_planner_b200.scenarios import rectangle_robot
+    sub = {k: v[:sample] for k, v in inputs.items()}
+    t0 = time.perf_counter()
+    cpu_port.solve_batch(rectangle_robot(), T, N, E, sub['nom_s'], sub['nom_u'], sub['ref_s'], sub['ref_speed'],
+                         sub['obs_A'], sub['obs_b'], sub['obs_kind'], sub['obs_count'], iter_num=iters,
+                         iter_threshold=0.0, threads=threads)
+    dt = time.perf_counter() - t0
+    return sample / dt, dt
+
+
+def run_reference(args):
+    """CPU arm: the path on the host cores.  The reference's own implementation (cvxpy/ECOS/pathos) is
+    not installable in this image, so this times the compiled port with all threads."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    sample = max(cores * 4, 16)
+    inputs = build_inputs(sample, 1000 * 9)
+    for _ in range(max(args.warmup, 1)):
+        cpu_port_rate(inputs, min(sample, cores), cores)
+    t = 0.0
+    for _ in range(args.steps):
+        _, dt = cpu_port_rate(inputs, sample, cores)
+        t += dt
+    value = sample * args.steps / t
+    line = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'solves/s', 'n_gpus': args.gpus,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * t / args.steps,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64/f32', 'data': 'synthetic',
+            'config': {'workload': WORKLOAD, 'batch_per_step': sample},
+            'cpu_baseline': {'value': value, 'unit': 'solves/s', 'cores': cores, 'kind': 'port',
+                             'sample': f'{sample} instances x {ITERS} ADMM iterations per step, OpenMP over instances'},
+            'e2e': {'value': value, 'unit': 'solves/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--batch', type=int, default=4096, help='instances per GPU per step')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from rda_planner_b200.rda_solver import RDA_solver
+    from rda_planner_b200.scenarios import rectangle_robot
+    from rda_planner_b200 import build as rbuild
+    from rda_planner_b200.sharding import gather_batch
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if args.warmup < 3:
+        args.warmup = 3
+    torch.cuda.set_device(local)
+    dev = torch.device(f'cuda:{local}')
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    rbuild.build()
+    B = args.batch
+    host = build_inputs(B, 1000 * 9 + rank * B)              # per-rank shard, generated in place (weak scaling)
+    pinned = {k: torch.from_numpy(v).pin_memory() for k, v in host.items()}
+    devin = {k: v.to(dev) for k, v in pinned.items()}
+    solver = RDA_solver(T, rectangle_robot(), max_edge_num=E, max_obs_num=N, iter_num=ITERS, iter_threshold=0.0,
+                        time_print=False, batch=B, device=dev)
+
+    def step(inp):
+        solver.cold_start()
+        return solver.iterative_solve_batch(inp['nom_s'], inp['nom_u'], inp['ref_s'], inp['ref_speed'], inp['obs_A'],
+                                            inp['obs_b'], inp['obs_kind'], inp['obs_count'], False)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        step(devin)
+    launches_per_step = solver.launch_count() + 1           # + the cold-start fill kernel
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        out = step(devin)
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    status = out['status'].clone()
+    # ---- end to end: pinned host inputs -> H2D -> solve -> D2H of the result, every step ----
+    hout = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in out.items()}
+    h2d = sum(v.numel() * v.element_size() for v in pinned.values())
+    d2h = sum(v.numel() * v.element_size() for v in hout.values())
+
+    def e2e_step():
+        inp = {k: v.to(dev, non_blocking=True) for k, v in pinned.items()}
+        o = step(inp)
+        for k, v in o.items():
+            hout[k].copy_(v, non_blocking=True)
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for _ in range(args.steps):
+        e2e_step()
+    e3.record()
+    barrier()
+    ms2 = torch.tensor([e2.elapsed_time(e3)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    ms2 = float(ms2.item())
+    clocks = sampler.stop() if rank == 0 else None
+    # trajectories to rank 0 (the only collective of the path; outside the ADMM loop)
+    full_u = gather_batch(out['u'], B * world) if world > 1 else out['u']
+    # ---- per-kernel durations for the roofline (CUDA events on the launching stream) ----
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(ITERS)]
+    solver.cold_start()
+    solver.begin(devin['nom_s'], devin['nom_u'], devin['ref_s'], devin['ref_speed'], devin['obs_A'], devin['obs_b'],
+                 devin['obs_kind'], devin['obs_count'], False, 0.0)
+    for i in range(ITERS):
+        ev[i][0].record(); solver.step_su(); ev[i][1].record(); solver.step_lammuz(); ev[i][2].record()
+    solver.finish()
+    torch.cuda.synchronize(dev)
+    t_su = float(np.mean([ev[i][0].elapsed_time(ev[i][1]) for i in range(1, ITERS)]))       # ms
+    t_cells = float(np.mean([ev[i][1].elapsed_time(ev[i][2]) for i in range(1, ITERS)]))    # cells + finalize
+    from rda_planner_b200 import _cabi
+    counters = solver.state_buffer(_cabi.BUF_COUNTERS).cpu().numpy().tolist()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(peaks_path):
+        peak, peak_src = json.load(open(peaks_path))['hbm_gbs'], 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    else:
+        peak, peak_src = 6650.0, 'fallback (B200_PROFILING.md)'
+    k2b, k1b = algorithmic_bytes()
+    dominant = 'k_su' if t_su >= t_cells else 'k_cells'
+    dur = max(t_su, t_cells) * 1e-3
+    alg = (k1b if dominant == 'k_su' else k2b) * B
+    traffic = None
+    tpath = os.path.join(ROOT, 'profiles', 'roofline_traffic.json')
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(dominant)
+    achieved = alg / dur / 1e9
+    total = B * world * args.steps
+    line = {
+        'metric': METRIC, 'value': total / (ms * 1e-3), 'unit': 'solves/s', 'n_gpus': world, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f32 state / f64 su-QP interior point', 'data': 'synthetic',
+        'config': {'workload': WORKLOAD, 'batch_per_gpu': B, 'global_batch': B * world,
+                   'parallelism': f'instances sharded over {world} GPU(s), no collective in the ADMM loop',
+                   'l2_policy': f'per-step working set {41 * B // 1000} MB of warm-start state > 126 MB L2'
+                   if B >= 3200 else 'working set below L2 size (small batch)'},
+        'e2e': {'value': total / (ms2 * 1e-3), 'unit': 'solves/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
+        'gpu_launches': launches_per_step * args.steps,
+        'clocks': clocks,
+        'roofline': {'bound': 'hbm', 'kernel': dominant, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+                     'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
+                     'algorithmic_bytes_per_launch': alg, 'kernel_ms': {'k_su': t_su, 'k_cells+k_finalize': t_cells},
+                     'k_cells': {'achieved': k2b * B / (t_cells * 1e-3) / 1e9, 'frac': k2b * B / (t_cells * 1e-3) / 1e9 / peak},
+                     'k_su': {'achieved': k1b * B / (t_su * 1e-3) / 1e9, 'frac': k1b * B / (t_su * 1e-3) / 1e9 / peak}},
+        'counters': {'cells_fast': counters[0], 'cells_slow': counters[1], 'cells_failed': counters[2],
+                     'su_ipm_iterations': counters[3], 'su_solves': counters[4]},
+        'status_nonzero': int((status.cpu() != 0).sum()),
+        'gathered_u_shape': list(full_u.shape),
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        sample = max(4 * cores, 16)
+        cpu_port_rate(host, min(cores, sample), cores)
+        v, dt = cpu_port_rate(host, sample, cores)
+        if dt < 5.0:
+            sample *= 4
+            v, dt = cpu_port_rate(host, min(sample, B), cores)
+        line['cpu_baseline'] = {'value': v, 'unit': 'solves/s', 'cores': cores, 'kind': 'port',
+                                'sample': f'{min(sample, B)} of the same instances x {ITERS} ADMM iterations, compiled C++ '
+                                          f'port (oracle/cpu_port), OpenMP over instances, {dt:.1f} s'}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

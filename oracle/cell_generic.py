@@ -39,7 +39,7 @@ def lp_vertex_poly(A, b, v):
     res = linprog(bn, A_eq=An.T, b_eq=v, bounds=bounds, method='highs-ds')
     if res.status != 0:
         raise RuntimeError('lp_vertex_poly failed: %s' % res.message)
-    return res.x / sc
+    return np.maximum(res.x, 0.0) / sc
 
 
 def lam_from_v(A, b, is_circle, v):

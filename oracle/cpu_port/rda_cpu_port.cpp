@@ -1,0 +1,170 @@
+// TEST / BASELINE INFRASTRUCTURE (oracle/): CPU build of the numerical cores of
+// rda_planner_b200/csrc (the same templates the CUDA kernels instantiate), compiled with g++.
+//   * shim_cell_*, shim_su_*: single sub-problem entry points, used by tests/ to compare the kernel
+//     arithmetic with the numpy oracle on a machine without a GPU;
+//   * port_solve_batch: the whole ADMM loop of rda_kernels.cu (k_begin / k_su / k_cells /
+//     k_finalize orchestration, float32 state, cold start) over a batch of instances with OpenMP
+//     over instances — the compiled multi-core CPU baseline bench.py reports ("port").
+// Never loaded by the product (rda_planner_b200/, RDA_planner/).
+#include <vector>
+#include <cstring>
+#include <cmath>
+#include <omp.h>
+#include "../../rda_planner_b200/csrc/cell_solver.cuh"
+#include "../../rda_planner_b200/csrc/su_solver.cuh"
+
+using namespace rda;
+
+template <typename Real>
+static int cell_impl(const float* G, const float* h, int R, int kind, int E, const float* A, const float* b,
+                     double px, double py, double phi, double dbar, double zeta, double xi0, double xi1,
+                     double ro2, double theta, double* out /* lam[8] mu[8] z zeta_new xi0 xi1 ax ay c0 gx gy hm0 hm1 path */) {
+  RobotGeom rb;
+  int rc = robot_geom_from_halfspaces(G, h, R, &rb);
+  if (rc) return rc;
+  CellOut<Real> o;
+  cell_solve<Real>(rb, kind, E, A, b, (Real)px, (Real)py, (Real)cos(phi), (Real)sin(phi), (Real)dbar,
+                   (Real)zeta, (Real)xi0, (Real)xi1, (Real)ro2, (Real)theta, o);
+  for (int i = 0; i < 8; ++i) out[i] = o.lam[i];
+  for (int i = 0; i < 8; ++i) out[8 + i] = o.mu[i];
+  double tail[] = {(double)o.z, (double)o.zeta_new, (double)o.xi0_new, (double)o.xi1_new, (double)o.ax,
+                   (double)o.ay, (double)o.c0, (double)o.gx, (double)o.gy, (double)o.hm0, (double)o.hm1,
+                   (double)o.path};
+  memcpy(out + 16, tail, sizeof(tail));
+  return 0;
+}
+
+template <typename Real>
+static int su_impl(const SuParams* P, const double* lins, const double* linu, const double* ref, double vref,
+                   const double* dis, const float* hx, const float* hy, const float* hc, const float* gx,
+                   const float* gy, const double* pref, double* s, double* u, double* d, int* iters) {
+  const int T = P->T, N = P->N;
+  SuWork<Real> W;
+  size_t bytes = su_work_layout<Real>(T, N, nullptr, nullptr);
+  std::vector<char> buf(bytes + 64);
+  char* base = (char*)(((uintptr_t)buf.data() + 63) & ~(uintptr_t)63);
+  su_work_layout<Real>(T, N, &W, base);
+  for (int i = 0; i < 3 * (T + 1); ++i) { W.lins[i] = (Real)lins[i]; W.ref[i] = (Real)ref[i]; }
+  for (int i = 0; i < 2 * T; ++i) { W.linu[i] = (Real)linu[i]; W.pref[i] = (Real)pref[i]; }
+  for (int i = 0; i < T; ++i) W.d[i] = (Real)dis[i];
+  for (int i = 0; i < N * T; ++i) { W.hx[i] = hx[i]; W.hy[i] = hy[i]; W.hc[i] = hc[i]; }
+  W.vref = (Real)vref;
+  SeqCtx ctx;
+  int st = su_solve<Real, SeqCtx>(*P, W, ctx, gx, gy, iters);
+  for (int i = 0; i < 3 * (T + 1); ++i) s[i] = W.s[i];
+  for (int i = 0; i < 2 * T; ++i) u[i] = W.u[i];
+  for (int i = 0; i < T; ++i) d[i] = W.d[i];
+  return st;
+}
+
+extern "C" {
+int shim_cell_d(const float* G, const float* h, int R, int kind, int E, const float* A, const float* b,
+                double px, double py, double phi, double dbar, double zeta, double xi0, double xi1, double ro2,
+                double theta, double* out) {
+  return cell_impl<double>(G, h, R, kind, E, A, b, px, py, phi, dbar, zeta, xi0, xi1, ro2, theta, out);
+}
+int shim_cell_f(const float* G, const float* h, int R, int kind, int E, const float* A, const float* b,
+                double px, double py, double phi, double dbar, double zeta, double xi0, double xi1, double ro2,
+                double theta, double* out) {
+  return cell_impl<float>(G, h, R, kind, E, A, b, px, py, phi, dbar, zeta, xi0, xi1, ro2, theta, out);
+}
+int shim_su_d(const SuParams* P, const double* lins, const double* linu, const double* ref, double vref,
+              const double* dis, const float* hx, const float* hy, const float* hc, const float* gx,
+              const float* gy, const double* pref, double* s, double* u, double* d, int* iters) {
+  return su_impl<double>(P, lins, linu, ref, vref, dis, hx, hy, hc, gx, gy, pref, s, u, d, iters);
+}
+int shim_su_f(const SuParams* P, const double* lins, const double* linu, const double* ref, double vref,
+              const double* dis, const float* hx, const float* hy, const float* hc, const float* gx,
+              const float* gy, const double* pref, double* s, double* u, double* d, int* iters) {
+  return su_impl<float>(P, lins, linu, ref, vref, dis, hx, hy, hc, gx, gy, pref, s, u, d, iters);
+}
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Whole hot path on the CPU (mirrors rda_kernels.cu; see the kernel comments for reference lines).
+// Layouts as in include/rda_b200.h.  Every instance starts cold (constructor state).
+// ------------------------------------------------------------------------------------------------
+extern "C" int port_solve_batch(const rda_config* cfg, const rda_tunables* tun, int B, const float* nom_s,
+                                const float* nom_u, const float* ref_s, const float* ref_speed,
+                                const float* obs_A, const float* obs_b, const int* obs_kind,
+                                const int* obs_count, int tv, int iter_num, float thr, float* u_opt,
+                                float* s_opt, float* resi_pri, float* resi_dual, int* iters_out, int nthreads) {
+  RobotGeom rb;
+  int rc = robot_geom_from_halfspaces(cfg->G, cfg->h, cfg->robot_edges, &rb);
+  if (rc) return rc;
+  const int T = cfg->receding, N = cfg->max_obs_num, E = cfg->max_edge_num, R = cfg->robot_edges, NT = N * T;
+  SuParams P;
+  P.T = T; P.N = N; P.dynamics = cfg->dynamics; P.accelerated = cfg->accelerated;
+  P.dt = cfg->step_time; P.L = cfg->wheelbase;
+  P.umax[0] = cfg->max_speed[0]; P.umax[1] = cfg->max_speed[1];
+  P.ab[0] = cfg->acce_bound[0]; P.ab[1] = cfg->acce_bound[1];
+  P.ws = cfg->ws; P.wu = cfg->wu; P.slack_gain = tun->slack_gain; P.dmin = tun->min_sd; P.dmax = tun->max_sd;
+  P.ro1 = tun->ro1; P.ro2 = tun->ro2; P.max_iter = 40;
+  const float theta = cfg->accelerated ? tun->z_theta : 1.0f;
+  if (nthreads > 0) omp_set_num_threads(nthreads);
+  const size_t bytes = su_work_layout<double>(T, N, nullptr, nullptr);
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int b = 0; b < B; ++b) {
+    std::vector<char> buf(bytes + 64);
+    char* base = (char*)(((uintptr_t)buf.data() + 63) & ~(uintptr_t)63);
+    SuWork<double> W;
+    su_work_layout<double>(T, N, &W, base);
+    std::vector<float> lam((size_t)N * E * T, 0.f), mu((size_t)N * R * T, 0.f), z(NT, 0.f), xi(2 * NT, 0.f),
+        zeta(NT, 0.f), dis(T, 1.f), coef(5 * (size_t)NT, 0.f), pref(2 * T, 0.f);
+    std::vector<float> cs(nom_s + (size_t)b * 3 * (T + 1), nom_s + (size_t)(b + 1) * 3 * (T + 1));
+    std::vector<float> cu(nom_u + (size_t)b * 2 * T, nom_u + (size_t)(b + 1) * 2 * T);
+    const float* rf = ref_s + (size_t)b * 3 * (T + 1);
+    float rp = 0.f, rd = 0.f;
+    int it = 0;
+    for (it = 0; it < iter_num; ++it) {
+      for (int i = 0; i < 3 * (T + 1); ++i) { int r = i / (T + 1), t = i % (T + 1); W.lins[3 * t + r] = cs[i]; W.ref[3 * t + r] = rf[i]; }
+      for (int i = 0; i < 2 * T; ++i) { int r = i / T, t = i % T; W.linu[2 * t + r] = cu[i]; W.pref[2 * t + r] = pref[i]; }
+      for (int t = 0; t < T; ++t) W.d[t] = dis[t];
+      for (int i = 0; i < NT; ++i) { W.hx[i] = coef[i]; W.hy[i] = coef[NT + i]; W.hc[i] = coef[2 * NT + i]; }
+      W.vref = ref_speed[b];
+      SeqCtx ctx;
+      int nit = 0;
+      int st = su_solve<double, SeqCtx>(P, W, ctx, coef.data() + 3 * NT, coef.data() + 4 * NT, &nit);
+      if (st != 2) {
+        for (int i = 0; i < 3 * (T + 1); ++i) { int r = i / (T + 1), t = i % (T + 1); cs[i] = (float)W.s[3 * t + r]; }
+        for (int i = 0; i < 2 * T; ++i) { int r = i / T, t = i % T; cu[i] = (float)W.u[2 * t + r]; }
+        for (int t = 0; t < T; ++t) dis[t] = (float)W.d[t];
+      }
+      double hm2 = 0, dual = 0;
+      if (N > 0 && obs_count[b] != 0) {
+        for (int o = 0; o < N; ++o)
+          for (int t = 0; t < T; ++t) {
+            int tc = tv ? t + 1 : 0, Tc = tv ? T + 1 : 1;
+            size_t ob = ((size_t)b * N + o) * Tc + tc;
+            float ph = cs[2 * (T + 1) + t];
+            CellOut<float> out;
+            cell_solve<float>(rb, obs_kind[(size_t)b * N + o], E, obs_A + ob * E * 2, obs_b + ob * E, cs[t + 1],
+                              cs[(T + 1) + t + 1], cosf(ph), sinf(ph), dis[t], zeta[o * T + t], xi[o * T + t],
+                              xi[NT + o * T + t], (float)P.ro2, theta, out);
+            if (out.path == CELL_FAILED) { dual = INFINITY; continue; }
+            float acc = 0.f;
+            for (int i = 0; i < E; ++i) { float nv = out.lam[i], df = nv - lam[((size_t)o * E + i) * T + t]; acc += df * df; lam[((size_t)o * E + i) * T + t] = nv; }
+            for (int j = 0; j < R; ++j) { float nv = out.mu[j], df = nv - mu[((size_t)o * R + j) * T + t]; acc += df * df; mu[((size_t)o * R + j) * T + t] = nv; }
+            float dz = out.z - z[o * T + t];
+            acc += dz * dz;
+            z[o * T + t] = out.z;
+            dual += acc;
+            zeta[o * T + t] = out.zeta_new;
+            xi[o * T + t] = out.xi0_new; xi[NT + o * T + t] = out.xi1_new;
+            hm2 += out.hm0 * out.hm0 + out.hm1 * out.hm1;
+            coef[o * T + t] = out.ax; coef[NT + o * T + t] = out.ay; coef[2 * NT + o * T + t] = out.c0;
+            coef[3 * NT + o * T + t] = out.gx; coef[4 * NT + o * T + t] = out.gy;
+            if (o == 0) { pref[t] = cs[t + 1]; pref[T + t] = cs[(T + 1) + t + 1]; }
+          }
+        rp = (float)sqrt(hm2); rd = (float)(dual / N);
+      } else { rp = 0.f; rd = 0.f; }
+      if (rd < thr && rp < thr) { ++it; break; }
+    }
+    for (int i = 0; i < 3 * (T + 1); ++i) s_opt[(size_t)b * 3 * (T + 1) + i] = cs[i];
+    for (int i = 0; i < 2 * T; ++i) u_opt[(size_t)b * 2 * T + i] = cu[i];
+    resi_pri[b] = rp; resi_dual[b] = rd;
+    if (iters_out) iters_out[b] = it;
+  }
+  return 0;
+}

@@ -11,8 +11,8 @@ import this module.
 import numpy as np
 
 
-def solve_qp(P, q, G, h, A=None, b=None, tol=1e-10, max_iter=80):
-    """Return (x, info).  info['status'] is 'optimal' or 'max_iter'."""
+def solve_qp(P, q, G, h, A=None, b=None, tol=1e-9, max_iter=80):
+    """Return (x, info).  info['status'] is 'optimal', 'optimal_inaccurate' or 'max_iter'."""
     P = np.asarray(P, float)
     q = np.asarray(q, float)
     G = np.asarray(G, float)
@@ -36,23 +36,27 @@ def solve_qp(P, q, G, h, A=None, b=None, tol=1e-10, max_iter=80):
         sol = np.linalg.solve(K, np.concatenate([r1, r2]))
         return sol[:n], sol[n:]
 
-    # initial point: least-squares like start, slacks pushed positive
+    # initial point: regularised least-squares start, slacks/multipliers at least 1
     x, y = kkt_solve(np.ones(m), -q + G.T @ h, b)
-    s = h - G @ x
-    shift = max(1.0, -1.5 * s.min()) if s.min() <= 1e-3 else 0.0
-    s = s + shift
-    lam = np.ones(m) * max(1.0, shift)
+    s = np.maximum(h - G @ x, 1.0)
+    lam = np.ones(m)
     scale = 1.0 + max(np.abs(q).max(initial=0.0), np.abs(h).max(initial=0.0))
     status = 'max_iter'
+    best = (np.inf, x, y, s, lam)
     it = 0
     for it in range(max_iter):
         rd = P @ x + q + G.T @ lam + A.T @ y
         rp = G @ x + s - h
         re = A @ x - b
         mu = float(s @ lam) / max(m, 1)
-        if (np.abs(rd).max(initial=0.0) < tol * scale and np.abs(rp).max(initial=0.0) < tol * scale
-                and np.abs(re).max(initial=0.0) < tol * scale and mu < tol * scale):
+        merit = max(np.abs(rd).max(initial=0.0), np.abs(rp).max(initial=0.0),
+                    np.abs(re).max(initial=0.0), mu)
+        if merit < best[0]:
+            best = (merit, x, y, s, lam)
+        if merit < tol * scale:
             status = 'optimal'
+            break
+        if mu < 1e-14 * scale:          # complementarity exhausted: nothing left to gain
             break
         W = lam / s
 
@@ -70,14 +74,20 @@ def solve_qp(P, q, G, h, A=None, b=None, tol=1e-10, max_iter=80):
                 return 1.0
             return min(1.0, float((-v[neg] / dv[neg]).min()))
 
-        dxa, dya, dsa, dla = direction(s * lam)
-        a_aff = min(max_step(s, dsa), max_step(lam, dla))
-        mu_aff = float((s + a_aff * dsa) @ (lam + a_aff * dla)) / max(m, 1)
-        sigma = (mu_aff / mu) ** 3 if mu > 0 else 0.0
-        dx, dy, ds, dl = direction(s * lam + dsa * dla - sigma * mu)
-        a = min(1.0, 0.995 * min(max_step(s, ds), max_step(lam, dl)))
+        try:
+            dxa, dya, dsa, dla = direction(s * lam)
+            a_aff = min(max_step(s, dsa), max_step(lam, dla))
+            mu_aff = float((s + a_aff * dsa) @ (lam + a_aff * dla)) / max(m, 1)
+            sigma = (mu_aff / mu) ** 3 if mu > 0 else 0.0
+            dx, dy, ds, dl = direction(s * lam + dsa * dla - sigma * mu)
+        except np.linalg.LinAlgError:
+            break
+        a = min(1.0, 0.99 * min(max_step(s, ds), max_step(lam, dl)))
         x = x + a * dx
         y = y + a * dy
         s = s + a * ds
         lam = lam + a * dl
-    return x, {'status': status, 'iters': it, 'ineq_dual': lam, 'eq_dual': y, 'slack': s}
+    merit, x, y, s, lam = best
+    if status != 'optimal' and merit < 1e3 * tol * scale:
+        status = 'optimal_inaccurate'      # accepted like cvxpy's OPTIMAL_INACCURATE (:696)
+    return x, {'status': status, 'iters': it, 'merit': merit, 'ineq_dual': lam, 'eq_dual': y, 'slack': s}

@@ -45,6 +45,8 @@ struct TinyQP {
   double a[MC][NV];
   double b[MC];
   int m;
+  int tv;   // -1: unit-ball constraint x0^2 + x1^2 <= 1;  k >= 0: cone constraint
+            // (x0^2 + x1^2)/x_k - x_k <= 0 (i.e. |x01| <= x_k, rows keep 0 <= x_k <= 1)
 };
 
 template <int NV>
@@ -79,6 +81,24 @@ RDA_HD bool chol_solve(double H[NV][NV], double* r1, double* r2) {
   return true;
 }
 
+// value, gradient (on x0, x1 and x_tv) and Hessian of the one nonlinear constraint
+struct ConeEval { double f, g0, g1, gt, h00, h11, h0t, h1t, htt; };
+RDA_HD ConeEval cone_eval(const double* x, int tv) {
+  ConeEval c;
+  if (tv < 0) {
+    c.f = x[0] * x[0] + x[1] * x[1] - 1.0;
+    c.g0 = 2 * x[0]; c.g1 = 2 * x[1]; c.gt = 0;
+    c.h00 = 2; c.h11 = 2; c.h0t = 0; c.h1t = 0; c.htt = 0;
+  } else {
+    double t = x[tv], n2 = x[0] * x[0] + x[1] * x[1];
+    c.f = n2 / t - t;
+    c.g0 = 2 * x[0] / t; c.g1 = 2 * x[1] / t; c.gt = -n2 / (t * t) - 1.0;
+    c.h00 = 2 / t; c.h11 = 2 / t; c.h0t = -2 * x[0] / (t * t); c.h1t = -2 * x[1] / (t * t);
+    c.htt = 2 * n2 / (t * t * t);
+  }
+  return c;
+}
+
 template <int NV, int MC>
 RDA_HD_NOINLINE bool tiny_ipm(const TinyQP<NV, MC>& P, double* x /* in: strictly feasible start */) {
   const int m = P.m;
@@ -89,9 +109,17 @@ RDA_HD_NOINLINE bool tiny_ipm(const TinyQP<NV, MC>& P, double* x /* in: strictly
     s[i] = rmax(P.b[i] - ax, 1e-3);
     l[i] = 1.0 / s[i];
   }
-  s[m] = rmax(1.0 - x[0] * x[0] - x[1] * x[1], 1e-3);
+  const int tv = P.tv;
+  s[m] = rmax(-cone_eval(x, tv).f, 1e-3);
   l[m] = 1.0 / s[m];
   const int M = m + 1;
+  double scale = 1.0;
+  for (int i = 0; i < m; ++i) {
+    scale = rmax(scale, fabs(P.b[i]));
+    for (int k = 0; k < NV; ++k) scale = rmax(scale, fabs(P.a[i][k]));
+  }
+  for (int k = 0; k < NV; ++k) scale = rmax(scale, fabs(P.c[k]));
+  bool acceptable = false;
   for (int it = 0; it < 40; ++it) {
     // residuals
     double rd[NV], rp[MC + 1];
@@ -110,16 +138,23 @@ RDA_HD_NOINLINE bool tiny_ipm(const TinyQP<NV, MC>& P, double* x /* in: strictly
       rp[i] = ax + s[i] - P.b[i];
       mu += s[i] * l[i];
     }
-    rd[0] += 2 * x[0] * l[m];
-    rd[1] += 2 * x[1] * l[m];
-    rp[m] = x[0] * x[0] + x[1] * x[1] - 1.0 + s[m];
+    const ConeEval ce = cone_eval(x, tv);
+    rd[0] += ce.g0 * l[m];
+    rd[1] += ce.g1 * l[m];
+    if (tv >= 0) rd[tv] += ce.gt * l[m];
+    rp[m] = ce.f + s[m];
     mu += s[m] * l[m];
     mu /= M;
     double rdn = 0, rpn = 0;
     for (int k = 0; k < NV; ++k) rdn = rmax(rdn, fabs(rd[k]));
     for (int i = 0; i < M; ++i) rpn = rmax(rpn, fabs(rp[i]));
-    if (rdn < 1e-10 && rpn < 1e-10 && mu < 1e-11) return true;
+#ifdef RDA_IPM_DEBUG
+    printf("it %d rd %.2e rp %.2e mu %.2e x0 %g x1 %g\n", it, rdn, rpn, mu, x[0], x[1]);
+#endif
     if (!(rdn == rdn) || !(mu == mu)) return false;
+    acceptable = rdn < 1e-6 * scale && rpn < 1e-6 * scale && mu < 1e-7;
+    if (rdn < 1e-9 * scale && rpn < 1e-9 * scale && mu < 1e-10) return true;
+    if (mu < 1e-14) return acceptable;     // complementarity exhausted (rounding floor reached)
     // Newton matrix
     double H[NV][NV];
     for (int k = 0; k < NV; ++k)
@@ -133,10 +168,15 @@ RDA_HD_NOINLINE bool tiny_ipm(const TinyQP<NV, MC>& P, double* x /* in: strictly
       }
     }
     {
-      double w = l[m] / s[m], g0 = 2 * x[0], g1 = 2 * x[1];
-      H[0][0] += 2 * l[m] + w * g0 * g0;
-      H[1][0] += w * g1 * g0;
-      H[1][1] += 2 * l[m] + w * g1 * g1;
+      double w = l[m] / s[m];
+      H[0][0] += l[m] * ce.h00 + w * ce.g0 * ce.g0;
+      H[1][0] += w * ce.g1 * ce.g0;
+      H[1][1] += l[m] * ce.h11 + w * ce.g1 * ce.g1;
+      if (tv >= 0) {   // tv > 1 always (lower triangle: row tv, columns 0, 1, tv)
+        H[tv][0] += l[m] * ce.h0t + w * ce.gt * ce.g0;
+        H[tv][1] += l[m] * ce.h1t + w * ce.gt * ce.g1;
+        H[tv][tv] += l[m] * ce.htt + w * ce.gt * ce.gt;
+      }
     }
     for (int k = 0; k < NV; ++k) H[k][k] += 1e-12;
     // affine right-hand side: -(rd + sum grad_i (l_i rp_i - rc_i)/s_i), rc_i = s_i l_i
@@ -147,15 +187,16 @@ RDA_HD_NOINLINE bool tiny_ipm(const TinyQP<NV, MC>& P, double* x /* in: strictly
       if (i < m) {
         for (int k = 0; k < NV; ++k) ra[k] -= P.a[i][k] * t;
       } else {
-        ra[0] -= 2 * x[0] * t;
-        ra[1] -= 2 * x[1] * t;
+        ra[0] -= ce.g0 * t;
+        ra[1] -= ce.g1 * t;
+        if (tv >= 0) ra[tv] -= ce.gt * t;
       }
     }
     for (int k = 0; k < NV; ++k) rc[k] = ra[k];
     double Hc[NV][NV];
     for (int k = 0; k < NV; ++k)
       for (int j = 0; j < NV; ++j) Hc[k][j] = H[k][j];
-    if (!chol_solve<NV>(Hc, ra, nullptr)) return false;
+    if (!chol_solve<NV>(Hc, ra, nullptr)) return acceptable;
     // affine step lengths
     double dsa[MC + 1], dla[MC + 1], aaff = 1.0;
     for (int i = 0; i < M; ++i) {
@@ -163,7 +204,7 @@ RDA_HD_NOINLINE bool tiny_ipm(const TinyQP<NV, MC>& P, double* x /* in: strictly
       if (i < m) {
         for (int k = 0; k < NV; ++k) gd += P.a[i][k] * ra[k];
       } else {
-        gd = 2 * x[0] * ra[0] + 2 * x[1] * ra[1];
+        gd = ce.g0 * ra[0] + ce.g1 * ra[1] + (tv >= 0 ? ce.gt * ra[tv] : 0.0);
       }
       dsa[i] = -rp[i] - gd;
       dla[i] = -(s[i] * l[i] + l[i] * dsa[i]) / s[i];
@@ -184,8 +225,9 @@ RDA_HD_NOINLINE bool tiny_ipm(const TinyQP<NV, MC>& P, double* x /* in: strictly
       if (i < m) {
         for (int k = 0; k < NV; ++k) rc[k] -= P.a[i][k] * t;
       } else {
-        rc[0] -= 2 * x[0] * t;
-        rc[1] -= 2 * x[1] * t;
+        rc[0] -= ce.g0 * t;
+        rc[1] -= ce.g1 * t;
+        if (tv >= 0) rc[tv] -= ce.gt * t;
       }
     }
     // Hc already holds the factor: only the triangular solves are needed
@@ -205,7 +247,7 @@ RDA_HD_NOINLINE bool tiny_ipm(const TinyQP<NV, MC>& P, double* x /* in: strictly
       if (i < m) {
         for (int k = 0; k < NV; ++k) gd += P.a[i][k] * rc[k];
       } else {
-        gd = 2 * x[0] * rc[0] + 2 * x[1] * rc[1];
+        gd = ce.g0 * rc[0] + ce.g1 * rc[1] + (tv >= 0 ? ce.gt * rc[tv] : 0.0);
       }
       ds[i] = -rp[i] - gd;
       dl[i] = -(rcs[i] + l[i] * ds[i]) / s[i];
@@ -218,7 +260,89 @@ RDA_HD_NOINLINE bool tiny_ipm(const TinyQP<NV, MC>& P, double* x /* in: strictly
       l[i] += alpha * dl[i];
     }
   }
-  return true;  // iteration cap reached: the iterate is still the best available point
+  return acceptable;  // iteration cap reached
+}
+
+// ---------------------------------------------------------------------------------------------
+// Feasible-start log-barrier method (damped Newton with backtracking) for the same problem class
+// with the second-order-cone constraint |x01| <= x_tv (P.tv >= 0) in its self-concordant form
+// -log(x_tv^2 - |x01|^2).  Slower than tiny_ipm but globally convergent; used for disc obstacles.
+// ---------------------------------------------------------------------------------------------
+template <int NV, int MC>
+RDA_HD double barrier_value(const TinyQP<NV, MC>& P, const double* x, double t) {
+  double f = 0;
+  for (int k = 0; k < NV; ++k) {
+    double qx = 0;
+    for (int j = 0; j < NV; ++j) qx += P.Q[k][j] * x[j];
+    f += x[k] * (0.5 * qx + P.c[k]);
+  }
+  f *= t;
+  for (int i = 0; i < P.m; ++i) {
+    double sl = P.b[i];
+    for (int k = 0; k < NV; ++k) sl -= P.a[i][k] * x[k];
+    if (!(sl > 0)) return 1e300;
+    f -= log(sl);
+  }
+  double psi = x[P.tv] * x[P.tv] - x[0] * x[0] - x[1] * x[1];
+  if (!(psi > 0) || !(x[P.tv] > 0)) return 1e300;
+  return f - log(psi);
+}
+
+template <int NV, int MC>
+RDA_HD_NOINLINE bool tiny_barrier(const TinyQP<NV, MC>& P, double* x /* strictly feasible */) {
+  const int m = P.m, tv = P.tv;
+  double t = 1.0;
+  for (int outer = 0; outer < 14; ++outer, t *= 8.0) {
+    for (int it = 0; it < 30; ++it) {
+      double g[NV], H[NV][NV];
+      for (int k = 0; k < NV; ++k) {
+        double qx = P.c[k];
+        for (int j = 0; j < NV; ++j) { qx += P.Q[k][j] * x[j]; H[k][j] = t * P.Q[k][j]; }
+        g[k] = t * qx;
+      }
+      for (int i = 0; i < m; ++i) {
+        double sl = P.b[i];
+        for (int k = 0; k < NV; ++k) sl -= P.a[i][k] * x[k];
+        double inv = 1.0 / sl, inv2 = inv * inv;
+        for (int k = 0; k < NV; ++k) {
+          double ak = P.a[i][k];
+          if (ak == 0) continue;
+          g[k] += ak * inv;
+          for (int j = 0; j <= k; ++j) H[k][j] += ak * P.a[i][j] * inv2;
+        }
+      }
+      {
+        double psi = x[tv] * x[tv] - x[0] * x[0] - x[1] * x[1];
+        double gp[3] = {-2 * x[0], -2 * x[1], 2 * x[tv]};       // grad psi on (0, 1, tv)
+        const int id[3] = {0, 1, tv};
+        double ip = 1.0 / psi;
+        for (int a = 0; a < 3; ++a) {
+          g[id[a]] -= gp[a] * ip;
+          for (int b2 = 0; b2 <= a; ++b2) H[id[a]][id[b2]] += gp[a] * gp[b2] * ip * ip;
+        }
+        H[0][0] += 2 * ip; H[1][1] += 2 * ip; H[tv][tv] -= 2 * ip;
+      }
+      for (int k = 0; k < NV; ++k) H[k][k] += 1e-13 * (1.0 + H[k][k]);
+      double dx[NV];
+      for (int k = 0; k < NV; ++k) dx[k] = -g[k];
+      if (!chol_solve<NV>(H, dx, nullptr)) return false;
+      double lam2 = 0;
+      for (int k = 0; k < NV; ++k) lam2 -= g[k] * dx[k];
+      if (!(lam2 == lam2)) return false;
+      if (lam2 < 1e-9) break;
+      double f0 = barrier_value<NV, MC>(P, x, t), step = 1.0;
+      double xn[NV];
+      bool moved = false;
+      for (int bt = 0; bt < 50; ++bt, step *= 0.5) {
+        for (int k = 0; k < NV; ++k) xn[k] = x[k] + step * dx[k];
+        double f1 = barrier_value<NV, MC>(P, xn, t);
+        if (f1 <= f0 - 0.1 * step * lam2) { moved = true; break; }
+      }
+      if (!moved) break;
+      for (int k = 0; k < NV; ++k) x[k] = xn[k];
+    }
+  }
+  return true;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -438,35 +562,44 @@ RDA_HD void cell_solve(const RobotGeom& rb, int kind, int E, const float* A, con
   }
   if (!have) {
     // ---- slow path: interior point in float64 ---------------------------------------------------
-    // A disc obstacle is handled as its centre point with k0 + rad (exact whenever the optimal
-    // contact point lies outside the disc).
-    const int nv_o = (kind == RDA_OBS_CIRCLE) ? 1 : ne;
+    // Polygon obstacle: sigma_O(v) = max_i v.x_i, |v| <= 1 (ball constraint).
+    // Disc obstacle:    sigma_O(v) = v.c + rad*tv with |v| <= tv <= 1 (cone constraint, extra
+    //                   variable tv), exact also when the robot overlaps the disc.
+    const bool circ = (kind == RDA_OBS_CIRCLE);
+    const int nv_o = circ ? 1 : ne;
     double ox[RDA_MAX_EDGE], oy[RDA_MAX_EDGE];
-    double k0d = (double)k0;
-    if (kind == RDA_OBS_CIRCLE) { ox[0] = g.cx; oy[0] = g.cy; k0d += (double)g.rad; }
+    const double k0d = (double)k0, radd = circ ? (double)g.rad : 0.0;
+    if (circ) { ox[0] = g.cx; oy[0] = g.cy; }
     else for (int i = 0; i < ne; ++i) { ox[i] = g.vx[i]; oy[i] = g.vy[i]; }
     const double c_ = cphi, s_ = sphi, x0 = xi0, x1 = xi1;
     bool ok = true, inactive = false;
     double va = 0, vb = 0, ga = 0, gb = 0;
-    {  // stage A: max margin with Hm + xi = 0; x = (v0, v1, so, sr)
-      TinyQP<4, 2 * RDA_MAX_EDGE> P;
-      for (int k = 0; k < 4; ++k) { for (int j = 0; j < 4; ++j) P.Q[k][j] = 0; P.c[k] = 0; }
+    {  // stage A: max margin with Hm + xi = 0; x = (v0, v1, so, sr, tv)
+      constexpr int NVA = 5;
+      TinyQP<NVA, 2 * RDA_MAX_EDGE + 2> P;
+      for (int k = 0; k < NVA; ++k) { for (int j = 0; j < NVA; ++j) P.Q[k][j] = 0; P.c[k] = 0; }
       P.c[2] = 1; P.c[3] = 1;
       int m = 0;
       for (int i = 0; i < nv_o; ++i, ++m) {
-        P.a[m][0] = ox[i]; P.a[m][1] = oy[i]; P.a[m][2] = -1; P.a[m][3] = 0; P.b[m] = 0;
+        for (int k = 0; k < NVA; ++k) P.a[m][k] = 0;
+        P.a[m][0] = ox[i]; P.a[m][1] = oy[i]; P.a[m][2] = -1; P.a[m][4] = radd; P.b[m] = 0;
       }
       for (int j = 0; j < R; ++j, ++m) {
         // g.y_j <= sr with g = -R'v - xi :  -(R y_j).v - sr <= xi.y_j
         double yx = rb.yx[j], yy = rb.yy[j];
+        for (int k = 0; k < NVA; ++k) P.a[m][k] = 0;
         P.a[m][0] = -(c_ * yx - s_ * yy); P.a[m][1] = -(s_ * yx + c_ * yy);
-        P.a[m][2] = 0; P.a[m][3] = -1; P.b[m] = x0 * yx + x1 * yy;
+        P.a[m][3] = -1; P.b[m] = x0 * yx + x1 * yy;
       }
+      for (int k = 0; k < NVA; ++k) { P.a[m][k] = 0; P.a[m + 1][k] = 0; }
+      P.a[m][4] = 1; P.b[m] = 1; ++m;          // tv <= 1
+      P.a[m][4] = -1; P.b[m] = 0; ++m;         // tv >= 0
       P.m = m;
+      P.tv = circ ? 4 : -1;
       double hmax = 0;
       for (int j = 0; j < R; ++j) hmax = rmax(hmax, fabs(x0 * (double)rb.yx[j] + x1 * (double)rb.yy[j]));
-      double xs[4] = {0, 0, 1.0, 1.0 + hmax};
-      ok = tiny_ipm<4, 2 * RDA_MAX_EDGE>(P, xs);
+      double xs[NVA] = {0, 0, 1.0 + radd, 1.0 + hmax, 0.5};
+      ok = circ ? tiny_barrier<NVA, 2 * RDA_MAX_EDGE + 2>(P, xs) : tiny_ipm<NVA, 2 * RDA_MAX_EDGE + 2>(P, xs);
       double cst = -xs[2] - xs[3] - k0d;
       if (ok && cst >= 0) {
         inactive = true;
@@ -476,9 +609,10 @@ RDA_HD void cell_solve(const RobotGeom& rb, int kind, int E, const float* A, con
         path = CELL_SLOW_A;
       }
     }
-    if (ok && !inactive) {  // stage B: x = (v0, v1, g0, g1, so, sr, w)
-      TinyQP<7, 2 * RDA_MAX_EDGE + 1> P;
-      for (int k = 0; k < 7; ++k) { for (int j = 0; j < 7; ++j) P.Q[k][j] = 0; P.c[k] = 0; }
+    if (ok && !inactive) {  // stage B: x = (v0, v1, g0, g1, so, sr, w, tv)
+      constexpr int NVB = 8;
+      TinyQP<NVB, 2 * RDA_MAX_EDGE + 3> P;
+      for (int k = 0; k < NVB; ++k) { for (int j = 0; j < NVB; ++j) P.Q[k][j] = 0; P.c[k] = 0; }
       // ro2/2 |g + R'v + xi|^2 : with u = (v, g), q = M u + xi, M = [R' I]
       const double r2 = ro2;
       const double Mx[4] = {c_, s_, 1, 0}, My[4] = {-s_, c_, 0, 1};
@@ -488,19 +622,22 @@ RDA_HD void cell_solve(const RobotGeom& rb, int kind, int E, const float* A, con
       P.Q[6][6] = 1.0;   // 1/2 w^2  (ro1 == 1 inside LamMuZ, rda_solver.py:257)
       int m = 0;
       for (int i = 0; i < nv_o; ++i, ++m) {
-        for (int k = 0; k < 7; ++k) P.a[m][k] = 0;
-        P.a[m][0] = ox[i]; P.a[m][1] = oy[i]; P.a[m][4] = -1; P.b[m] = 0;
+        for (int k = 0; k < NVB; ++k) P.a[m][k] = 0;
+        P.a[m][0] = ox[i]; P.a[m][1] = oy[i]; P.a[m][4] = -1; P.a[m][7] = radd; P.b[m] = 0;
       }
       for (int j = 0; j < R; ++j, ++m) {
-        for (int k = 0; k < 7; ++k) P.a[m][k] = 0;
+        for (int k = 0; k < NVB; ++k) P.a[m][k] = 0;
         P.a[m][2] = rb.yx[j]; P.a[m][3] = rb.yy[j]; P.a[m][5] = -1; P.b[m] = 0;
       }
-      for (int k = 0; k < 7; ++k) P.a[m][k] = 0;
-      P.a[m][4] = 1; P.a[m][5] = 1; P.a[m][6] = -1; P.b[m] = -k0d;   // so + sr + k0 <= w
-      ++m;
+      for (int k = 0; k < NVB; ++k) { P.a[m][k] = 0; P.a[m + 1][k] = 0; P.a[m + 2][k] = 0; }
+      P.a[m][4] = 1; P.a[m][5] = 1; P.a[m][6] = -1; P.b[m] = -k0d; ++m;   // so + sr + k0 <= w
+      P.a[m][7] = 1; P.b[m] = 1; ++m;          // tv <= 1
+      P.a[m][7] = -1; P.b[m] = 0; ++m;         // tv >= 0
       P.m = m;
-      double xs[7] = {0, 0, 0, 0, 1.0, 1.0, rmax(3.0 + k0d, 1.0)};
-      ok = tiny_ipm<7, 2 * RDA_MAX_EDGE + 1>(P, xs);
+      P.tv = circ ? 7 : -1;
+      double so0 = 1.0 + radd;
+      double xs[NVB] = {0, 0, 0, 0, so0, 1.0, rmax(so0 + 2.0 + k0d, 1.0), 0.5};
+      ok = circ ? tiny_barrier<NVB, 2 * RDA_MAX_EDGE + 3>(P, xs) : tiny_ipm<NVB, 2 * RDA_MAX_EDGE + 3>(P, xs);
       va = xs[0]; vb = xs[1]; ga = xs[2]; gb = xs[3];
       path = CELL_SLOW_B;
     }

@@ -248,6 +248,28 @@ class RDA_solver:
                                            self._stream()), 'rda_solve')
         return self._out
 
+    # phase API (rda_begin / rda_step_su / rda_step_lammuz / rda_finish): unit tests, profiling
+    def begin(self, nom_s, nom_u, ref_s, ref_speed, obs_A=None, obs_b=None, obs_kind=None, obs_count=None,
+              time_varying=False, iter_threshold=None):
+        inp = self._inputs(nom_s, nom_u, ref_s, ref_speed, obs_A, obs_b, obs_kind, obs_count, time_varying)
+        thr = self.iter_threshold if iter_threshold is None else iter_threshold
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.rda_begin(self._h, C.byref(inp), float(thr), self._stream()), 'rda_begin')
+
+    def step_su(self):
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.rda_step_su(self._h, self._stream()), 'rda_step_su')
+
+    def step_lammuz(self):
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.rda_step_lammuz(self._h, self._stream()), 'rda_step_lammuz')
+
+    def finish(self):
+        out = self._outputs()
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.rda_finish(self._h, C.byref(out), self._stream()), 'rda_finish')
+        return self._out
+
     def launch_count(self):
         return self.lib.rda_last_launch_count(self._h)
 

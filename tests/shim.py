@@ -1,13 +1,13 @@
-"""ctypes access to tests/_build/libhost_shim.so (g++ build of the CUDA kernels' numerical
-cores) — test infrastructure only."""
+"""ctypes access to oracle/_build/librda_cpu_port.so (g++ build of the CUDA kernels' numerical
+cores, oracle/cpu_port) — test infrastructure only."""
 import ctypes as C
 import os
-import subprocess
+import sys
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO = os.path.join(HERE, '_build', 'libhost_shim.so')
-SRC = os.path.join(HERE, 'host_shim', 'host_shim.cpp')
+sys.path.insert(0, os.path.dirname(HERE))
+from oracle import build_port
 
 
 class SuParams(C.Structure):
@@ -18,13 +18,7 @@ class SuParams(C.Structure):
 
 
 def build(force=False):
-    csrc = os.path.join(HERE, '..', 'rda_planner_b200', 'csrc')
-    deps = [SRC] + [os.path.join(csrc, f) for f in os.listdir(csrc)]
-    if (not force) and os.path.exists(SO) and all(os.path.getmtime(SO) >= os.path.getmtime(d) for d in deps):
-        return SO
-    os.makedirs(os.path.dirname(SO), exist_ok=True)
-    subprocess.check_call(['g++', '-O2', '-std=c++17', '-shared', '-fPIC', '-o', SO, SRC])
-    return SO
+    return build_port.build(force)
 
 
 _lib = None

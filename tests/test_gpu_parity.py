@@ -1,0 +1,196 @@
+"""-m gpu: the CUDA path through the C ABI (librda_b200.so) against the oracle, plus
+size-independent properties at the full benchmark size."""
+import numpy as np
+import pytest
+import torch
+
+from rda_planner_b200.scenarios import rectangle_robot, make_instance
+
+pytestmark = pytest.mark.gpu
+
+# Stated float32 tolerances (BASELINE.json north_star: "match ... to a stated fp32 tolerance"):
+TRAJ_TOL = 1e-3      # states (m, rad) and controls, absolute, after <= 8 ADMM iterations
+RESI_RTOL = 2e-3     # residuals, relative
+
+
+def _solvers(T, N, iters, dyn='acker', **kw):
+    from rda_planner_b200.rda_solver import RDA_solver
+    from oracle.rda_oracle import OracleRDA
+    car = rectangle_robot(dynamics=dyn)
+    g = RDA_solver(T, car, max_edge_num=4, max_obs_num=N, iter_num=iters, iter_threshold=kw.pop('thr', 0.0),
+                   time_print=False, **kw)
+    o = OracleRDA(T, car, max_edge_num=4, max_obs_num=N, iter_num=iters, iter_threshold=g.iter_threshold,
+                  **{k: v for k, v in kw.items() if k in ('accelerated', 'ro1', 'ro2', 'slack_gain', 'min_sd', 'max_sd', 'ws', 'wu')})
+    return car, g, o
+
+
+@pytest.mark.parametrize('seed,T,N,iters,kind,dyn,moving', [
+    (3, 10, 4, 4, 'polygon', 'acker', False),      # BASELINE configs[0] geometry (path_track)
+    (11, 10, 5, 6, 'polygon', 'acker', False),     # obstacles on the path: active hinges, overlap
+    (13, 10, 5, 6, 'circle', 'acker', False),
+    (14, 10, 5, 6, 'polygon', 'diff', False),
+    (15, 10, 5, 6, 'polygon', 'omni', False),
+    (17, 12, 5, 5, 'circle', 'acker', True),       # moving discs: per-stage obstacle copies
+    (18, 12, 5, 5, 'polygon', 'diff', True),
+    (16, 20, 10, 8, 'polygon', 'acker', False),    # BASELINE configs[1] size (corridor)
+])
+def test_trajectory_matches_oracle(seed, T, N, iters, kind, dyn, moving):
+    car, g, o = _solvers(T, N, iters, dyn)
+    inst = make_instance(seed, T=T, N=N, E=4, lateral=(0.3, 3.5), kind=kind, dynamics=dyn, moving=moving)
+    ref = [inst['ref'][:, t:t + 1] for t in range(T + 1)]
+    ug, ig = g.iterative_solve(inst['nom_s'], inst['nom_u'], ref, inst['ref_speed'], list(inst['obstacles']))
+    uo, io = o.iterative_solve(inst['nom_s'], inst['nom_u'], ref, inst['ref_speed'], list(inst['obstacles']))
+    assert ig['status'] & 7 == 0
+    np.testing.assert_allclose(ug, uo, atol=TRAJ_TOL)
+    np.testing.assert_allclose(np.hstack(ig['opt_state_list']), np.hstack(io['opt_state_list']), atol=TRAJ_TOL)
+    assert abs(ig['resi_dual'] - io['resi_dual']) <= RESI_RTOL * (1 + io['resi_dual'])
+    assert abs(ig['resi_pri'] - io['resi_pri']) <= RESI_RTOL * (1 + io['resi_pri'])
+
+
+def test_non_accelerated_mode_and_tunables():
+    car, g, o = _solvers(8, 3, 4, accelerated=False, ro1=1, slack_gain=5, min_sd=0.2)
+    inst = make_instance(21, T=8, N=3, E=4, lateral=(0.5, 3.0))
+    ref = [inst['ref'][:, t:t + 1] for t in range(9)]
+    ug, ig = g.iterative_solve(inst['nom_s'], inst['nom_u'], ref, 4.0, list(inst['obstacles']))
+    uo, io = o.iterative_solve(inst['nom_s'], inst['nom_u'], ref, 4.0, list(inst['obstacles']))
+    np.testing.assert_allclose(ug, uo, atol=TRAJ_TOL)
+    p = g.get_adjust_parameter()
+    assert p['ro1'] == 1 and p['slack_gain'] == 5 and abs(p['min_sd'] - 0.2) < 1e-7
+    g.assign_adjust_parameter(ro1=150, max_sd=0.8)
+    assert g.get_adjust_parameter()['ro1'] == 150
+
+
+def test_warm_start_across_calls_reset_and_early_stop():
+    """Second control step reuses lam/mu/z/xi/zeta/d (never cleared); reset()
+    clears only lam'A, lam'b (:1060-1068); early stop follows :594-596."""
+    car, g, o = _solvers(8, 3, 3)
+    a = make_instance(31, T=8, N=3, E=4, lateral=(0.5, 3.0))
+    ref = [a['ref'][:, t:t + 1] for t in range(9)]
+    for k in range(3):
+        if k == 2:
+            g.reset(); o.reset()
+        ug, ig = g.iterative_solve(a['nom_s'], a['nom_u'], ref, 4.0, list(a['obstacles']))
+        uo, io = o.iterative_solve(a['nom_s'], a['nom_u'], ref, 4.0, list(a['obstacles']))
+        np.testing.assert_allclose(ug, uo, atol=TRAJ_TOL)
+    car, g, o = _solvers(8, 3, 10, thr=0.5)
+    ug, ig = g.iterative_solve(a['nom_s'], a['nom_u'], ref, 4.0, list(a['obstacles']))
+    uo, io = o.iterative_solve(a['nom_s'], a['nom_u'], ref, 4.0, list(a['obstacles']))
+    assert ig['iterations'] == len(o.trace) and ig['iterations'] < 10
+    np.testing.assert_allclose(ug, uo, atol=TRAJ_TOL)
+
+
+def test_empty_and_short_obstacle_lists():
+    car, g, o = _solvers(6, 3, 2)
+    a = make_instance(41, T=6, N=2, E=4, lateral=(0.5, 3.0))
+    ref = [a['ref'][:, t:t + 1] for t in range(7)]
+    ug, ig = g.iterative_solve(a['nom_s'], a['nom_u'], ref, 4.0, list(a['obstacles']))      # padded by repetition
+    uo, io = o.iterative_solve(a['nom_s'], a['nom_u'], ref, 4.0, list(a['obstacles']))
+    np.testing.assert_allclose(ug, uo, atol=TRAJ_TOL)
+    ug, ig = g.iterative_solve(a['nom_s'], a['nom_u'], ref, 4.0, [])                        # stale terms quirk
+    uo, io = o.iterative_solve(a['nom_s'], a['nom_u'], ref, 4.0, [])
+    np.testing.assert_allclose(ug, uo, atol=TRAJ_TOL)
+    assert ig['resi_pri'] == 0 and ig['resi_dual'] == 0
+
+
+def test_mpc_front_end_on_gpu_matches_oracle_backed_front_end():
+    """example/path_track geometry: MPC.control for a few steps, CUDA solver vs oracle solver."""
+    import os
+    from collections import namedtuple
+    from RDA_planner.mpc import MPC
+    from oracle.rda_oracle import OracleRDA
+    here = os.path.dirname(os.path.abspath(__file__))
+    path = list(np.load(os.path.join(here, 'golden', 'path_track_ref.npy'), allow_pickle=True))
+    Obs = namedtuple('Obs', 'center radius vertex cone_type velocity')
+    obs = [Obs(np.array([[20.], [34.]]), 1.5, None, 'norm2', np.zeros((2, 1))),
+           Obs(np.array([[10.5], [44.5]]), 1.0, None, 'norm2', np.zeros((2, 1))),
+           Obs(None, None, np.array([[12., 14, 14, 12], [41, 41, 39, 39]]), 'Rpositive', np.zeros((2, 1)))]
+    car = rectangle_robot()
+    import copy
+    kw = dict(receding=10, sample_time=0.1, iter_num=2, ro1=300, max_edge_num=4, max_obs_num=4, slack_gain=8)
+    mg = MPC(car, copy.deepcopy(path), **kw)
+    mo = MPC(car, copy.deepcopy(path), solver_cls=OracleRDA, **kw)
+    state = np.array([[10.], [42.], [1.57]])
+    for k in range(3):
+        ug, ig = mg.control(state.copy(), 4, obs)
+        uo, io = mo.control(state.copy(), 4, obs)
+        np.testing.assert_allclose(ug, uo, atol=2e-3)
+        th = state[2, 0]
+        state = state + 0.1 * np.array([[uo[0, 0] * np.cos(th)], [uo[0, 0] * np.sin(th)], [uo[0, 0] * np.tan(uo[1, 0]) / 3.0]])
+
+
+def _batch_inputs(B, T, N, seed0, **kw):
+    from rda_planner_b200.rda_solver import pack_obstacles
+    insts = [make_instance(seed0 + i, T=T, N=N, E=4, **kw) for i in range(B)]
+    packs = [pack_obstacles(list(i['obstacles']), T, N, 4) for i in insts]
+    return insts, dict(nom_s=np.stack([i['nom_s'] for i in insts]), nom_u=np.stack([i['nom_u'] for i in insts]),
+                       ref_s=np.stack([i['ref'] for i in insts]), ref_speed=np.array([i['ref_speed'] for i in insts]),
+                       obs_A=np.stack([p[0] for p in packs]), obs_b=np.stack([p[1] for p in packs]),
+                       obs_kind=np.stack([p[2] for p in packs]), obs_count=np.array([p[3] for p in packs]))
+
+
+def test_batch_equals_single_instances_and_cpu_port():
+    """Instances of a batch do not interact; the compiled CPU port (same cores) agrees."""
+    from rda_planner_b200.rda_solver import RDA_solver
+    from oracle import cpu_port
+    T, N, B, iters = 12, 6, 37, 6
+    car = rectangle_robot()
+    insts, inp = _batch_inputs(B, T, N, 500, lateral=(0.3, 3.5))
+    gb = RDA_solver(T, car, 4, N, iter_num=iters, iter_threshold=0.0, time_print=False, batch=B)
+    out = {k: v.clone() for k, v in gb.iterative_solve_batch(**inp).items()}
+    assert int((out['status'] & 7).sum()) == 0
+    port = cpu_port.solve_batch(car, T, N, 4, **inp, iter_num=iters)
+    np.testing.assert_allclose(out['u'].cpu().numpy(), port['u'], atol=TRAJ_TOL)
+    np.testing.assert_allclose(out['s'].cpu().numpy(), port['s'], atol=TRAJ_TOL)
+    g1 = RDA_solver(T, car, 4, N, iter_num=iters, iter_threshold=0.0, time_print=False)
+    for i in (0, 17, 36):
+        g1.cold_start()
+        ref = [insts[i]['ref'][:, t:t + 1] for t in range(T + 1)]
+        u1, _ = g1.iterative_solve(insts[i]['nom_s'], insts[i]['nom_u'], ref, 4.0, list(insts[i]['obstacles']))
+        np.testing.assert_allclose(out['u'][i].cpu().numpy(), u1, atol=1e-6)
+
+
+def test_full_size_properties():
+    """BASELINE metric size (T=30, N=20, 50 iterations), B=256: finite, bounds respected, deterministic,
+    permutation-equivariant over instances, invariant to duplicating the last obstacle slot."""
+    from rda_planner_b200.rda_solver import RDA_solver
+    T, N, B = 30, 20, 256
+    car = rectangle_robot()
+    insts, inp = _batch_inputs(B, T, N, 9000)
+    g = RDA_solver(T, car, 4, N, iter_num=50, iter_threshold=0.0, time_print=False, batch=B)
+    a = {k: v.clone() for k, v in g.iterative_solve_batch(**inp).items()}
+    assert torch.isfinite(a['u']).all() and torch.isfinite(a['s']).all()
+    assert int((a['status'] & 6).sum()) == 0
+    assert float(a['u'][:, 0].abs().max()) <= 10 + 1e-4 and float(a['u'][:, 1].abs().max()) <= 1 + 1e-4
+    du = (a['u'][:, :, 1:] - a['u'][:, :, :-1]).abs()
+    assert float(du[:, 0].max()) <= 1.0 + 1e-4 and float(du[:, 1].max()) <= 0.05 + 1e-4
+    assert (a['iters'] == 50).all()
+    g.cold_start()
+    b = {k: v.clone() for k, v in g.iterative_solve_batch(**inp).items()}
+    assert torch.equal(a['u'], b['u']) and torch.equal(a['s'], b['s'])            # deterministic
+    perm = np.random.default_rng(0).permutation(B)
+    g.cold_start()
+    c = g.iterative_solve_batch(**{k: v[perm] for k, v in inp.items()})
+    assert torch.equal(c['u'], a['u'][torch.as_tensor(perm, device=a['u'].device)])
+    # early stop enabled: every instance stops with both residuals below the threshold or runs out
+    g.cold_start()
+    d = g.iterative_solve_batch(**inp, iter_threshold=0.2)
+    stopped = (d['status'] & 8) != 0
+    assert bool(((d['resi_pri'] < 0.2) & (d['resi_dual'] < 0.2))[stopped].all())
+    assert bool((d['iters'][~stopped] == 50).all())
+
+
+def test_golden_trajectory_fixture():
+    """Committed oracle output at the metric size (tests/golden/oracle_metric_T30N20.npz, made by
+    tests/golden/make_oracle_fixture.py) after 6 ADMM iterations."""
+    import os
+    from rda_planner_b200.rda_solver import RDA_solver
+    here = os.path.dirname(os.path.abspath(__file__))
+    fx = np.load(os.path.join(here, 'golden', 'oracle_metric_T30N20.npz'))
+    T, N = 30, 20
+    car = rectangle_robot()
+    inst = make_instance(int(fx['seed']), T=T, N=N, E=4)
+    ref = [inst['ref'][:, t:t + 1] for t in range(T + 1)]
+    g = RDA_solver(T, car, 4, N, iter_num=int(fx['iters']), iter_threshold=0.0, time_print=False)
+    u, info = g.iterative_solve(inst['nom_s'], inst['nom_u'], ref, inst['ref_speed'], list(inst['obstacles']))
+    np.testing.assert_allclose(u, fx['u'], atol=TRAJ_TOL)
+    np.testing.assert_allclose(np.hstack(info['opt_state_list']), fx['s'], atol=TRAJ_TOL)

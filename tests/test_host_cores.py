@@ -1,0 +1,91 @@
+"""The numerical cores of the CUDA kernels (csrc/su_solver.cuh, csrc/cell_solver.cuh), compiled
+for the host by tests/host_shim, against the oracle.  This is the CPU-side guard of the kernel
+arithmetic; the -m gpu tests repeat the comparison through the C ABI on the device."""
+import numpy as np
+import pytest
+
+import shim
+from pipeline_shim import ShimPipeline
+from rda_planner_b200.scenarios import rectangle_robot, make_instance
+from oracle.rda_oracle import OracleRDA
+from oracle.cell_geo import solve_cell_geo
+
+# fp32 tolerance of the cell kernel on (lam, mu, z): obstacle rows are stored in float32
+CELL_TOL_F32 = 2e-4
+CELL_TOL_F64 = 5e-6      # float64 arithmetic on float32-rounded obstacle data
+TRAJ_TOL = 5e-4          # trajectory (m, rad) and control gap after a few ADMM iterations
+
+
+def oracle_state(seed, T, N, iters, kind='polygon', dyn='acker', lateral=(0.3, 3.0)):
+    car = rectangle_robot(dynamics=dyn)
+    inst = make_instance(seed, T=T, N=N, E=4, lateral=lateral, kind=kind, dynamics=dyn)
+    o = OracleRDA(T, car, max_edge_num=4, max_obs_num=N, iter_num=iters, iter_threshold=0.0)
+    ref = [inst['ref'][:, t:t + 1] for t in range(T + 1)]
+    o.iterative_solve(inst['nom_s'], inst['nom_u'], ref, inst['ref_speed'], list(inst['obstacles']))
+    return o, inst, car
+
+
+@pytest.mark.parametrize('kind,seed', [('polygon', 41), ('circle', 42)])
+def test_cell_core_matches_oracle(kind, seed):
+    o, inst, car = oracle_state(seed, 6, 3, 2, kind=kind)
+    s, u, d, _ = o.su_prob_solve()
+    o.assign_state_parameter(s, u, d)
+    paths = set()
+    for n in range(o.max_obs_num):
+        for t in range(o.T):
+            args = (o.obs_A[n, t + 1], o.obs_b[n, t + 1], bool(o.obs_cone[n]), o.G, o.h, o.para_s[0:2, t + 1],
+                    o.para_s[2, t], o.para_dis[0, t], o.para_zeta[n, t], o.para_xi[n, t + 1], o.ro2)
+            r = solve_cell_geo(*args)
+            for prec, tol in (('d', CELL_TOL_F64), ('f', CELL_TOL_F32)):
+                k = shim.cell(o.G, o.h, int(o.obs_cone[n]), args[0], args[1], *args[5:11], prec=prec)
+                assert k['path'] != 5
+                paths.add(k['path'])
+                np.testing.assert_allclose(k['lam'], r['lam'], atol=tol)
+                np.testing.assert_allclose(k['mu'], r['mu'], atol=tol)
+                assert abs(k['z'] - r['z']) < tol
+                # the update the kernel fuses: zeta + Im - d - z and xi + Hm (:666, :683)
+                assert abs(k['zeta_new'] - (r['stuff'] - r['z'])) < 10 * tol
+                np.testing.assert_allclose([k['hm0'], k['hm1']], r['Hm'], atol=10 * tol)
+    assert len(paths) >= 2
+
+
+@pytest.mark.parametrize('dyn', ['acker', 'diff', 'omni'])
+def test_su_core_matches_oracle(dyn):
+    o, inst, car = oracle_state(43, 8, 3, 3, dyn=dyn)
+    T, N = o.T, o.max_obs_num
+    s_o, u_o, d_o, info = o.su_prob_solve()
+    P = shim.SuParams(T=T, N=N, dynamics=shim.DYN[dyn], accelerated=1, dt=0.1, L=3.0,
+                      umax=(shim.C.c_float * 2)(10, 1), ab=(shim.C.c_float * 2)(1.0, 0.05), ws=1, wu=1,
+                      slack_gain=8, dmin=0.1, dmax=1.0, ro1=200, ro2=1, max_iter=40)
+    pref = o.para_s[0:2, 1:]
+    hx, hy = o.para_obsA_lam[:, 1:, 0], o.para_obsA_lam[:, 1:, 1]
+    hc = np.zeros((N, T)); gx = np.zeros((N, T)); gy = np.zeros((N, T))
+    for n in range(N):
+        for t in range(T):
+            hc[n, t] = (o.para_obsA_lam[n, t + 1] @ pref[:, t] - o.para_obsb_lam[n, t + 1] - o.para_mu[n, :, t + 1] @ o.h
+                        - o.para_z[n, t] + o.para_zeta[n, t])
+            gx[n, t], gy[n, t] = o.para_mu[n, :, t + 1] @ o.G + o.para_xi[n, t + 1]
+    for prec, tol in (('d', 2e-5), ('f', 5e-4)):
+        s, u, d, st, it = shim.su(P, o.para_s, o.para_u, o.ref_s, o.ref_speed, o.para_dis, hx, hy, hc, gx, gy, pref, prec=prec)
+        assert st == 0 and it < 40
+        np.testing.assert_allclose(s, s_o, atol=tol)
+        np.testing.assert_allclose(u, u_o, atol=tol)
+        np.testing.assert_allclose(d, d_o.ravel(), atol=tol)
+
+
+@pytest.mark.parametrize('seed,kind,dyn', [(51, 'polygon', 'acker'), (52, 'circle', 'acker'), (53, 'polygon', 'diff')])
+def test_pipeline_emulation_matches_oracle(seed, kind, dyn):
+    """k_su -> k_cells -> k_finalize orchestration (float32 state, fused updates) vs the oracle."""
+    T, N, iters = 8, 4, 4
+    car = rectangle_robot(dynamics=dyn)
+    inst = make_instance(seed, T=T, N=N, E=4, lateral=(0.3, 3.0), kind=kind, dynamics=dyn)
+    ref = [inst['ref'][:, t:t + 1] for t in range(T + 1)]
+    o = OracleRDA(T, car, max_edge_num=4, max_obs_num=N, iter_num=iters, iter_threshold=0.0)
+    uo, io = o.iterative_solve(inst['nom_s'], inst['nom_u'], ref, inst['ref_speed'], list(inst['obstacles']))
+    p = ShimPipeline(T, car, 4, N)
+    ug, sg, rd, rp = p.solve(inst['nom_s'], inst['nom_u'], inst['ref'], inst['ref_speed'], list(inst['obstacles']), iters)
+    np.testing.assert_allclose(ug, uo, atol=TRAJ_TOL)
+    np.testing.assert_allclose(sg, np.hstack(io['opt_state_list']), atol=TRAJ_TOL)
+    assert abs(rd - io['resi_dual']) < 1e-3 * (1 + io['resi_dual'])
+    assert abs(rp - io['resi_pri']) < 1e-3 * (1 + io['resi_pri'])
+    assert 5 not in p.paths

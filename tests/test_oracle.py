@@ -1,0 +1,141 @@
+"""Pin the oracle: (i) Jacobians against values produced by executing the reference,
+(ii) every sub-problem solve against an independent generic solver."""
+import json
+import os
+
+import numpy as np
+import pytest
+from scipy.optimize import minimize
+
+from rda_planner_b200.scenarios import rectangle_robot, make_instance
+from oracle.rda_oracle import OracleRDA
+from oracle.cell_generic import solve_cell_generic, cell_objective
+from oracle.cell_geo import solve_cell_geo
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = json.load(open(os.path.join(HERE, 'golden', 'boundary_golden.json')))
+
+
+@pytest.mark.parametrize('dyn', ['acker', 'diff', 'omni'])
+def test_jacobians_match_reference(dyn):
+    o = OracleRDA(5, rectangle_robot(dynamics=dyn), 4, 2)
+    for rec in GOLD['models']:
+        s, u = np.array(rec['s'])[:, 0], np.array(rec['u'])[:, 0]
+        A, B, C = o.linear_model(s, u)
+        Ar, Br, Cr = (np.array(x) for x in rec['lin_' + dyn])
+        np.testing.assert_allclose(A, Ar, atol=1e-13)
+        np.testing.assert_allclose(B, Br, atol=1e-13)
+        np.testing.assert_allclose(C, Cr[:, 0], atol=1e-13)
+
+
+def _run(seed, T, N, iters, kind='polygon', dyn='acker', lateral=(0.3, 3.0), cell_solver='geo', **kw):
+    car = rectangle_robot(dynamics=dyn)
+    inst = make_instance(seed, T=T, N=N, E=4, lateral=lateral, kind=kind, dynamics=dyn)
+    o = OracleRDA(T, car, max_edge_num=4, max_obs_num=N, iter_num=iters, iter_threshold=0.0,
+                  cell_solver=cell_solver, **kw)
+    ref = [inst['ref'][:, t:t + 1] for t in range(T + 1)]
+    u, info = o.iterative_solve(inst['nom_s'], inst['nom_u'], ref, inst['ref_speed'], list(inst['obstacles']))
+    return o, u, info
+
+
+def test_su_qp_against_generic_nlp():
+    """The condensed QP + IPM solution minimises the literal (non-smooth) su objective."""
+    o, u, info = _run(5, 5, 2, 2)
+    T, N = o.T, o.max_obs_num
+    # literal objective in (u, d) with states rolled out through the linearised dynamics
+    def rollout(uv):
+        s = np.zeros((3, T + 1)); s[:, 0] = o.para_s[:, 0]
+        for t in range(T):
+            A, B, C = o.lin[t]
+            s[:, t + 1] = A @ s[:, t] + B @ uv[:, t] + C
+        return s
+    def cost(x):
+        uv = x[:2 * T].reshape(T, 2).T; d = x[2 * T:]
+        s = rollout(uv)
+        c = o.ws * np.sum((s - o.ref_s) ** 2) + o.wu * np.sum((uv[0] - o.ref_speed) ** 2) - o.slack_gain * d.sum()
+        for n in range(N):
+            for t in range(T):
+                a = o.para_obsA_lam[n, t + 1]
+                Im = a @ s[0:2, t + 1] - o.para_obsb_lam[n, t + 1] - o.para_mu[n, :, t + 1] @ o.h - d[t] - o.para_z[n, t] + o.para_zeta[n, t]
+                c += 0.5 * o.ro1 * min(Im, 0.0) ** 2
+                ph = o.para_s[2, t]; cs, sn = np.cos(ph), np.sin(ph)
+                Rb = np.array([[cs, -sn], [sn, cs]]); dR = np.array([[-sn, -cs], [cs, -sn]])
+                rot = Rb - ph * dR + dR * s[2, t + 1]
+                Hm = o.para_mu[n, :, t + 1] @ o.G + a @ rot + o.para_xi[n, t + 1]
+                c += 0.5 * o.ro2 * Hm @ Hm
+        return c
+    s_o, u_o, d_o, qinfo = o.su_prob_solve()
+    assert qinfo['status'] in ('optimal', 'optimal_inaccurate')
+    x_o = np.concatenate([u_o.T.ravel(), d_o.ravel()])
+    bounds = [(-10, 10), (-1, 1)] * T + [(0.1, 1.0)] * T
+    cons = []
+    for t in range(T - 1):
+        for k in range(2):
+            i0, i1 = 2 * t + k, 2 * (t + 1) + k
+            cons.append({'type': 'ineq', 'fun': lambda x, i0=i0, i1=i1, k=k: o.acce_bound[k] - (x[i1] - x[i0])})
+            cons.append({'type': 'ineq', 'fun': lambda x, i0=i0, i1=i1, k=k: o.acce_bound[k] + (x[i1] - x[i0])})
+    res = minimize(cost, x_o + 0.01, bounds=bounds, constraints=cons, method='SLSQP', options={'ftol': 1e-14, 'maxiter': 500})
+    assert cost(x_o) <= res.fun + 1e-6 * (1 + abs(res.fun))
+    assert np.abs(res.x - x_o).max() < 2e-3
+
+
+@pytest.mark.parametrize('kind,seed', [('polygon', 21), ('polygon', 22), ('circle', 23)])
+def test_cell_shortcut_equals_generic(kind, seed):
+    """oracle/cell_geo.py (closed forms) == oracle/cell_generic.py (SLSQP in lam, mu, z)."""
+    o, _, _ = _run(seed, 6, 3, 2, kind=kind)
+    rng = np.random.default_rng(seed)
+    checked = 0
+    for n in range(o.max_obs_num):
+        for t in range(o.T):
+            args = (o.obs_A[n, t + 1], o.obs_b[n, t + 1], bool(o.obs_cone[n]), o.G, o.h, o.para_s[0:2, t + 1],
+                    o.para_s[2, t], o.para_dis[0, t], o.para_zeta[n, t] + rng.normal(0, 0.1),
+                    o.para_xi[n, t + 1] * (rng.random() < 0.5), o.ro2)
+            a = solve_cell_geo(*args)
+            b = solve_cell_generic(*args)
+            fa = cell_objective(args[0], args[1], *args[3:], a['lam'], a['mu'], a['z'])
+            fb = cell_objective(args[0], args[1], *args[3:], b['lam'], b['mu'], b['z'])
+            assert abs(fa - fb) < 1e-9
+            np.testing.assert_allclose(a['lam'], b['lam'], atol=2e-6)
+            np.testing.assert_allclose(a['mu'], b['mu'], atol=2e-6)
+            assert abs(a['z'] - b['z']) < 2e-6
+            # feasibility of the reference constraints (:408-419)
+            assert np.linalg.norm(args[0].T @ a['lam']) <= 1 + 1e-7
+            assert (a["mu"] >= -1e-9).all() and a["z"] >= 0
+            checked += 1
+    assert checked == o.max_obs_num * o.T
+
+
+def test_margin_equals_signed_distance_when_converged():
+    """Geometric known answer: with xi = 0 the max-margin certificate equals the distance between
+    the robot footprint and the obstacle."""
+    car = rectangle_robot()
+    G, h = car.G, np.asarray(car.h).ravel()
+    from rda_planner_b200.mpc import polygon_halfspaces
+    box = np.array([[6.0, 8.0, 8.0, 6.0], [-1.0, -1.0, 1.0, 1.0]])
+    A, b = polygon_halfspaces(box)
+    r = solve_cell_generic(A, b.ravel(), False, G, h, np.zeros(2), 0.0, 0.0, 0.0, np.zeros(2), 1.0)
+    # robot spans x in [-0.8, 3.8]: gap to the box = 6.0 - 3.8
+    assert abs(r['stuff'] - 2.2) < 1e-7
+    r = solve_cell_generic(np.array([[1.0, 0], [0, 1.0], [0, 0]]), np.array([7.0, 0.0, -1.5]), True, G, h,
+                           np.zeros(2), 0.0, 0.0, 0.0, np.zeros(2), 1.0)
+    assert abs(r['stuff'] - (7.0 - 1.5 - 3.8)) < 1e-7
+
+
+def test_admm_runs_and_is_deterministic():
+    o1, u1, i1 = _run(31, 8, 3, 3)
+    o2, u2, i2 = _run(31, 8, 3, 3)
+    assert np.array_equal(u1, u2)
+    assert np.isfinite(u1).all() and np.isfinite(i1['resi_pri'])
+
+
+def test_padding_invariance():
+    """Padding the obstacle list by repeating its last element (rda_solver.py:488-490) must give
+    the same trajectory as passing the repeated list explicitly."""
+    car = rectangle_robot()
+    inst = make_instance(33, T=6, N=2, E=4, lateral=(0.5, 3.0))
+    ref = [inst['ref'][:, t:t + 1] for t in range(7)]
+    oa = OracleRDA(6, car, 4, 3, iter_num=2, iter_threshold=0.0)
+    ua, _ = oa.iterative_solve(inst['nom_s'], inst['nom_u'], ref, 4.0, list(inst['obstacles']))
+    ob = OracleRDA(6, car, 4, 3, iter_num=2, iter_threshold=0.0)
+    ub, _ = ob.iterative_solve(inst['nom_s'], inst['nom_u'], ref, 4.0, list(inst['obstacles']) + [inst['obstacles'][-1]])
+    np.testing.assert_allclose(ua, ub, atol=1e-12)
