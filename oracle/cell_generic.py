@@ -137,8 +137,19 @@ def solve_cell_generic(A, b, is_circle, G, h, p, phi, dbar, zeta, xi, ro2,
             return min(m, 0.0) * gm + ro2 * np.hstack([AR.T, G.T]).T @ q
 
         bestB = None
-        for trial in range(4):
-            th0 = best[1] if trial == 0 else best[1] * (0.5 + 0.2 * trial)
+        starts = [best[1]] + [best[1] * (0.5 + 0.2 * k) for k in (1, 2, 3)]
+        # the cone constraints are non-smooth at lam = 0 (overlapping sets end stage A there):
+        # also start from small multipliers in a fan of directions
+        for k in range(6):
+            ang = np.pi * k / 3.0
+            th0 = np.zeros(E + R)
+            if is_circle:
+                th0[0:3] = 0.05 * np.cos(ang), 0.05 * np.sin(ang), -0.05
+            else:
+                th0[:E] = 0.05 * np.maximum(An @ np.array([np.cos(ang), np.sin(ang)]), 0.0)
+            th0[E:] = 0.01
+            starts.append(th0)
+        for th0 in starts:
             res = minimize(obj, th0, jac=jac, bounds=bounds, constraints=cons, method='SLSQP',
                            options={'ftol': 1e-15, 'maxiter': 600})
             if bestB is None or res.fun < bestB[0]:

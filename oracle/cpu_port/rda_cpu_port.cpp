@@ -89,7 +89,7 @@ extern "C" int port_solve_batch(const rda_config* cfg, const rda_tunables* tun, 
                                 const float* nom_u, const float* ref_s, const float* ref_speed,
                                 const float* obs_A, const float* obs_b, const int* obs_kind,
                                 const int* obs_count, int tv, int iter_num, float thr, float* u_opt,
-                                float* s_opt, float* resi_pri, float* resi_dual, int* iters_out, int nthreads) {
+                                float* s_opt, float* resi_pri, float* resi_dual, int* iters_out, int* fails_out, int nthreads) {
   RobotGeom rb;
   int rc = robot_geom_from_halfspaces(cfg->G, cfg->h, cfg->robot_edges, &rb);
   if (rc) return rc;
@@ -116,7 +116,7 @@ extern "C" int port_solve_batch(const rda_config* cfg, const rda_tunables* tun, 
     std::vector<float> cu(nom_u + (size_t)b * 2 * T, nom_u + (size_t)(b + 1) * 2 * T);
     const float* rf = ref_s + (size_t)b * 3 * (T + 1);
     float rp = 0.f, rd = 0.f;
-    int it = 0;
+    int it = 0, nfail = 0, first_fail = -1;
     for (it = 0; it < iter_num; ++it) {
       for (int i = 0; i < 3 * (T + 1); ++i) { int r = i / (T + 1), t = i % (T + 1); W.lins[3 * t + r] = cs[i]; W.ref[3 * t + r] = rf[i]; }
       for (int i = 0; i < 2 * T; ++i) { int r = i / T, t = i % T; W.linu[2 * t + r] = cu[i]; W.pref[2 * t + r] = pref[i]; }
@@ -142,7 +142,7 @@ extern "C" int port_solve_batch(const rda_config* cfg, const rda_tunables* tun, 
             cell_solve<float>(rb, obs_kind[(size_t)b * N + o], E, obs_A + ob * E * 2, obs_b + ob * E, cs[t + 1],
                               cs[(T + 1) + t + 1], cosf(ph), sinf(ph), dis[t], zeta[o * T + t], xi[o * T + t],
                               xi[NT + o * T + t], (float)P.ro2, theta, out);
-            if (out.path == CELL_FAILED) { dual = INFINITY; continue; }
+            if (out.path == CELL_FAILED) { dual = INFINITY; ++nfail; if (first_fail < 0) first_fail = (it * N + o) * T + t; continue; }
             float acc = 0.f;
             for (int i = 0; i < E; ++i) { float nv = out.lam[i], df = nv - lam[((size_t)o * E + i) * T + t]; acc += df * df; lam[((size_t)o * E + i) * T + t] = nv; }
             for (int j = 0; j < R; ++j) { float nv = out.mu[j], df = nv - mu[((size_t)o * R + j) * T + t]; acc += df * df; mu[((size_t)o * R + j) * T + t] = nv; }
@@ -165,6 +165,7 @@ extern "C" int port_solve_batch(const rda_config* cfg, const rda_tunables* tun, 
     for (int i = 0; i < 2 * T; ++i) u_opt[(size_t)b * 2 * T + i] = cu[i];
     resi_pri[b] = rp; resi_dual[b] = rd;
     if (iters_out) iters_out[b] = it;
+    if (fails_out) { fails_out[2 * b] = nfail; fails_out[2 * b + 1] = first_fail; }
   }
   return 0;
 }

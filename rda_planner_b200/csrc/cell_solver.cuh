@@ -21,7 +21,7 @@
 namespace rda {
 
 enum { CELL_FAST_INACTIVE = 0, CELL_FAST_VERTEX = 1, CELL_SLOW_A = 2, CELL_SLOW_B = 3,
-       CELL_OVERLAP_FREE = 4, CELL_FAILED = 5 };
+       CELL_OVERLAP_FREE = 4, CELL_FAILED = 5, CELL_NEEDS_SLOW = 6 };
 
 template <typename Real>
 struct CellOut {
@@ -283,8 +283,9 @@ RDA_HD double barrier_value(const TinyQP<NV, MC>& P, const double* x, double t) 
     if (!(sl > 0)) return 1e300;
     f -= log(sl);
   }
-  double psi = x[P.tv] * x[P.tv] - x[0] * x[0] - x[1] * x[1];
-  if (!(psi > 0) || !(x[P.tv] > 0)) return 1e300;
+  double tq = P.tv >= 0 ? x[P.tv] : 1.0;
+  double psi = tq * tq - x[0] * x[0] - x[1] * x[1];
+  if (!(psi > 0) || !(tq > 0)) return 1e300;
   return f - log(psi);
 }
 
@@ -312,15 +313,18 @@ RDA_HD_NOINLINE bool tiny_barrier(const TinyQP<NV, MC>& P, double* x /* strictly
         }
       }
       {
-        double psi = x[tv] * x[tv] - x[0] * x[0] - x[1] * x[1];
-        double gp[3] = {-2 * x[0], -2 * x[1], 2 * x[tv]};       // grad psi on (0, 1, tv)
+        const double tq = tv >= 0 ? x[tv] : 1.0;
+        double psi = tq * tq - x[0] * x[0] - x[1] * x[1];
+        double gp[3] = {-2 * x[0], -2 * x[1], 2 * tq};          // grad psi on (0, 1, tv)
         const int id[3] = {0, 1, tv};
+        const int na = tv >= 0 ? 3 : 2;
         double ip = 1.0 / psi;
-        for (int a = 0; a < 3; ++a) {
+        for (int a = 0; a < na; ++a) {
           g[id[a]] -= gp[a] * ip;
           for (int b2 = 0; b2 <= a; ++b2) H[id[a]][id[b2]] += gp[a] * gp[b2] * ip * ip;
         }
-        H[0][0] += 2 * ip; H[1][1] += 2 * ip; H[tv][tv] -= 2 * ip;
+        H[0][0] += 2 * ip; H[1][1] += 2 * ip;
+        if (tv >= 0) H[tv][tv] -= 2 * ip;
       }
       for (int k = 0; k < NV; ++k) H[k][k] += 1e-13 * (1.0 + H[k][k]);
       double dx[NV];
@@ -399,7 +403,9 @@ RDA_HD bool in_cone_rob(const RobotGeom& rb, int j, Real gx, Real gy, Real tol) 
   return a >= -tol * gn * sqrt_(epx * epx + epy * epy) && b <= tol * gn * sqrt_(enx * enx + eny * eny);
 }
 
-template <typename Real>
+// FAST_ONLY = true compiles the closed-form paths only and reports CELL_NEEDS_SLOW (no outputs
+// written) for cells that need the interior point method (first pass of the two-pass kernel).
+template <typename Real, bool FAST_ONLY = false>
 RDA_HD void cell_solve(const RobotGeom& rb, int kind, int E, const float* A, const float* b,
                        Real px, Real py, Real cphi, Real sphi, Real dbar, Real zeta, Real xi0,
                        Real xi1, Real ro2, Real theta, CellOut<Real>& out) {
@@ -560,7 +566,9 @@ RDA_HD void cell_solve(const RobotGeom& rb, int kind, int E, const float* A, con
       }
     }
   }
-  if (!have) {
+  if (FAST_ONLY) {
+    if (!have) { out.path = CELL_NEEDS_SLOW; return; }
+  } else if (!have) {
     // ---- slow path: interior point in float64 ---------------------------------------------------
     // Polygon obstacle: sigma_O(v) = max_i v.x_i, |v| <= 1 (ball constraint).
     // Disc obstacle:    sigma_O(v) = v.c + rad*tv with |v| <= tv <= 1 (cone constraint, extra
@@ -599,7 +607,11 @@ RDA_HD void cell_solve(const RobotGeom& rb, int kind, int E, const float* A, con
       double hmax = 0;
       for (int j = 0; j < R; ++j) hmax = rmax(hmax, fabs(x0 * (double)rb.yx[j] + x1 * (double)rb.yy[j]));
       double xs[NVA] = {0, 0, 1.0 + radd, 1.0 + hmax, 0.5};
-      ok = circ ? tiny_barrier<NVA, 2 * RDA_MAX_EDGE + 2>(P, xs) : tiny_ipm<NVA, 2 * RDA_MAX_EDGE + 2>(P, xs);
+      ok = !circ && tiny_ipm<NVA, 2 * RDA_MAX_EDGE + 2>(P, xs);
+      if (!ok) {   // discs, and the rare polygon cell on which the primal-dual iteration cycles
+        xs[0] = 0; xs[1] = 0; xs[2] = 1.0 + radd; xs[3] = 1.0 + hmax; xs[4] = 0.5;
+        ok = tiny_barrier<NVA, 2 * RDA_MAX_EDGE + 2>(P, xs);
+      }
       double cst = -xs[2] - xs[3] - k0d;
       if (ok && cst >= 0) {
         inactive = true;
@@ -636,8 +648,13 @@ RDA_HD void cell_solve(const RobotGeom& rb, int kind, int E, const float* A, con
       P.m = m;
       P.tv = circ ? 7 : -1;
       double so0 = 1.0 + radd;
-      double xs[NVB] = {0, 0, 0, 0, so0, 1.0, rmax(so0 + 2.0 + k0d, 1.0), 0.5};
-      ok = circ ? tiny_barrier<NVB, 2 * RDA_MAX_EDGE + 3>(P, xs) : tiny_ipm<NVB, 2 * RDA_MAX_EDGE + 3>(P, xs);
+      const double w0 = rmax(so0 + 2.0 + k0d, 1.0);
+      double xs[NVB] = {0, 0, 0, 0, so0, 1.0, w0, 0.5};
+      ok = !circ && tiny_ipm<NVB, 2 * RDA_MAX_EDGE + 3>(P, xs);
+      if (!ok) {
+        xs[0] = xs[1] = xs[2] = xs[3] = 0; xs[4] = so0; xs[5] = 1.0; xs[6] = w0; xs[7] = 0.5;
+        ok = tiny_barrier<NVB, 2 * RDA_MAX_EDGE + 3>(P, xs);
+      }
       va = xs[0]; vb = xs[1]; ga = xs[2]; gb = xs[3];
       path = CELL_SLOW_B;
     }

@@ -1,9 +1,9 @@
 // rda_kernels.cu — sm_100a kernels and the C ABI (include/rda_b200.h) of the RDA ADMM hot path.
 //
-// One ADMM iteration (rda_solver.py:612-637) is three launches on the caller's stream:
+// One ADMM iteration (rda_solver.py:612-637) is four launches on the caller's stream:
 //   k_su      one warp per planning instance: su-QP (su_solver.cuh), state staged in shared memory
-//   k_cells   one thread per (instance, obstacle, stage) cell: (lam, mu, z) + xi/zeta update +
-//             residual partial sums + the next su-QP's hinge inputs (cell_solver.cuh)
+//   k_cells_fast / k_cells_slow   one thread per (instance, obstacle, stage) cell: (lam, mu, z) +
+//             xi/zeta update + residual partial sums + the next su-QP's hinge inputs (cell_solver.cuh)
 //   k_finalize per instance: residuals, early-stop flag (:594-596)
 // No host synchronisation, no allocation, CUDA-graph capturable.
 #include <cuda_runtime.h>
@@ -23,7 +23,7 @@ struct rda_handle {
   int B, T, N, E, R;
   float *lam, *mu, *z, *xi, *zeta, *dis, *coef, *pref, *cur_s, *cur_u, *ref_s, *ref_speed;
   float *resi_acc, *resi_pri, *resi_dual;
-  int *status, *iters, *done, *counters;
+  int *status, *iters, *done, *counters, *worklist;
   const float *obs_A, *obs_b;
   const int *obs_kind, *obs_count;
   int obs_tv;
@@ -58,7 +58,7 @@ struct WarpCtx {
 struct DevPtrs {
   float *lam, *mu, *z, *xi, *zeta, *dis, *coef, *pref, *cur_s, *cur_u, *ref_s, *ref_speed;
   float *resi_acc, *resi_pri, *resi_dual;
-  int *status, *iters, *done, *counters;
+  int *status, *iters, *done, *counters, *worklist;
   const float *obs_A, *obs_b;
   const int *obs_kind, *obs_count;
   int obs_tv;
@@ -163,12 +163,89 @@ __global__ void __launch_bounds__(32) k_su(DevPtrs d, SuParams P) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// K2: (lam, mu, z) cells + multiplier update, one thread per cell.
+// K2: (lam, mu, z) cells + multiplier update.  Two passes:
+//   k_cells_fast  one thread per cell, closed-form paths only; cells that need the interior point
+//                 method are appended to a worklist (warp-aggregated atomic);
+//   k_cells_slow  one thread per worklist entry (dense: no lane idles behind a slow neighbour).
 // ------------------------------------------------------------------------------------------------
-template <typename Real>
-__global__ void __launch_bounds__(128) k_cells(DevPtrs d, RobotGeom rb, float ro2, float theta) {
-  const int T = d.T, N = d.N, E = d.E, R = d.R;
-  const int NT = N * T;
+struct CellCtx {
+  int b, o, t;
+  size_t cell;
+};
+
+template <typename Real, bool FAST_ONLY>
+__device__ __forceinline__ int cell_run(const DevPtrs& d, const RobotGeom& rb, float ro2, float theta,
+                                        long long idx, float* hm2, float* dual) {
+  const int T = d.T, N = d.N, E = d.E, R = d.R, NT = N * T;
+  const int b = (int)(idx / NT);
+  const int rem = (int)(idx - (long long)b * NT);
+  const int o = rem / T, t = rem - o * T;
+  const float* cs = d.cur_s + (size_t)b * 3 * (T + 1);
+  Real px = cs[t + 1], py = cs[(T + 1) + t + 1];
+  float phib = cs[2 * (T + 1) + t];                 // NB column t (rda_solver.py:457-460)
+  float spf, cpf;
+  sincosf(phib, &spf, &cpf);
+  Real dbar = d.dis[(size_t)b * T + t];
+  const size_t cell = (size_t)b * NT + (size_t)o * T + t;
+  Real zeta = d.zeta[cell];
+  float* xi = d.xi + (size_t)b * 2 * NT;
+  Real xi0 = xi[(size_t)o * T + t], xi1 = xi[NT + (size_t)o * T + t];
+  const int tc = d.obs_tv ? (t + 1) : 0;
+  const int Tc = d.obs_tv ? (T + 1) : 1;
+  const size_t ob = ((size_t)b * N + o) * Tc + tc;
+  const float* A = d.obs_A + ob * E * 2;
+  const float* bb = d.obs_b + ob * E;
+  const int kind = d.obs_kind[(size_t)b * N + o];
+  CellOut<Real> out;
+  cell_solve<Real, FAST_ONLY>(rb, kind, E, A, bb, px, py, (Real)cpf, (Real)spf, dbar, zeta, xi0, xi1, (Real)ro2,
+                              (Real)theta, out);
+  if (out.path == CELL_NEEDS_SLOW) return out.path;
+  if (out.path == CELL_FAILED) {
+    // "Update Lam Mu Fail": previous duals kept, residual inf (:791-793)
+    *dual = INFINITY;
+    atomicOr(&d.status[b], RDA_ST_CELL_FALLBACK);
+    return out.path;
+  }
+  // dual residual |lam - lam_prev|^2 + |mu - mu_prev|^2 + |z - z_prev|^2 (:783-787)
+  float* lam = d.lam + ((size_t)b * N + o) * E * T + t;
+  float acc = 0.f;
+  for (int i = 0; i < E; ++i) {
+    float nv = (float)out.lam[i];
+    float df = nv - lam[(size_t)i * T];
+    acc += df * df;
+    lam[(size_t)i * T] = nv;
+  }
+  float* mu = d.mu + ((size_t)b * N + o) * R * T + t;
+  for (int j = 0; j < R; ++j) {
+    float nv = (float)out.mu[j];
+    float df = nv - mu[(size_t)j * T];
+    acc += df * df;
+    mu[(size_t)j * T] = nv;
+  }
+  float zn = (float)out.z;
+  float dz = zn - d.z[cell];
+  acc += dz * dz;
+  d.z[cell] = zn;
+  *dual = acc;
+  d.zeta[cell] = (float)out.zeta_new;
+  xi[(size_t)o * T + t] = (float)out.xi0_new;
+  xi[NT + (size_t)o * T + t] = (float)out.xi1_new;
+  *hm2 = (float)(out.hm0 * out.hm0 + out.hm1 * out.hm1);
+  float* cf = d.coef + (size_t)b * 5 * NT + (size_t)o * T + t;
+  cf[0] = (float)out.ax;
+  cf[NT] = (float)out.ay;
+  cf[2 * NT] = (float)out.c0;
+  cf[3 * NT] = (float)out.gx;
+  cf[4 * NT] = (float)out.gy;
+  if (o == 0) {
+    d.pref[(size_t)b * 2 * T + t] = (float)px;
+    d.pref[(size_t)b * 2 * T + T + t] = (float)py;
+  }
+  return out.path;
+}
+
+__global__ void __launch_bounds__(128) k_cells_fast(DevPtrs d, RobotGeom rb, float ro2, float theta) {
+  const int NT = d.N * d.T;
   const long long total = (long long)d.B * NT;
   const int lane = threadIdx.x & 31;
   for (long long base = (long long)blockIdx.x * blockDim.x; base < total; base += (long long)gridDim.x * blockDim.x) {
@@ -178,79 +255,23 @@ __global__ void __launch_bounds__(128) k_cells(DevPtrs d, RobotGeom rb, float ro
     float hm2 = 0.f, dual = 0.f;
     int path = -1;
     if (live && (d.done[b] || d.obs_count[b] == 0)) live = false;
-    if (live) {
-      int rem = (int)(idx - (long long)b * NT);
-      int o = rem / T, t = rem - o * T;
-      const float* cs = d.cur_s + (size_t)b * 3 * (T + 1);
-      Real px = cs[t + 1], py = cs[(T + 1) + t + 1];
-      Real phib = cs[2 * (T + 1) + t];                 // NB column t (rda_solver.py:457-460)
-      float spf, cpf;
-      sincosf((float)phib, &spf, &cpf);
-      Real sp = spf, cp = cpf;
-      Real dbar = d.dis[(size_t)b * T + t];
-      size_t cell = (size_t)b * NT + (size_t)o * T + t;
-      Real zeta = d.zeta[cell];
-      float* xi = d.xi + (size_t)b * 2 * NT;
-      Real xi0 = xi[(size_t)o * T + t], xi1 = xi[NT + (size_t)o * T + t];
-      int tc = d.obs_tv ? (t + 1) : 0;
-      int Tc = d.obs_tv ? (T + 1) : 1;
-      size_t ob = ((size_t)b * N + o) * Tc + tc;
-      const float* A = d.obs_A + ob * E * 2;
-      const float* bb = d.obs_b + ob * E;
-      int kind = d.obs_kind[(size_t)b * N + o];
-      CellOut<Real> out;
-      cell_solve<Real>(rb, kind, E, A, bb, px, py, cp, sp, dbar, zeta, xi0, xi1, (Real)ro2, (Real)theta, out);
-      path = out.path;
-      if (out.path != CELL_FAILED) {
-        // dual residual |lam - lam_prev|^2 + |mu - mu_prev|^2 + |z - z_prev|^2 (:783-787)
-        float* lam = d.lam + ((size_t)b * N + o) * E * T + t;
-        float acc = 0.f;
-        for (int i = 0; i < E; ++i) {
-          float nv = (float)out.lam[i];
-          float df = nv - lam[(size_t)i * T];
-          acc += df * df;
-          lam[(size_t)i * T] = nv;
-        }
-        float* mu = d.mu + ((size_t)b * N + o) * R * T + t;
-        for (int j = 0; j < R; ++j) {
-          float nv = (float)out.mu[j];
-          float df = nv - mu[(size_t)j * T];
-          acc += df * df;
-          mu[(size_t)j * T] = nv;
-        }
-        float zn = (float)out.z;
-        float dz = zn - d.z[cell];
-        acc += dz * dz;
-        d.z[cell] = zn;
-        dual = acc;
-        d.zeta[cell] = (float)out.zeta_new;
-        xi[(size_t)o * T + t] = (float)out.xi0_new;
-        xi[NT + (size_t)o * T + t] = (float)out.xi1_new;
-        hm2 = (float)(out.hm0 * out.hm0 + out.hm1 * out.hm1);
-        float* cf = d.coef + (size_t)b * 5 * NT + (size_t)o * T + t;
-        cf[0] = (float)out.ax;
-        cf[NT] = (float)out.ay;
-        cf[2 * NT] = (float)out.c0;
-        cf[3 * NT] = (float)out.gx;
-        cf[4 * NT] = (float)out.gy;
-        if (o == 0) {
-          d.pref[(size_t)b * 2 * T + t] = (float)px;
-          d.pref[(size_t)b * 2 * T + T + t] = (float)py;
-        }
-      } else {
-        // "Update Lam Mu Fail": previous duals kept, residual inf (:791-793)
-        dual = INFINITY;
-        atomicOr(&d.status[b], RDA_ST_CELL_FALLBACK);
-      }
+    if (live) path = cell_run<float, true>(d, rb, ro2, theta, idx, &hm2, &dual);
+    // worklist of cells for the slow pass (one atomic per warp)
+    unsigned need = __ballot_sync(0xffffffffu, path == CELL_NEEDS_SLOW);
+    if (need) {
+      int leader = __ffs(need) - 1, pos = 0;
+      if (lane == leader) pos = atomicAdd(&d.counters[5], __popc(need));
+      pos = __shfl_sync(0xffffffffu, pos, leader);
+      if (path == CELL_NEEDS_SLOW) d.worklist[pos + __popc(need & ((1u << lane) - 1))] = (int)idx;
     }
+    const bool solved = live && path != CELL_NEEDS_SLOW;
     // residual partial sums: a warp spans at most two instances when N*T >= 32
     int b0 = __shfl_sync(0xffffffffu, b, 0);
     for (int pass = 0; pass < 2; ++pass) {
-      bool mine = live && ((pass == 0) ? (b == b0) : (b != b0));
+      bool mine = solved && ((pass == 0) ? (b == b0) : (b != b0));
       unsigned m = __ballot_sync(0xffffffffu, mine);
       if (m == 0) continue;
       float h = mine ? hm2 : 0.f, q = mine ? dual : 0.f;
-      // general case (N*T < 32): fall back to per-thread atomics for the second group
       int leader = __ffs(m) - 1;
       int bl = __shfl_sync(0xffffffffu, b, leader);
       bool uniform = __all_sync(0xffffffffu, !mine || b == bl);
@@ -263,26 +284,34 @@ __global__ void __launch_bounds__(128) k_cells(DevPtrs d, RobotGeom rb, float ro
           atomicAdd(&d.resi_acc[2 * bl], h);
           atomicAdd(&d.resi_acc[2 * bl + 1], q);
         }
-      } else if (mine) {
+      } else if (mine) {      // N*T < 32: several instances per warp
         atomicAdd(&d.resi_acc[2 * b], h);
         atomicAdd(&d.resi_acc[2 * b + 1], q);
       }
     }
-    // path statistics
-    unsigned fast = __ballot_sync(0xffffffffu, path == CELL_FAST_INACTIVE || path == CELL_FAST_VERTEX || path == CELL_OVERLAP_FREE);
-    unsigned slow = __ballot_sync(0xffffffffu, path == CELL_SLOW_A || path == CELL_SLOW_B);
-    unsigned fail = __ballot_sync(0xffffffffu, path == CELL_FAILED);
-    if (lane == 0) {
-      if (fast) atomicAdd(&d.counters[0], __popc(fast));
-      if (slow) atomicAdd(&d.counters[1], __popc(slow));
-      if (fail) atomicAdd(&d.counters[2], __popc(fail));
-    }
+    unsigned fast = __ballot_sync(0xffffffffu, solved);
+    if (lane == 0 && fast) atomicAdd(&d.counters[0], __popc(fast));
+  }
+}
+
+__global__ void __launch_bounds__(64) k_cells_slow(DevPtrs d, RobotGeom rb, float ro2, float theta) {
+  const int NT = d.N * d.T;
+  const int count = d.counters[5];
+  for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < count; w += gridDim.x * blockDim.x) {
+    long long idx = d.worklist[w];
+    int b = (int)(idx / NT);
+    float hm2 = 0.f, dual = 0.f;
+    int path = cell_run<float, false>(d, rb, ro2, theta, idx, &hm2, &dual);
+    atomicAdd(&d.resi_acc[2 * b], hm2);
+    atomicAdd(&d.resi_acc[2 * b + 1], dual);
+    atomicAdd(&d.counters[path == CELL_FAILED ? 2 : 1], 1);
   }
 }
 
 // per instance: residuals (:688, :735-739), early stop (:594-596), empty-list quirk (:564-568)
 __global__ void k_finalize(DevPtrs d, RobotGeom rb, float thr) {
   int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b == 0) d.counters[5] = 0;          // worklist of the slow pass consumed
   if (b >= d.B) return;
   if (d.done[b]) return;
   const int T = d.T, N = d.N, NT = N * T, R = d.R;
@@ -349,7 +378,7 @@ DevPtrs dev_ptrs(const rda_handle* h) {
   d.lam = h->lam; d.mu = h->mu; d.z = h->z; d.xi = h->xi; d.zeta = h->zeta; d.dis = h->dis;
   d.coef = h->coef; d.pref = h->pref; d.cur_s = h->cur_s; d.cur_u = h->cur_u; d.ref_s = h->ref_s;
   d.ref_speed = h->ref_speed; d.resi_acc = h->resi_acc; d.resi_pri = h->resi_pri; d.resi_dual = h->resi_dual;
-  d.status = h->status; d.iters = h->iters; d.done = h->done; d.counters = h->counters;
+  d.status = h->status; d.iters = h->iters; d.done = h->done; d.counters = h->counters; d.worklist = h->worklist;
   d.obs_A = h->obs_A; d.obs_b = h->obs_b; d.obs_kind = h->obs_kind; d.obs_count = h->obs_count;
   d.obs_tv = h->obs_tv;
   d.B = h->B; d.T = h->T; d.N = h->N; d.E = h->E; d.R = h->R;
@@ -409,6 +438,7 @@ int rda_create(const rda_config* cfg, const rda_tunables* tun, rda_handle** out)
   alloc(&h->resi_acc, B * 2); alloc(&h->resi_pri, B); alloc(&h->resi_dual, B);
   alloc((float**)&h->status, B); alloc((float**)&h->iters, B); alloc((float**)&h->done, B);
   alloc((float**)&h->counters, 8);
+  alloc((float**)&h->worklist, B * NT);
   if (e != cudaSuccess) { rda_destroy(h); return (int)e; }
   if (cfg->su_fp64) e = cudaFuncSetAttribute(k_su<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->su_smem);
   else e = cudaFuncSetAttribute(k_su<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->su_smem);
@@ -425,7 +455,7 @@ int rda_destroy(rda_handle* h) {
   if (!h) return RDA_E_ARG;
   float* bufs[] = {h->lam, h->mu, h->z, h->xi, h->zeta, h->dis, h->coef, h->pref, h->cur_s, h->cur_u,
                    h->ref_s, h->ref_speed, h->resi_acc, h->resi_pri, h->resi_dual, (float*)h->status,
-                   (float*)h->iters, (float*)h->done, (float*)h->counters};
+                   (float*)h->iters, (float*)h->done, (float*)h->counters, (float*)h->worklist};
   for (float* p : bufs) if (p) cudaFree(p);
   delete h;
   return 0;
@@ -510,10 +540,12 @@ int rda_step_lammuz(rda_handle* h, void* stream) {
   DevPtrs d = dev_ptrs(h);
   cudaStream_t s = (cudaStream_t)stream;
   if (h->N > 0) {
-    k_cells<float><<<grid_for((long long)h->B * h->N * h->T, 128), 128, 0, s>>>(d, h->rb, h->tun.ro2,
-        h->cfg.accelerated ? h->tun.z_theta : 1.0f);
+    const float theta = h->cfg.accelerated ? h->tun.z_theta : 1.0f;
+    k_cells_fast<<<grid_for((long long)h->B * h->N * h->T, 128), 128, 0, s>>>(d, h->rb, h->tun.ro2, theta);
     RDA_CUDA(cudaGetLastError());
-    h->launches += 1;
+    k_cells_slow<<<148 * 8, 64, 0, s>>>(d, h->rb, h->tun.ro2, theta);
+    RDA_CUDA(cudaGetLastError());
+    h->launches += 2;
   }
   k_finalize<<<(h->B + 127) / 128, 128, 0, s>>>(d, h->rb, h->iter_threshold);
   RDA_CUDA(cudaGetLastError());

@@ -163,82 +163,116 @@ RDA_HD Real su_row_dir(const Row<Real>& r, const Real* dz_t, const Real* dv_t) {
 
 template <typename Real, typename Ctx>
 RDA_HD void su_riccati(const SuParams& P, SuWork<Real>& W, Ctx& ctx, bool factor, Real* dz, Real* dv) {
-  // Backward sweep (all lanes execute the same recursion; lane 0 stores), then forward sweep.
+  // Riccati recursion of the Newton step (banded KKT system).  Stage t: state z = (s_t, u_{t-1}),
+  // control v = (u_t, d_t); the stage cost is quadratic in q = (s_{t+1}, u_t, d_t) = J [z; v] with
+  // J = [[A 0 B 0], [0 0 I 0], [0 0 0 1]] plus the rate-limit coupling between u_t and u_{t-1}.
+  // The sparsity of J is written out by hand (about 300 multiply-adds per stage).  Every lane
+  // runs the same recursion (no broadcast needed); lane 0 stores the gains.
   const int T = P.T;
   const Real reg = (Real)1e-9;
+  const Real tw = 2 * (Real)P.ws, tw3 = (P.dynamics == RDA_DYN_OMNI ? (Real)0 : tw);
   Real Pm[5][5], pv[5];
   for (int a = 0; a < 5; ++a) { pv[a] = 0; for (int b = 0; b < 5; ++b) Pm[a][b] = 0; }
   const bool writer = ctx.lane() == 0;
   for (int t = T - 1; t >= 0; --t) {
-    Real E[8][8];
-    for (int a = 0; a < 8; ++a) for (int b = 0; b < 8; ++b) E[a][b] = 0;
-    E[0][0] = 1; E[1][1] = 1; E[2][2] = 1;
-    E[0][2] = W.Aj[2 * t]; E[1][2] = W.Aj[2 * t + 1];
-    for (int r = 0; r < 3; ++r) { E[r][5] = W.Bj[6 * t + 2 * r]; E[r][6] = W.Bj[6 * t + 2 * r + 1]; }
-    E[3][5] = 1; E[4][6] = 1; E[5][7] = 1; E[6][3] = 1; E[7][4] = 1;
-    Real gy[8];
-    for (int a = 0; a < 8; ++a) gy[a] = W.gw[8 * t + a];
-    for (int a = 0; a < 5; ++a) gy[a] += pv[a];
-    Real g[8];
-    for (int c = 0; c < 8; ++c) { Real sacc = 0; for (int r = 0; r < 8; ++r) sacc += E[r][c] * gy[r]; g[c] = sacc; }
-    Real L00, L10, L11, L20, L21, L22;
+    const Real a02 = W.Aj[2 * t], a12 = W.Aj[2 * t + 1];
+    const Real* Bt = W.Bj + 6 * t;
+    const Real b00 = Bt[0], b01 = Bt[1], b10 = Bt[2], b11 = Bt[3], b20 = Bt[4], b21 = Bt[5];
+    const Real* wb = W.wb + 5 * t;
+    const Real wr0 = wb[3], wr1 = wb[4];
+    // gradient in q-space (+ cost-to-go), pulled back through J
+    const Real* gw = W.gw + 8 * t;
+    const Real q0 = gw[0] + pv[0], q1 = gw[1] + pv[1], q2 = gw[2] + pv[2], q3 = gw[3] + pv[3],
+               q4 = gw[4] + pv[4], q5 = gw[5];
+    const Real gz0 = q0, gz1 = q1, gz2 = a02 * q0 + a12 * q1 + q2, gz3 = gw[6], gz4 = gw[7];
+    const Real gv0 = b00 * q0 + b10 * q1 + b20 * q2 + q3;
+    const Real gv1 = b01 * q0 + b11 * q1 + b21 * q2 + q4;
+    const Real gv2 = q5;
+    Real i00, L10, i11, L20, L21, i22;   // Cholesky of Hvv, reciprocal diagonal
     Real Kt[3][5];
     if (factor) {
-      Real Wt[8][8];
-      for (int a = 0; a < 8; ++a) for (int b = 0; b < 8; ++b) Wt[a][b] = 0;
-      for (int a = 0; a < 5; ++a) for (int b = 0; b < 5; ++b) Wt[a][b] = Pm[a][b];
-      const Real tw = 2 * (Real)P.ws;
-      Wt[0][0] += tw; Wt[1][1] += tw;
-      Wt[2][2] += (P.dynamics == RDA_DYN_OMNI ? (Real)0 : tw) + (Real)P.ro2 * W.Skk[t];
+      Real Q[6][6];
+      for (int a = 0; a < 5; ++a) { for (int b = 0; b < 5; ++b) Q[a][b] = Pm[a][b]; Q[a][5] = 0; Q[5][a] = 0; }
       const Real* M = W.Wm + 6 * t;
-      Wt[0][0] += M[0]; Wt[0][1] += M[1]; Wt[1][0] += M[1]; Wt[0][5] += M[2]; Wt[5][0] += M[2];
-      Wt[1][1] += M[3]; Wt[1][5] += M[4]; Wt[5][1] += M[4]; Wt[5][5] += M[5];
-      const Real* wb = W.wb + 5 * t;
-      Wt[3][3] += 2 * (Real)P.wu + reg + wb[0] + wb[3];
-      Wt[4][4] += reg + wb[1] + wb[4];
-      Wt[5][5] += (P.N > 0 ? reg + wb[2] : (Real)1);
-      Wt[6][6] += wb[3]; Wt[3][6] -= wb[3]; Wt[6][3] -= wb[3];
-      Wt[7][7] += wb[4]; Wt[4][7] -= wb[4]; Wt[7][4] -= wb[4];
-      Real T1[8][8];
-      for (int a = 0; a < 8; ++a)
-        for (int c = 0; c < 8; ++c) { Real sacc = 0; for (int r = 0; r < 8; ++r) sacc += Wt[a][r] * E[r][c]; T1[a][c] = sacc; }
-      Real H[8][8];
-      for (int a = 0; a < 8; ++a)
-        for (int c = a; c < 8; ++c) { Real sacc = 0; for (int r = 0; r < 8; ++r) sacc += E[r][a] * T1[r][c]; H[a][c] = sacc; H[c][a] = sacc; }
-      // Cholesky of Hvv (indices 5..7)
-      L00 = sqrt_(H[5][5]);
-      L10 = H[6][5] / L00;
-      L11 = sqrt_(H[6][6] - L10 * L10);
-      L20 = H[7][5] / L00;
-      L21 = (H[7][6] - L20 * L10) / L11;
-      L22 = sqrt_(H[7][7] - L20 * L20 - L21 * L21);
+      Q[0][0] += tw + M[0]; Q[0][1] += M[1]; Q[1][0] += M[1]; Q[0][5] = M[2]; Q[5][0] = M[2];
+      Q[1][1] += tw + M[3]; Q[1][5] = M[4]; Q[5][1] = M[4];
+      Q[2][2] += tw3 + (Real)P.ro2 * W.Skk[t];
+      Q[3][3] += 2 * (Real)P.wu + reg + wb[0] + wr0;
+      Q[4][4] += reg + wb[1] + wr1;
+      Q[5][5] = (P.N > 0 ? reg + wb[2] + M[5] : (Real)1);
+      // T1 = Q J for the columns of J that are not unit vectors
+      Real t2[6], t5[6], t6[6];
+      for (int r = 0; r < 6; ++r) {
+        t2[r] = a02 * Q[r][0] + a12 * Q[r][1] + Q[r][2];
+        t5[r] = b00 * Q[r][0] + b10 * Q[r][1] + b20 * Q[r][2] + Q[r][3];
+        t6[r] = b01 * Q[r][0] + b11 * Q[r][1] + b21 * Q[r][2] + Q[r][4];
+      }
+#define RDA_J2(x) (a02 * (x)[0] + a12 * (x)[1] + (x)[2])
+#define RDA_J5(x) (b00 * (x)[0] + b10 * (x)[1] + b20 * (x)[2] + (x)[3])
+#define RDA_J6(x) (b01 * (x)[0] + b11 * (x)[1] + b21 * (x)[2] + (x)[4])
+      // Hzz (rows/cols 0..2 dense, 3..4 only the rate terms)
+      Real Hzz[5][5];
+      for (int a = 0; a < 5; ++a) for (int b = 0; b < 5; ++b) Hzz[a][b] = 0;
+      Hzz[0][0] = Q[0][0]; Hzz[0][1] = Q[0][1]; Hzz[1][1] = Q[1][1];
+      Hzz[0][2] = t2[0]; Hzz[1][2] = t2[1]; Hzz[2][2] = RDA_J2(t2);
+      Hzz[1][0] = Hzz[0][1]; Hzz[2][0] = Hzz[0][2]; Hzz[2][1] = Hzz[1][2];
+      Hzz[3][3] = wr0; Hzz[4][4] = wr1;
+      // Hvz (3 x 5)
+      Real Hvz[3][5];
+      Hvz[0][0] = t5[0]; Hvz[0][1] = t5[1]; Hvz[0][2] = RDA_J2(t5); Hvz[0][3] = -wr0; Hvz[0][4] = 0;
+      Hvz[1][0] = t6[0]; Hvz[1][1] = t6[1]; Hvz[1][2] = RDA_J2(t6); Hvz[1][3] = 0; Hvz[1][4] = -wr1;
+      Hvz[2][0] = Q[5][0]; Hvz[2][1] = Q[5][1]; Hvz[2][2] = RDA_J2(Q[5]); Hvz[2][3] = 0; Hvz[2][4] = 0;
+      // Hvv (3 x 3)
+      const Real h00 = RDA_J5(t5), h10 = RDA_J6(t5), h11 = RDA_J6(t6), h20 = t5[5], h21 = t6[5], h22 = Q[5][5];
+#undef RDA_J2
+#undef RDA_J5
+#undef RDA_J6
+      const Real L00 = sqrt_(h00);
+      i00 = (Real)1 / L00;
+      L10 = h10 * i00;
+      const Real L11 = sqrt_(h11 - L10 * L10);
+      i11 = (Real)1 / L11;
+      L20 = h20 * i00;
+      L21 = (h21 - L20 * L10) * i11;
+      const Real L22 = sqrt_(h22 - L20 * L20 - L21 * L21);
+      i22 = (Real)1 / L22;
       for (int b = 0; b < 5; ++b) {
-        Real r0 = -H[5][b], r1 = -H[6][b], r2 = -H[7][b];
-        Real y0 = r0 / L00, y1 = (r1 - L10 * y0) / L11, y2 = (r2 - L20 * y0 - L21 * y1) / L22;
-        Real x2 = y2 / L22, x1 = (y1 - L21 * x2) / L11, x0 = (y0 - L10 * x1 - L20 * x2) / L00;
+        Real y0 = -Hvz[0][b] * i00;
+        Real y1 = (-Hvz[1][b] - L10 * y0) * i11;
+        Real y2 = (-Hvz[2][b] - L20 * y0 - L21 * y1) * i22;
+        Real x2 = y2 * i22;
+        Real x1 = (y1 - L21 * x2) * i11;
+        Real x0 = (y0 - L10 * x1 - L20 * x2) * i00;
         Kt[0][b] = x0; Kt[1][b] = x1; Kt[2][b] = x2;
       }
       for (int a = 0; a < 5; ++a)
         for (int b = a; b < 5; ++b) {
-          Real v = H[a][b] + H[5][a] * Kt[0][b] + H[6][a] * Kt[1][b] + H[7][a] * Kt[2][b];
+          Real v = Hzz[a][b] + Hvz[0][a] * Kt[0][b] + Hvz[1][a] * Kt[1][b] + Hvz[2][a] * Kt[2][b];
           Pm[a][b] = v; Pm[b][a] = v;
         }
       if (writer) {
         Real* Ls = W.Lc + 6 * t;
-        Ls[0] = L00; Ls[1] = L10; Ls[2] = L11; Ls[3] = L20; Ls[4] = L21; Ls[5] = L22;
+        Ls[0] = i00; Ls[1] = L10; Ls[2] = i11; Ls[3] = L20; Ls[4] = L21; Ls[5] = i22;
         for (int k = 0; k < 3; ++k) for (int b = 0; b < 5; ++b) W.K[15 * t + 5 * k + b] = Kt[k][b];
       }
     } else {
       const Real* Ls = W.Lc + 6 * t;
-      L00 = Ls[0]; L10 = Ls[1]; L11 = Ls[2]; L20 = Ls[3]; L21 = Ls[4]; L22 = Ls[5];
+      i00 = Ls[0]; L10 = Ls[1]; i11 = Ls[2]; L20 = Ls[3]; L21 = Ls[4]; i22 = Ls[5];
       for (int k = 0; k < 3; ++k) for (int b = 0; b < 5; ++b) Kt[k][b] = W.K[15 * t + 5 * k + b];
     }
     {
-      Real r0 = -g[5], r1 = -g[6], r2 = -g[7];
-      Real y0 = r0 / L00, y1 = (r1 - L10 * y0) / L11, y2 = (r2 - L20 * y0 - L21 * y1) / L22;
-      Real x2 = y2 / L22, x1 = (y1 - L21 * x2) / L11, x0 = (y0 - L10 * x1 - L20 * x2) / L00;
+      Real y0 = -gv0 * i00;
+      Real y1 = (-gv1 - L10 * y0) * i11;
+      Real y2 = (-gv2 - L20 * y0 - L21 * y1) * i22;
+      Real x2 = y2 * i22;
+      Real x1 = (y1 - L21 * x2) * i11;
+      Real x0 = (y0 - L10 * x1 - L20 * x2) * i00;
       if (writer) { W.kf[3 * t] = x0; W.kf[3 * t + 1] = x1; W.kf[3 * t + 2] = x2; }
-      for (int a = 0; a < 5; ++a) pv[a] = g[a] + Kt[0][a] * g[5] + Kt[1][a] * g[6] + Kt[2][a] * g[7];
+      pv[0] = gz0 + Kt[0][0] * gv0 + Kt[1][0] * gv1 + Kt[2][0] * gv2;
+      pv[1] = gz1 + Kt[0][1] * gv0 + Kt[1][1] * gv1 + Kt[2][1] * gv2;
+      pv[2] = gz2 + Kt[0][2] * gv0 + Kt[1][2] * gv1 + Kt[2][2] * gv2;
+      pv[3] = gz3 + Kt[0][3] * gv0 + Kt[1][3] * gv1 + Kt[2][3] * gv2;
+      pv[4] = gz4 + Kt[0][4] * gv0 + Kt[1][4] * gv1 + Kt[2][4] * gv2;
     }
   }
   ctx.sync();
