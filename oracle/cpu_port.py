@@ -48,7 +48,7 @@ def solve_batch(car, T, N, E, nom_s, nom_u, ref_s, ref_speed, obs_A, obs_b, obs_
     arrs = [f32(nom_s), f32(nom_u), f32(ref_s), f32(ref_speed), f32(obs_A), f32(obs_b), i32(obs_kind), i32(obs_count)]
     u = np.zeros((B, 2, T), np.float32); s = np.zeros((B, 3, T + 1), np.float32)
     rp = np.zeros(B, np.float32); rd = np.zeros(B, np.float32); it = np.zeros(B, np.int32)
-    fails = np.zeros((B, 2), np.int32)
+    fails = np.zeros((B, 4), np.int32)
     p = lambda a: a.ctypes.data_as(C.c_void_p)
     lib.port_solve_batch.restype = C.c_int
     rc = lib.port_solve_batch(C.byref(cfg), C.byref(tun), C.c_int(B), *[p(a) for a in arrs], C.c_int(int(time_varying)),

@@ -9,6 +9,7 @@
 #include <vector>
 #include <cstring>
 #include <cmath>
+#include <cstdlib>
 #include <omp.h>
 #include "../../rda_planner_b200/csrc/cell_solver.cuh"
 #include "../../rda_planner_b200/csrc/su_solver.cuh"
@@ -101,6 +102,7 @@ extern "C" int port_solve_batch(const rda_config* cfg, const rda_tunables* tun, 
   P.ab[0] = cfg->acce_bound[0]; P.ab[1] = cfg->acce_bound[1];
   P.ws = cfg->ws; P.wu = cfg->wu; P.slack_gain = tun->slack_gain; P.dmin = tun->min_sd; P.dmax = tun->max_sd;
   P.ro1 = tun->ro1; P.ro2 = tun->ro2; P.max_iter = 40;
+  P.mu0 = getenv("RDA_PORT_MU0") ? (float)atof(getenv("RDA_PORT_MU0")) : 1.0f;
   const float theta = cfg->accelerated ? tun->z_theta : 1.0f;
   if (nthreads > 0) omp_set_num_threads(nthreads);
   const size_t bytes = su_work_layout<double>(T, N, nullptr, nullptr);
@@ -116,7 +118,7 @@ extern "C" int port_solve_batch(const rda_config* cfg, const rda_tunables* tun, 
     std::vector<float> cu(nom_u + (size_t)b * 2 * T, nom_u + (size_t)(b + 1) * 2 * T);
     const float* rf = ref_s + (size_t)b * 3 * (T + 1);
     float rp = 0.f, rd = 0.f;
-    int it = 0, nfail = 0, first_fail = -1;
+    int it = 0, nfail = 0, first_fail = -1, su_iters = 0, su_bad = 0;
     for (it = 0; it < iter_num; ++it) {
       for (int i = 0; i < 3 * (T + 1); ++i) { int r = i / (T + 1), t = i % (T + 1); W.lins[3 * t + r] = cs[i]; W.ref[3 * t + r] = rf[i]; }
       for (int i = 0; i < 2 * T; ++i) { int r = i / T, t = i % T; W.linu[2 * t + r] = cu[i]; W.pref[2 * t + r] = pref[i]; }
@@ -126,6 +128,8 @@ extern "C" int port_solve_batch(const rda_config* cfg, const rda_tunables* tun, 
       SeqCtx ctx;
       int nit = 0;
       int st = su_solve<double, SeqCtx>(P, W, ctx, coef.data() + 3 * NT, coef.data() + 4 * NT, &nit);
+      su_iters += nit;
+      if (st != 0) ++su_bad;
       if (st != 2) {
         for (int i = 0; i < 3 * (T + 1); ++i) { int r = i / (T + 1), t = i % (T + 1); cs[i] = (float)W.s[3 * t + r]; }
         for (int i = 0; i < 2 * T; ++i) { int r = i / T, t = i % T; cu[i] = (float)W.u[2 * t + r]; }
@@ -165,7 +169,7 @@ extern "C" int port_solve_batch(const rda_config* cfg, const rda_tunables* tun, 
     for (int i = 0; i < 2 * T; ++i) u_opt[(size_t)b * 2 * T + i] = cu[i];
     resi_pri[b] = rp; resi_dual[b] = rd;
     if (iters_out) iters_out[b] = it;
-    if (fails_out) { fails_out[2 * b] = nfail; fails_out[2 * b + 1] = first_fail; }
+    if (fails_out) { fails_out[4 * b] = nfail; fails_out[4 * b + 1] = first_fail; fails_out[4 * b + 2] = su_iters; fails_out[4 * b + 3] = su_bad; }
   }
   return 0;
 }

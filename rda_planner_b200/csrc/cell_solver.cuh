@@ -42,9 +42,32 @@ template <int NV, int MC>
 struct TinyQP {
   double Q[NV][NV];
   double c[NV];
-  double a[MC][NV];
+  // sparse rows a_i'x <= b_i: at most 4 non-zeros each
+  double av[MC][4];
+  int ai[MC][4];
+  int an[MC];
   double b[MC];
   int m;
+  RDA_HD void row(int n, int i0, double v0, int i1, double v1, int i2, double v2, int i3, double v3, double rhs) {
+    av[m][0] = v0; av[m][1] = v1; av[m][2] = v2; av[m][3] = v3;
+    ai[m][0] = i0; ai[m][1] = i1; ai[m][2] = i2; ai[m][3] = i3;
+    an[m] = n; b[m] = rhs; ++m;
+  }
+  RDA_HD double dot(int i, const double* x) const {
+    double sacc = 0;
+    for (int e = 0; e < an[i]; ++e) sacc += av[i][e] * x[ai[i][e]];
+    return sacc;
+  }
+  RDA_HD void axpy(int i, double w, double* y) const {      // y += w * a_i
+    for (int e = 0; e < an[i]; ++e) y[ai[i][e]] += w * av[i][e];
+  }
+  RDA_HD void rank1(int i, double w, double H[NV][NV]) const {   // lower triangle of H += w a_i a_i'
+    for (int e = 0; e < an[i]; ++e)
+      for (int f = 0; f < an[i]; ++f) {
+        int r = ai[i][e], cidx = ai[i][f];
+        if (r >= cidx) H[r][cidx] += w * av[i][e] * av[i][f];
+      }
+  }
   int tv;   // -1: unit-ball constraint x0^2 + x1^2 <= 1;  k >= 0: cone constraint
             // (x0^2 + x1^2)/x_k - x_k <= 0 (i.e. |x01| <= x_k, rows keep 0 <= x_k <= 1)
 };
@@ -104,9 +127,7 @@ RDA_HD_NOINLINE bool tiny_ipm(const TinyQP<NV, MC>& P, double* x /* in: strictly
   const int m = P.m;
   double s[MC + 1], l[MC + 1];
   for (int i = 0; i < m; ++i) {
-    double ax = 0;
-    for (int k = 0; k < NV; ++k) ax += P.a[i][k] * x[k];
-    s[i] = rmax(P.b[i] - ax, 1e-3);
+    s[i] = rmax(P.b[i] - P.dot(i, x), 1e-3);
     l[i] = 1.0 / s[i];
   }
   const int tv = P.tv;
@@ -116,7 +137,7 @@ RDA_HD_NOINLINE bool tiny_ipm(const TinyQP<NV, MC>& P, double* x /* in: strictly
   double scale = 1.0;
   for (int i = 0; i < m; ++i) {
     scale = rmax(scale, fabs(P.b[i]));
-    for (int k = 0; k < NV; ++k) scale = rmax(scale, fabs(P.a[i][k]));
+    for (int e = 0; e < P.an[i]; ++e) scale = rmax(scale, fabs(P.av[i][e]));
   }
   for (int k = 0; k < NV; ++k) scale = rmax(scale, fabs(P.c[k]));
   bool acceptable = false;
@@ -130,12 +151,8 @@ RDA_HD_NOINLINE bool tiny_ipm(const TinyQP<NV, MC>& P, double* x /* in: strictly
     }
     double mu = 0;
     for (int i = 0; i < m; ++i) {
-      double ax = 0;
-      for (int k = 0; k < NV; ++k) {
-        ax += P.a[i][k] * x[k];
-        rd[k] += P.a[i][k] * l[i];
-      }
-      rp[i] = ax + s[i] - P.b[i];
+      P.axpy(i, l[i], rd);
+      rp[i] = P.dot(i, x) + s[i] - P.b[i];
       mu += s[i] * l[i];
     }
     const ConeEval ce = cone_eval(x, tv);
@@ -159,14 +176,7 @@ RDA_HD_NOINLINE bool tiny_ipm(const TinyQP<NV, MC>& P, double* x /* in: strictly
     double H[NV][NV];
     for (int k = 0; k < NV; ++k)
       for (int j = 0; j < NV; ++j) H[k][j] = P.Q[k][j];
-    for (int i = 0; i < m; ++i) {
-      double w = l[i] / s[i];
-      for (int k = 0; k < NV; ++k) {
-        double wk = w * P.a[i][k];
-        if (wk != 0)
-          for (int j = 0; j <= k; ++j) H[k][j] += wk * P.a[i][j];
-      }
-    }
+    for (int i = 0; i < m; ++i) P.rank1(i, l[i] / s[i], H);
     {
       double w = l[m] / s[m];
       H[0][0] += l[m] * ce.h00 + w * ce.g0 * ce.g0;
@@ -185,7 +195,7 @@ RDA_HD_NOINLINE bool tiny_ipm(const TinyQP<NV, MC>& P, double* x /* in: strictly
     for (int i = 0; i < M; ++i) {
       double t = (l[i] * rp[i] - s[i] * l[i]) / s[i];
       if (i < m) {
-        for (int k = 0; k < NV; ++k) ra[k] -= P.a[i][k] * t;
+        P.axpy(i, -t, ra);
       } else {
         ra[0] -= ce.g0 * t;
         ra[1] -= ce.g1 * t;
@@ -202,7 +212,7 @@ RDA_HD_NOINLINE bool tiny_ipm(const TinyQP<NV, MC>& P, double* x /* in: strictly
     for (int i = 0; i < M; ++i) {
       double gd = 0;
       if (i < m) {
-        for (int k = 0; k < NV; ++k) gd += P.a[i][k] * ra[k];
+        gd = P.dot(i, ra);
       } else {
         gd = ce.g0 * ra[0] + ce.g1 * ra[1] + (tv >= 0 ? ce.gt * ra[tv] : 0.0);
       }
@@ -223,7 +233,7 @@ RDA_HD_NOINLINE bool tiny_ipm(const TinyQP<NV, MC>& P, double* x /* in: strictly
       rcs[i] = s[i] * l[i] + dsa[i] * dla[i] - sig * mu;
       double t = (l[i] * rp[i] - rcs[i]) / s[i];
       if (i < m) {
-        for (int k = 0; k < NV; ++k) rc[k] -= P.a[i][k] * t;
+        P.axpy(i, -t, rc);
       } else {
         rc[0] -= ce.g0 * t;
         rc[1] -= ce.g1 * t;
@@ -245,7 +255,7 @@ RDA_HD_NOINLINE bool tiny_ipm(const TinyQP<NV, MC>& P, double* x /* in: strictly
     for (int i = 0; i < M; ++i) {
       double gd = 0;
       if (i < m) {
-        for (int k = 0; k < NV; ++k) gd += P.a[i][k] * rc[k];
+        gd = P.dot(i, rc);
       } else {
         gd = ce.g0 * rc[0] + ce.g1 * rc[1] + (tv >= 0 ? ce.gt * rc[tv] : 0.0);
       }
@@ -278,8 +288,7 @@ RDA_HD double barrier_value(const TinyQP<NV, MC>& P, const double* x, double t) 
   }
   f *= t;
   for (int i = 0; i < P.m; ++i) {
-    double sl = P.b[i];
-    for (int k = 0; k < NV; ++k) sl -= P.a[i][k] * x[k];
+    double sl = P.b[i] - P.dot(i, x);
     if (!(sl > 0)) return 1e300;
     f -= log(sl);
   }
@@ -302,15 +311,9 @@ RDA_HD_NOINLINE bool tiny_barrier(const TinyQP<NV, MC>& P, double* x /* strictly
         g[k] = t * qx;
       }
       for (int i = 0; i < m; ++i) {
-        double sl = P.b[i];
-        for (int k = 0; k < NV; ++k) sl -= P.a[i][k] * x[k];
-        double inv = 1.0 / sl, inv2 = inv * inv;
-        for (int k = 0; k < NV; ++k) {
-          double ak = P.a[i][k];
-          if (ak == 0) continue;
-          g[k] += ak * inv;
-          for (int j = 0; j <= k; ++j) H[k][j] += ak * P.a[i][j] * inv2;
-        }
+        double inv = 1.0 / (P.b[i] - P.dot(i, x));
+        P.axpy(i, inv, g);
+        P.rank1(i, inv * inv, H);
       }
       {
         const double tq = tv >= 0 ? x[tv] : 1.0;
@@ -454,6 +457,9 @@ RDA_HD void cell_solve(const RobotGeom& rb, int kind, int E, const float* A, con
   // ---- closest pair / separation -------------------------------------------------------------
   bool sep = false;
   Real best = 1e30f, bdx = 0, bdy = 0;
+  Real byx = 0, byy = 0;            // robot-side point of the closest pair, body frame
+  Real rob_in[RDA_MAX_ROBOT_EDGE], obs_in[RDA_MAX_EDGE];
+  bool have_in = false;
   Real dj2[RDA_MAX_ROBOT_EDGE], djx[RDA_MAX_ROBOT_EDGE], djy[RDA_MAX_ROBOT_EDGE];
   for (int j = 0; j < R; ++j) dj2[j] = 1e30f;
   if (kind == RDA_OBS_CIRCLE) {
@@ -466,7 +472,11 @@ RDA_HD void cell_solve(const RobotGeom& rb, int kind, int E, const float* A, con
       Real t = rclamp((rx * fx + ry * fy) / (fx * fx + fy * fy), (Real)0, (Real)1);
       Real dx = -(rx - t * fx), dy = -(ry - t * fy);       // robot point minus centre
       Real d2 = dx * dx + dy * dy;
-      if (d2 < best) { best = d2; bdx = dx; bdy = dy; }
+      if (d2 < best) {
+        best = d2; bdx = dx; bdy = dy;
+        byx = (Real)rb.yx[j] + t * ((Real)rb.yx[jn] - (Real)rb.yx[j]);
+        byy = (Real)rb.yy[j] + t * ((Real)rb.yy[jn] - (Real)rb.yy[j]);
+      }
       Real vx_ = g.yx[j] - g.cx, vy_ = g.yy[j] - g.cy;     // robot vertex minus centre
       Real dv = sqrt_(vx_ * vx_ + vy_ * vy_);
       Real dd = dv - g.rad;
@@ -487,6 +497,7 @@ RDA_HD void cell_solve(const RobotGeom& rb, int kind, int E, const float* A, con
       best = dd * dd;
     }
   } else {
+    for (int j = 0; j < R; ++j) rob_in[j] = -1e30f;
     for (int i = 0; i < ne; ++i) {
       int in = (i + 1) % ne;
       Real ex = g.vx[in] - g.vx[i], ey = g.vy[in] - g.vy[i];
@@ -496,6 +507,7 @@ RDA_HD void cell_solve(const RobotGeom& rb, int kind, int E, const float* A, con
         Real rx = g.yx[j] - g.vx[i], ry = g.yy[j] - g.vy[i];
         Real sd = g.nx[i] * rx + g.ny[i] * ry;
         mins = rmin(mins, sd);
+        rob_in[j] = rmax(rob_in[j], sd);        // <= 0 for every edge: robot vertex j inside O
         Real t = rclamp((rx * ex + ry * ey) * ie2, (Real)0, (Real)1);
         Real dx = rx - t * ex, dy = ry - t * ey;
         Real d2 = dx * dx + dy * dy;
@@ -504,7 +516,7 @@ RDA_HD void cell_solve(const RobotGeom& rb, int kind, int E, const float* A, con
       if (mins > eps) sep = true;
     }
     for (int j = 0; j < R; ++j)
-      if (dj2[j] < best) { best = dj2[j]; bdx = djx[j]; bdy = djy[j]; }
+      if (dj2[j] < best) { best = dj2[j]; bdx = djx[j]; bdy = djy[j]; byx = rb.yx[j]; byy = rb.yy[j]; }
     for (int j = 0; j < R; ++j) {
       int jn = (j + 1) % R;
       Real fx = g.yx[jn] - g.yx[j], fy = g.yy[jn] - g.yy[j];
@@ -514,10 +526,15 @@ RDA_HD void cell_solve(const RobotGeom& rb, int kind, int E, const float* A, con
         Real rx = g.vx[i] - g.yx[j], ry = g.vy[i] - g.yy[j];
         Real sd = g.mx[j] * rx + g.my[j] * ry;
         mins = rmin(mins, sd);
+        obs_in[i] = (j == 0) ? sd : rmax(obs_in[i], sd);   // <= 0: obstacle vertex i inside the robot
         Real t = rclamp((rx * fx + ry * fy) * if2, (Real)0, (Real)1);
         Real dx = -(rx - t * fx), dy = -(ry - t * fy);
         Real d2 = dx * dx + dy * dy;
-        if (d2 < best) { best = d2; bdx = dx; bdy = dy; }
+        if (d2 < best) {
+          best = d2; bdx = dx; bdy = dy;
+          byx = (Real)rb.yx[j] + t * ((Real)rb.yx[jn] - (Real)rb.yx[j]);
+          byy = (Real)rb.yy[j] + t * ((Real)rb.yy[jn] - (Real)rb.yy[j]);
+        }
       }
       if (mins > eps) sep = true;
     }
@@ -566,6 +583,12 @@ RDA_HD void cell_solve(const RobotGeom& rb, int kind, int E, const float* A, con
       }
     }
   }
+#ifdef RDA_CELL_STATS
+  if (!have) {
+    extern long long g_cell_stats[8];
+    __sync_fetch_and_add(&g_cell_stats[(sep ? 0 : 2) + (xi_zero ? 0 : 1)], 1);
+  }
+#endif
   if (FAST_ONLY) {
     if (!have) { out.path = CELL_NEEDS_SLOW; return; }
   } else if (!have) {
@@ -582,27 +605,43 @@ RDA_HD void cell_solve(const RobotGeom& rb, int kind, int E, const float* A, con
     const double c_ = cphi, s_ = sphi, x0 = xi0, x1 = xi1;
     bool ok = true, inactive = false;
     double va = 0, vb = 0, ga = 0, gb = 0;
-    {  // stage A: max margin with Hm + xi = 0; x = (v0, v1, so, sr, tv)
+    // The max margin c* = min_{x in O, y in Rob} |P(y) - x| + xi.y - k0 is bounded above by its value
+    // at the closest pair (disjoint sets): if that is negative the hinge is active for sure and
+    // stage A can be skipped.
+    bool need_a = true;
+    if (sep) {
+      double ub = sqrt((double)best) + x0 * (double)byx + x1 * (double)byy - k0d;
+      if (ub < -1e-9) need_a = false;
+    } else if (!circ) {
+      // overlapping polygons: any common point y gives the bound xi.y - k0
+      double ub = 1e300;
+      for (int j = 0; j < R; ++j)
+        if (rob_in[j] <= 0) ub = rmin(ub, x0 * (double)rb.yx[j] + x1 * (double)rb.yy[j]);
+      for (int i = 0; i < ne; ++i)
+        if (obs_in[i] <= 0) {
+          double wx = g.vx[i], wy = g.vy[i];
+          ub = rmin(ub, x0 * (c_ * wx + s_ * wy) + x1 * (-s_ * wx + c_ * wy));
+        }
+      if (ub - k0d < -1e-9) need_a = false;
+    }
+    (void)have_in;
+#ifdef RDA_CELL_STATS
+    if (need_a) { extern long long g_cell_stats[8]; __sync_fetch_and_add(&g_cell_stats[6], 1); }
+#endif
+    if (need_a) {  // stage A: max margin with Hm + xi = 0; x = (v0, v1, so, sr, tv)
       constexpr int NVA = 5;
       TinyQP<NVA, 2 * RDA_MAX_EDGE + 2> P;
       for (int k = 0; k < NVA; ++k) { for (int j = 0; j < NVA; ++j) P.Q[k][j] = 0; P.c[k] = 0; }
       P.c[2] = 1; P.c[3] = 1;
-      int m = 0;
-      for (int i = 0; i < nv_o; ++i, ++m) {
-        for (int k = 0; k < NVA; ++k) P.a[m][k] = 0;
-        P.a[m][0] = ox[i]; P.a[m][1] = oy[i]; P.a[m][2] = -1; P.a[m][4] = radd; P.b[m] = 0;
-      }
-      for (int j = 0; j < R; ++j, ++m) {
+      P.m = 0;
+      for (int i = 0; i < nv_o; ++i) P.row(4, 0, ox[i], 1, oy[i], 2, -1.0, 4, radd, 0.0);   // v.x_i + rad tv <= so
+      for (int j = 0; j < R; ++j) {
         // g.y_j <= sr with g = -R'v - xi :  -(R y_j).v - sr <= xi.y_j
         double yx = rb.yx[j], yy = rb.yy[j];
-        for (int k = 0; k < NVA; ++k) P.a[m][k] = 0;
-        P.a[m][0] = -(c_ * yx - s_ * yy); P.a[m][1] = -(s_ * yx + c_ * yy);
-        P.a[m][3] = -1; P.b[m] = x0 * yx + x1 * yy;
+        P.row(3, 0, -(c_ * yx - s_ * yy), 1, -(s_ * yx + c_ * yy), 3, -1.0, 0, 0.0, x0 * yx + x1 * yy);
       }
-      for (int k = 0; k < NVA; ++k) { P.a[m][k] = 0; P.a[m + 1][k] = 0; }
-      P.a[m][4] = 1; P.b[m] = 1; ++m;          // tv <= 1
-      P.a[m][4] = -1; P.b[m] = 0; ++m;         // tv >= 0
-      P.m = m;
+      P.row(1, 4, 1.0, 0, 0.0, 0, 0.0, 0, 0.0, 1.0);          // tv <= 1
+      P.row(1, 4, -1.0, 0, 0.0, 0, 0.0, 0, 0.0, 0.0);         // tv >= 0
       P.tv = circ ? 4 : -1;
       double hmax = 0;
       for (int j = 0; j < R; ++j) hmax = rmax(hmax, fabs(x0 * (double)rb.yx[j] + x1 * (double)rb.yy[j]));
@@ -619,6 +658,9 @@ RDA_HD void cell_solve(const RobotGeom& rb, int kind, int E, const float* A, con
         ga = -(c_ * va + s_ * vb) - x0;
         gb = -(-s_ * va + c_ * vb) - x1;
         path = CELL_SLOW_A;
+#ifdef RDA_CELL_STATS
+        { extern long long g_cell_stats[8]; __sync_fetch_and_add(&g_cell_stats[4 + (sep ? 0 : 1)], 1); }
+#endif
       }
     }
     if (ok && !inactive) {  // stage B: x = (v0, v1, g0, g1, so, sr, w, tv)
@@ -632,20 +674,12 @@ RDA_HD void cell_solve(const RobotGeom& rb, int kind, int E, const float* A, con
         for (int j = 0; j < 4; ++j) P.Q[k][j] = r2 * (Mx[k] * Mx[j] + My[k] * My[j]);
       for (int k = 0; k < 4; ++k) P.c[k] = r2 * (Mx[k] * x0 + My[k] * x1);
       P.Q[6][6] = 1.0;   // 1/2 w^2  (ro1 == 1 inside LamMuZ, rda_solver.py:257)
-      int m = 0;
-      for (int i = 0; i < nv_o; ++i, ++m) {
-        for (int k = 0; k < NVB; ++k) P.a[m][k] = 0;
-        P.a[m][0] = ox[i]; P.a[m][1] = oy[i]; P.a[m][4] = -1; P.a[m][7] = radd; P.b[m] = 0;
-      }
-      for (int j = 0; j < R; ++j, ++m) {
-        for (int k = 0; k < NVB; ++k) P.a[m][k] = 0;
-        P.a[m][2] = rb.yx[j]; P.a[m][3] = rb.yy[j]; P.a[m][5] = -1; P.b[m] = 0;
-      }
-      for (int k = 0; k < NVB; ++k) { P.a[m][k] = 0; P.a[m + 1][k] = 0; P.a[m + 2][k] = 0; }
-      P.a[m][4] = 1; P.a[m][5] = 1; P.a[m][6] = -1; P.b[m] = -k0d; ++m;   // so + sr + k0 <= w
-      P.a[m][7] = 1; P.b[m] = 1; ++m;          // tv <= 1
-      P.a[m][7] = -1; P.b[m] = 0; ++m;         // tv >= 0
-      P.m = m;
+      P.m = 0;
+      for (int i = 0; i < nv_o; ++i) P.row(4, 0, ox[i], 1, oy[i], 4, -1.0, 7, radd, 0.0);
+      for (int j = 0; j < R; ++j) P.row(3, 2, (double)rb.yx[j], 3, (double)rb.yy[j], 5, -1.0, 0, 0.0, 0.0);
+      P.row(3, 4, 1.0, 5, 1.0, 6, -1.0, 0, 0.0, -k0d);        // so + sr + k0 <= w
+      P.row(1, 7, 1.0, 0, 0.0, 0, 0.0, 0, 0.0, 1.0);          // tv <= 1
+      P.row(1, 7, -1.0, 0, 0.0, 0, 0.0, 0, 0.0, 0.0);         // tv >= 0
       P.tv = circ ? 7 : -1;
       double so0 = 1.0 + radd;
       const double w0 = rmax(so0 + 2.0 + k0d, 1.0);

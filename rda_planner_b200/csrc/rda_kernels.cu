@@ -395,6 +395,7 @@ SuParams su_params(const rda_handle* h) {
   P.slack_gain = h->tun.slack_gain; P.dmin = h->tun.min_sd; P.dmax = h->tun.max_sd;
   P.ro1 = h->tun.ro1; P.ro2 = h->tun.ro2;
   P.max_iter = 40;
+  P.mu0 = 1.0f;
   return P;
 }
 

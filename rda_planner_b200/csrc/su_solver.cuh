@@ -27,6 +27,7 @@ struct SuParams {
   float dt, L, umax[2], ab[2], ws, wu;
   float slack_gain, dmin, dmax, ro1, ro2;
   int max_iter;
+  float mu0;      // initial complementarity of the interior point iteration
 };
 
 // Per-instance workspace (shared memory on the GPU).  All arrays indexed by stage t (0..T-1)
@@ -308,6 +309,7 @@ RDA_HD int su_solve(const SuParams& P, SuWork<Real>& W, Ctx& ctx, const float* g
   const int T = P.T, N = P.N;
   const int lane = ctx.lane(), nl = ctx.nlanes();
   const Real ro1 = P.ro1, ro2 = P.ro2;
+  const Real iro1 = (Real)1 / ro1;
   const bool acc = P.accelerated != 0;
   // ---- linearisation and aggregated rotation terms (lane-parallel over stages) ----
   for (int t = lane; t < T; t += nl) {
@@ -340,7 +342,7 @@ RDA_HD int su_solve(const SuParams& P, SuWork<Real>& W, Ctx& ctx, const float* g
     }
   }
   ctx.sync();
-  const Real mu0 = 1;
+  const Real mu0 = P.mu0 > 0 ? (Real)P.mu0 : (Real)1;
   int nrows = 0;
   for (int t = lane; t < T; t += nl) {
     for (int c = 0; c < 10; ++c) {
@@ -366,6 +368,9 @@ RDA_HD int su_solve(const SuParams& P, SuWork<Real>& W, Ctx& ctx, const float* g
   const Real tol_mu = sizeof(Real) == 4 ? (Real)1e-6 : (Real)1e-10;
   const Real tol_r = sizeof(Real) == 4 ? (Real)1e-5 : (Real)1e-9;
   const Real reg = (Real)1e-9;
+  const Real tol_step = sizeof(Real) == 4 ? (Real)2e-4 : (Real)1e-7;
+  const Real tol_floor = sizeof(Real) == 4 ? (Real)1e-7 : (Real)1e-13;
+  Real last_step = 1e30f;       // size of the previous Newton update (stationarity proxy)
   int status = 1, it = 0;
   for (it = 0; it < P.max_iter; ++it) {
     Real sigma_mu = 0;
@@ -391,7 +396,8 @@ RDA_HD int su_solve(const SuParams& P, SuWork<Real>& W, Ctx& ctx, const float* g
           if (!r.live) continue;
           Real sv = W.bs[10 * t + c], nu = W.bnu[10 * t + c];
           Real res = r.g - sv;
-          Real om = nu / sv;
+          const Real isv = (Real)1 / sv;
+          Real om = nu * isv;
           Real term;
           if (phase == 0) {
             term = -om * res;
@@ -400,8 +406,8 @@ RDA_HD int su_solve(const SuParams& P, SuWork<Real>& W, Ctx& ctx, const float* g
           } else {
             Real dir = su_row_dir<Real>(r, W.dza + 5 * t, W.dva + 3 * t);
             Real dsa = dir + res;
-            Real dna = (-sv * nu - nu * dsa) / sv;
-            term = (sigma_mu - dsa * dna) / sv - om * res;
+            Real dna = -nu - om * dsa;
+            term = (sigma_mu - dsa * dna) * isv - om * res;
           }
           // g -= grad * term
           gw[r.comp] -= r.sgn * term;
@@ -418,19 +424,20 @@ RDA_HD int su_solve(const SuParams& P, SuWork<Real>& W, Ctx& ctx, const float* g
           Real tk, om;
           if (acc) {
             Real sv = W.hs[o * T + t], nu = W.hnu[o * T + t];
-            Real res = l + nu / ro1 - sv;
-            Real den = sv + nu / ro1;
-            om = nu / den;
+            const Real nr = nu * iro1;
+            Real res = l + nr - sv;
+            const Real iden = (Real)1 / (sv + nr);
+            om = nu * iden;
             if (phase == 0) {
-              tk = om * (nu / ro1 - res);
+              tk = om * (nr - res);
               acc_mu += sv * nu;
               acc_r = rmax(acc_r, abs_(res));
             } else {
               Real dir = ax * W.dza[5 * t + 5] + ay * W.dza[5 * t + 6] - W.dva[3 * t + 2];
-              Real dna = -(sv * nu + nu * res + nu * dir) / den;
-              Real dsa = dir + dna / ro1 + res;
+              Real dna = -om * (sv + res + dir);
+              Real dsa = dir + dna * iro1 + res;
               Real cc = sv * nu - sigma_mu + dsa * dna;
-              tk = nu - (cc + nu * res) / den;
+              tk = nu - (cc + nu * res) * iden;
             }
           } else {
             om = ro1;               // plain quadratic 1/2 ro1 Im^2  (rda_solver.py:378-379)
@@ -450,15 +457,20 @@ RDA_HD int su_solve(const SuParams& P, SuWork<Real>& W, Ctx& ctx, const float* g
       if (phase == 0) {
         mu = ctx.sum(acc_mu) / Mrows;
         Real rmx = ctx.max(acc_r);
+#ifdef RDA_SU_DEBUG
+        printf("it %d mu %.3e rmx %.3e last_step %.3e\n", it, (double)mu, (double)rmx, (double)last_step);
+#endif
         if (!finite_(mu)) { status = 2; break; }
-        if (mu < tol_mu && rmx < tol_r && it > 0) { status = 0; break; }
+        // converged: complementarity and residuals small, and the last Newton update small
+        // (degenerate problems approach the solution like sqrt(mu): stop at the rounding floor)
+        if (mu < tol_mu && rmx < tol_r && (last_step < tol_step || mu < tol_floor)) { status = 0; break; }
       }
       ctx.sync();
       su_riccati<Real, Ctx>(P, W, ctx, phase == 0, phase == 0 ? W.dza : W.dz, phase == 0 ? W.dva : W.dv);
       // ---- step lengths ----
       const Real* dz = phase == 0 ? W.dza : W.dz;
       const Real* dv = phase == 0 ? W.dva : W.dv;
-      Real amax = 1e30f, s0 = 0, s1 = 0, s2 = 0;
+      Real rmaxr = 0, s0 = 0, s1 = 0, s2 = 0;   // rmaxr = max over rows of (-delta / value): 1 / max step
       for (int t = lane; t < T; t += nl) {
         for (int c = 0; c < 10; ++c) {
           Row<Real> r = su_row<Real>(P, W, t, c);
@@ -467,15 +479,16 @@ RDA_HD int su_solve(const SuParams& P, SuWork<Real>& W, Ctx& ctx, const float* g
           Real res = r.g - sv;
           Real dir = su_row_dir<Real>(r, dz + 5 * t, dv + 3 * t);
           Real ds = dir + res, dn;
-          if (phase == 0) dn = (-sv * nu - nu * ds) / sv;
+          const Real ip = (Real)1 / (sv * nu);
+          const Real isv = nu * ip, inu = sv * ip, om = nu * isv;
+          if (phase == 0) dn = -nu - om * ds;
           else {
             Real dira = su_row_dir<Real>(r, W.dza + 5 * t, W.dva + 3 * t);
             Real dsa = dira + res;
-            Real dna = (-sv * nu - nu * dsa) / sv;
-            dn = (-(sv * nu - sigma_mu + dsa * dna) - nu * ds) / sv;
+            Real dna = -nu - om * dsa;
+            dn = (sigma_mu - dsa * dna) * isv - nu - om * ds;
           }
-          if (ds < 0) amax = rmin(amax, -sv / ds);
-          if (dn < 0) amax = rmin(amax, -nu / dn);
+          rmaxr = rmax(rmaxr, rmax(-ds * isv, -dn * inu));
           s0 += sv * nu; s1 += sv * dn + nu * ds; s2 += ds * dn;
         }
         if (acc) {
@@ -484,24 +497,28 @@ RDA_HD int su_solve(const SuParams& P, SuWork<Real>& W, Ctx& ctx, const float* g
             Real ax = W.hx[o * T + t], ay = W.hy[o * T + t];
             Real l = ax * dx + ay * dy + (Real)W.hc[o * T + t] - W.d[t];
             Real sv = W.hs[o * T + t], nu = W.hnu[o * T + t];
-            Real res = l + nu / ro1 - sv, den = sv + nu / ro1;
+            const Real nr = nu * iro1;
+            Real res = l + nr - sv;
+            const Real iden = (Real)1 / (sv + nr);
+            const Real om = nu * iden;
             Real dir = ax * dz[5 * t + 5] + ay * dz[5 * t + 6] - dv[3 * t + 2];
             Real cc = sv * nu;
             if (phase == 1) {
               Real dira = ax * W.dza[5 * t + 5] + ay * W.dza[5 * t + 6] - W.dva[3 * t + 2];
-              Real dna = -(sv * nu + nu * res + nu * dira) / den;
-              Real dsa = dira + dna / ro1 + res;
+              Real dna = -om * (sv + res + dira);
+              Real dsa = dira + dna * iro1 + res;
               cc = sv * nu - sigma_mu + dsa * dna;
             }
-            Real dn = -(cc + nu * res + nu * dir) / den;
-            Real ds = dir + dn / ro1 + res;
-            if (ds < 0) amax = rmin(amax, -sv / ds);
-            if (dn < 0) amax = rmin(amax, -nu / dn);
+            Real dn = -(cc + nu * res + nu * dir) * iden;
+            Real ds = dir + dn * iro1 + res;
+            const Real ip = (Real)1 / (sv * nu);
+            rmaxr = rmax(rmaxr, rmax(-ds * nu * ip, -dn * sv * ip));
             s0 += sv * nu; s1 += sv * dn + nu * ds; s2 += ds * dn;
           }
         }
       }
-      amax = ctx.min(amax);
+      rmaxr = ctx.max(rmaxr);
+      const Real amax = rmaxr > (Real)1e-30 ? (Real)1 / rmaxr : (Real)1e30;
       if (phase == 0) {
         Real a = rmin((Real)1, amax);
         Real mua = (ctx.sum(s0) + a * ctx.sum(s1) + a * a * ctx.sum(s2)) / Mrows;
@@ -510,11 +527,13 @@ RDA_HD int su_solve(const SuParams& P, SuWork<Real>& W, Ctx& ctx, const float* g
         sigma_mu = rmin(sg, (Real)1) * mu;
       } else {
         Real a = rmin((Real)1, (Real)0.995 * amax);
+#ifdef RDA_SU_DEBUG
+        printf("   alpha %.3e sigma_mu %.3e\n", (double)a, (double)sigma_mu);
+#endif
         // ---- update (needs the corrector quantities once more) ----
         for (int t = lane; t < T; t += nl) {
           // rows first: they read the OLD iterate through su_row
-          Real gsave[10], lsave[RDA_MAX_EDGE > 0 ? 1 : 1];
-          (void)lsave;
+          Real gsave[10];
           for (int c = 0; c < 10; ++c) { Row<Real> r = su_row<Real>(P, W, t, c); gsave[c] = r.g; }
           for (int c = 0; c < 10; ++c) {
             Row<Real> r = su_row<Real>(P, W, t, c);
@@ -525,8 +544,9 @@ RDA_HD int su_solve(const SuParams& P, SuWork<Real>& W, Ctx& ctx, const float* g
             Real ds = dir + res;
             Real dira = su_row_dir<Real>(r, W.dza + 5 * t, W.dva + 3 * t);
             Real dsa = dira + res;
-            Real dna = (-sv * nu - nu * dsa) / sv;
-            Real dn = (-(sv * nu - sigma_mu + dsa * dna) - nu * ds) / sv;
+            const Real isv = (Real)1 / sv, om = nu * isv;
+            Real dna = -nu - om * dsa;
+            Real dn = (sigma_mu - dsa * dna) * isv - nu - om * ds;
             W.bs[10 * t + c] = sv + a * ds;
             W.bnu[10 * t + c] = nu + a * dn;
           }
@@ -536,27 +556,33 @@ RDA_HD int su_solve(const SuParams& P, SuWork<Real>& W, Ctx& ctx, const float* g
               Real ax = W.hx[o * T + t], ay = W.hy[o * T + t];
               Real l = ax * dx + ay * dy + (Real)W.hc[o * T + t] - W.d[t];
               Real sv = W.hs[o * T + t], nu = W.hnu[o * T + t];
-              Real res = l + nu / ro1 - sv, den = sv + nu / ro1;
+              const Real nr = nu * iro1;
+              Real res = l + nr - sv;
+              const Real iden = (Real)1 / (sv + nr);
+              const Real om = nu * iden;
               Real dir = ax * W.dz[5 * t + 5] + ay * W.dz[5 * t + 6] - W.dv[3 * t + 2];
               Real dira = ax * W.dza[5 * t + 5] + ay * W.dza[5 * t + 6] - W.dva[3 * t + 2];
-              Real dna = -(sv * nu + nu * res + nu * dira) / den;
-              Real dsa = dira + dna / ro1 + res;
+              Real dna = -om * (sv + res + dira);
+              Real dsa = dira + dna * iro1 + res;
               Real cc = sv * nu - sigma_mu + dsa * dna;
-              Real dn = -(cc + nu * res + nu * dir) / den;
-              Real ds = dir + dn / ro1 + res;
+              Real dn = -(cc + nu * res + nu * dir) * iden;
+              Real ds = dir + dn * iro1 + res;
               W.hs[o * T + t] = sv + a * ds;
               W.hnu[o * T + t] = nu + a * dn;
             }
           }
         }
         ctx.sync();   // every lane has finished reading the old (s, u, d) of its neighbours
+        Real stepmax = 0;
         for (int t = lane; t < T; t += nl) {
+          stepmax = rmax(stepmax, rmax(abs_(W.dv[3 * t]), rmax(abs_(W.dv[3 * t + 1]), abs_(W.dv[3 * t + 2]))));
           W.u[2 * t] += a * W.dv[3 * t]; W.u[2 * t + 1] += a * W.dv[3 * t + 1];
           if (N > 0) W.d[t] += a * W.dv[3 * t + 2];
           W.s[3 * t + 3] += a * W.dz[5 * t + 5];
           W.s[3 * t + 4] += a * W.dz[5 * t + 6];
           W.s[3 * t + 5] += a * W.dz[5 * t + 7];
         }
+        last_step = a * ctx.max(stepmax);
         ctx.sync();
       }
     }

@@ -14,7 +14,8 @@ class SuParams(C.Structure):
     _fields_ = [('T', C.c_int), ('N', C.c_int), ('dynamics', C.c_int), ('accelerated', C.c_int),
                 ('dt', C.c_float), ('L', C.c_float), ('umax', C.c_float * 2), ('ab', C.c_float * 2),
                 ('ws', C.c_float), ('wu', C.c_float), ('slack_gain', C.c_float), ('dmin', C.c_float),
-                ('dmax', C.c_float), ('ro1', C.c_float), ('ro2', C.c_float), ('max_iter', C.c_int)]
+                ('dmax', C.c_float), ('ro1', C.c_float), ('ro2', C.c_float), ('max_iter', C.c_int),
+                ('mu0', C.c_float)]
 
 
 def build(force=False):
