@@ -33,77 +33,6 @@ struct CellOut {
   int path;
 };
 
-// ---------------------------------------------------------------------------------------------
-// Small dense primal-dual interior point method:
-//    min 1/2 x'Qx + c'x   s.t.  a_i'x <= b_i (i < m),  x0^2 + x1^2 <= 1
-// NV <= 7 variables, m <= 2*8+1 rows.  Mehrotra predictor-corrector, float64.
-// ---------------------------------------------------------------------------------------------
-template <int NV, int MC>
-struct TinyQP {
-  double Q[NV][NV];
-  double c[NV];
-  // sparse rows a_i'x <= b_i: at most 4 non-zeros each
-  double av[MC][4];
-  int ai[MC][4];
-  int an[MC];
-  double b[MC];
-  int m;
-  RDA_HD void row(int n, int i0, double v0, int i1, double v1, int i2, double v2, int i3, double v3, double rhs) {
-    av[m][0] = v0; av[m][1] = v1; av[m][2] = v2; av[m][3] = v3;
-    ai[m][0] = i0; ai[m][1] = i1; ai[m][2] = i2; ai[m][3] = i3;
-    an[m] = n; b[m] = rhs; ++m;
-  }
-  RDA_HD double dot(int i, const double* x) const {
-    double sacc = 0;
-    for (int e = 0; e < an[i]; ++e) sacc += av[i][e] * x[ai[i][e]];
-    return sacc;
-  }
-  RDA_HD void axpy(int i, double w, double* y) const {      // y += w * a_i
-    for (int e = 0; e < an[i]; ++e) y[ai[i][e]] += w * av[i][e];
-  }
-  RDA_HD void rank1(int i, double w, double H[NV][NV]) const {   // lower triangle of H += w a_i a_i'
-    for (int e = 0; e < an[i]; ++e)
-      for (int f = 0; f < an[i]; ++f) {
-        int r = ai[i][e], cidx = ai[i][f];
-        if (r >= cidx) H[r][cidx] += w * av[i][e] * av[i][f];
-      }
-  }
-  int tv;   // -1: unit-ball constraint x0^2 + x1^2 <= 1;  k >= 0: cone constraint
-            // (x0^2 + x1^2)/x_k - x_k <= 0 (i.e. |x01| <= x_k, rows keep 0 <= x_k <= 1)
-};
-
-template <int NV>
-RDA_HD bool chol_solve(double H[NV][NV], double* r1, double* r2) {
-  // in-place Cholesky H = LL', then solve for two right-hand sides
-  for (int j = 0; j < NV; ++j) {
-    double d = H[j][j];
-    for (int k = 0; k < j; ++k) d -= H[j][k] * H[j][k];
-    if (!(d > 0)) return false;
-    d = sqrt(d);
-    H[j][j] = d;
-    for (int i = j + 1; i < NV; ++i) {
-      double s = H[i][j];
-      for (int k = 0; k < j; ++k) s -= H[i][k] * H[j][k];
-      H[i][j] = s / d;
-    }
-  }
-  for (int pass = 0; pass < 2; ++pass) {
-    double* r = pass ? r2 : r1;
-    if (!r) continue;
-    for (int i = 0; i < NV; ++i) {
-      double s = r[i];
-      for (int k = 0; k < i; ++k) s -= H[i][k] * r[k];
-      r[i] = s / H[i][i];
-    }
-    for (int i = NV - 1; i >= 0; --i) {
-      double s = r[i];
-      for (int k = i + 1; k < NV; ++k) s -= H[k][i] * r[k];
-      r[i] = s / H[i][i];
-    }
-  }
-  return true;
-}
-
 // value, gradient (on x0, x1 and x_tv) and Hessian of the one nonlinear constraint
 struct ConeEval { double f, g0, g1, gt, h00, h11, h0t, h1t, htt; };
 RDA_HD ConeEval cone_eval(const double* x, int tv) {
@@ -120,236 +49,6 @@ RDA_HD ConeEval cone_eval(const double* x, int tv) {
     c.htt = 2 * n2 / (t * t * t);
   }
   return c;
-}
-
-template <int NV, int MC>
-RDA_HD_NOINLINE bool tiny_ipm(const TinyQP<NV, MC>& P, double* x /* in: strictly feasible start */) {
-  const int m = P.m;
-  double s[MC + 1], l[MC + 1];
-  for (int i = 0; i < m; ++i) {
-    s[i] = rmax(P.b[i] - P.dot(i, x), 1e-3);
-    l[i] = 1.0 / s[i];
-  }
-  const int tv = P.tv;
-  s[m] = rmax(-cone_eval(x, tv).f, 1e-3);
-  l[m] = 1.0 / s[m];
-  const int M = m + 1;
-  double scale = 1.0;
-  for (int i = 0; i < m; ++i) {
-    scale = rmax(scale, fabs(P.b[i]));
-    for (int e = 0; e < P.an[i]; ++e) scale = rmax(scale, fabs(P.av[i][e]));
-  }
-  for (int k = 0; k < NV; ++k) scale = rmax(scale, fabs(P.c[k]));
-  bool acceptable = false;
-  for (int it = 0; it < 40; ++it) {
-    // residuals
-    double rd[NV], rp[MC + 1];
-    for (int k = 0; k < NV; ++k) {
-      double v = P.c[k];
-      for (int j = 0; j < NV; ++j) v += P.Q[k][j] * x[j];
-      rd[k] = v;
-    }
-    double mu = 0;
-    for (int i = 0; i < m; ++i) {
-      P.axpy(i, l[i], rd);
-      rp[i] = P.dot(i, x) + s[i] - P.b[i];
-      mu += s[i] * l[i];
-    }
-    const ConeEval ce = cone_eval(x, tv);
-    rd[0] += ce.g0 * l[m];
-    rd[1] += ce.g1 * l[m];
-    if (tv >= 0) rd[tv] += ce.gt * l[m];
-    rp[m] = ce.f + s[m];
-    mu += s[m] * l[m];
-    mu /= M;
-    double rdn = 0, rpn = 0;
-    for (int k = 0; k < NV; ++k) rdn = rmax(rdn, fabs(rd[k]));
-    for (int i = 0; i < M; ++i) rpn = rmax(rpn, fabs(rp[i]));
-#ifdef RDA_IPM_DEBUG
-    printf("it %d rd %.2e rp %.2e mu %.2e x0 %g x1 %g\n", it, rdn, rpn, mu, x[0], x[1]);
-#endif
-    if (!(rdn == rdn) || !(mu == mu)) return false;
-    acceptable = rdn < 1e-6 * scale && rpn < 1e-6 * scale && mu < 1e-7;
-    if (rdn < 1e-9 * scale && rpn < 1e-9 * scale && mu < 1e-10) return true;
-    if (mu < 1e-14) return acceptable;     // complementarity exhausted (rounding floor reached)
-    // Newton matrix
-    double H[NV][NV];
-    for (int k = 0; k < NV; ++k)
-      for (int j = 0; j < NV; ++j) H[k][j] = P.Q[k][j];
-    for (int i = 0; i < m; ++i) P.rank1(i, l[i] / s[i], H);
-    {
-      double w = l[m] / s[m];
-      H[0][0] += l[m] * ce.h00 + w * ce.g0 * ce.g0;
-      H[1][0] += w * ce.g1 * ce.g0;
-      H[1][1] += l[m] * ce.h11 + w * ce.g1 * ce.g1;
-      if (tv >= 0) {   // tv > 1 always (lower triangle: row tv, columns 0, 1, tv)
-        H[tv][0] += l[m] * ce.h0t + w * ce.gt * ce.g0;
-        H[tv][1] += l[m] * ce.h1t + w * ce.gt * ce.g1;
-        H[tv][tv] += l[m] * ce.htt + w * ce.gt * ce.gt;
-      }
-    }
-    for (int k = 0; k < NV; ++k) H[k][k] += 1e-12;
-    // affine right-hand side: -(rd + sum grad_i (l_i rp_i - rc_i)/s_i), rc_i = s_i l_i
-    double ra[NV], rc[NV];
-    for (int k = 0; k < NV; ++k) ra[k] = -rd[k];
-    for (int i = 0; i < M; ++i) {
-      double t = (l[i] * rp[i] - s[i] * l[i]) / s[i];
-      if (i < m) {
-        P.axpy(i, -t, ra);
-      } else {
-        ra[0] -= ce.g0 * t;
-        ra[1] -= ce.g1 * t;
-        if (tv >= 0) ra[tv] -= ce.gt * t;
-      }
-    }
-    for (int k = 0; k < NV; ++k) rc[k] = ra[k];
-    double Hc[NV][NV];
-    for (int k = 0; k < NV; ++k)
-      for (int j = 0; j < NV; ++j) Hc[k][j] = H[k][j];
-    if (!chol_solve<NV>(Hc, ra, nullptr)) return acceptable;
-    // affine step lengths
-    double dsa[MC + 1], dla[MC + 1], aaff = 1.0;
-    for (int i = 0; i < M; ++i) {
-      double gd = 0;
-      if (i < m) {
-        gd = P.dot(i, ra);
-      } else {
-        gd = ce.g0 * ra[0] + ce.g1 * ra[1] + (tv >= 0 ? ce.gt * ra[tv] : 0.0);
-      }
-      dsa[i] = -rp[i] - gd;
-      dla[i] = -(s[i] * l[i] + l[i] * dsa[i]) / s[i];
-      if (dsa[i] < 0) aaff = rmin(aaff, -s[i] / dsa[i]);
-      if (dla[i] < 0) aaff = rmin(aaff, -l[i] / dla[i]);
-    }
-    double mua = 0;
-    for (int i = 0; i < M; ++i) mua += (s[i] + aaff * dsa[i]) * (l[i] + aaff * dla[i]);
-    mua /= M;
-    double sig = mua / mu;
-    sig = sig * sig * sig;
-    // corrector right-hand side
-    for (int k = 0; k < NV; ++k) rc[k] = -rd[k];
-    double rcs[MC + 1];
-    for (int i = 0; i < M; ++i) {
-      rcs[i] = s[i] * l[i] + dsa[i] * dla[i] - sig * mu;
-      double t = (l[i] * rp[i] - rcs[i]) / s[i];
-      if (i < m) {
-        P.axpy(i, -t, rc);
-      } else {
-        rc[0] -= ce.g0 * t;
-        rc[1] -= ce.g1 * t;
-        if (tv >= 0) rc[tv] -= ce.gt * t;
-      }
-    }
-    // Hc already holds the factor: only the triangular solves are needed
-    for (int i = 0; i < NV; ++i) {
-      double sv = rc[i];
-      for (int k = 0; k < i; ++k) sv -= Hc[i][k] * rc[k];
-      rc[i] = sv / Hc[i][i];
-    }
-    for (int i = NV - 1; i >= 0; --i) {
-      double sv = rc[i];
-      for (int k = i + 1; k < NV; ++k) sv -= Hc[k][i] * rc[k];
-      rc[i] = sv / Hc[i][i];
-    }
-    double alpha = 1.0, ds[MC + 1], dl[MC + 1];
-    for (int i = 0; i < M; ++i) {
-      double gd = 0;
-      if (i < m) {
-        gd = P.dot(i, rc);
-      } else {
-        gd = ce.g0 * rc[0] + ce.g1 * rc[1] + (tv >= 0 ? ce.gt * rc[tv] : 0.0);
-      }
-      ds[i] = -rp[i] - gd;
-      dl[i] = -(rcs[i] + l[i] * ds[i]) / s[i];
-      if (ds[i] < 0) alpha = rmin(alpha, -0.995 * s[i] / ds[i]);
-      if (dl[i] < 0) alpha = rmin(alpha, -0.995 * l[i] / dl[i]);
-    }
-    for (int k = 0; k < NV; ++k) x[k] += alpha * rc[k];
-    for (int i = 0; i < M; ++i) {
-      s[i] += alpha * ds[i];
-      l[i] += alpha * dl[i];
-    }
-  }
-  return acceptable;  // iteration cap reached
-}
-
-// ---------------------------------------------------------------------------------------------
-// Feasible-start log-barrier method (damped Newton with backtracking) for the same problem class
-// with the second-order-cone constraint |x01| <= x_tv (P.tv >= 0) in its self-concordant form
-// -log(x_tv^2 - |x01|^2).  Slower than tiny_ipm but globally convergent; used for disc obstacles.
-// ---------------------------------------------------------------------------------------------
-template <int NV, int MC>
-RDA_HD double barrier_value(const TinyQP<NV, MC>& P, const double* x, double t) {
-  double f = 0;
-  for (int k = 0; k < NV; ++k) {
-    double qx = 0;
-    for (int j = 0; j < NV; ++j) qx += P.Q[k][j] * x[j];
-    f += x[k] * (0.5 * qx + P.c[k]);
-  }
-  f *= t;
-  for (int i = 0; i < P.m; ++i) {
-    double sl = P.b[i] - P.dot(i, x);
-    if (!(sl > 0)) return 1e300;
-    f -= log(sl);
-  }
-  double tq = P.tv >= 0 ? x[P.tv] : 1.0;
-  double psi = tq * tq - x[0] * x[0] - x[1] * x[1];
-  if (!(psi > 0) || !(tq > 0)) return 1e300;
-  return f - log(psi);
-}
-
-template <int NV, int MC>
-RDA_HD_NOINLINE bool tiny_barrier(const TinyQP<NV, MC>& P, double* x /* strictly feasible */) {
-  const int m = P.m, tv = P.tv;
-  double t = 1.0;
-  for (int outer = 0; outer < 14; ++outer, t *= 8.0) {
-    for (int it = 0; it < 30; ++it) {
-      double g[NV], H[NV][NV];
-      for (int k = 0; k < NV; ++k) {
-        double qx = P.c[k];
-        for (int j = 0; j < NV; ++j) { qx += P.Q[k][j] * x[j]; H[k][j] = t * P.Q[k][j]; }
-        g[k] = t * qx;
-      }
-      for (int i = 0; i < m; ++i) {
-        double inv = 1.0 / (P.b[i] - P.dot(i, x));
-        P.axpy(i, inv, g);
-        P.rank1(i, inv * inv, H);
-      }
-      {
-        const double tq = tv >= 0 ? x[tv] : 1.0;
-        double psi = tq * tq - x[0] * x[0] - x[1] * x[1];
-        double gp[3] = {-2 * x[0], -2 * x[1], 2 * tq};          // grad psi on (0, 1, tv)
-        const int id[3] = {0, 1, tv};
-        const int na = tv >= 0 ? 3 : 2;
-        double ip = 1.0 / psi;
-        for (int a = 0; a < na; ++a) {
-          g[id[a]] -= gp[a] * ip;
-          for (int b2 = 0; b2 <= a; ++b2) H[id[a]][id[b2]] += gp[a] * gp[b2] * ip * ip;
-        }
-        H[0][0] += 2 * ip; H[1][1] += 2 * ip;
-        if (tv >= 0) H[tv][tv] -= 2 * ip;
-      }
-      for (int k = 0; k < NV; ++k) H[k][k] += 1e-13 * (1.0 + H[k][k]);
-      double dx[NV];
-      for (int k = 0; k < NV; ++k) dx[k] = -g[k];
-      if (!chol_solve<NV>(H, dx, nullptr)) return false;
-      double lam2 = 0;
-      for (int k = 0; k < NV; ++k) lam2 -= g[k] * dx[k];
-      if (!(lam2 == lam2)) return false;
-      if (lam2 < 1e-9) break;
-      double f0 = barrier_value<NV, MC>(P, x, t), step = 1.0;
-      double xn[NV];
-      bool moved = false;
-      for (int bt = 0; bt < 50; ++bt, step *= 0.5) {
-        for (int k = 0; k < NV; ++k) xn[k] = x[k] + step * dx[k];
-        double f1 = barrier_value<NV, MC>(P, xn, t);
-        if (f1 <= f0 - 0.1 * step * lam2) { moved = true; break; }
-      }
-      if (!moved) break;
-      for (int k = 0; k < NV; ++k) x[k] = xn[k];
-    }
-  }
-  return true;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -406,16 +105,31 @@ RDA_HD bool in_cone_rob(const RobotGeom& rb, int j, Real gx, Real gy, Real tol) 
   return a >= -tol * gn * sqrt_(epx * epx + epy * epy) && b <= tol * gn * sqrt_(enx * enx + eny * eny);
 }
 
-// FAST_ONLY = true compiles the closed-form paths only and reports CELL_NEEDS_SLOW (no outputs
-// written) for cells that need the interior point method (first pass of the two-pass kernel).
-template <typename Real, bool FAST_ONLY = false>
-RDA_HD void cell_solve(const RobotGeom& rb, int kind, int E, const float* A, const float* b,
-                       Real px, Real py, Real cphi, Real sphi, Real dbar, Real zeta, Real xi0,
-                       Real xi1, Real ro2, Real theta, CellOut<Real>& out) {
+// Everything one cell carries between its three stages (front: geometry + closed forms,
+// slow: interior point, back: multipliers and updates).
+template <typename Real>
+struct CellWork {
+  CellGeom<Real> g;
+  Real k0, cphi, sphi, xi0, xi1, ro2;
+  bool sep, xi_zero, circ;
+  Real best, byx, byy;
+  Real rob_in[RDA_MAX_ROBOT_EDGE], obs_in[RDA_MAX_EDGE];
+  Real v0, v1, g0, g1;
+  bool exact_zero_q, have;
+  int path;
+};
+
+// ---- stage 1: geometry relative to the robot reference point and the closed-form cases ----------
+template <typename Real>
+RDA_HD void cell_front(const RobotGeom& rb, int kind, int E, const float* A, const float* b, Real px, Real py,
+                       Real cphi, Real sphi, Real dbar, Real zeta, Real xi0, Real xi1, Real ro2,
+                       CellWork<Real>& w) {
   const int R = rb.R;
   const Real k0 = dbar - zeta;
   const Real eps = sizeof(Real) == 4 ? (Real)1e-5 : (Real)1e-11;
-  CellGeom<Real> g;
+  CellGeom<Real>& g = w.g;
+  w.k0 = k0; w.cphi = cphi; w.sphi = sphi; w.xi0 = xi0; w.xi1 = xi1; w.ro2 = ro2;
+  w.circ = (kind == RDA_OBS_CIRCLE);
   g.kind = kind;
   for (int j = 0; j < R; ++j) {
     Real yx = rb.yx[j], yy = rb.yy[j];
@@ -425,7 +139,6 @@ RDA_HD void cell_solve(const RobotGeom& rb, int kind, int E, const float* A, con
     g.mx[j] = cphi * nx - sphi * ny;
     g.my[j] = sphi * nx + cphi * ny;
   }
-  // ---- obstacle in coordinates relative to p ------------------------------------------------
   int ne = 0;
   Real brel[RDA_MAX_EDGE];
   if (kind == RDA_OBS_CIRCLE) {
@@ -454,14 +167,12 @@ RDA_HD void cell_solve(const RobotGeom& rb, int kind, int E, const float* A, con
       g.vy[i] = (g.nx[a] * brel[i] - g.nx[i] * brel[a]) * inv;
     }
   }
-  // ---- closest pair / separation -------------------------------------------------------------
+  // ---- closest pair / separation ----
   bool sep = false;
   Real best = 1e30f, bdx = 0, bdy = 0;
   Real byx = 0, byy = 0;            // robot-side point of the closest pair, body frame
-  Real rob_in[RDA_MAX_ROBOT_EDGE], obs_in[RDA_MAX_EDGE];
-  bool have_in = false;
   Real dj2[RDA_MAX_ROBOT_EDGE], djx[RDA_MAX_ROBOT_EDGE], djy[RDA_MAX_ROBOT_EDGE];
-  for (int j = 0; j < R; ++j) dj2[j] = 1e30f;
+  for (int j = 0; j < R; ++j) { dj2[j] = 1e30f; w.rob_in[j] = -1e30f; }
   if (kind == RDA_OBS_CIRCLE) {
     bool inside = true;
     for (int j = 0; j < R; ++j) {
@@ -497,7 +208,6 @@ RDA_HD void cell_solve(const RobotGeom& rb, int kind, int E, const float* A, con
       best = dd * dd;
     }
   } else {
-    for (int j = 0; j < R; ++j) rob_in[j] = -1e30f;
     for (int i = 0; i < ne; ++i) {
       int in = (i + 1) % ne;
       Real ex = g.vx[in] - g.vx[i], ey = g.vy[in] - g.vy[i];
@@ -507,7 +217,7 @@ RDA_HD void cell_solve(const RobotGeom& rb, int kind, int E, const float* A, con
         Real rx = g.yx[j] - g.vx[i], ry = g.yy[j] - g.vy[i];
         Real sd = g.nx[i] * rx + g.ny[i] * ry;
         mins = rmin(mins, sd);
-        rob_in[j] = rmax(rob_in[j], sd);        // <= 0 for every edge: robot vertex j inside O
+        w.rob_in[j] = rmax(w.rob_in[j], sd);        // <= 0 for every edge: robot vertex j inside O
         Real t = rclamp((rx * ex + ry * ey) * ie2, (Real)0, (Real)1);
         Real dx = rx - t * ex, dy = ry - t * ey;
         Real d2 = dx * dx + dy * dy;
@@ -526,7 +236,7 @@ RDA_HD void cell_solve(const RobotGeom& rb, int kind, int E, const float* A, con
         Real rx = g.vx[i] - g.yx[j], ry = g.vy[i] - g.yy[j];
         Real sd = g.mx[j] * rx + g.my[j] * ry;
         mins = rmin(mins, sd);
-        obs_in[i] = (j == 0) ? sd : rmax(obs_in[i], sd);   // <= 0: obstacle vertex i inside the robot
+        w.obs_in[i] = (j == 0) ? sd : rmax(w.obs_in[i], sd);   // <= 0: obstacle vertex i inside the robot
         Real t = rclamp((rx * fx + ry * fy) * if2, (Real)0, (Real)1);
         Real dx = -(rx - t * fx), dy = -(ry - t * fy);
         Real d2 = dx * dx + dy * dy;
@@ -539,11 +249,13 @@ RDA_HD void cell_solve(const RobotGeom& rb, int kind, int E, const float* A, con
       if (mins > eps) sep = true;
     }
   }
-  // ---- candidate (v, g) -------------------------------------------------------------------------
+  w.sep = sep; w.best = best; w.byx = byx; w.byy = byy;
+  // ---- closed-form candidates ----
   Real v0 = 0, v1 = 0, g0 = 0, g1 = 0;
   bool exact_zero_q = false, have = false;
   int path = CELL_FAILED;
   const bool xi_zero = (xi0 == (Real)0) && (xi1 == (Real)0);
+  w.xi_zero = xi_zero;
   if (sep && xi_zero) {
     Real dist = sqrt_(best);
     if (dist - k0 >= 0) {
@@ -583,128 +295,163 @@ RDA_HD void cell_solve(const RobotGeom& rb, int kind, int E, const float* A, con
       }
     }
   }
-#ifdef RDA_CELL_STATS
-  if (!have) {
-    extern long long g_cell_stats[8];
-    __sync_fetch_and_add(&g_cell_stats[(sep ? 0 : 2) + (xi_zero ? 0 : 1)], 1);
-  }
-#endif
-  if (FAST_ONLY) {
-    if (!have) { out.path = CELL_NEEDS_SLOW; return; }
-  } else if (!have) {
-    // ---- slow path: interior point in float64 ---------------------------------------------------
-    // Polygon obstacle: sigma_O(v) = max_i v.x_i, |v| <= 1 (ball constraint).
-    // Disc obstacle:    sigma_O(v) = v.c + rad*tv with |v| <= tv <= 1 (cone constraint, extra
-    //                   variable tv), exact also when the robot overlaps the disc.
-    const bool circ = (kind == RDA_OBS_CIRCLE);
-    const int nv_o = circ ? 1 : ne;
-    double ox[RDA_MAX_EDGE], oy[RDA_MAX_EDGE];
-    const double k0d = (double)k0, radd = circ ? (double)g.rad : 0.0;
-    if (circ) { ox[0] = g.cx; oy[0] = g.cy; }
-    else for (int i = 0; i < ne; ++i) { ox[i] = g.vx[i]; oy[i] = g.vy[i]; }
-    const double c_ = cphi, s_ = sphi, x0 = xi0, x1 = xi1;
-    bool ok = true, inactive = false;
-    double va = 0, vb = 0, ga = 0, gb = 0;
+  w.v0 = v0; w.v1 = v1; w.g0 = g0; w.g1 = g1;
+  w.exact_zero_q = exact_zero_q; w.have = have; w.path = path;
+}
+
+}  // namespace rda
+#include "coop_ipm.cuh"
+namespace rda {
+
+// ---- stage 2: interior point (float64) for the cells the closed forms do not cover -------------
+// Polygon obstacle: sigma_O(v) = max_i v.x_i, |v| <= 1 (ball).  Disc: sigma_O(v) = v.c + rad*tv with
+// |v| <= tv <= 1 (cone constraint, extra variable tv), exact also when the robot overlaps the disc.
+constexpr int CELL_NVA = 5, CELL_MCA = 2 * RDA_MAX_EDGE + 2;
+constexpr int CELL_NVB = 8, CELL_MCB = 2 * RDA_MAX_EDGE + 3;
+struct CellSlowStore {
+  union U {
+    CoopQP<CELL_NVA, CELL_MCA> a;
+    CoopQP<CELL_NVB, CELL_MCB> b;
+    RDA_HD U() {}
+  } u;
+  int need_a, ok, inactive, circ;
+};
+
+template <typename Real, typename Ctx>
+RDA_HD void cell_slow(const RobotGeom& rb, CellWork<Real>& w, CellSlowStore& S, Ctx& ctx) {
+  // Lane 0 owns `w` (the other lanes' copies are never read); all lanes run the solver loops.
+  const int lane = ctx.lane();
+  const int R = rb.R;
+  if (lane == 0) {
+    const CellGeom<Real>& g = w.g;
+    const double x0 = w.xi0, x1 = w.xi1, k0d = (double)w.k0, c_ = w.cphi, s_ = w.sphi;
     // The max margin c* = min_{x in O, y in Rob} |P(y) - x| + xi.y - k0 is bounded above by its value
-    // at the closest pair (disjoint sets): if that is negative the hinge is active for sure and
-    // stage A can be skipped.
+    // at any feasible pair: if that is negative the hinge is active for sure and stage A is skipped.
     bool need_a = true;
-    if (sep) {
-      double ub = sqrt((double)best) + x0 * (double)byx + x1 * (double)byy - k0d;
+    if (w.sep) {
+      double ub = sqrt((double)w.best) + x0 * (double)w.byx + x1 * (double)w.byy - k0d;
       if (ub < -1e-9) need_a = false;
-    } else if (!circ) {
-      // overlapping polygons: any common point y gives the bound xi.y - k0
+    } else if (!w.circ) {
       double ub = 1e300;
       for (int j = 0; j < R; ++j)
-        if (rob_in[j] <= 0) ub = rmin(ub, x0 * (double)rb.yx[j] + x1 * (double)rb.yy[j]);
-      for (int i = 0; i < ne; ++i)
-        if (obs_in[i] <= 0) {
+        if (w.rob_in[j] <= 0) ub = rmin(ub, x0 * (double)rb.yx[j] + x1 * (double)rb.yy[j]);
+      for (int i = 0; i < g.ne; ++i)
+        if (w.obs_in[i] <= 0) {
           double wx = g.vx[i], wy = g.vy[i];
           ub = rmin(ub, x0 * (c_ * wx + s_ * wy) + x1 * (-s_ * wx + c_ * wy));
         }
       if (ub - k0d < -1e-9) need_a = false;
     }
-    (void)have_in;
-#ifdef RDA_CELL_STATS
-    if (need_a) { extern long long g_cell_stats[8]; __sync_fetch_and_add(&g_cell_stats[6], 1); }
-#endif
-    if (need_a) {  // stage A: max margin with Hm + xi = 0; x = (v0, v1, so, sr, tv)
-      constexpr int NVA = 5;
-      TinyQP<NVA, 2 * RDA_MAX_EDGE + 2> P;
-      for (int k = 0; k < NVA; ++k) { for (int j = 0; j < NVA; ++j) P.Q[k][j] = 0; P.c[k] = 0; }
+    S.need_a = need_a ? 1 : 0;
+    S.ok = 1; S.inactive = 0; S.circ = w.circ ? 1 : 0;
+    if (need_a) {   // stage A: max margin with Hm + xi = 0; x = (v0, v1, so, sr, tv)
+      CoopQP<CELL_NVA, CELL_MCA>& P = S.u.a;
+      P.clear();
       P.c[2] = 1; P.c[3] = 1;
-      P.m = 0;
-      for (int i = 0; i < nv_o; ++i) P.row(4, 0, ox[i], 1, oy[i], 2, -1.0, 4, radd, 0.0);   // v.x_i + rad tv <= so
+      const double radd = w.circ ? (double)g.rad : 0.0;
+      const int nv_o = w.circ ? 1 : g.ne;
+      for (int i = 0; i < nv_o; ++i) {
+        double ox = w.circ ? (double)g.cx : (double)g.vx[i], oy = w.circ ? (double)g.cy : (double)g.vy[i];
+        P.row(0, ox, 1, oy, 2, -1.0, 4, radd, 0.0);                      // v.x_i + rad tv <= so
+      }
+      double hmax = 0;
       for (int j = 0; j < R; ++j) {
         // g.y_j <= sr with g = -R'v - xi :  -(R y_j).v - sr <= xi.y_j
         double yx = rb.yx[j], yy = rb.yy[j];
-        P.row(3, 0, -(c_ * yx - s_ * yy), 1, -(s_ * yx + c_ * yy), 3, -1.0, 0, 0.0, x0 * yx + x1 * yy);
+        P.row(0, -(c_ * yx - s_ * yy), 1, -(s_ * yx + c_ * yy), 3, -1.0, 3, 0.0, x0 * yx + x1 * yy);
+        hmax = rmax(hmax, fabs(x0 * yx + x1 * yy));
       }
-      P.row(1, 4, 1.0, 0, 0.0, 0, 0.0, 0, 0.0, 1.0);          // tv <= 1
-      P.row(1, 4, -1.0, 0, 0.0, 0, 0.0, 0, 0.0, 0.0);         // tv >= 0
-      P.tv = circ ? 4 : -1;
-      double hmax = 0;
-      for (int j = 0; j < R; ++j) hmax = rmax(hmax, fabs(x0 * (double)rb.yx[j] + x1 * (double)rb.yy[j]));
-      double xs[NVA] = {0, 0, 1.0 + radd, 1.0 + hmax, 0.5};
-      ok = !circ && tiny_ipm<NVA, 2 * RDA_MAX_EDGE + 2>(P, xs);
-      if (!ok) {   // discs, and the rare polygon cell on which the primal-dual iteration cycles
-        xs[0] = 0; xs[1] = 0; xs[2] = 1.0 + radd; xs[3] = 1.0 + hmax; xs[4] = 0.5;
-        ok = tiny_barrier<NVA, 2 * RDA_MAX_EDGE + 2>(P, xs);
-      }
-      double cst = -xs[2] - xs[3] - k0d;
+      P.row(4, 1.0, 4, 0.0, 4, 0.0, 4, 0.0, 1.0);          // tv <= 1
+      P.row(4, -1.0, 4, 0.0, 4, 0.0, 4, 0.0, 0.0);         // tv >= 0
+      P.tv = w.circ ? 4 : -1;
+      P.x[0] = 0; P.x[1] = 0; P.x[2] = 1.0 + radd; P.x[3] = 1.0 + hmax; P.x[4] = 0.5;
+      for (int k = 0; k < CELL_NVA; ++k) P.x0[k] = P.x[k];
+    }
+  }
+  ctx.sync();
+  if (S.need_a) {
+    CoopQP<CELL_NVA, CELL_MCA>& P = S.u.a;
+    bool ok = !(S.circ != 0) && coop_ipm<CELL_NVA, CELL_MCA, Ctx>(P, ctx);
+    if (!ok) {   // discs, and the rare polygon cell on which the primal-dual iteration cycles
+      ctx.sync();
+      if (lane == 0) for (int k = 0; k < CELL_NVA; ++k) P.x[k] = P.x0[k];
+      ctx.sync();
+      ok = coop_barrier<CELL_NVA, CELL_MCA, Ctx>(P, ctx);
+    }
+    ctx.sync();
+    if (lane == 0) {
+      S.ok = ok ? 1 : 0;
+      double cst = -P.x[2] - P.x[3] - (double)w.k0;
       if (ok && cst >= 0) {
-        inactive = true;
-        va = xs[0]; vb = xs[1];
-        ga = -(c_ * va + s_ * vb) - x0;
-        gb = -(-s_ * va + c_ * vb) - x1;
-        path = CELL_SLOW_A;
-#ifdef RDA_CELL_STATS
-        { extern long long g_cell_stats[8]; __sync_fetch_and_add(&g_cell_stats[4 + (sep ? 0 : 1)], 1); }
-#endif
+        S.inactive = 1;
+        double va = P.x[0], vb = P.x[1];
+        w.v0 = (Real)va; w.v1 = (Real)vb;
+        w.g0 = (Real)(-((double)w.cphi * va + (double)w.sphi * vb) - (double)w.xi0);
+        w.g1 = (Real)(-(-(double)w.sphi * va + (double)w.cphi * vb) - (double)w.xi1);
+        w.exact_zero_q = true; w.have = true; w.path = CELL_SLOW_A;
       }
     }
-    if (ok && !inactive) {  // stage B: x = (v0, v1, g0, g1, so, sr, w, tv)
-      constexpr int NVB = 8;
-      TinyQP<NVB, 2 * RDA_MAX_EDGE + 3> P;
-      for (int k = 0; k < NVB; ++k) { for (int j = 0; j < NVB; ++j) P.Q[k][j] = 0; P.c[k] = 0; }
+    ctx.sync();
+  }
+  if (S.ok && !S.inactive) {   // stage B: x = (v0, v1, g0, g1, so, sr, w, tv)
+    CoopQP<CELL_NVB, CELL_MCB>& P = S.u.b;
+    if (lane == 0) {
+      const CellGeom<Real>& g = w.g;
+      const double x0 = w.xi0, x1 = w.xi1, k0d = (double)w.k0, c_ = w.cphi, s_ = w.sphi, r2 = w.ro2;
+      P.clear();
       // ro2/2 |g + R'v + xi|^2 : with u = (v, g), q = M u + xi, M = [R' I]
-      const double r2 = ro2;
       const double Mx[4] = {c_, s_, 1, 0}, My[4] = {-s_, c_, 0, 1};
       for (int k = 0; k < 4; ++k)
         for (int j = 0; j < 4; ++j) P.Q[k][j] = r2 * (Mx[k] * Mx[j] + My[k] * My[j]);
       for (int k = 0; k < 4; ++k) P.c[k] = r2 * (Mx[k] * x0 + My[k] * x1);
       P.Q[6][6] = 1.0;   // 1/2 w^2  (ro1 == 1 inside LamMuZ, rda_solver.py:257)
-      P.m = 0;
-      for (int i = 0; i < nv_o; ++i) P.row(4, 0, ox[i], 1, oy[i], 4, -1.0, 7, radd, 0.0);
-      for (int j = 0; j < R; ++j) P.row(3, 2, (double)rb.yx[j], 3, (double)rb.yy[j], 5, -1.0, 0, 0.0, 0.0);
-      P.row(3, 4, 1.0, 5, 1.0, 6, -1.0, 0, 0.0, -k0d);        // so + sr + k0 <= w
-      P.row(1, 7, 1.0, 0, 0.0, 0, 0.0, 0, 0.0, 1.0);          // tv <= 1
-      P.row(1, 7, -1.0, 0, 0.0, 0, 0.0, 0, 0.0, 0.0);         // tv >= 0
-      P.tv = circ ? 7 : -1;
-      double so0 = 1.0 + radd;
-      const double w0 = rmax(so0 + 2.0 + k0d, 1.0);
-      double xs[NVB] = {0, 0, 0, 0, so0, 1.0, w0, 0.5};
-      ok = !circ && tiny_ipm<NVB, 2 * RDA_MAX_EDGE + 3>(P, xs);
-      if (!ok) {
-        xs[0] = xs[1] = xs[2] = xs[3] = 0; xs[4] = so0; xs[5] = 1.0; xs[6] = w0; xs[7] = 0.5;
-        ok = tiny_barrier<NVB, 2 * RDA_MAX_EDGE + 3>(P, xs);
+      const double radd = w.circ ? (double)g.rad : 0.0;
+      const int nv_o = w.circ ? 1 : g.ne;
+      for (int i = 0; i < nv_o; ++i) {
+        double ox = w.circ ? (double)g.cx : (double)g.vx[i], oy = w.circ ? (double)g.cy : (double)g.vy[i];
+        P.row(0, ox, 1, oy, 4, -1.0, 7, radd, 0.0);
       }
-      va = xs[0]; vb = xs[1]; ga = xs[2]; gb = xs[3];
-      path = CELL_SLOW_B;
+      for (int j = 0; j < R; ++j) P.row(2, (double)rb.yx[j], 3, (double)rb.yy[j], 5, -1.0, 5, 0.0, 0.0);
+      P.row(4, 1.0, 5, 1.0, 6, -1.0, 6, 0.0, -k0d);        // so + sr + k0 <= w
+      P.row(7, 1.0, 7, 0.0, 7, 0.0, 7, 0.0, 1.0);          // tv <= 1
+      P.row(7, -1.0, 7, 0.0, 7, 0.0, 7, 0.0, 0.0);         // tv >= 0
+      P.tv = w.circ ? 7 : -1;
+      const double so0 = 1.0 + radd;
+      const double xs[CELL_NVB] = {0, 0, 0, 0, so0, 1.0, rmax(so0 + 2.0 + k0d, 1.0), 0.5};
+      for (int k = 0; k < CELL_NVB; ++k) { P.x[k] = xs[k]; P.x0[k] = xs[k]; }
     }
+    ctx.sync();
+    bool ok = !(S.circ != 0) && coop_ipm<CELL_NVB, CELL_MCB, Ctx>(P, ctx);
     if (!ok) {
-      path = CELL_FAILED;
-    } else {
-      v0 = (Real)va; v1 = (Real)vb; g0 = (Real)ga; g1 = (Real)gb;
-      exact_zero_q = inactive;
-      have = true;
+      ctx.sync();
+      if (lane == 0) for (int k = 0; k < CELL_NVB; ++k) P.x[k] = P.x0[k];
+      ctx.sync();
+      ok = coop_barrier<CELL_NVB, CELL_MCB, Ctx>(P, ctx);
     }
+    ctx.sync();
+    if (lane == 0) {
+      S.ok = ok ? 1 : 0;
+      if (ok) {
+        w.v0 = (Real)P.x[0]; w.v1 = (Real)P.x[1]; w.g0 = (Real)P.x[2]; w.g1 = (Real)P.x[3];
+        w.exact_zero_q = false; w.have = true; w.path = CELL_SLOW_B;
+      }
+    }
+    ctx.sync();
   }
-  // ---- epilogue: multipliers, updates, su-QP inputs ------------------------------------------
+  if (lane == 0 && !S.ok) { w.have = false; w.path = CELL_FAILED; }
+}
+
+// ---- stage 3: multipliers, updates, su-QP inputs ----------------------------------------------
+template <typename Real>
+RDA_HD void cell_back(const RobotGeom& rb, const CellWork<Real>& w, Real zeta, Real theta, CellOut<Real>& out) {
+  const CellGeom<Real>& g = w.g;
+  const int R = rb.R, ne = g.ne, kind = g.kind;
+  const Real v0 = w.v0, v1 = w.v1, g0 = w.g0, g1 = w.g1, cphi = w.cphi, sphi = w.sphi;
+  const Real xi0 = w.xi0, xi1 = w.xi1, k0 = w.k0;
   for (int i = 0; i < RDA_MAX_EDGE; ++i) out.lam[i] = 0;
   for (int j = 0; j < RDA_MAX_ROBOT_EDGE; ++j) out.mu[j] = 0;
-  out.path = path;
-  if (!have) {
+  out.path = w.path;
+  if (!w.have) {
     // keep-previous-iterate rule (rda_solver.py:791-793) is applied by the caller
     out.z = 0; out.zeta_new = zeta; out.xi0_new = xi0; out.xi1_new = xi1;
     out.ax = out.ay = out.c0 = out.gx = out.gy = out.hm0 = out.hm1 = 0;
@@ -738,7 +485,7 @@ RDA_HD void cell_solve(const RobotGeom& rb, int kind, int E, const float* A, con
   Real stuff = marg - k0;
   Real z = theta * rmax(stuff, (Real)0);
   Real q0, q1;
-  if (exact_zero_q) { q0 = 0; q1 = 0; }
+  if (w.exact_zero_q) { q0 = 0; q1 = 0; }
   else {
     q0 = g0 + (cphi * v0 + sphi * v1) + xi0;
     q1 = g1 + (-sphi * v0 + cphi * v1) + xi1;
@@ -754,6 +501,21 @@ RDA_HD void cell_solve(const RobotGeom& rb, int kind, int E, const float* A, con
   out.c0 = marg - z + out.zeta_new;     // a.p - lam'b - mu'h - z + zeta   (Im_su without -d, :846-851)
   out.gx = g0 + q0;                     // mu'G + xi                       (:868)
   out.gy = g1 + q1;
+}
+
+// One cell, one thread (CPU port, tests): front -> slow (single lane) -> back.
+template <typename Real>
+RDA_HD void cell_solve(const RobotGeom& rb, int kind, int E, const float* A, const float* b,
+                       Real px, Real py, Real cphi, Real sphi, Real dbar, Real zeta, Real xi0,
+                       Real xi1, Real ro2, Real theta, CellOut<Real>& out) {
+  CellWork<Real> w;
+  cell_front<Real>(rb, kind, E, A, b, px, py, cphi, sphi, dbar, zeta, xi0, xi1, ro2, w);
+  if (!w.have) {
+    CellSlowStore S;
+    SeqCtx ctx;
+    cell_slow<Real, SeqCtx>(rb, w, S, ctx);
+  }
+  cell_back<Real>(rb, w, zeta, theta, out);
 }
 
 }  // namespace rda

@@ -28,6 +28,16 @@ RDA_HD double abs_(double x) { return fabs(x); }
 RDA_HD bool finite_(float x) { return isfinite(x); }
 RDA_HD bool finite_(double x) { return isfinite(x); }
 
+// Single-lane context (host tests; also valid on the device for a thread-per-instance launch).
+struct SeqCtx {
+  RDA_HD int lane() const { return 0; }
+  RDA_HD int nlanes() const { return 1; }
+  RDA_HD void sync() const {}
+  template <typename R> RDA_HD R sum(R x) const { return x; }
+  template <typename R> RDA_HD R min(R x) const { return x; }
+  template <typename R> RDA_HD R max(R x) const { return x; }
+};
+
 // Robot body (convex polygon, car_tuple.G/h with Rpositive cone), prepared once at
 // rda_create: vertices y_j (vertex j joins rows j-1 and j, rda mpc.py:476-510 ordering),
 // unit outward normals and row norms.

@@ -168,80 +168,76 @@ __global__ void __launch_bounds__(32) k_su(DevPtrs d, SuParams P) {
 //                 method are appended to a worklist (warp-aggregated atomic);
 //   k_cells_slow  one thread per worklist entry (dense: no lane idles behind a slow neighbour).
 // ------------------------------------------------------------------------------------------------
-struct CellCtx {
-  int b, o, t;
+// inputs of one cell gathered from the persistent state
+struct CellIn {
+  int b, o, t, kind;
   size_t cell;
+  float px, py, cp, sp, dbar, zeta, xi0, xi1;
+  const float *A, *bb;
 };
 
-template <typename Real, bool FAST_ONLY>
-__device__ __forceinline__ int cell_run(const DevPtrs& d, const RobotGeom& rb, float ro2, float theta,
-                                        long long idx, float* hm2, float* dual) {
-  const int T = d.T, N = d.N, E = d.E, R = d.R, NT = N * T;
-  const int b = (int)(idx / NT);
-  const int rem = (int)(idx - (long long)b * NT);
-  const int o = rem / T, t = rem - o * T;
-  const float* cs = d.cur_s + (size_t)b * 3 * (T + 1);
-  Real px = cs[t + 1], py = cs[(T + 1) + t + 1];
-  float phib = cs[2 * (T + 1) + t];                 // NB column t (rda_solver.py:457-460)
-  float spf, cpf;
-  sincosf(phib, &spf, &cpf);
-  Real dbar = d.dis[(size_t)b * T + t];
-  const size_t cell = (size_t)b * NT + (size_t)o * T + t;
-  Real zeta = d.zeta[cell];
-  float* xi = d.xi + (size_t)b * 2 * NT;
-  Real xi0 = xi[(size_t)o * T + t], xi1 = xi[NT + (size_t)o * T + t];
-  const int tc = d.obs_tv ? (t + 1) : 0;
+__device__ __forceinline__ CellIn cell_load(const DevPtrs& d, long long idx) {
+  const int T = d.T, N = d.N, E = d.E, NT = N * T;
+  CellIn c;
+  c.b = (int)(idx / NT);
+  const int rem = (int)(idx - (long long)c.b * NT);
+  c.o = rem / T; c.t = rem - c.o * T;
+  const float* cs = d.cur_s + (size_t)c.b * 3 * (T + 1);
+  c.px = cs[c.t + 1]; c.py = cs[(T + 1) + c.t + 1];
+  sincosf(cs[2 * (T + 1) + c.t], &c.sp, &c.cp);      // NB column t (rda_solver.py:457-460)
+  c.dbar = d.dis[(size_t)c.b * T + c.t];
+  c.cell = (size_t)c.b * NT + (size_t)c.o * T + c.t;
+  c.zeta = d.zeta[c.cell];
+  const float* xi = d.xi + (size_t)c.b * 2 * NT;
+  c.xi0 = xi[(size_t)c.o * T + c.t]; c.xi1 = xi[NT + (size_t)c.o * T + c.t];
+  const int tc = d.obs_tv ? (c.t + 1) : 0;
   const int Tc = d.obs_tv ? (T + 1) : 1;
-  const size_t ob = ((size_t)b * N + o) * Tc + tc;
-  const float* A = d.obs_A + ob * E * 2;
-  const float* bb = d.obs_b + ob * E;
-  const int kind = d.obs_kind[(size_t)b * N + o];
-  CellOut<Real> out;
-  cell_solve<Real, FAST_ONLY>(rb, kind, E, A, bb, px, py, (Real)cpf, (Real)spf, dbar, zeta, xi0, xi1, (Real)ro2,
-                              (Real)theta, out);
-  if (out.path == CELL_NEEDS_SLOW) return out.path;
-  if (out.path == CELL_FAILED) {
-    // "Update Lam Mu Fail": previous duals kept, residual inf (:791-793)
-    *dual = INFINITY;
-    atomicOr(&d.status[b], RDA_ST_CELL_FALLBACK);
-    return out.path;
-  }
+  const size_t ob = ((size_t)c.b * N + c.o) * Tc + tc;
+  c.A = d.obs_A + ob * E * 2;
+  c.bb = d.obs_b + ob * E;
+  c.kind = d.obs_kind[(size_t)c.b * N + c.o];
+  return c;
+}
+
+// write (lam, mu, z), the multiplier updates and the next su-QP's hinge inputs of one cell
+__device__ __forceinline__ void cell_store(const DevPtrs& d, const CellIn& c, const CellOut<float>& out, float* hm2,
+                                           float* dual) {
+  const int T = d.T, N = d.N, E = d.E, R = d.R, NT = N * T;
   // dual residual |lam - lam_prev|^2 + |mu - mu_prev|^2 + |z - z_prev|^2 (:783-787)
-  float* lam = d.lam + ((size_t)b * N + o) * E * T + t;
+  float* lam = d.lam + ((size_t)c.b * N + c.o) * E * T + c.t;
   float acc = 0.f;
   for (int i = 0; i < E; ++i) {
-    float nv = (float)out.lam[i];
+    float nv = out.lam[i];
     float df = nv - lam[(size_t)i * T];
     acc += df * df;
     lam[(size_t)i * T] = nv;
   }
-  float* mu = d.mu + ((size_t)b * N + o) * R * T + t;
+  float* mu = d.mu + ((size_t)c.b * N + c.o) * R * T + c.t;
   for (int j = 0; j < R; ++j) {
-    float nv = (float)out.mu[j];
+    float nv = out.mu[j];
     float df = nv - mu[(size_t)j * T];
     acc += df * df;
     mu[(size_t)j * T] = nv;
   }
-  float zn = (float)out.z;
-  float dz = zn - d.z[cell];
+  float dz = out.z - d.z[c.cell];
   acc += dz * dz;
-  d.z[cell] = zn;
+  d.z[c.cell] = out.z;
   *dual = acc;
-  d.zeta[cell] = (float)out.zeta_new;
-  xi[(size_t)o * T + t] = (float)out.xi0_new;
-  xi[NT + (size_t)o * T + t] = (float)out.xi1_new;
-  *hm2 = (float)(out.hm0 * out.hm0 + out.hm1 * out.hm1);
-  float* cf = d.coef + (size_t)b * 5 * NT + (size_t)o * T + t;
-  cf[0] = (float)out.ax;
-  cf[NT] = (float)out.ay;
-  cf[2 * NT] = (float)out.c0;
-  cf[3 * NT] = (float)out.gx;
-  cf[4 * NT] = (float)out.gy;
-  if (o == 0) {
-    d.pref[(size_t)b * 2 * T + t] = (float)px;
-    d.pref[(size_t)b * 2 * T + T + t] = (float)py;
+  d.zeta[c.cell] = out.zeta_new;
+  float* xi = d.xi + (size_t)c.b * 2 * NT;
+  xi[(size_t)c.o * T + c.t] = out.xi0_new;
+  xi[NT + (size_t)c.o * T + c.t] = out.xi1_new;
+  *hm2 = out.hm0 * out.hm0 + out.hm1 * out.hm1;
+  float* cf = d.coef + (size_t)c.b * 5 * NT + (size_t)c.o * T + c.t;
+  cf[0] = out.ax;
+  cf[NT] = out.ay;
+  cf[2 * NT] = out.c0;
+  cf[3 * NT] = out.gx;
+  cf[4 * NT] = out.gy;
+  if (c.o == 0) {
+    d.pref[(size_t)c.b * 2 * T + c.t] = c.px;
+    d.pref[(size_t)c.b * 2 * T + T + c.t] = c.py;
   }
-  return out.path;
 }
 
 __global__ void __launch_bounds__(128) k_cells_fast(DevPtrs d, RobotGeom rb, float ro2, float theta) {
@@ -255,7 +251,19 @@ __global__ void __launch_bounds__(128) k_cells_fast(DevPtrs d, RobotGeom rb, flo
     float hm2 = 0.f, dual = 0.f;
     int path = -1;
     if (live && (d.done[b] || d.obs_count[b] == 0)) live = false;
-    if (live) path = cell_run<float, true>(d, rb, ro2, theta, idx, &hm2, &dual);
+    if (live) {
+      CellIn c = cell_load(d, idx);
+      CellWork<float> w;
+      cell_front<float>(rb, c.kind, d.E, c.A, c.bb, c.px, c.py, c.cp, c.sp, c.dbar, c.zeta, c.xi0, c.xi1, ro2, w);
+      if (w.have) {
+        CellOut<float> out;
+        cell_back<float>(rb, w, c.zeta, theta, out);
+        cell_store(d, c, out, &hm2, &dual);
+        path = out.path;
+      } else {
+        path = CELL_NEEDS_SLOW;
+      }
+    }
     // worklist of cells for the slow pass (one atomic per warp)
     unsigned need = __ballot_sync(0xffffffffu, path == CELL_NEEDS_SLOW);
     if (need) {
@@ -294,17 +302,42 @@ __global__ void __launch_bounds__(128) k_cells_fast(DevPtrs d, RobotGeom rb, flo
   }
 }
 
-__global__ void __launch_bounds__(64) k_cells_slow(DevPtrs d, RobotGeom rb, float ro2, float theta) {
-  const int NT = d.N * d.T;
+// One warp per worklist cell: lane 0 prepares the problem in shared memory, all lanes run the
+// interior point iteration (coop_ipm.cuh), lane 0 writes the result.
+constexpr int SLOW_WARPS = 4;
+__global__ void __launch_bounds__(32 * SLOW_WARPS) k_cells_slow(DevPtrs d, RobotGeom rb, float ro2, float theta) {
+  __shared__ CellSlowStore store[SLOW_WARPS];
   const int count = d.counters[5];
-  for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < count; w += gridDim.x * blockDim.x) {
-    long long idx = d.worklist[w];
-    int b = (int)(idx / NT);
-    float hm2 = 0.f, dual = 0.f;
-    int path = cell_run<float, false>(d, rb, ro2, theta, idx, &hm2, &dual);
-    atomicAdd(&d.resi_acc[2 * b], hm2);
-    atomicAdd(&d.resi_acc[2 * b + 1], dual);
-    atomicAdd(&d.counters[path == CELL_FAILED ? 2 : 1], 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  CellSlowStore& S = store[warp];
+  WarpCtx ctx;
+  for (int wi = blockIdx.x * SLOW_WARPS + warp; wi < count; wi += gridDim.x * SLOW_WARPS) {
+    const long long idx = d.worklist[wi];
+    CellIn c;
+    CellWork<float> w;
+    if (lane == 0) {
+      c = cell_load(d, idx);
+      cell_front<float>(rb, c.kind, d.E, c.A, c.bb, c.px, c.py, c.cp, c.sp, c.dbar, c.zeta, c.xi0, c.xi1, ro2, w);
+    }
+    __syncwarp();
+    cell_slow<float, WarpCtx>(rb, w, S, ctx);
+    __syncwarp();
+    if (lane == 0) {
+      CellOut<float> out;
+      cell_back<float>(rb, w, c.zeta, theta, out);
+      float hm2 = 0.f, dual = 0.f;
+      if (out.path == CELL_FAILED) {
+        // "Update Lam Mu Fail": previous duals kept, residual inf (:791-793)
+        dual = INFINITY;
+        atomicOr(&d.status[c.b], RDA_ST_CELL_FALLBACK);
+      } else {
+        cell_store(d, c, out, &hm2, &dual);
+      }
+      atomicAdd(&d.resi_acc[2 * c.b], hm2);
+      atomicAdd(&d.resi_acc[2 * c.b + 1], dual);
+      atomicAdd(&d.counters[out.path == CELL_FAILED ? 2 : 1], 1);
+    }
+    __syncwarp();
   }
 }
 
@@ -544,7 +577,7 @@ int rda_step_lammuz(rda_handle* h, void* stream) {
     const float theta = h->cfg.accelerated ? h->tun.z_theta : 1.0f;
     k_cells_fast<<<grid_for((long long)h->B * h->N * h->T, 128), 128, 0, s>>>(d, h->rb, h->tun.ro2, theta);
     RDA_CUDA(cudaGetLastError());
-    k_cells_slow<<<148 * 8, 64, 0, s>>>(d, h->rb, h->tun.ro2, theta);
+    k_cells_slow<<<148 * 8, 32 * SLOW_WARPS, 0, s>>>(d, h->rb, h->tun.ro2, theta);
     RDA_CUDA(cudaGetLastError());
     h->launches += 2;
   }

@@ -80,16 +80,6 @@ RDA_HD size_t su_work_layout(int T, int N, SuWork<Real>* w, char* base) {
   return (off + 15) & ~(size_t)15;
 }
 
-// Single-lane context (host tests; also valid on the device for a thread-per-instance launch).
-struct SeqCtx {
-  RDA_HD int lane() const { return 0; }
-  RDA_HD int nlanes() const { return 1; }
-  RDA_HD void sync() const {}
-  template <typename R> RDA_HD R sum(R x) const { return x; }
-  template <typename R> RDA_HD R min(R x) const { return x; }
-  template <typename R> RDA_HD R max(R x) const { return x; }
-};
-
 // Jacobians of the discrete model about (s, u): linear_ackermann_model :949-963,
 // linear_diff_model :966-979, linear_omni_model :982-994.
 template <typename Real>
