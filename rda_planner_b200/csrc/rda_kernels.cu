@@ -302,42 +302,35 @@ __global__ void __launch_bounds__(128) k_cells_fast(DevPtrs d, RobotGeom rb, flo
   }
 }
 
-// One warp per worklist cell: lane 0 prepares the problem in shared memory, all lanes run the
-// interior point iteration (coop_ipm.cuh), lane 0 writes the result.
-constexpr int SLOW_WARPS = 4;
-__global__ void __launch_bounds__(32 * SLOW_WARPS) k_cells_slow(DevPtrs d, RobotGeom rb, float ro2, float theta) {
-  __shared__ CellSlowStore store[SLOW_WARPS];
+// One thread per worklist entry (dense: no lane idles behind a closed-form neighbour).
+#ifndef RDA_SLOW_MINBLOCKS
+#define RDA_SLOW_MINBLOCKS 16
+#endif
+__global__ void __launch_bounds__(64, RDA_SLOW_MINBLOCKS) k_cells_slow(DevPtrs d, RobotGeom rb, float ro2, float theta) {
   const int count = d.counters[5];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  CellSlowStore& S = store[warp];
-  WarpCtx ctx;
-  for (int wi = blockIdx.x * SLOW_WARPS + warp; wi < count; wi += gridDim.x * SLOW_WARPS) {
+  for (int wi = blockIdx.x * blockDim.x + threadIdx.x; wi < count; wi += gridDim.x * blockDim.x) {
     const long long idx = d.worklist[wi];
-    CellIn c;
+    CellIn c = cell_load(d, idx);
     CellWork<float> w;
-    if (lane == 0) {
-      c = cell_load(d, idx);
-      cell_front<float>(rb, c.kind, d.E, c.A, c.bb, c.px, c.py, c.cp, c.sp, c.dbar, c.zeta, c.xi0, c.xi1, ro2, w);
+    cell_front<float>(rb, c.kind, d.E, c.A, c.bb, c.px, c.py, c.cp, c.sp, c.dbar, c.zeta, c.xi0, c.xi1, ro2, w);
+    if (!w.have) {
+      CellSlowStore S;
+      SeqCtx ctx;
+      cell_slow<float, SeqCtx>(rb, w, S, ctx);
     }
-    __syncwarp();
-    cell_slow<float, WarpCtx>(rb, w, S, ctx);
-    __syncwarp();
-    if (lane == 0) {
-      CellOut<float> out;
-      cell_back<float>(rb, w, c.zeta, theta, out);
-      float hm2 = 0.f, dual = 0.f;
-      if (out.path == CELL_FAILED) {
-        // "Update Lam Mu Fail": previous duals kept, residual inf (:791-793)
-        dual = INFINITY;
-        atomicOr(&d.status[c.b], RDA_ST_CELL_FALLBACK);
-      } else {
-        cell_store(d, c, out, &hm2, &dual);
-      }
-      atomicAdd(&d.resi_acc[2 * c.b], hm2);
-      atomicAdd(&d.resi_acc[2 * c.b + 1], dual);
-      atomicAdd(&d.counters[out.path == CELL_FAILED ? 2 : 1], 1);
+    CellOut<float> out;
+    cell_back<float>(rb, w, c.zeta, theta, out);
+    float hm2 = 0.f, dual = 0.f;
+    if (out.path == CELL_FAILED) {
+      // "Update Lam Mu Fail": previous duals kept, residual inf (:791-793)
+      dual = INFINITY;
+      atomicOr(&d.status[c.b], RDA_ST_CELL_FALLBACK);
+    } else {
+      cell_store(d, c, out, &hm2, &dual);
     }
-    __syncwarp();
+    atomicAdd(&d.resi_acc[2 * c.b], hm2);
+    atomicAdd(&d.resi_acc[2 * c.b + 1], dual);
+    atomicAdd(&d.counters[out.path == CELL_FAILED ? 2 : 1], 1);
   }
 }
 
@@ -577,7 +570,7 @@ int rda_step_lammuz(rda_handle* h, void* stream) {
     const float theta = h->cfg.accelerated ? h->tun.z_theta : 1.0f;
     k_cells_fast<<<grid_for((long long)h->B * h->N * h->T, 128), 128, 0, s>>>(d, h->rb, h->tun.ro2, theta);
     RDA_CUDA(cudaGetLastError());
-    k_cells_slow<<<148 * 8, 32 * SLOW_WARPS, 0, s>>>(d, h->rb, h->tun.ro2, theta);
+    k_cells_slow<<<148 * 16, 64, 0, s>>>(d, h->rb, h->tun.ro2, theta);
     RDA_CUDA(cudaGetLastError());
     h->launches += 2;
   }
