@@ -171,6 +171,7 @@ RDA_HD void cell_front(const RobotGeom& rb, int kind, int E, const float* A, con
   bool sep = false;
   Real best = 1e30f, bdx = 0, bdy = 0;
   Real byx = 0, byy = 0;            // robot-side point of the closest pair, body frame
+  int ce_i = -1, ce_j = -1;         // closest pair = (obstacle vertex i / disc, interior of robot edge j)
   Real dj2[RDA_MAX_ROBOT_EDGE], djx[RDA_MAX_ROBOT_EDGE], djy[RDA_MAX_ROBOT_EDGE];
   for (int j = 0; j < R; ++j) { dj2[j] = 1e30f; w.rob_in[j] = -1e30f; }
   if (kind == RDA_OBS_CIRCLE) {
@@ -187,6 +188,7 @@ RDA_HD void cell_front(const RobotGeom& rb, int kind, int E, const float* A, con
         best = d2; bdx = dx; bdy = dy;
         byx = (Real)rb.yx[j] + t * ((Real)rb.yx[jn] - (Real)rb.yx[j]);
         byy = (Real)rb.yy[j] + t * ((Real)rb.yy[jn] - (Real)rb.yy[j]);
+        ce_i = 0; ce_j = (t > (Real)0 && t < (Real)1) ? j : -1;
       }
       Real vx_ = g.yx[j] - g.cx, vy_ = g.yy[j] - g.cy;     // robot vertex minus centre
       Real dv = sqrt_(vx_ * vx_ + vy_ * vy_);
@@ -226,7 +228,7 @@ RDA_HD void cell_front(const RobotGeom& rb, int kind, int E, const float* A, con
       if (mins > eps) sep = true;
     }
     for (int j = 0; j < R; ++j)
-      if (dj2[j] < best) { best = dj2[j]; bdx = djx[j]; bdy = djy[j]; byx = rb.yx[j]; byy = rb.yy[j]; }
+      if (dj2[j] < best) { best = dj2[j]; bdx = djx[j]; bdy = djy[j]; byx = rb.yx[j]; byy = rb.yy[j]; ce_j = -1; }
     for (int j = 0; j < R; ++j) {
       int jn = (j + 1) % R;
       Real fx = g.yx[jn] - g.yx[j], fy = g.yy[jn] - g.yy[j];
@@ -244,6 +246,7 @@ RDA_HD void cell_front(const RobotGeom& rb, int kind, int E, const float* A, con
           best = d2; bdx = dx; bdy = dy;
           byx = (Real)rb.yx[j] + t * ((Real)rb.yx[jn] - (Real)rb.yx[j]);
           byy = (Real)rb.yy[j] + t * ((Real)rb.yy[jn] - (Real)rb.yy[j]);
+          ce_i = i; ce_j = (t > (Real)0 && t < (Real)1) ? j : -1;
         }
       }
       if (mins > eps) sep = true;
@@ -295,6 +298,186 @@ RDA_HD void cell_front(const RobotGeom& rb, int kind, int E, const float* A, con
       }
     }
   }
+  if (!have && sep && ce_j >= 0) {
+    // Robot-EDGE contact: the optimal body point lies in the interior of edge j, the obstacle point is
+    // the vertex (or disc centre) ce_i.  One-dimensional problem along the edge,
+    //    maximise  N(s)/W(s),  N = k0 - xi.y - rho(s),  W^2 = 1 + |y|^2/ro2   (W = 1: max-margin stage)
+    // solved by safeguarded Newton on h(s) = N' W^2 - N (y.f)/ro2, then accepted by the KKT conditions
+    // of the (convex) cell problem: multiplier of the edge >= 0 and v in the obstacle's normal cone.
+    const int j = ce_j, jn = (j + 1) % R;
+    const Real yjx = rb.yx[j], yjy = rb.yy[j];
+    const Real fx = (Real)rb.yx[jn] - yjx, fy = (Real)rb.yy[jn] - yjy;           // body frame
+    const Real wfx = cphi * fx - sphi * fy, wfy = sphi * fx + cphi * fy;         // R f
+    const Real ox = (kind == RDA_OBS_CIRCLE) ? g.cx : g.vx[ce_i], oy = (kind == RDA_OBS_CIRCLE) ? g.cy : g.vy[ce_i];
+    const Real rad = (kind == RDA_OBS_CIRCLE) ? g.rad : (Real)0;
+    const Real xf = xi0 * fx + xi1 * fy;
+    for (int stage = 0; stage < 2 && !have; ++stage) {
+      const bool weighted = stage == 1;
+      Real lo = 0, hi = 1, sc = (Real)0.5;
+      Real hv = 0, Nv = 0, W2 = 1, vx_ = 0, vy_ = 0, yx = 0, yy = 0;
+      bool bracket = true;
+      for (int itn = 0; itn < 24; ++itn) {
+        yx = yjx + sc * fx; yy = yjy + sc * fy;
+        const Real rx = (cphi * yx - sphi * yy) - ox, ry = (sphi * yx + cphi * yy) - oy;
+        const Real rn = sqrt_(rx * rx + ry * ry);
+        vx_ = rx / rn; vy_ = ry / rn;
+        Nv = k0 - (xi0 * yx + xi1 * yy) - (rn - rad);
+        const Real Np = -xf - (vx_ * wfx + vy_ * wfy);
+        const Real yf = yx * fx + yy * fy;
+        W2 = weighted ? (Real)1 + (yx * yx + yy * yy) / ro2 : (Real)1;
+        hv = weighted ? Np * W2 - Nv * yf / ro2 : Np;
+        if (itn == 0) {
+          // need a sign change of h on (0, 1): evaluate the ends once
+          Real h0, h1;
+          {
+            const Real ax = (cphi * yjx - sphi * yjy) - ox, ay = (sphi * yjx + cphi * yjy) - oy;
+            const Real an = sqrt_(ax * ax + ay * ay);
+            const Real Na = k0 - (xi0 * yjx + xi1 * yjy) - (an - rad);
+            const Real Npa = -xf - ((ax * wfx + ay * wfy) / an);
+            h0 = weighted ? Npa * ((Real)1 + (yjx * yjx + yjy * yjy) / ro2) - Na * (yjx * fx + yjy * fy) / ro2 : Npa;
+            const Real ex = (Real)rb.yx[jn], ey = (Real)rb.yy[jn];
+            const Real bx = (cphi * ex - sphi * ey) - ox, by = (sphi * ex + cphi * ey) - oy;
+            const Real bn = sqrt_(bx * bx + by * by);
+            const Real Nb = k0 - (xi0 * ex + xi1 * ey) - (bn - rad);
+            const Real Npb = -xf - ((bx * wfx + by * wfy) / bn);
+            h1 = weighted ? Npb * ((Real)1 + (ex * ex + ey * ey) / ro2) - Nb * (ex * fx + ey * fy) / ro2 : Npb;
+          }
+          if (!(h0 > 0 && h1 < 0)) { bracket = false; break; }
+        }
+        if (hv > 0) lo = sc; else hi = sc;
+        if (hi - lo < (sizeof(Real) == 4 ? (Real)2e-7 : (Real)1e-13)) break;
+        sc = (Real)0.5 * (lo + hi);
+      }
+      if (!bracket) continue;
+      // KKT of the cell problem at this point
+      const Real rvx = cphi * vx_ + sphi * vy_, rvy = -sphi * vx_ + cphi * vy_;   // R'v
+      const Real tolc = sizeof(Real) == 4 ? (Real)1e-5 : (Real)1e-11;
+      bool cone_ok = true;
+      if (kind != RDA_OBS_CIRCLE) {
+        const int ip = (ce_i + ne - 1) % ne, inx = (ce_i + 1) % ne;
+        const Real epx = g.vx[ce_i] - g.vx[ip], epy = g.vy[ce_i] - g.vy[ip];
+        const Real enx = g.vx[inx] - g.vx[ce_i], eny = g.vy[inx] - g.vy[ce_i];
+        cone_ok = (vx_ * epx + vy_ * epy >= -tolc * sqrt_(epx * epx + epy * epy)) &&
+                  (vx_ * enx + vy_ * eny <= tolc * sqrt_(enx * enx + eny * eny));
+      }
+      if (!cone_ok) continue;
+      if (!weighted) {
+        if (Nv <= 0) {   // max margin -N >= 0 with Hm + xi = 0: inactive
+          const Real cgx = -rvx - xi0, cgy = -rvy - xi1;
+          if (cgx * (Real)rb.nx[j] + cgy * (Real)rb.ny[j] >= -tolc) {
+            v0 = vx_; v1 = vy_; g0 = cgx; g1 = cgy;
+            exact_zero_q = true; have = true; path = CELL_FAST_VERTEX;
+          }
+        }
+      } else if (Nv > 0) {
+        const Real tau = Nv / W2;
+        const Real cgx = -tau * yx / ro2 - rvx - xi0, cgy = -tau * yy / ro2 - rvy - xi1;
+        if (cgx * (Real)rb.nx[j] + cgy * (Real)rb.ny[j] >= -tolc) {
+          v0 = vx_; v1 = vy_; g0 = cgx; g1 = cgy;
+          have = true; path = CELL_FAST_VERTEX;
+        }
+      }
+    }
+  }
+  if (!have && !sep && k0 > 0) {
+    // Deep overlap: the optimal contact point y = -ro2 xi / k0 lies inside the robot AND inside the
+    // obstacle; then v = 0, g = 0 (lam = mu = 0), tau = k0 and q = xi satisfy the KKT conditions.
+    const Real yx = -ro2 * xi0 / k0, yy = -ro2 * xi1 / k0;
+    bool inside = true;
+    for (int j = 0; j < R; ++j) {
+      const Real sd = (Real)rb.nx[j] * (yx - (Real)rb.yx[j]) + (Real)rb.ny[j] * (yy - (Real)rb.yy[j]);
+      if (sd > -eps) inside = false;
+    }
+    const Real wx = cphi * yx - sphi * yy, wy = sphi * yx + cphi * yy;
+    if (kind == RDA_OBS_CIRCLE) {
+      const Real dx = wx - g.cx, dy = wy - g.cy;
+      if (dx * dx + dy * dy > (g.rad - eps) * (g.rad - eps) || g.rad <= eps) inside = false;
+    } else {
+      for (int i = 0; i < ne; ++i) {
+        const Real sd = g.nx[i] * (wx - g.vx[i]) + g.ny[i] * (wy - g.vy[i]);
+        if (sd > -eps) inside = false;
+      }
+    }
+    if (inside) {
+      v0 = 0; v1 = 0; g0 = 0; g1 = 0;
+      exact_zero_q = false; have = true; path = CELL_OVERLAP_FREE;
+    }
+  }
+  if (!have && !sep) {
+    // Overlapping sets, contact point with zero distance.  Along a line y = p + s d (body frame) the
+    // weighted margin (k0 - xi.y)/sqrt(1 + |y|^2/ro2) has the closed-form stationary point
+    //    s* = -(beta a + alpha b)/(beta b + alpha c),  alpha = k0 - xi.p, beta = xi.d,
+    //    a = 1 + |p|^2/ro2, b = p.d/ro2, c = |d|^2/ro2.
+    const Real tolc = sizeof(Real) == 4 ? (Real)1e-5 : (Real)1e-11;
+    // (ii) y on robot edge j, P(y) strictly inside the obstacle: v = 0, g = gamma m_j
+    for (int j = 0; j < R && !have; ++j) {
+      const int jn = (j + 1) % R;
+      const Real px_ = rb.yx[j], py_ = rb.yy[j];
+      const Real dx_ = (Real)rb.yx[jn] - px_, dy_ = (Real)rb.yy[jn] - py_;
+      const Real al = k0 - (xi0 * px_ + xi1 * py_), be = xi0 * dx_ + xi1 * dy_;
+      const Real a_ = (Real)1 + (px_ * px_ + py_ * py_) / ro2, b_ = (px_ * dx_ + py_ * dy_) / ro2;
+      const Real c_ = (dx_ * dx_ + dy_ * dy_) / ro2;
+      const Real den = be * b_ + al * c_;
+      if (!(abs_(den) > (Real)1e-20)) continue;
+      const Real sst = -(be * a_ + al * b_) / den;
+      if (!(sst > tolc && sst < (Real)1 - tolc)) continue;
+      const Real yx = px_ + sst * dx_, yy = py_ + sst * dy_;
+      const Real Nv = k0 - (xi0 * yx + xi1 * yy);
+      if (!(Nv > 0)) continue;
+      const Real wx = cphi * yx - sphi * yy, wy = sphi * yx + cphi * yy;
+      bool inside = true;
+      if (kind == RDA_OBS_CIRCLE) {
+        const Real ex = wx - g.cx, ey = wy - g.cy;
+        inside = g.rad > eps && ex * ex + ey * ey < (g.rad - eps) * (g.rad - eps);
+      } else {
+        for (int i = 0; i < ne; ++i)
+          if (g.nx[i] * (wx - g.vx[i]) + g.ny[i] * (wy - g.vy[i]) > -eps) inside = false;
+      }
+      if (!inside) continue;
+      const Real tau = Nv / ((Real)1 + (yx * yx + yy * yy) / ro2);
+      const Real cgx = -tau * yx / ro2 - xi0, cgy = -tau * yy / ro2 - xi1;
+      if (cgx * (Real)rb.nx[j] + cgy * (Real)rb.ny[j] < -tolc) continue;
+      v0 = 0; v1 = 0; g0 = cgx; g1 = cgy;
+      have = true; path = CELL_OVERLAP_FREE;
+    }
+    // (iii) P(y) on obstacle edge i, y strictly inside the robot: g = 0, v = alpha n_i, 0 <= alpha <= 1
+    if (kind != RDA_OBS_CIRCLE) {
+      for (int i = 0; i < ne && !have; ++i) {
+        const int in = (i + 1) % ne;
+        const Real px_ = cphi * g.vx[i] + sphi * g.vy[i], py_ = -sphi * g.vx[i] + cphi * g.vy[i];   // R'V_i
+        const Real ex = g.vx[in] - g.vx[i], ey = g.vy[in] - g.vy[i];
+        const Real dx_ = cphi * ex + sphi * ey, dy_ = -sphi * ex + cphi * ey;
+        const Real al = k0 - (xi0 * px_ + xi1 * py_), be = xi0 * dx_ + xi1 * dy_;
+        const Real a_ = (Real)1 + (px_ * px_ + py_ * py_) / ro2, b_ = (px_ * dx_ + py_ * dy_) / ro2;
+        const Real c_ = (dx_ * dx_ + dy_ * dy_) / ro2;
+        const Real den = be * b_ + al * c_;
+        if (!(abs_(den) > (Real)1e-20)) continue;
+        const Real sst = -(be * a_ + al * b_) / den;
+        if (!(sst > tolc && sst < (Real)1 - tolc)) continue;
+        const Real yx = px_ + sst * dx_, yy = py_ + sst * dy_;
+        const Real Nv = k0 - (xi0 * yx + xi1 * yy);
+        if (!(Nv > 0)) continue;
+        bool inside = true;
+        for (int j = 0; j < R; ++j)
+          if ((Real)rb.nx[j] * (yx - (Real)rb.yx[j]) + (Real)rb.ny[j] * (yy - (Real)rb.yy[j]) > -eps) inside = false;
+        if (!inside) continue;
+        const Real tau = Nv / ((Real)1 + (yx * yx + yy * yy) / ro2);
+        const Real rx = -tau * yx / ro2 - xi0, ry = -tau * yy / ro2 - xi1;      // must equal R'v
+        const Real nbx = cphi * g.nx[i] + sphi * g.ny[i], nby = -sphi * g.nx[i] + cphi * g.ny[i];
+        const Real alpha = rx * nbx + ry * nby;
+        if (!(alpha >= -tolc && alpha <= (Real)1 + tolc)) continue;
+        const Real ac = rclamp(alpha, (Real)0, (Real)1);
+        v0 = ac * g.nx[i]; v1 = ac * g.ny[i]; g0 = 0; g1 = 0;
+        have = true; path = CELL_OVERLAP_FREE;
+      }
+    }
+  }
+#ifdef RDA_CELL_STATS
+  if (!have) {
+    extern long long g_cell_stats[8];
+    __sync_fetch_and_add(&g_cell_stats[(sep ? 0 : 2) + (xi_zero ? 0 : 1)], 1);
+  }
+#endif
   w.v0 = v0; w.v1 = v1; w.g0 = g0; w.g1 = g1;
   w.exact_zero_q = exact_zero_q; w.have = have; w.path = path;
 }

@@ -158,26 +158,14 @@ RDA_HD void su_riccati(const SuParams& P, SuWork<Real>& W, Ctx& ctx, bool factor
   // Riccati recursion of the Newton step (banded KKT system).  Stage t: state z = (s_t, u_{t-1}),
   // control v = (u_t, d_t); the stage cost is quadratic in q = (s_{t+1}, u_t, d_t) = J [z; v] with
   // J = [[A 0 B 0], [0 0 I 0], [0 0 0 1]] plus the rate-limit coupling between u_t and u_{t-1}.
-  // Factor pass: the matrix work of a stage is spread over the lanes entry by entry (Q = P+ + stage
-  // terms, T = Q J, H = J'T, K = -Hvv^-1 Hvz, P = Hzz + Hvz'K) with the blocks staged in shared
-  // memory (W.rw); the small vector recursion (cost-to-go gradient) is carried redundantly in
-  // registers by every lane.
+  // The sparsity of J is written out by hand (about 300 multiply-adds per stage).  Every lane
+  // runs the same recursion (no broadcast needed); lane 0 stores the gains.
   const int T = P.T;
-  const int lane = ctx.lane(), nl = ctx.nlanes();
   const Real reg = (Real)1e-9;
   const Real tw = 2 * (Real)P.ws, tw3 = (P.dynamics == RDA_DYN_OMNI ? (Real)0 : tw);
-  Real* Qs = W.rw;          // 36  Q[a*6+b]
-  Real* Ts = W.rw + 36;     // 18  t2[r], t5[r], t6[r]  (r = 0..5)
-  Real* Hz = W.rw + 54;     // 6   Hzz dense part: (0,0) (0,1) (1,1) (0,2) (1,2) (2,2)
-  Real* Hv = W.rw + 60;     // 15  Hvz[k*5+b]
-  Real* Hh = W.rw + 75;     // 6   Hvv: h00 h10 h11 h20 h21 h22
-  Real* Pm = W.rw + 81;     // 25  cost-to-go Hessian P[a*5+b]
-  Real pv[5] = {0, 0, 0, 0, 0};
-  const bool writer = lane == 0;
-  if (factor) {
-    for (int e = lane; e < 25; e += nl) Pm[e] = 0;
-    ctx.sync();
-  }
+  Real Pm[5][5], pv[5];
+  for (int a = 0; a < 5; ++a) { pv[a] = 0; for (int b = 0; b < 5; ++b) Pm[a][b] = 0; }
+  const bool writer = ctx.lane() == 0;
   for (int t = T - 1; t >= 0; --t) {
     const Real a02 = W.Aj[2 * t], a12 = W.Aj[2 * t + 1];
     const Real* Bt = W.Bj + 6 * t;
@@ -193,123 +181,76 @@ RDA_HD void su_riccati(const SuParams& P, SuWork<Real>& W, Ctx& ctx, bool factor
     const Real gv1 = b01 * q0 + b11 * q1 + b21 * q2 + q4;
     const Real gv2 = q5;
     Real i00, L10, i11, L20, L21, i22;   // Cholesky of Hvv, reciprocal diagonal
-    Real* Kt = W.K + 15 * t;             // K[k*5+b]
+    Real Kt[3][5];
     if (factor) {
+      Real Q[6][6];
+      for (int a = 0; a < 5; ++a) { for (int b = 0; b < 5; ++b) Q[a][b] = Pm[a][b]; Q[a][5] = 0; Q[5][a] = 0; }
       const Real* M = W.Wm + 6 * t;
-      // S1: Q = P+ (5x5, zero-padded) + stage terms
-      for (int e = lane; e < 36; e += nl) {
-        const int a = e / 6, b = e - 6 * a;
-        Real v = (a < 5 && b < 5) ? Pm[a * 5 + b] : (Real)0;
-        if (a == b) {
-          if (a == 0) v += tw + M[0];
-          else if (a == 1) v += tw + M[3];
-          else if (a == 2) v += tw3 + (Real)P.ro2 * W.Skk[t];
-          else if (a == 3) v += 2 * (Real)P.wu + reg + wb[0] + wr0;
-          else if (a == 4) v += reg + wb[1] + wr1;
-          else v = (P.N > 0 ? reg + wb[2] + M[5] : (Real)1);
-        } else {
-          const int lo = a < b ? a : b, hi = a < b ? b : a;
-          if (lo == 0 && hi == 1) v += M[1];
-          else if (lo == 0 && hi == 5) v = M[2];
-          else if (lo == 1 && hi == 5) v = M[4];
-        }
-        Qs[e] = v;
+      Q[0][0] += tw + M[0]; Q[0][1] += M[1]; Q[1][0] += M[1]; Q[0][5] = M[2]; Q[5][0] = M[2];
+      Q[1][1] += tw + M[3]; Q[1][5] = M[4]; Q[5][1] = M[4];
+      Q[2][2] += tw3 + (Real)P.ro2 * W.Skk[t];
+      Q[3][3] += 2 * (Real)P.wu + reg + wb[0] + wr0;
+      Q[4][4] += reg + wb[1] + wr1;
+      Q[5][5] = (P.N > 0 ? reg + wb[2] + M[5] : (Real)1);
+      // T1 = Q J for the columns of J that are not unit vectors
+      Real t2[6], t5[6], t6[6];
+      for (int r = 0; r < 6; ++r) {
+        t2[r] = a02 * Q[r][0] + a12 * Q[r][1] + Q[r][2];
+        t5[r] = b00 * Q[r][0] + b10 * Q[r][1] + b20 * Q[r][2] + Q[r][3];
+        t6[r] = b01 * Q[r][0] + b11 * Q[r][1] + b21 * Q[r][2] + Q[r][4];
       }
-      ctx.sync();
-      // S2: T = Q J for the three columns of J that are not unit vectors
-      for (int e = lane; e < 18; e += nl) {
-        const int c = e / 6, r = e - 6 * c;
-        const Real* Qr = Qs + 6 * r;
-        Real v;
-        if (c == 0) v = a02 * Qr[0] + a12 * Qr[1] + Qr[2];
-        else if (c == 1) v = b00 * Qr[0] + b10 * Qr[1] + b20 * Qr[2] + Qr[3];
-        else v = b01 * Qr[0] + b11 * Qr[1] + b21 * Qr[2] + Qr[4];
-        Ts[e] = v;
-      }
-      ctx.sync();
-      // S3: H = J'T (27 entries: 6 of Hzz, 15 of Hvz, 6 of Hvv)
-      for (int e = lane; e < 27; e += nl) {
-        const Real* t2 = Ts; const Real* t5 = Ts + 6; const Real* t6 = Ts + 12;
 #define RDA_J2(x) (a02 * (x)[0] + a12 * (x)[1] + (x)[2])
 #define RDA_J5(x) (b00 * (x)[0] + b10 * (x)[1] + b20 * (x)[2] + (x)[3])
 #define RDA_J6(x) (b01 * (x)[0] + b11 * (x)[1] + b21 * (x)[2] + (x)[4])
-        Real v;
-        switch (e) {
-          case 0: v = Qs[0]; break;               // Hzz(0,0)
-          case 1: v = Qs[1]; break;               // Hzz(0,1)
-          case 2: v = Qs[7]; break;               // Hzz(1,1)
-          case 3: v = t2[0]; break;               // Hzz(0,2)
-          case 4: v = t2[1]; break;               // Hzz(1,2)
-          case 5: v = RDA_J2(t2); break;          // Hzz(2,2)
-          case 6: v = t5[0]; break;               // Hvz(0,0..4)
-          case 7: v = t5[1]; break;
-          case 8: v = RDA_J2(t5); break;
-          case 9: v = -wr0; break;
-          case 10: v = 0; break;
-          case 11: v = t6[0]; break;              // Hvz(1,0..4)
-          case 12: v = t6[1]; break;
-          case 13: v = RDA_J2(t6); break;
-          case 14: v = 0; break;
-          case 15: v = -wr1; break;
-          case 16: v = Qs[30]; break;             // Hvz(2,0..4): row 5 of Q
-          case 17: v = Qs[31]; break;
-          case 18: v = RDA_J2(Qs + 30); break;
-          case 19: v = 0; break;
-          case 20: v = 0; break;
-          case 21: v = RDA_J5(t5); break;         // h00
-          case 22: v = RDA_J6(t5); break;         // h10
-          case 23: v = RDA_J6(t6); break;         // h11
-          case 24: v = t5[5]; break;              // h20
-          case 25: v = t6[5]; break;              // h21
-          default: v = Qs[35]; break;             // h22
-        }
+      // Hzz (rows/cols 0..2 dense, 3..4 only the rate terms)
+      Real Hzz[5][5];
+      for (int a = 0; a < 5; ++a) for (int b = 0; b < 5; ++b) Hzz[a][b] = 0;
+      Hzz[0][0] = Q[0][0]; Hzz[0][1] = Q[0][1]; Hzz[1][1] = Q[1][1];
+      Hzz[0][2] = t2[0]; Hzz[1][2] = t2[1]; Hzz[2][2] = RDA_J2(t2);
+      Hzz[1][0] = Hzz[0][1]; Hzz[2][0] = Hzz[0][2]; Hzz[2][1] = Hzz[1][2];
+      Hzz[3][3] = wr0; Hzz[4][4] = wr1;
+      // Hvz (3 x 5)
+      Real Hvz[3][5];
+      Hvz[0][0] = t5[0]; Hvz[0][1] = t5[1]; Hvz[0][2] = RDA_J2(t5); Hvz[0][3] = -wr0; Hvz[0][4] = 0;
+      Hvz[1][0] = t6[0]; Hvz[1][1] = t6[1]; Hvz[1][2] = RDA_J2(t6); Hvz[1][3] = 0; Hvz[1][4] = -wr1;
+      Hvz[2][0] = Q[5][0]; Hvz[2][1] = Q[5][1]; Hvz[2][2] = RDA_J2(Q[5]); Hvz[2][3] = 0; Hvz[2][4] = 0;
+      // Hvv (3 x 3)
+      const Real h00 = RDA_J5(t5), h10 = RDA_J6(t5), h11 = RDA_J6(t6), h20 = t5[5], h21 = t6[5], h22 = Q[5][5];
 #undef RDA_J2
 #undef RDA_J5
 #undef RDA_J6
-        if (e < 6) Hz[e] = v;
-        else if (e < 21) Hv[e - 6] = v;
-        else Hh[e - 21] = v;
-      }
-      ctx.sync();
-      // S4: Cholesky of Hvv (every lane, registers)
-      const Real L00 = sqrt_(Hh[0]);
+      const Real L00 = sqrt_(h00);
       i00 = (Real)1 / L00;
-      L10 = Hh[1] * i00;
-      const Real L11 = sqrt_(Hh[2] - L10 * L10);
+      L10 = h10 * i00;
+      const Real L11 = sqrt_(h11 - L10 * L10);
       i11 = (Real)1 / L11;
-      L20 = Hh[3] * i00;
-      L21 = (Hh[4] - L20 * L10) * i11;
-      const Real L22 = sqrt_(Hh[5] - L20 * L20 - L21 * L21);
+      L20 = h20 * i00;
+      L21 = (h21 - L20 * L10) * i11;
+      const Real L22 = sqrt_(h22 - L20 * L20 - L21 * L21);
       i22 = (Real)1 / L22;
-      // S5: K = -Hvv^-1 Hvz, one column per lane
-      for (int b = lane; b < 5; b += nl) {
-        Real y0 = -Hv[b] * i00;
-        Real y1 = (-Hv[5 + b] - L10 * y0) * i11;
-        Real y2 = (-Hv[10 + b] - L20 * y0 - L21 * y1) * i22;
+      for (int b = 0; b < 5; ++b) {
+        Real y0 = -Hvz[0][b] * i00;
+        Real y1 = (-Hvz[1][b] - L10 * y0) * i11;
+        Real y2 = (-Hvz[2][b] - L20 * y0 - L21 * y1) * i22;
         Real x2 = y2 * i22;
         Real x1 = (y1 - L21 * x2) * i11;
         Real x0 = (y0 - L10 * x1 - L20 * x2) * i00;
-        Kt[b] = x0; Kt[5 + b] = x1; Kt[10 + b] = x2;
+        Kt[0][b] = x0; Kt[1][b] = x1; Kt[2][b] = x2;
       }
+      for (int a = 0; a < 5; ++a)
+        for (int b = a; b < 5; ++b) {
+          Real v = Hzz[a][b] + Hvz[0][a] * Kt[0][b] + Hvz[1][a] * Kt[1][b] + Hvz[2][a] * Kt[2][b];
+          Pm[a][b] = v; Pm[b][a] = v;
+        }
       if (writer) {
         Real* Ls = W.Lc + 6 * t;
         Ls[0] = i00; Ls[1] = L10; Ls[2] = i11; Ls[3] = L20; Ls[4] = L21; Ls[5] = i22;
+        for (int k = 0; k < 3; ++k) for (int b = 0; b < 5; ++b) W.K[15 * t + 5 * k + b] = Kt[k][b];
       }
-      ctx.sync();
-      // S6: P = Hzz + Hvz'K (25 entries)
-      for (int e = lane; e < 25; e += nl) {
-        const int a = e / 5, b = e - 5 * a;
-        const int lo = a < b ? a : b, hi = a < b ? b : a;
-        Real hzz = 0;
-        if (hi < 3) hzz = Hz[lo == 0 ? (hi == 0 ? 0 : hi == 1 ? 1 : 3) : lo == 1 ? (hi == 1 ? 2 : 4) : 5];
-        else if (lo == hi) hzz = (hi == 3 ? wr0 : wr1);
-        // symmetric evaluation: use (lo, hi) ordering so both triangles get identical values
-        Pm[e] = hzz + Hv[lo] * Kt[hi] + Hv[5 + lo] * Kt[5 + hi] + Hv[10 + lo] * Kt[10 + hi];
-      }
-      ctx.sync();
     } else {
       const Real* Ls = W.Lc + 6 * t;
       i00 = Ls[0]; L10 = Ls[1]; i11 = Ls[2]; L20 = Ls[3]; L21 = Ls[4]; i22 = Ls[5];
+      for (int k = 0; k < 3; ++k) for (int b = 0; b < 5; ++b) Kt[k][b] = W.K[15 * t + 5 * k + b];
     }
     {
       Real y0 = -gv0 * i00;
@@ -319,11 +260,11 @@ RDA_HD void su_riccati(const SuParams& P, SuWork<Real>& W, Ctx& ctx, bool factor
       Real x1 = (y1 - L21 * x2) * i11;
       Real x0 = (y0 - L10 * x1 - L20 * x2) * i00;
       if (writer) { W.kf[3 * t] = x0; W.kf[3 * t + 1] = x1; W.kf[3 * t + 2] = x2; }
-      pv[0] = gz0 + Kt[0] * gv0 + Kt[5] * gv1 + Kt[10] * gv2;
-      pv[1] = gz1 + Kt[1] * gv0 + Kt[6] * gv1 + Kt[11] * gv2;
-      pv[2] = gz2 + Kt[2] * gv0 + Kt[7] * gv1 + Kt[12] * gv2;
-      pv[3] = gz3 + Kt[3] * gv0 + Kt[8] * gv1 + Kt[13] * gv2;
-      pv[4] = gz4 + Kt[4] * gv0 + Kt[9] * gv1 + Kt[14] * gv2;
+      pv[0] = gz0 + Kt[0][0] * gv0 + Kt[1][0] * gv1 + Kt[2][0] * gv2;
+      pv[1] = gz1 + Kt[0][1] * gv0 + Kt[1][1] * gv1 + Kt[2][1] * gv2;
+      pv[2] = gz2 + Kt[0][2] * gv0 + Kt[1][2] * gv1 + Kt[2][2] * gv2;
+      pv[3] = gz3 + Kt[0][3] * gv0 + Kt[1][3] * gv1 + Kt[2][3] * gv2;
+      pv[4] = gz4 + Kt[0][4] * gv0 + Kt[1][4] * gv1 + Kt[2][4] * gv2;
     }
   }
   ctx.sync();
@@ -415,10 +356,10 @@ RDA_HD int su_solve(const SuParams& P, SuWork<Real>& W, Ctx& ctx, const float* g
   }
   const Real Mrows = ctx.sum((Real)nrows);
   ctx.sync();
-  const Real tol_mu = sizeof(Real) == 4 ? (Real)1e-6 : (Real)1e-10;
+  const Real tol_mu = sizeof(Real) == 4 ? (Real)1e-6 : (Real)1e-9;
   const Real tol_r = sizeof(Real) == 4 ? (Real)1e-5 : (Real)1e-9;
   const Real reg = (Real)1e-9;
-  const Real tol_step = sizeof(Real) == 4 ? (Real)2e-4 : (Real)1e-7;
+  const Real tol_step = sizeof(Real) == 4 ? (Real)2e-4 : (Real)1e-6;
   const Real tol_floor = sizeof(Real) == 4 ? (Real)1e-7 : (Real)1e-13;
   Real last_step = 1e30f;       // size of the previous Newton update (stationarity proxy)
   int status = 1, it = 0;
