@@ -172,6 +172,8 @@ RDA_HD void cell_front(const RobotGeom& rb, int kind, int E, const float* A, con
   Real best = 1e30f, bdx = 0, bdy = 0;
   Real byx = 0, byy = 0;            // robot-side point of the closest pair, body frame
   int ce_i = -1, ce_j = -1;         // closest pair = (obstacle vertex i / disc, interior of robot edge j)
+  int ei_of[RDA_MAX_ROBOT_EDGE];    // per robot edge: nearest obstacle vertex
+  for (int j = 0; j < R; ++j) ei_of[j] = 0;
   Real dj2[RDA_MAX_ROBOT_EDGE], djx[RDA_MAX_ROBOT_EDGE], djy[RDA_MAX_ROBOT_EDGE];
   for (int j = 0; j < R; ++j) { dj2[j] = 1e30f; w.rob_in[j] = -1e30f; }
   if (kind == RDA_OBS_CIRCLE) {
@@ -233,7 +235,7 @@ RDA_HD void cell_front(const RobotGeom& rb, int kind, int E, const float* A, con
       int jn = (j + 1) % R;
       Real fx = g.yx[jn] - g.yx[j], fy = g.yy[jn] - g.yy[j];
       Real if2 = (Real)1 / (fx * fx + fy * fy);
-      Real mins = 1e30f;
+      Real mins = 1e30f, ebest = 1e30f;
       for (int i = 0; i < ne; ++i) {
         Real rx = g.vx[i] - g.yx[j], ry = g.vy[i] - g.yy[j];
         Real sd = g.mx[j] * rx + g.my[j] * ry;
@@ -242,6 +244,7 @@ RDA_HD void cell_front(const RobotGeom& rb, int kind, int E, const float* A, con
         Real t = rclamp((rx * fx + ry * fy) * if2, (Real)0, (Real)1);
         Real dx = -(rx - t * fx), dy = -(ry - t * fy);
         Real d2 = dx * dx + dy * dy;
+        if (d2 < ebest && sd > 0) { ebest = d2; ei_of[j] = i; }
         if (d2 < best) {
           best = d2; bdx = dx; bdy = dy;
           byx = (Real)rb.yx[j] + t * ((Real)rb.yx[jn] - (Real)rb.yx[j]);
@@ -298,7 +301,11 @@ RDA_HD void cell_front(const RobotGeom& rb, int kind, int E, const float* A, con
       }
     }
   }
-  if (!have && sep && ce_j >= 0) {
+  for (int ecand = 0; ecand <= R && !have; ++ecand) {
+    // candidate edges: the closest pair's edge (disjoint sets); for overlapping sets every robot edge
+    // with the nearest obstacle vertex in front of it
+    if (ecand == 0) { if (!sep || ce_j < 0) continue; }
+    else { if (kind == RDA_OBS_CIRCLE) break; ce_j = ecand - 1; ce_i = ei_of[ce_j]; }
     // Robot-EDGE contact: the optimal body point lies in the interior of edge j, the obstacle point is
     // the vertex (or disc centre) ce_i.  One-dimensional problem along the edge,
     //    maximise  N(s)/W(s),  N = k0 - xi.y - rho(s),  W^2 = 1 + |y|^2/ro2   (W = 1: max-margin stage)
@@ -311,47 +318,54 @@ RDA_HD void cell_front(const RobotGeom& rb, int kind, int E, const float* A, con
     const Real ox = (kind == RDA_OBS_CIRCLE) ? g.cx : g.vx[ce_i], oy = (kind == RDA_OBS_CIRCLE) ? g.cy : g.vy[ce_i];
     const Real rad = (kind == RDA_OBS_CIRCLE) ? g.rad : (Real)0;
     const Real xf = xi0 * fx + xi1 * fy;
+    Real sA = -1;                    // maximiser of the unweighted margin N along the edge (stage A)
     for (int stage = 0; stage < 2 && !have; ++stage) {
       const bool weighted = stage == 1;
-      Real lo = 0, hi = 1, sc = (Real)0.5;
       Real hv = 0, Nv = 0, W2 = 1, vx_ = 0, vy_ = 0, yx = 0, yy = 0;
-      bool bracket = true;
-      for (int itn = 0; itn < 24; ++itn) {
+      // h(s) = d/ds of N/W (times W^3): N' W^2 - N (y.f)/ro2;  unweighted: N'
+      auto eval = [&](Real sc) {
         yx = yjx + sc * fx; yy = yjy + sc * fy;
         const Real rx = (cphi * yx - sphi * yy) - ox, ry = (sphi * yx + cphi * yy) - oy;
         const Real rn = sqrt_(rx * rx + ry * ry);
         vx_ = rx / rn; vy_ = ry / rn;
         Nv = k0 - (xi0 * yx + xi1 * yy) - (rn - rad);
         const Real Np = -xf - (vx_ * wfx + vy_ * wfy);
-        const Real yf = yx * fx + yy * fy;
         W2 = weighted ? (Real)1 + (yx * yx + yy * yy) / ro2 : (Real)1;
-        hv = weighted ? Np * W2 - Nv * yf / ro2 : Np;
-        if (itn == 0) {
-          // need a sign change of h on (0, 1): evaluate the ends once
-          Real h0, h1;
-          {
-            const Real ax = (cphi * yjx - sphi * yjy) - ox, ay = (sphi * yjx + cphi * yjy) - oy;
-            const Real an = sqrt_(ax * ax + ay * ay);
-            const Real Na = k0 - (xi0 * yjx + xi1 * yjy) - (an - rad);
-            const Real Npa = -xf - ((ax * wfx + ay * wfy) / an);
-            h0 = weighted ? Npa * ((Real)1 + (yjx * yjx + yjy * yjy) / ro2) - Na * (yjx * fx + yjy * fy) / ro2 : Npa;
-            const Real ex = (Real)rb.yx[jn], ey = (Real)rb.yy[jn];
-            const Real bx = (cphi * ex - sphi * ey) - ox, by = (sphi * ex + cphi * ey) - oy;
-            const Real bn = sqrt_(bx * bx + by * by);
-            const Real Nb = k0 - (xi0 * ex + xi1 * ey) - (bn - rad);
-            const Real Npb = -xf - ((bx * wfx + by * wfy) / bn);
-            h1 = weighted ? Npb * ((Real)1 + (ex * ex + ey * ey) / ro2) - Nb * (ex * fx + ey * fy) / ro2 : Npb;
-          }
-          if (!(h0 > 0 && h1 < 0)) { bracket = false; break; }
+        hv = weighted ? Np * W2 - Nv * (yx * fx + yy * fy) / ro2 : Np;
+      };
+      Real lo = 0, hi = 1;
+      int dir = 0;                   // weighted stage: which side of sA the maximiser lies on
+      bool bracket = true;
+      if (!weighted) {
+        eval((Real)0); const Real h0 = hv;
+        eval((Real)1); const Real h1 = hv;
+        if (!(h0 > 0 && h1 < 0)) bracket = false;      // N has no interior maximum on this edge
+      } else {
+        if (!(sA > 0)) { bracket = false; }
+        else {
+          eval(sA);
+          if (!(Nv > 0)) bracket = false;              // hinge cannot be active with contact on this edge
+          else if (hv > 0) { dir = 1; lo = sA; hi = 1; eval((Real)1); if (Nv > 0 && hv > 0) bracket = false; }
+          else { dir = -1; lo = 0; hi = sA; eval((Real)0); if (Nv > 0 && hv < 0) bracket = false; }
         }
-        if (hv > 0) lo = sc; else hi = sc;
-        if (hi - lo < (sizeof(Real) == 4 ? (Real)2e-7 : (Real)1e-13)) break;
-        sc = (Real)0.5 * (lo + hi);
+      }
+      if (bracket) {
+        for (int itn = 0; itn < 26; ++itn) {
+          const Real sc = (Real)0.5 * (lo + hi);
+          eval(sc);
+          // outside the region N > 0 the ratio N/W is not quasi-concave: steer back towards sA
+          const bool pos = weighted ? (Nv > 0 ? hv > 0 : dir < 0) : hv > 0;
+          if (pos) lo = sc; else hi = sc;
+          if (hi - lo < (sizeof(Real) == 4 ? (Real)2e-7 : (Real)1e-13)) break;
+        }
+        eval((Real)0.5 * (lo + hi));
+        if (!weighted) sA = (Real)0.5 * (lo + hi);
       }
       if (!bracket) continue;
       // KKT of the cell problem at this point
       const Real rvx = cphi * vx_ + sphi * vy_, rvy = -sphi * vx_ + cphi * vy_;   // R'v
       const Real tolc = sizeof(Real) == 4 ? (Real)1e-5 : (Real)1e-11;
+      const Real tole = sizeof(Real) == 4 ? (Real)3e-5 : (Real)1e-9;   // tangential residual of g on the edge
       bool cone_ok = true;
       if (kind != RDA_OBS_CIRCLE) {
         const int ip = (ce_i + ne - 1) % ne, inx = (ce_i + 1) % ne;
@@ -364,7 +378,9 @@ RDA_HD void cell_front(const RobotGeom& rb, int kind, int E, const float* A, con
       if (!weighted) {
         if (Nv <= 0) {   // max margin -N >= 0 with Hm + xi = 0: inactive
           const Real cgx = -rvx - xi0, cgy = -rvy - xi1;
-          if (cgx * (Real)rb.nx[j] + cgy * (Real)rb.ny[j] >= -tolc) {
+          // g must be a non-negative multiple of the edge normal: no tangential component left
+          const Real tang = abs_(cgx * fx + cgy * fy) * rsqrt_(fx * fx + fy * fy);
+          if (cgx * (Real)rb.nx[j] + cgy * (Real)rb.ny[j] >= -tolc && tang <= tole) {
             v0 = vx_; v1 = vy_; g0 = cgx; g1 = cgy;
             exact_zero_q = true; have = true; path = CELL_FAST_VERTEX;
           }
@@ -372,7 +388,8 @@ RDA_HD void cell_front(const RobotGeom& rb, int kind, int E, const float* A, con
       } else if (Nv > 0) {
         const Real tau = Nv / W2;
         const Real cgx = -tau * yx / ro2 - rvx - xi0, cgy = -tau * yy / ro2 - rvy - xi1;
-        if (cgx * (Real)rb.nx[j] + cgy * (Real)rb.ny[j] >= -tolc) {
+        const Real tang = abs_(cgx * fx + cgy * fy) * rsqrt_(fx * fx + fy * fy);
+        if (cgx * (Real)rb.nx[j] + cgy * (Real)rb.ny[j] >= -tolc && tang <= tole) {
           v0 = vx_; v1 = vy_; g0 = cgx; g1 = cgy;
           have = true; path = CELL_FAST_VERTEX;
         }
@@ -469,6 +486,58 @@ RDA_HD void cell_front(const RobotGeom& rb, int kind, int E, const float* A, con
         const Real ac = rclamp(alpha, (Real)0, (Real)1);
         v0 = ac * g.nx[i]; v1 = ac * g.ny[i]; g0 = 0; g1 = 0;
         have = true; path = CELL_OVERLAP_FREE;
+      }
+      // (iv) obstacle vertex i strictly inside the robot: y = R'V_i, g = 0, v = R(-tau y/ro2 - xi) must lie
+      //      in the normal cone of the vertex with |v| <= 1
+      for (int i = 0; i < ne && !have; ++i) {
+        if (!(w.obs_in[i] < -eps)) continue;
+        const Real yx = cphi * g.vx[i] + sphi * g.vy[i], yy = -sphi * g.vx[i] + cphi * g.vy[i];
+        const Real Nv = k0 - (xi0 * yx + xi1 * yy);
+        if (!(Nv > 0)) continue;
+        const Real tau = Nv / ((Real)1 + (yx * yx + yy * yy) / ro2);
+        const Real rx = -tau * yx / ro2 - xi0, ry = -tau * yy / ro2 - xi1;
+        const Real vx_ = cphi * rx - sphi * ry, vy_ = sphi * rx + cphi * ry;          // v = R r
+        if (vx_ * vx_ + vy_ * vy_ > (Real)1 + tolc) continue;
+        const int ip = (i + ne - 1) % ne, in = (i + 1) % ne;
+        const Real epx = g.vx[i] - g.vx[ip], epy = g.vy[i] - g.vy[ip];
+        const Real enx = g.vx[in] - g.vx[i], eny = g.vy[in] - g.vy[i];
+        if (vx_ * epx + vy_ * epy < -tolc * sqrt_(epx * epx + epy * epy)) continue;
+        if (vx_ * enx + vy_ * eny > tolc * sqrt_(enx * enx + eny * eny)) continue;
+        v0 = vx_; v1 = vy_; g0 = 0; g1 = 0;
+        have = true; path = CELL_OVERLAP_FREE;
+      }
+      // (v) crossing of robot edge j and obstacle edge i: y fixed, g = gamma m_j, v = alpha n_i with
+      //     gamma m_j + alpha R'n_i = -tau y/ro2 - xi  (2 x 2 linear system), gamma >= 0, 0 <= alpha <= 1
+      for (int j = 0; j < R && !have; ++j) {
+        const int jn = (j + 1) % R;
+        const Real ax_ = g.yx[j], ay_ = g.yy[j];
+        const Real fx_ = g.yx[jn] - ax_, fy_ = g.yy[jn] - ay_;                        // world frame
+        for (int i = 0; i < ne && !have; ++i) {
+          const int in = (i + 1) % ne;
+          const Real ex = g.vx[in] - g.vx[i], ey = g.vy[in] - g.vy[i];
+          const Real det = fx_ * ey - fy_ * ex;
+          if (!(abs_(det) > (Real)1e-12)) continue;
+          const Real wx_ = g.vx[i] - ax_, wy_ = g.vy[i] - ay_;
+          const Real sr = (wx_ * ey - wy_ * ex) / det;          // along the robot edge
+          const Real so_ = (wx_ * fy_ - wy_ * fx_) / det;       // along the obstacle edge
+          if (!(sr > tolc && sr < (Real)1 - tolc && so_ > tolc && so_ < (Real)1 - tolc)) continue;
+          const Real yx = (Real)rb.yx[j] + sr * ((Real)rb.yx[jn] - (Real)rb.yx[j]);
+          const Real yy = (Real)rb.yy[j] + sr * ((Real)rb.yy[jn] - (Real)rb.yy[j]);
+          const Real Nv = k0 - (xi0 * yx + xi1 * yy);
+          if (!(Nv > 0)) continue;
+          const Real tau = Nv / ((Real)1 + (yx * yx + yy * yy) / ro2);
+          const Real rx = -tau * yx / ro2 - xi0, ry = -tau * yy / ro2 - xi1;
+          const Real mjx = rb.nx[j], mjy = rb.ny[j];
+          const Real nbx = cphi * g.nx[i] + sphi * g.ny[i], nby = -sphi * g.nx[i] + cphi * g.ny[i];
+          const Real d2 = mjx * nby - mjy * nbx;
+          if (!(abs_(d2) > (Real)1e-9)) continue;
+          const Real gam = (rx * nby - ry * nbx) / d2;
+          const Real alp = (mjx * ry - mjy * rx) / d2;
+          if (!(gam >= -tolc && alp >= -tolc && alp <= (Real)1 + tolc)) continue;
+          const Real ac = rclamp(alp, (Real)0, (Real)1), gc = rmax(gam, (Real)0);
+          v0 = ac * g.nx[i]; v1 = ac * g.ny[i]; g0 = gc * mjx; g1 = gc * mjy;
+          have = true; path = CELL_OVERLAP_FREE;
+        }
       }
     }
   }
