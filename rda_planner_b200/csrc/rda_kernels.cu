@@ -24,6 +24,7 @@ struct rda_handle {
   float *lam, *mu, *z, *xi, *zeta, *dis, *coef, *pref, *cur_s, *cur_u, *ref_s, *ref_speed;
   float *resi_acc, *resi_pri, *resi_dual;
   int *status, *iters, *done, *counters, *worklist;
+  double* su_scratch;    // [B][2][N*T] hinge slack / multiplier of the su-QP interior point iteration
   const float *obs_A, *obs_b;
   const int *obs_kind, *obs_count;
   int obs_tv;
@@ -59,6 +60,7 @@ struct DevPtrs {
   float *lam, *mu, *z, *xi, *zeta, *dis, *coef, *pref, *cur_s, *cur_u, *ref_s, *ref_speed;
   float *resi_acc, *resi_pri, *resi_dual;
   int *status, *iters, *done, *counters, *worklist;
+  double* su_scratch;
   const float *obs_A, *obs_b;
   const int *obs_kind, *obs_count;
   int obs_tv;
@@ -96,7 +98,7 @@ __global__ void __launch_bounds__(32) k_su(DevPtrs d, SuParams P) {
   const int T = P.T, N = P.N, NT = N * T;
   const int lane = threadIdx.x;
   SuWork<Real> W;
-  su_work_layout<Real>(T, N, &W, smem);
+  su_work_layout<Real>(T, N, &W, smem, false);
   const float* cs = d.cur_s + (size_t)b * 3 * (T + 1);   // [3][T+1]
   const float* cu = d.cur_u + (size_t)b * 2 * T;         // [2][T]
   const float* rf = d.ref_s + (size_t)b * 3 * (T + 1);
@@ -111,12 +113,12 @@ __global__ void __launch_bounds__(32) k_su(DevPtrs d, SuParams P) {
     W.pref[2 * t + r] = d.pref[(size_t)b * 2 * T + i];
   }
   for (int t = lane; t < T; t += 32) W.d[t] = d.dis[(size_t)b * T + t];
-  const float* cf = d.coef + (size_t)b * 5 * NT;
-  for (int i = lane; i < NT; i += 32) {
-    W.hx[i] = cf[i];
-    W.hy[i] = cf[NT + i];
-    W.hc[i] = cf[2 * NT + i];
-  }
+  // per-hinge data stays in global memory (L2): every entry is touched only by the lane that owns
+  // its stage, consecutive lanes read consecutive addresses
+  float* cf = d.coef + (size_t)b * 5 * NT;
+  W.hx = cf; W.hy = cf + NT; W.hc = cf + 2 * NT;
+  W.hs = (Real*)(d.su_scratch + (size_t)b * 2 * NT);
+  W.hnu = W.hs + NT;
   W.vref = d.ref_speed[b];
   __syncwarp();
   WarpCtx ctx;
@@ -404,7 +406,7 @@ DevPtrs dev_ptrs(const rda_handle* h) {
   d.lam = h->lam; d.mu = h->mu; d.z = h->z; d.xi = h->xi; d.zeta = h->zeta; d.dis = h->dis;
   d.coef = h->coef; d.pref = h->pref; d.cur_s = h->cur_s; d.cur_u = h->cur_u; d.ref_s = h->ref_s;
   d.ref_speed = h->ref_speed; d.resi_acc = h->resi_acc; d.resi_pri = h->resi_pri; d.resi_dual = h->resi_dual;
-  d.status = h->status; d.iters = h->iters; d.done = h->done; d.counters = h->counters; d.worklist = h->worklist;
+  d.status = h->status; d.iters = h->iters; d.done = h->done; d.counters = h->counters; d.worklist = h->worklist; d.su_scratch = h->su_scratch;
   d.obs_A = h->obs_A; d.obs_b = h->obs_b; d.obs_kind = h->obs_kind; d.obs_count = h->obs_count;
   d.obs_tv = h->obs_tv;
   d.B = h->B; d.T = h->T; d.N = h->N; d.E = h->E; d.R = h->R;
@@ -453,8 +455,8 @@ int rda_create(const rda_config* cfg, const rda_tunables* tun, rda_handle** out)
   h->B = cfg->batch; h->T = cfg->receding; h->N = cfg->max_obs_num; h->E = cfg->max_edge_num;
   h->R = cfg->robot_edges;
   const size_t B = h->B, T = h->T, N = h->N, E = h->E, R = h->R, NT = N * T;
-  h->su_smem = cfg->su_fp64 ? su_work_layout<double>((int)T, (int)N, nullptr, nullptr)
-                            : su_work_layout<float>((int)T, (int)N, nullptr, nullptr);
+  h->su_smem = cfg->su_fp64 ? su_work_layout<double>((int)T, (int)N, nullptr, nullptr, false)
+                            : su_work_layout<float>((int)T, (int)N, nullptr, nullptr, false);
   if (h->su_smem > 227 * 1024) { delete h; return RDA_E_UNSUPPORTED; }
   cudaError_t e = cudaSuccess;
   auto alloc = [&](float** p, size_t n) { if (e == cudaSuccess) e = cudaMalloc((void**)p, (n ? n : 1) * sizeof(float)); };
@@ -466,6 +468,7 @@ int rda_create(const rda_config* cfg, const rda_tunables* tun, rda_handle** out)
   alloc((float**)&h->status, B); alloc((float**)&h->iters, B); alloc((float**)&h->done, B);
   alloc((float**)&h->counters, 8);
   alloc((float**)&h->worklist, B * NT);
+  alloc((float**)&h->su_scratch, B * 2 * NT * 2 * 2);      // doubles: 2 arrays x NT x (8/4 floats)
   if (e != cudaSuccess) { rda_destroy(h); return (int)e; }
   if (cfg->su_fp64) e = cudaFuncSetAttribute(k_su<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->su_smem);
   else e = cudaFuncSetAttribute(k_su<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->su_smem);
@@ -482,7 +485,7 @@ int rda_destroy(rda_handle* h) {
   if (!h) return RDA_E_ARG;
   float* bufs[] = {h->lam, h->mu, h->z, h->xi, h->zeta, h->dis, h->coef, h->pref, h->cur_s, h->cur_u,
                    h->ref_s, h->ref_speed, h->resi_acc, h->resi_pri, h->resi_dual, (float*)h->status,
-                   (float*)h->iters, (float*)h->done, (float*)h->counters, (float*)h->worklist};
+                   (float*)h->iters, (float*)h->done, (float*)h->counters, (float*)h->worklist, (float*)h->su_scratch};
   for (float* p : bufs) if (p) cudaFree(p);
   delete h;
   return 0;

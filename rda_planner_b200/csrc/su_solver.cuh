@@ -55,8 +55,10 @@ struct SuWork {
 };
 
 template <typename Real>
-RDA_HD size_t su_work_layout(int T, int N, SuWork<Real>* w, char* base) {
-  // returns bytes used; if base != nullptr the pointers are set
+RDA_HD size_t su_work_layout(int T, int N, SuWork<Real>* w, char* base, bool hinge_arrays = true) {
+  // returns bytes used; if base != nullptr the pointers are set.  hinge_arrays = false leaves the
+  // per-hinge arrays (hx, hy, hc, hs, hnu: touched only by the lane that owns the stage) to the
+  // caller, who points them at global memory to keep the shared-memory footprint small.
   size_t off = 0;
   auto take = [&](size_t n, size_t elt) {
     off = (off + 15) & ~(size_t)15;
@@ -70,8 +72,10 @@ RDA_HD size_t su_work_layout(int T, int N, SuWork<Real>* w, char* base) {
   RDA_TAKE(cph, T, Real) RDA_TAKE(sph, T, Real)
   RDA_TAKE(Aj, 2 * T, Real) RDA_TAKE(Bj, 6 * T, Real) RDA_TAKE(Cj, 3 * T, Real)
   RDA_TAKE(Skk, T, Real) RDA_TAKE(Sgk, T, Real) RDA_TAKE(pref, 2 * T, Real)
-  RDA_TAKE(hx, N * T, float) RDA_TAKE(hy, N * T, float) RDA_TAKE(hc, N * T, float)
-  RDA_TAKE(hs, N * T, Real) RDA_TAKE(hnu, N * T, Real)
+  if (hinge_arrays) {
+    RDA_TAKE(hx, N * T, float) RDA_TAKE(hy, N * T, float) RDA_TAKE(hc, N * T, float)
+    RDA_TAKE(hs, N * T, Real) RDA_TAKE(hnu, N * T, Real)
+  }
   RDA_TAKE(bs, 10 * T, Real) RDA_TAKE(bnu, 10 * T, Real)
   RDA_TAKE(Wm, 6 * T, Real) RDA_TAKE(gw, 8 * T, Real) RDA_TAKE(wb, 5 * T, Real)
   RDA_TAKE(K, 15 * T, Real) RDA_TAKE(Lc, 6 * T, Real) RDA_TAKE(kf, 3 * T, Real) RDA_TAKE(rw, 128, Real)
