@@ -25,6 +25,20 @@ RDA_HD float sqrt_(float x) { return sqrtf(x); }
 RDA_HD double sqrt_(double x) { return sqrt(x); }
 RDA_HD float abs_(float x) { return fabsf(x); }
 RDA_HD double abs_(double x) { return fabs(x); }
+// reciprocal: on the device a float seed refined by two Newton steps (full double accuracy for
+// arguments inside the float range, which every caller guarantees) — shorter dependent chain than
+// the IEEE division sequence; plain division on the host.
+RDA_HD float rcp_(float x) { return 1.0f / x; }
+RDA_HD double rcp_(double x) {
+#if defined(__CUDA_ARCH__)
+  double r = (double)__frcp_rn((float)x);
+  r = r * (2.0 - x * r);
+  r = r * (2.0 - x * r);
+  return r;
+#else
+  return 1.0 / x;
+#endif
+}
 RDA_HD bool finite_(float x) { return isfinite(x); }
 RDA_HD bool finite_(double x) { return isfinite(x); }
 

@@ -184,7 +184,7 @@ RDA_HD void su_riccati(const SuParams& P, SuWork<Real>& W, Ctx& ctx, bool factor
     const Real gv0 = b00 * q0 + b10 * q1 + b20 * q2 + q3;
     const Real gv1 = b01 * q0 + b11 * q1 + b21 * q2 + q4;
     const Real gv2 = q5;
-    Real i00, L10, i11, L20, L21, i22;   // Cholesky of Hvv, reciprocal diagonal
+    Real i00, L10, i11, L20, L21, i22;   // L D L' of Hvv: unit-lower entries and reciprocal pivots
     Real Kt[3][5];
     if (factor) {
       Real Q[6][6];
@@ -223,22 +223,21 @@ RDA_HD void su_riccati(const SuParams& P, SuWork<Real>& W, Ctx& ctx, bool factor
 #undef RDA_J2
 #undef RDA_J5
 #undef RDA_J6
-      const Real L00 = sqrt_(h00);
-      i00 = (Real)1 / L00;
+      // Hvv = L D L' (unit lower L: L10, L20, L21; reciprocal pivots i00, i11, i22) — no square roots
+      i00 = rcp_(h00);
       L10 = h10 * i00;
-      const Real L11 = sqrt_(h11 - L10 * L10);
-      i11 = (Real)1 / L11;
+      i11 = rcp_(h11 - L10 * h10);
       L20 = h20 * i00;
-      L21 = (h21 - L20 * L10) * i11;
-      const Real L22 = sqrt_(h22 - L20 * L20 - L21 * L21);
-      i22 = (Real)1 / L22;
+      const Real w21 = h21 - L20 * h10;          // = L21 * d1
+      L21 = w21 * i11;
+      i22 = rcp_(h22 - L20 * h20 - L21 * w21);
       for (int b = 0; b < 5; ++b) {
-        Real y0 = -Hvz[0][b] * i00;
-        Real y1 = (-Hvz[1][b] - L10 * y0) * i11;
-        Real y2 = (-Hvz[2][b] - L20 * y0 - L21 * y1) * i22;
+        Real y0 = -Hvz[0][b];
+        Real y1 = -Hvz[1][b] - L10 * y0;
+        Real y2 = -Hvz[2][b] - L20 * y0 - L21 * y1;
         Real x2 = y2 * i22;
-        Real x1 = (y1 - L21 * x2) * i11;
-        Real x0 = (y0 - L10 * x1 - L20 * x2) * i00;
+        Real x1 = y1 * i11 - L21 * x2;
+        Real x0 = y0 * i00 - L10 * x1 - L20 * x2;
         Kt[0][b] = x0; Kt[1][b] = x1; Kt[2][b] = x2;
       }
       for (int a = 0; a < 5; ++a)
@@ -257,12 +256,12 @@ RDA_HD void su_riccati(const SuParams& P, SuWork<Real>& W, Ctx& ctx, bool factor
       for (int k = 0; k < 3; ++k) for (int b = 0; b < 5; ++b) Kt[k][b] = W.K[15 * t + 5 * k + b];
     }
     {
-      Real y0 = -gv0 * i00;
-      Real y1 = (-gv1 - L10 * y0) * i11;
-      Real y2 = (-gv2 - L20 * y0 - L21 * y1) * i22;
+      Real y0 = -gv0;
+      Real y1 = -gv1 - L10 * y0;
+      Real y2 = -gv2 - L20 * y0 - L21 * y1;
       Real x2 = y2 * i22;
-      Real x1 = (y1 - L21 * x2) * i11;
-      Real x0 = (y0 - L10 * x1 - L20 * x2) * i00;
+      Real x1 = y1 * i11 - L21 * x2;
+      Real x0 = y0 * i00 - L10 * x1 - L20 * x2;
       if (writer) { W.kf[3 * t] = x0; W.kf[3 * t + 1] = x1; W.kf[3 * t + 2] = x2; }
       pv[0] = gz0 + Kt[0][0] * gv0 + Kt[1][0] * gv1 + Kt[2][0] * gv2;
       pv[1] = gz1 + Kt[0][1] * gv0 + Kt[1][1] * gv1 + Kt[2][1] * gv2;
@@ -391,7 +390,7 @@ RDA_HD int su_solve(const SuParams& P, SuWork<Real>& W, Ctx& ctx, const float* g
           if (!r.live) continue;
           Real sv = W.bs[10 * t + c], nu = W.bnu[10 * t + c];
           Real res = r.g - sv;
-          const Real isv = (Real)1 / sv;
+          const Real isv = rcp_(sv);
           Real om = nu * isv;
           Real term;
           if (phase == 0) {
@@ -421,7 +420,7 @@ RDA_HD int su_solve(const SuParams& P, SuWork<Real>& W, Ctx& ctx, const float* g
             Real sv = W.hs[o * T + t], nu = W.hnu[o * T + t];
             const Real nr = nu * iro1;
             Real res = l + nr - sv;
-            const Real iden = (Real)1 / (sv + nr);
+            const Real iden = rcp_(sv + nr);
             om = nu * iden;
             if (phase == 0) {
               tk = om * (nr - res);
@@ -474,7 +473,7 @@ RDA_HD int su_solve(const SuParams& P, SuWork<Real>& W, Ctx& ctx, const float* g
           Real res = r.g - sv;
           Real dir = su_row_dir<Real>(r, dz + 5 * t, dv + 3 * t);
           Real ds = dir + res, dn;
-          const Real ip = (Real)1 / (sv * nu);
+          const Real ip = rcp_(sv * nu);
           const Real isv = nu * ip, inu = sv * ip, om = nu * isv;
           if (phase == 0) dn = -nu - om * ds;
           else {
@@ -494,7 +493,7 @@ RDA_HD int su_solve(const SuParams& P, SuWork<Real>& W, Ctx& ctx, const float* g
             Real sv = W.hs[o * T + t], nu = W.hnu[o * T + t];
             const Real nr = nu * iro1;
             Real res = l + nr - sv;
-            const Real iden = (Real)1 / (sv + nr);
+            const Real iden = rcp_(sv + nr);
             const Real om = nu * iden;
             Real dir = ax * dz[5 * t + 5] + ay * dz[5 * t + 6] - dv[3 * t + 2];
             Real cc = sv * nu;
@@ -506,7 +505,7 @@ RDA_HD int su_solve(const SuParams& P, SuWork<Real>& W, Ctx& ctx, const float* g
             }
             Real dn = -(cc + nu * res + nu * dir) * iden;
             Real ds = dir + dn * iro1 + res;
-            const Real ip = (Real)1 / (sv * nu);
+            const Real ip = rcp_(sv * nu);
             rmaxr = rmax(rmaxr, rmax(-ds * nu * ip, -dn * sv * ip));
             s0 += sv * nu; s1 += sv * dn + nu * ds; s2 += ds * dn;
           }
@@ -539,7 +538,7 @@ RDA_HD int su_solve(const SuParams& P, SuWork<Real>& W, Ctx& ctx, const float* g
             Real ds = dir + res;
             Real dira = su_row_dir<Real>(r, W.dza + 5 * t, W.dva + 3 * t);
             Real dsa = dira + res;
-            const Real isv = (Real)1 / sv, om = nu * isv;
+            const Real isv = rcp_(sv), om = nu * isv;
             Real dna = -nu - om * dsa;
             Real dn = (sigma_mu - dsa * dna) * isv - nu - om * ds;
             W.bs[10 * t + c] = sv + a * ds;
@@ -553,7 +552,7 @@ RDA_HD int su_solve(const SuParams& P, SuWork<Real>& W, Ctx& ctx, const float* g
               Real sv = W.hs[o * T + t], nu = W.hnu[o * T + t];
               const Real nr = nu * iro1;
               Real res = l + nr - sv;
-              const Real iden = (Real)1 / (sv + nr);
+              const Real iden = rcp_(sv + nr);
               const Real om = nu * iden;
               Real dir = ax * W.dz[5 * t + 5] + ay * W.dz[5 * t + 6] - W.dv[3 * t + 2];
               Real dira = ax * W.dza[5 * t + 5] + ay * W.dza[5 * t + 6] - W.dva[3 * t + 2];
