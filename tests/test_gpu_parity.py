@@ -196,3 +196,85 @@ def test_golden_trajectory_fixture():
     u, info = g.iterative_solve(inst['nom_s'], inst['nom_u'], ref, inst['ref_speed'], list(inst['obstacles']))
     np.testing.assert_allclose(u, fx['u'], atol=TRAJ_TOL)
     np.testing.assert_allclose(np.hstack(info['opt_state_list']), fx['s'], atol=TRAJ_TOL)
+
+
+def test_golden_trajectory_fixture_moving_circles():
+    """BASELINE configs[2] geometry: T=30, 20 moving discs, min_sd=0.5, wu=0.2
+    (tests/golden/oracle_circles_T30N20.npz, made by tests/golden/make_oracle_fixture_circles.py)."""
+    import os
+    from rda_planner_b200.rda_solver import RDA_solver
+    here = os.path.dirname(os.path.abspath(__file__))
+    fx = np.load(os.path.join(here, 'golden', 'oracle_circles_T30N20.npz'))
+    T, N = 30, 20
+    car = rectangle_robot(max_acce=(10, 1.0))
+    inst = make_instance(int(fx['seed']), T=T, N=N, E=4, kind='circle', moving=True, lateral=(1.0, 6.0))
+    ref = [inst['ref'][:, t:t + 1] for t in range(T + 1)]
+    g = RDA_solver(T, car, 4, N, iter_num=int(fx['iters']), iter_threshold=0.0, time_print=False, min_sd=0.5, wu=0.2)
+    u, info = g.iterative_solve(inst['nom_s'], inst['nom_u'], ref, inst['ref_speed'], list(inst['obstacles']))
+    np.testing.assert_allclose(u, fx['u'], atol=TRAJ_TOL)
+    np.testing.assert_allclose(np.hstack(info['opt_state_list']), fx['s'], atol=TRAJ_TOL)
+
+
+def test_cuda_graph_capture_replays_identically():
+    """rda_solve enqueues only kernels on the caller's stream (no sync, no allocation): it can be
+    captured in a CUDA graph and replayed."""
+    from rda_planner_b200.rda_solver import RDA_solver
+    T, N, B = 12, 6, 64
+    car = rectangle_robot()
+    insts, inp = _batch_inputs(B, T, N, 700, lateral=(0.5, 3.5))
+    g = RDA_solver(T, car, 4, N, iter_num=5, iter_threshold=0.0, time_print=False, batch=B)
+    dev = {k: torch.as_tensor(v, device='cuda', dtype=torch.int32 if 'kind' in k or 'count' in k else torch.float32)
+           for k, v in inp.items()}
+    eager = {k: v.clone() for k, v in g.iterative_solve_batch(**dev).items()}
+    stream = torch.cuda.Stream()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(stream):
+        g.cold_start()
+        g.iterative_solve_batch(**dev)               # warm-up on the side stream
+        stream.synchronize()
+        with torch.cuda.graph(graph, stream=stream):
+            g.cold_start()
+            out = g.iterative_solve_batch(**dev)
+    for _ in range(2):
+        graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out['u'], eager['u']) and torch.equal(out['s'], eager['s'])
+
+
+def test_float32_su_mode_and_residual_gap():
+    """BASELINE configs[4] asks for a float32-vs-float64 comparison: su-QP interior point in float32
+    (su_fp64=False) against the default float64 arithmetic on the same instances."""
+    from rda_planner_b200.rda_solver import RDA_solver
+    T, N, B = 20, 10, 128
+    car = rectangle_robot()
+    insts, inp = _batch_inputs(B, T, N, 800)
+    out = {}
+    for fp64 in (True, False):
+        g = RDA_solver(T, car, 4, N, iter_num=6, iter_threshold=0.0, time_print=False, batch=B, su_fp64=fp64)
+        out[fp64] = {k: v.clone() for k, v in g.iterative_solve_batch(**inp).items()}
+    gap = (out[True]['u'] - out[False]['u']).abs().flatten(1).max(1).values
+    assert torch.isfinite(out[False]['u']).all()
+    assert float(gap.median()) < 5e-3
+    rp = (out[True]['resi_pri'] - out[False]['resi_pri']).abs() / (1 + out[True]['resi_pri'])
+    assert float(rp.median()) < 1e-2
+
+
+def test_large_polytopes_config():
+    """BASELINE configs[3]/[4] shapes: convex hulls with up to 8 faces, T=40, N=32 (E=8 code paths,
+    two stages per lane in the su kernel); GPU against the compiled CPU port of the same cores."""
+    from rda_planner_b200.rda_solver import RDA_solver, pack_obstacles
+    from oracle import cpu_port
+    T, N, E, B, iters = 40, 32, 8, 8, 4
+    car = rectangle_robot()
+    insts = [make_instance(900 + i, T=T, N=N, E=E, lateral=(1.0, 8.0)) for i in range(B)]
+    packs = [pack_obstacles(list(i['obstacles']), T, N, E) for i in insts]
+    inp = dict(nom_s=np.stack([i['nom_s'] for i in insts]), nom_u=np.stack([i['nom_u'] for i in insts]),
+               ref_s=np.stack([i['ref'] for i in insts]), ref_speed=np.array([i['ref_speed'] for i in insts]),
+               obs_A=np.stack([p[0] for p in packs]), obs_b=np.stack([p[1] for p in packs]),
+               obs_kind=np.stack([p[2] for p in packs]), obs_count=np.array([p[3] for p in packs]))
+    g = RDA_solver(T, car, E, N, iter_num=iters, iter_threshold=0.0, time_print=False, batch=B, slack_gain=13)
+    out = g.iterative_solve_batch(**inp)
+    port = cpu_port.solve_batch(car, T, N, E, **inp, iter_num=iters, slack_gain=13)
+    assert int((out['status'] & 6).sum()) == 0
+    np.testing.assert_allclose(out['u'].cpu().numpy(), port['u'], atol=3 * TRAJ_TOL)
+    np.testing.assert_allclose(out['s'].cpu().numpy(), port['s'], atol=3 * TRAJ_TOL)
