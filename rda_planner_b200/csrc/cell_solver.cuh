@@ -120,7 +120,9 @@ struct CellWork {
 };
 
 // ---- stage 1: geometry relative to the robot reference point and the closed-form cases ----------
-template <typename Real>
+// LEAN = true stops after the two cases that need no search (xi = 0 and a non-negative margin): the
+// first pass of the GPU pipeline, kept small so that its code stays resident in the instruction cache.
+template <typename Real, bool LEAN = false>
 RDA_HD void cell_front(const RobotGeom& rb, int kind, int E, const float* A, const float* b, Real px, Real py,
                        Real cphi, Real sphi, Real dbar, Real zeta, Real xi0, Real xi1, Real ro2,
                        CellWork<Real>& w) {
@@ -274,6 +276,11 @@ RDA_HD void cell_front(const RobotGeom& rb, int kind, int E, const float* A, con
   if (!have && !sep && xi_zero && k0 <= 0) {
     // overlapping sets, no tilt: max margin is 0 at v = 0 (stuff = -k0 >= 0)
     exact_zero_q = true; have = true; path = CELL_OVERLAP_FREE;
+  }
+  if (LEAN) {
+    w.v0 = v0; w.v1 = v1; w.g0 = g0; w.g1 = g1;
+    w.exact_zero_q = exact_zero_q; w.have = have; w.path = path;
+    return;
   }
   if (!have && sep) {
     const Real tolc = sizeof(Real) == 4 ? (Real)1e-5 : (Real)1e-11;

@@ -1,8 +1,8 @@
 // rda_kernels.cu — sm_100a kernels and the C ABI (include/rda_b200.h) of the RDA ADMM hot path.
 //
-// One ADMM iteration (rda_solver.py:612-637) is four launches on the caller's stream:
+// One ADMM iteration (rda_solver.py:612-637) is five launches on the caller's stream:
 //   k_su      one warp per planning instance: su-QP (su_solver.cuh), state staged in shared memory
-//   k_cells_fast / k_cells_slow   one thread per (instance, obstacle, stage) cell: (lam, mu, z) +
+//   k_cells_fast / k_cells_mid / k_cells_slow   one thread per (instance, obstacle, stage) cell: (lam, mu, z) +
 //             xi/zeta update + residual partial sums + the next su-QP's hinge inputs (cell_solver.cuh)
 //   k_finalize per instance: residuals, early-stop flag (:594-596)
 // No host synchronisation, no allocation, CUDA-graph capturable.
@@ -23,7 +23,7 @@ struct rda_handle {
   int B, T, N, E, R;
   float *lam, *mu, *z, *xi, *zeta, *dis, *coef, *pref, *cur_s, *cur_u, *ref_s, *ref_speed;
   float *resi_acc, *resi_pri, *resi_dual;
-  int *status, *iters, *done, *counters, *worklist;
+  int *status, *iters, *done, *counters, *worklist, *worklist2;
   double* su_scratch;    // [B][2][N*T] hinge slack / multiplier of the su-QP interior point iteration
   const float *obs_A, *obs_b;
   const int *obs_kind, *obs_count;
@@ -59,7 +59,7 @@ struct WarpCtx {
 struct DevPtrs {
   float *lam, *mu, *z, *xi, *zeta, *dis, *coef, *pref, *cur_s, *cur_u, *ref_s, *ref_speed;
   float *resi_acc, *resi_pri, *resi_dual;
-  int *status, *iters, *done, *counters, *worklist;
+  int *status, *iters, *done, *counters, *worklist, *worklist2;
   double* su_scratch;
   const float *obs_A, *obs_b;
   const int *obs_kind, *obs_count;
@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(128) k_cells_fast(DevPtrs d, RobotGeom rb, flo
     if (live) {
       CellIn c = cell_load(d, idx);
       CellWork<float> w;
-      cell_front<float>(rb, c.kind, d.E, c.A, c.bb, c.px, c.py, c.cp, c.sp, c.dbar, c.zeta, c.xi0, c.xi1, ro2, w);
+      cell_front<float, true>(rb, c.kind, d.E, c.A, c.bb, c.px, c.py, c.cp, c.sp, c.dbar, c.zeta, c.xi0, c.xi1, ro2, w);
       if (w.have) {
         CellOut<float> out;
         cell_back<float>(rb, w, c.zeta, theta, out);
@@ -304,14 +304,52 @@ __global__ void __launch_bounds__(128) k_cells_fast(DevPtrs d, RobotGeom rb, flo
   }
 }
 
+// Second pass: the searched closed forms (vertex / edge contact, overlap cases) for the cells of the
+// first worklist, one thread per entry; what is still unresolved goes to the second worklist.
+__global__ void __launch_bounds__(128) k_cells_mid(DevPtrs d, RobotGeom rb, float ro2, float theta) {
+  const int count = d.counters[5];
+  const int lane = threadIdx.x & 31;
+  for (int base = blockIdx.x * blockDim.x; base < count; base += gridDim.x * blockDim.x) {
+    const int wi = base + threadIdx.x;
+    const bool live = wi < count;
+    bool need = false;
+    long long idx = 0;
+    if (live) {
+      idx = d.worklist[wi];
+      CellIn c = cell_load(d, idx);
+      CellWork<float> w;
+      cell_front<float, false>(rb, c.kind, d.E, c.A, c.bb, c.px, c.py, c.cp, c.sp, c.dbar, c.zeta, c.xi0, c.xi1, ro2, w);
+      if (w.have) {
+        CellOut<float> out;
+        cell_back<float>(rb, w, c.zeta, theta, out);
+        float hm2 = 0.f, dual = 0.f;
+        cell_store(d, c, out, &hm2, &dual);
+        atomicAdd(&d.resi_acc[2 * c.b], hm2);
+        atomicAdd(&d.resi_acc[2 * c.b + 1], dual);
+      } else {
+        need = true;
+      }
+    }
+    unsigned m = __ballot_sync(0xffffffffu, need);
+    if (m) {
+      int leader = __ffs(m) - 1, pos = 0;
+      if (lane == leader) pos = atomicAdd(&d.counters[6], __popc(m));
+      pos = __shfl_sync(0xffffffffu, pos, leader);
+      if (need) d.worklist2[pos + __popc(m & ((1u << lane) - 1))] = (int)idx;
+    }
+    unsigned solved = __ballot_sync(0xffffffffu, live && !need);
+    if (lane == 0 && solved) atomicAdd(&d.counters[0], __popc(solved));
+  }
+}
+
 // One thread per worklist entry (dense: no lane idles behind a closed-form neighbour).
 #ifndef RDA_SLOW_MINBLOCKS
 #define RDA_SLOW_MINBLOCKS 16
 #endif
 __global__ void __launch_bounds__(64, RDA_SLOW_MINBLOCKS) k_cells_slow(DevPtrs d, RobotGeom rb, float ro2, float theta) {
-  const int count = d.counters[5];
+  const int count = d.counters[6];
   for (int wi = blockIdx.x * blockDim.x + threadIdx.x; wi < count; wi += gridDim.x * blockDim.x) {
-    const long long idx = d.worklist[wi];
+    const long long idx = d.worklist2[wi];
     CellIn c = cell_load(d, idx);
     CellWork<float> w;
     cell_front<float>(rb, c.kind, d.E, c.A, c.bb, c.px, c.py, c.cp, c.sp, c.dbar, c.zeta, c.xi0, c.xi1, ro2, w);
@@ -339,7 +377,7 @@ __global__ void __launch_bounds__(64, RDA_SLOW_MINBLOCKS) k_cells_slow(DevPtrs d
 // per instance: residuals (:688, :735-739), early stop (:594-596), empty-list quirk (:564-568)
 __global__ void k_finalize(DevPtrs d, RobotGeom rb, float thr) {
   int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b == 0) d.counters[5] = 0;          // worklist of the slow pass consumed
+  if (b == 0) { d.counters[5] = 0; d.counters[6] = 0; }   // worklists consumed
   if (b >= d.B) return;
   if (d.done[b]) return;
   const int T = d.T, N = d.N, NT = N * T, R = d.R;
@@ -406,7 +444,7 @@ DevPtrs dev_ptrs(const rda_handle* h) {
   d.lam = h->lam; d.mu = h->mu; d.z = h->z; d.xi = h->xi; d.zeta = h->zeta; d.dis = h->dis;
   d.coef = h->coef; d.pref = h->pref; d.cur_s = h->cur_s; d.cur_u = h->cur_u; d.ref_s = h->ref_s;
   d.ref_speed = h->ref_speed; d.resi_acc = h->resi_acc; d.resi_pri = h->resi_pri; d.resi_dual = h->resi_dual;
-  d.status = h->status; d.iters = h->iters; d.done = h->done; d.counters = h->counters; d.worklist = h->worklist; d.su_scratch = h->su_scratch;
+  d.status = h->status; d.iters = h->iters; d.done = h->done; d.counters = h->counters; d.worklist = h->worklist; d.worklist2 = h->worklist2; d.su_scratch = h->su_scratch;
   d.obs_A = h->obs_A; d.obs_b = h->obs_b; d.obs_kind = h->obs_kind; d.obs_count = h->obs_count;
   d.obs_tv = h->obs_tv;
   d.B = h->B; d.T = h->T; d.N = h->N; d.E = h->E; d.R = h->R;
@@ -468,6 +506,7 @@ int rda_create(const rda_config* cfg, const rda_tunables* tun, rda_handle** out)
   alloc((float**)&h->status, B); alloc((float**)&h->iters, B); alloc((float**)&h->done, B);
   alloc((float**)&h->counters, 8);
   alloc((float**)&h->worklist, B * NT);
+  alloc((float**)&h->worklist2, B * NT);
   alloc((float**)&h->su_scratch, B * 2 * NT * 2 * 2);      // doubles: 2 arrays x NT x (8/4 floats)
   if (e != cudaSuccess) { rda_destroy(h); return (int)e; }
   if (cfg->su_fp64) e = cudaFuncSetAttribute(k_su<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->su_smem);
@@ -485,7 +524,7 @@ int rda_destroy(rda_handle* h) {
   if (!h) return RDA_E_ARG;
   float* bufs[] = {h->lam, h->mu, h->z, h->xi, h->zeta, h->dis, h->coef, h->pref, h->cur_s, h->cur_u,
                    h->ref_s, h->ref_speed, h->resi_acc, h->resi_pri, h->resi_dual, (float*)h->status,
-                   (float*)h->iters, (float*)h->done, (float*)h->counters, (float*)h->worklist, (float*)h->su_scratch};
+                   (float*)h->iters, (float*)h->done, (float*)h->counters, (float*)h->worklist, (float*)h->worklist2, (float*)h->su_scratch};
   for (float* p : bufs) if (p) cudaFree(p);
   delete h;
   return 0;
@@ -573,9 +612,11 @@ int rda_step_lammuz(rda_handle* h, void* stream) {
     const float theta = h->cfg.accelerated ? h->tun.z_theta : 1.0f;
     k_cells_fast<<<grid_for((long long)h->B * h->N * h->T, 128), 128, 0, s>>>(d, h->rb, h->tun.ro2, theta);
     RDA_CUDA(cudaGetLastError());
+    k_cells_mid<<<148 * 8, 128, 0, s>>>(d, h->rb, h->tun.ro2, theta);
+    RDA_CUDA(cudaGetLastError());
     k_cells_slow<<<148 * 16, 64, 0, s>>>(d, h->rb, h->tun.ro2, theta);
     RDA_CUDA(cudaGetLastError());
-    h->launches += 2;
+    h->launches += 3;
   }
   k_finalize<<<(h->B + 127) / 128, 128, 0, s>>>(d, h->rb, h->iter_threshold);
   RDA_CUDA(cudaGetLastError());
