@@ -13,6 +13,7 @@
 #include <omp.h>
 #include "../../rda_planner_b200/csrc/cell_solver.cuh"
 #include "../../rda_planner_b200/csrc/su_solver.cuh"
+#include "../../rda_planner_b200/csrc/cell_lean.cuh"
 
 using namespace rda;
 
@@ -58,7 +59,38 @@ static int su_impl(const SuParams* P, const double* lins, const double* linu, co
   return st;
 }
 
+template <int EC, int RC>
+static int lean_impl(const float* G, const float* h, int R, int kind, int E, const float* A, const float* b, double px,
+                     double py, double phi, double dbar, double zeta, double xi0, double xi1, double theta, double* out) {
+  RobotGeom rb;
+  int rc = robot_geom_from_halfspaces(G, h, R, &rb);
+  if (rc) return rc;
+  LeanOut<EC, RC> o;
+  bool ok = cell_lean<EC, RC>(rb, kind, E, A, b, (float)px, (float)py, (float)cos(phi), (float)sin(phi), (float)dbar,
+                              (float)zeta, (float)xi0, (float)xi1, (float)theta, o);
+  for (int i = 0; i < 28; ++i) out[i] = 0;
+  out[27] = ok ? 0 : 6;
+  if (!ok) return 0;
+  for (int i = 0; i < EC; ++i) out[i] = o.lam[i];
+  for (int j = 0; j < RC; ++j) out[8 + j] = o.mu[j];
+  out[16] = o.z; out[17] = o.zeta_new; out[18] = 0; out[19] = 0; out[20] = o.ax; out[21] = o.ay; out[22] = o.c0;
+  out[23] = o.gx; out[24] = o.gy; out[25] = 0; out[26] = 0;
+  return 0;
+}
+
 extern "C" {
+int shim_cell_lean4(const float* G, const float* h, int R, int kind, int E, const float* A, const float* b, double px,
+                    double py, double phi, double dbar, double zeta, double xi0, double xi1, double ro2, double theta,
+                    double* out) {
+  (void)ro2;
+  return lean_impl<4, 4>(G, h, R, kind, E, A, b, px, py, phi, dbar, zeta, xi0, xi1, theta, out);
+}
+int shim_cell_lean8(const float* G, const float* h, int R, int kind, int E, const float* A, const float* b, double px,
+                    double py, double phi, double dbar, double zeta, double xi0, double xi1, double ro2, double theta,
+                    double* out) {
+  (void)ro2;
+  return lean_impl<8, 8>(G, h, R, kind, E, A, b, px, py, phi, dbar, zeta, xi0, xi1, theta, out);
+}
 int shim_cell_d(const float* G, const float* h, int R, int kind, int E, const float* A, const float* b,
                 double px, double py, double phi, double dbar, double zeta, double xi0, double xi1, double ro2,
                 double theta, double* out) {

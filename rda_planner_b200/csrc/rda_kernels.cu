@@ -13,6 +13,7 @@
 #include "rda_hd.h"
 #include "cell_solver.cuh"
 #include "su_solver.cuh"
+#include "cell_lean.cuh"
 
 using namespace rda;
 
@@ -242,60 +243,86 @@ __device__ __forceinline__ void cell_store(const DevPtrs& d, const CellIn& c, co
   }
 }
 
-__global__ void __launch_bounds__(128) k_cells_fast(DevPtrs d, RobotGeom rb, float ro2, float theta) {
-  const int NT = d.N * d.T;
+// First pass: compile-time specialised lean solver (cell_lean.cuh), geometry in registers.
+template <int EC, int RC>
+__global__ void __launch_bounds__(128) k_cells_fast(DevPtrs d, RobotGeom rb, float theta) {
+  const int T = d.T, N = d.N, E = d.E, R = d.R;
+  const int NT = N * T;
   const long long total = (long long)d.B * NT;
   const int lane = threadIdx.x & 31;
   for (long long base = (long long)blockIdx.x * blockDim.x; base < total; base += (long long)gridDim.x * blockDim.x) {
     long long idx = base + threadIdx.x;
     bool live = idx < total;
     int b = live ? (int)(idx / NT) : -1;
-    float hm2 = 0.f, dual = 0.f;
-    int path = -1;
+    float dual = 0.f;
+    bool need = false;
     if (live && (d.done[b] || d.obs_count[b] == 0)) live = false;
     if (live) {
       CellIn c = cell_load(d, idx);
-      CellWork<float> w;
-      cell_front<float, true>(rb, c.kind, d.E, c.A, c.bb, c.px, c.py, c.cp, c.sp, c.dbar, c.zeta, c.xi0, c.xi1, ro2, w);
-      if (w.have) {
-        CellOut<float> out;
-        cell_back<float>(rb, w, c.zeta, theta, out);
-        cell_store(d, c, out, &hm2, &dual);
-        path = out.path;
+      LeanOut<EC, RC> o;
+      const bool ok = cell_lean<EC, RC>(rb, c.kind, E, c.A, c.bb, c.px, c.py, c.cp, c.sp, c.dbar, c.zeta, c.xi0,
+                                        c.xi1, theta, o);
+      if (ok) {
+        // dual residual |lam - lam_prev|^2 + |mu - mu_prev|^2 + |z - z_prev|^2 (:783-787)
+        float* lam = d.lam + ((size_t)c.b * N + c.o) * E * T + c.t;
+        float acc = 0.f;
+#pragma unroll
+        for (int i = 0; i < EC; ++i) {
+          if (i < E) {
+            const float df = o.lam[i] - lam[(size_t)i * T];
+            acc += df * df;
+            lam[(size_t)i * T] = o.lam[i];
+          }
+        }
+        float* mu = d.mu + ((size_t)c.b * N + c.o) * R * T + c.t;
+#pragma unroll
+        for (int j = 0; j < RC; ++j) {
+          if (j < R) {
+            const float df = o.mu[j] - mu[(size_t)j * T];
+            acc += df * df;
+            mu[(size_t)j * T] = o.mu[j];
+          }
+        }
+        const float dz = o.z - d.z[c.cell];
+        acc += dz * dz;
+        d.z[c.cell] = o.z;
+        dual = acc;
+        d.zeta[c.cell] = o.zeta_new;
+        // xi stays 0 (Hm + xi = 0 and xi was 0): nothing to write, Hm = 0
+        float* cf = d.coef + (size_t)c.b * 5 * NT + (size_t)c.o * T + c.t;
+        cf[0] = o.ax; cf[NT] = o.ay; cf[2 * NT] = o.c0; cf[3 * NT] = o.gx; cf[4 * NT] = o.gy;
+        if (c.o == 0) {
+          d.pref[(size_t)c.b * 2 * T + c.t] = c.px;
+          d.pref[(size_t)c.b * 2 * T + T + c.t] = c.py;
+        }
       } else {
-        path = CELL_NEEDS_SLOW;
+        need = true;
       }
     }
-    // worklist of cells for the slow pass (one atomic per warp)
-    unsigned need = __ballot_sync(0xffffffffu, path == CELL_NEEDS_SLOW);
-    if (need) {
-      int leader = __ffs(need) - 1, pos = 0;
-      if (lane == leader) pos = atomicAdd(&d.counters[5], __popc(need));
+    // worklist of cells for the second pass (one atomic per warp)
+    unsigned nm = __ballot_sync(0xffffffffu, need);
+    if (nm) {
+      int leader = __ffs(nm) - 1, pos = 0;
+      if (lane == leader) pos = atomicAdd(&d.counters[5], __popc(nm));
       pos = __shfl_sync(0xffffffffu, pos, leader);
-      if (path == CELL_NEEDS_SLOW) d.worklist[pos + __popc(need & ((1u << lane) - 1))] = (int)idx;
+      if (need) d.worklist[pos + __popc(nm & ((1u << lane) - 1))] = (int)idx;
     }
-    const bool solved = live && path != CELL_NEEDS_SLOW;
-    // residual partial sums: a warp spans at most two instances when N*T >= 32
+    const bool solved = live && !need;
+    // dual-residual partial sums (Hm = 0 for every cell solved here): a warp spans at most two
+    // instances when N*T >= 32
     int b0 = __shfl_sync(0xffffffffu, b, 0);
     for (int pass = 0; pass < 2; ++pass) {
       bool mine = solved && ((pass == 0) ? (b == b0) : (b != b0));
       unsigned m = __ballot_sync(0xffffffffu, mine);
       if (m == 0) continue;
-      float h = mine ? hm2 : 0.f, q = mine ? dual : 0.f;
+      float q = mine ? dual : 0.f;
       int leader = __ffs(m) - 1;
       int bl = __shfl_sync(0xffffffffu, b, leader);
       bool uniform = __all_sync(0xffffffffu, !mine || b == bl);
       if (uniform) {
-        for (int o2 = 16; o2 > 0; o2 >>= 1) {
-          h += __shfl_xor_sync(0xffffffffu, h, o2);
-          q += __shfl_xor_sync(0xffffffffu, q, o2);
-        }
-        if (lane == leader) {
-          atomicAdd(&d.resi_acc[2 * bl], h);
-          atomicAdd(&d.resi_acc[2 * bl + 1], q);
-        }
+        for (int o2 = 16; o2 > 0; o2 >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o2);
+        if (lane == leader) atomicAdd(&d.resi_acc[2 * bl + 1], q);
       } else if (mine) {      // N*T < 32: several instances per warp
-        atomicAdd(&d.resi_acc[2 * b], h);
         atomicAdd(&d.resi_acc[2 * b + 1], q);
       }
     }
@@ -610,7 +637,10 @@ int rda_step_lammuz(rda_handle* h, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   if (h->N > 0) {
     const float theta = h->cfg.accelerated ? h->tun.z_theta : 1.0f;
-    k_cells_fast<<<grid_for((long long)h->B * h->N * h->T, 128), 128, 0, s>>>(d, h->rb, h->tun.ro2, theta);
+    if (h->E <= 4 && h->R <= 4)
+      k_cells_fast<4, 4><<<grid_for((long long)h->B * h->N * h->T, 128), 128, 0, s>>>(d, h->rb, theta);
+    else
+      k_cells_fast<8, 8><<<grid_for((long long)h->B * h->N * h->T, 128), 128, 0, s>>>(d, h->rb, theta);
     RDA_CUDA(cudaGetLastError());
     k_cells_mid<<<148 * 8, 128, 0, s>>>(d, h->rb, h->tun.ro2, theta);
     RDA_CUDA(cudaGetLastError());
