@@ -245,7 +245,7 @@ __device__ __forceinline__ void cell_store(const DevPtrs& d, const CellIn& c, co
 
 // First pass: compile-time specialised lean solver (cell_lean.cuh), geometry in registers.
 template <int EC, int RC>
-__global__ void __launch_bounds__(128) k_cells_fast(DevPtrs d, RobotGeom rb, float theta) {
+__global__ void __launch_bounds__(128, (EC <= 4 ? 6 : 3)) k_cells_fast(DevPtrs d, RobotGeom rb, float theta) {
   const int T = d.T, N = d.N, E = d.E, R = d.R;
   const int NT = N * T;
   const long long total = (long long)d.B * NT;
@@ -259,8 +259,33 @@ __global__ void __launch_bounds__(128) k_cells_fast(DevPtrs d, RobotGeom rb, flo
     if (live && (d.done[b] || d.obs_count[b] == 0)) live = false;
     if (live) {
       CellIn c = cell_load(d, idx);
+      // issue every global load of this cell before the arithmetic (memory-level parallelism): the
+      // obstacle rows (128-bit loads when E == 4) and the previous duals needed for the residual
+      float Ar[2 * EC], br[EC], lamo[EC], muo[RC];
+      if (EC == 4 && E == 4) {
+        const float4 a0 = __ldg(reinterpret_cast<const float4*>(c.A));
+        const float4 a1 = __ldg(reinterpret_cast<const float4*>(c.A) + 1);
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(c.bb));
+        Ar[0] = a0.x; Ar[1] = a0.y; Ar[2] = a0.z; Ar[3] = a0.w;
+        Ar[(4) % (2 * EC)] = a1.x; Ar[(5) % (2 * EC)] = a1.y; Ar[(6) % (2 * EC)] = a1.z; Ar[(7) % (2 * EC)] = a1.w;
+        br[0] = b0.x; br[1 % EC] = b0.y; br[2 % EC] = b0.z; br[3 % EC] = b0.w;
+      } else {
+#pragma unroll
+        for (int i = 0; i < EC; ++i) {
+          Ar[2 * i] = (i < E) ? __ldg(c.A + 2 * i) : 0.f;
+          Ar[2 * i + 1] = (i < E) ? __ldg(c.A + 2 * i + 1) : 0.f;
+          br[i] = (i < E) ? __ldg(c.bb + i) : 0.f;
+        }
+      }
+      const float* lamp = d.lam + ((size_t)c.b * N + c.o) * E * T + c.t;
+      const float* mup = d.mu + ((size_t)c.b * N + c.o) * R * T + c.t;
+#pragma unroll
+      for (int i = 0; i < EC; ++i) lamo[i] = (i < E) ? lamp[(size_t)i * T] : 0.f;
+#pragma unroll
+      for (int j = 0; j < RC; ++j) muo[j] = (j < R) ? mup[(size_t)j * T] : 0.f;
+      const float zo = d.z[c.cell];
       LeanOut<EC, RC> o;
-      const bool ok = cell_lean<EC, RC>(rb, c.kind, E, c.A, c.bb, c.px, c.py, c.cp, c.sp, c.dbar, c.zeta, c.xi0,
+      const bool ok = cell_lean<EC, RC>(rb, c.kind, EC, Ar, br, c.px, c.py, c.cp, c.sp, c.dbar, c.zeta, c.xi0,
                                         c.xi1, theta, o);
       if (ok) {
         // dual residual |lam - lam_prev|^2 + |mu - mu_prev|^2 + |z - z_prev|^2 (:783-787)
@@ -269,7 +294,7 @@ __global__ void __launch_bounds__(128) k_cells_fast(DevPtrs d, RobotGeom rb, flo
 #pragma unroll
         for (int i = 0; i < EC; ++i) {
           if (i < E) {
-            const float df = o.lam[i] - lam[(size_t)i * T];
+            const float df = o.lam[i] - lamo[i];
             acc += df * df;
             lam[(size_t)i * T] = o.lam[i];
           }
@@ -278,12 +303,12 @@ __global__ void __launch_bounds__(128) k_cells_fast(DevPtrs d, RobotGeom rb, flo
 #pragma unroll
         for (int j = 0; j < RC; ++j) {
           if (j < R) {
-            const float df = o.mu[j] - mu[(size_t)j * T];
+            const float df = o.mu[j] - muo[j];
             acc += df * df;
             mu[(size_t)j * T] = o.mu[j];
           }
         }
-        const float dz = o.z - d.z[c.cell];
+        const float dz = o.z - zo;
         acc += dz * dz;
         d.z[c.cell] = o.z;
         dual = acc;
