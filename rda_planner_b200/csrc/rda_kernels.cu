@@ -17,6 +17,12 @@
 
 using namespace rda;
 
+// lanes per planning instance in the su-QP kernel (32: one warp per instance; 16 / 8: 2 / 4 instances
+// share a warp and its FP64 issue slots)
+#ifndef RDA_SU_GROUP
+#define RDA_SU_GROUP 32
+#endif
+
 struct rda_handle {
   rda_config cfg;
   rda_tunables tun;
@@ -57,6 +63,34 @@ struct WarpCtx {
   }
 };
 
+// Sub-warp group of G lanes (G = 16, 8): several instances share one warp.  All synchronisation and
+// shuffles use the group's own lane mask, so the groups of a warp may diverge (different interior
+// point iteration counts) and re-converge freely (independent thread scheduling); while they run in
+// lock-step one FP64 instruction serves G-lane pieces of several instances.
+template <int G>
+struct GroupCtx {
+  unsigned mask;
+  __device__ __forceinline__ GroupCtx() {
+    const int l = threadIdx.x & 31;
+    mask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (l / G * G));
+  }
+  __device__ __forceinline__ int lane() const { return threadIdx.x & (G - 1); }
+  __device__ __forceinline__ int nlanes() const { return G; }
+  __device__ __forceinline__ void sync() const { __syncwarp(mask); }
+  template <typename R> __device__ __forceinline__ R sum(R x) const {
+    for (int o = G / 2; o > 0; o >>= 1) x += __shfl_xor_sync(mask, x, o);
+    return x;
+  }
+  template <typename R> __device__ __forceinline__ R min(R x) const {
+    for (int o = G / 2; o > 0; o >>= 1) { R y = __shfl_xor_sync(mask, x, o); x = y < x ? y : x; }
+    return x;
+  }
+  template <typename R> __device__ __forceinline__ R max(R x) const {
+    for (int o = G / 2; o > 0; o >>= 1) { R y = __shfl_xor_sync(mask, x, o); x = y > x ? y : x; }
+    return x;
+  }
+};
+
 struct DevPtrs {
   float *lam, *mu, *z, *xi, *zeta, *dis, *coef, *pref, *cur_s, *cur_u, *ref_s, *ref_speed;
   float *resi_acc, *resi_pri, *resi_dual;
@@ -90,30 +124,33 @@ __global__ void k_begin(DevPtrs d, const float* nom_s, const float* nom_u, const
 // ------------------------------------------------------------------------------------------------
 // K1: su-QP, one warp per instance.
 // ------------------------------------------------------------------------------------------------
-template <typename Real>
-__global__ void __launch_bounds__(32) k_su(DevPtrs d, SuParams P) {
+template <typename Real, int G>
+__global__ void __launch_bounds__(32) k_su(DevPtrs d, SuParams P, int smem_per_instance) {
   extern __shared__ __align__(16) char smem[];
-  const int b = blockIdx.x;
+  constexpr int PER_WARP = 32 / G;
+  const int grp = (threadIdx.x & 31) / G;
+  const int b = blockIdx.x * PER_WARP + grp;
   if (b >= d.B) return;
   if (d.done[b]) return;
+  GroupCtx<G> ctx;
   const int T = P.T, N = P.N, NT = N * T;
-  const int lane = threadIdx.x;
+  const int lane = ctx.lane();
   SuWork<Real> W;
-  su_work_layout<Real>(T, N, &W, smem, false);
+  su_work_layout<Real>(T, N, &W, smem + (size_t)grp * smem_per_instance, false);
   const float* cs = d.cur_s + (size_t)b * 3 * (T + 1);   // [3][T+1]
   const float* cu = d.cur_u + (size_t)b * 2 * T;         // [2][T]
   const float* rf = d.ref_s + (size_t)b * 3 * (T + 1);
-  for (int i = lane; i < 3 * (T + 1); i += 32) {
+  for (int i = lane; i < 3 * (T + 1); i += G) {
     int r = i / (T + 1), t = i - r * (T + 1);
     W.lins[3 * t + r] = cs[i];
     W.ref[3 * t + r] = rf[i];
   }
-  for (int i = lane; i < 2 * T; i += 32) {
+  for (int i = lane; i < 2 * T; i += G) {
     int r = i / T, t = i - r * T;
     W.linu[2 * t + r] = cu[i];
     W.pref[2 * t + r] = d.pref[(size_t)b * 2 * T + i];
   }
-  for (int t = lane; t < T; t += 32) W.d[t] = d.dis[(size_t)b * T + t];
+  for (int t = lane; t < T; t += G) W.d[t] = d.dis[(size_t)b * T + t];
   // per-hinge data stays in global memory (L2): every entry is touched only by the lane that owns
   // its stage, consecutive lanes read consecutive addresses
   float* cf = d.coef + (size_t)b * 5 * NT;
@@ -121,38 +158,37 @@ __global__ void __launch_bounds__(32) k_su(DevPtrs d, SuParams P) {
   W.hs = (Real*)(d.su_scratch + (size_t)b * 2 * NT);
   W.hnu = W.hs + NT;
   W.vref = d.ref_speed[b];
-  __syncwarp();
-  WarpCtx ctx;
+  ctx.sync();
   int iters = 0;
-  int st = su_solve<Real, WarpCtx>(P, W, ctx, cf + 3 * NT, cf + 4 * NT, &iters);
-  __syncwarp();
+  int st = su_solve<Real, GroupCtx<G>>(P, W, ctx, cf + 3 * NT, cf + 4 * NT, &iters);
+  ctx.sync();
   // accept OPTIMAL and OPTIMAL_INACCURATE (iteration cap), else keep the previous nominal
   // ("No update of state and control vector", rda_solver.py:696-700)
   bool ok = st != 2;
   if (ok) {
-    for (int i = lane; i < 3 * (T + 1); i += 32) {
+    for (int i = lane; i < 3 * (T + 1); i += G) {
       int r = i / (T + 1), t = i - r * (T + 1);
       float v = (float)W.s[3 * t + r];
       if (!isfinite(v)) ok = false;
     }
-    for (int i = lane; i < 2 * T; i += 32) {
+    for (int i = lane; i < 2 * T; i += G) {
       int r = i / T, t = i - r * T;
       if (!isfinite((float)W.u[2 * t + r])) ok = false;
     }
-    ok = __all_sync(0xffffffffu, ok);
+    ok = ctx.min((int)ok) != 0;
   }
   if (ok) {
     float* ws = d.cur_s + (size_t)b * 3 * (T + 1);
     float* wu = d.cur_u + (size_t)b * 2 * T;
-    for (int i = lane; i < 3 * (T + 1); i += 32) {
+    for (int i = lane; i < 3 * (T + 1); i += G) {
       int r = i / (T + 1), t = i - r * (T + 1);
       ws[i] = (float)W.s[3 * t + r];
     }
-    for (int i = lane; i < 2 * T; i += 32) {
+    for (int i = lane; i < 2 * T; i += G) {
       int r = i / T, t = i - r * T;
       wu[i] = (float)W.u[2 * t + r];
     }
-    for (int t = lane; t < T; t += 32) d.dis[(size_t)b * T + t] = (float)W.d[t];
+    for (int t = lane; t < T; t += G) d.dis[(size_t)b * T + t] = (float)W.d[t];
   }
   if (lane == 0) {
     d.iters[b] += 1;
@@ -165,12 +201,6 @@ __global__ void __launch_bounds__(32) k_su(DevPtrs d, SuParams P) {
   }
 }
 
-// ------------------------------------------------------------------------------------------------
-// K2: (lam, mu, z) cells + multiplier update.  Two passes:
-//   k_cells_fast  one thread per cell, closed-form paths only; cells that need the interior point
-//                 method are appended to a worklist (warp-aggregated atomic);
-//   k_cells_slow  one thread per worklist entry (dense: no lane idles behind a slow neighbour).
-// ------------------------------------------------------------------------------------------------
 // inputs of one cell gathered from the persistent state
 struct CellIn {
   int b, o, t, kind;
@@ -561,8 +591,10 @@ int rda_create(const rda_config* cfg, const rda_tunables* tun, rda_handle** out)
   alloc((float**)&h->worklist2, B * NT);
   alloc((float**)&h->su_scratch, B * 2 * NT * 2 * 2);      // doubles: 2 arrays x NT x (8/4 floats)
   if (e != cudaSuccess) { rda_destroy(h); return (int)e; }
-  if (cfg->su_fp64) e = cudaFuncSetAttribute(k_su<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->su_smem);
-  else e = cudaFuncSetAttribute(k_su<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->su_smem);
+  const int su_cta_smem = (int)h->su_smem * (32 / RDA_SU_GROUP);
+  if (su_cta_smem > 227 * 1024) { rda_destroy(h); return RDA_E_UNSUPPORTED; }
+  if (cfg->su_fp64) e = cudaFuncSetAttribute(k_su<double, RDA_SU_GROUP>, cudaFuncAttributeMaxDynamicSharedMemorySize, su_cta_smem);
+  else e = cudaFuncSetAttribute(k_su<float, RDA_SU_GROUP>, cudaFuncAttributeMaxDynamicSharedMemorySize, su_cta_smem);
   if (e != cudaSuccess) { rda_destroy(h); return (int)e; }
   rc = rda_cold_start(h, nullptr);
   if (rc) { rda_destroy(h); return rc; }
@@ -649,8 +681,11 @@ int rda_step_su(rda_handle* h, void* stream) {
   if (!h || !h->began) return RDA_E_ARG;
   DevPtrs d = dev_ptrs(h);
   SuParams P = su_params(h);
-  if (h->cfg.su_fp64) k_su<double><<<h->B, 32, h->su_smem, (cudaStream_t)stream>>>(d, P);
-  else k_su<float><<<h->B, 32, h->su_smem, (cudaStream_t)stream>>>(d, P);
+  constexpr int per_warp = 32 / RDA_SU_GROUP;
+  const int grid = (h->B + per_warp - 1) / per_warp;
+  const size_t cta_smem = h->su_smem * per_warp;
+  if (h->cfg.su_fp64) k_su<double, RDA_SU_GROUP><<<grid, 32, cta_smem, (cudaStream_t)stream>>>(d, P, (int)h->su_smem);
+  else k_su<float, RDA_SU_GROUP><<<grid, 32, cta_smem, (cudaStream_t)stream>>>(d, P, (int)h->su_smem);
   RDA_CUDA(cudaGetLastError());
   h->launches += 1;
   return 0;
