@@ -45,24 +45,6 @@ struct rda_handle {
 
 namespace {
 
-struct WarpCtx {
-  __device__ __forceinline__ int lane() const { return threadIdx.x & 31; }
-  __device__ __forceinline__ int nlanes() const { return 32; }
-  __device__ __forceinline__ void sync() const { __syncwarp(); }
-  template <typename R> __device__ __forceinline__ R sum(R x) const {
-    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-    return x;
-  }
-  template <typename R> __device__ __forceinline__ R min(R x) const {
-    for (int o = 16; o > 0; o >>= 1) { R y = __shfl_xor_sync(0xffffffffu, x, o); x = y < x ? y : x; }
-    return x;
-  }
-  template <typename R> __device__ __forceinline__ R max(R x) const {
-    for (int o = 16; o > 0; o >>= 1) { R y = __shfl_xor_sync(0xffffffffu, x, o); x = y > x ? y : x; }
-    return x;
-  }
-};
-
 // Sub-warp group of G lanes (G = 16, 8): several instances share one warp.  All synchronisation and
 // shuffles use the group's own lane mask, so the groups of a warp may diverge (different interior
 // point iteration counts) and re-converge freely (independent thread scheduling); while they run in
