@@ -19,5 +19,5 @@ s = RDA_solver(30, rectangle_robot(), max_edge_num=4, max_obs_num=20, iter_num=I
 s.iterative_solve_batch(d['nom_s'], d['nom_u'], d['ref_s'], d['ref_speed'], d['obs_A'], d['obs_b'], d['obs_kind'], d['obs_count'], False)
 torch.cuda.synchronize()
 os.makedirs('gpurun_out', exist_ok=True)
-json.dump({'batch': B, 'admm_iterations': ITERS, 'captured": "one launch of each kernel in ADMM iteration 8"},
+json.dump({'batch': B, 'admm_iterations': ITERS, 'captured': 'one launch of each kernel of an ADMM iteration in steady state'},
           open('gpurun_out/prof_r01_meta.json', 'w'))

@@ -71,7 +71,7 @@ if os.path.exists(rp):
             def gb(key):
                 v, u = float(r[idx[key]].replace(',', '')), units[idx[key]]
                 return v * {'Gbyte': 1e9, 'Mbyte': 1e6, 'Kbyte': 1e3, 'byte': 1.0}[u]
-            key = 'k_su' if name.startswith('k_su') else name
+            key = name.split('<')[0]
             traffic[key] = gb('dram__bytes_read.sum') + gb('dram__bytes_write.sum')
     meta = {}
     mp = os.path.join(ROOT, 'gpurun_out', f'prof_{tag}_meta.json')
