@@ -166,6 +166,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device(f'cuda:{local}')
     if world > 1:
+        os.environ.setdefault('NCCL_DEBUG', 'WARN')      # keep stdout to the one JSON line
         dist.init_process_group('nccl', device_id=dev)
     rbuild.build()
     B = args.batch
