@@ -35,22 +35,23 @@ struct SuParams {
 template <typename Real>
 struct SuWork {
   Real *s, *u, *d;            // iterate: 3(T+1), 2T, T
-  Real *ref;                  // 3(T+1)
-  Real *lins, *linu;          // linearisation point 3(T+1), 2T
-  Real *cph, *sph;            // cos/sin of nominal heading (column t)
-  Real *Aj, *Bj, *Cj;         // 2T (A02, A12), 6T, 3T
+  float *ref;                 // 3(T+1)   (inputs stay in the float32 they arrive in)
+  float *lins, *linu;         // linearisation point 3(T+1), 2T; linu is dead after the setup (shares dv)
+  Real *Aj, *Bj, *Cj;         // 2T (A02, A12), 6T, 3T; Cj is dead after the initial rollout (shares kf)
   Real *Skk, *Sgk;            // aggregated rotation-consensus terms
-  Real *pref;                 // 2T positions the hinge offsets refer to
+  float *pref;                // 2T positions the hinge offsets refer to
   float *hx, *hy, *hc;        // hinge rows: lam'A (2) and offset
   Real *hs, *hnu;             // hinge slack / multiplier
   Real *bs, *bnu;             // 10T box/rate slack / multiplier
   Real *Wm;                   // 6T hinge Hessian (xx, xy, xd, yy, yd, dd)
   Real *gw;                   // 8T gradient in stage coordinates
   Real *wb;                   // 5T barrier weights (u0, u1, d, rate0, rate1)
-  Real *K, *Lc, *kf;          // 15T, 6T, 3T Riccati gains / Cholesky of Hvv / feed-forward
-  Real *rw;                   // 128 scratch of the lane-parallel Riccati step (Q, t-columns, H blocks, P)
+  Real *K, *Lc, *kf;          // 15T, 6T, 3T Riccati gains / L D L' of Hvv / feed-forward
   Real *dz, *dv;              // 5(T+1), 3T Newton step
-  Real *dza, *dva;            // affine (predictor) step
+  Real *dza, *dva;            // affine (predictor) step.  Shares the storage of (Wm, wb): those are
+                              // consumed by the factorising backward sweep of the predictor, the affine
+                              // step is produced by the forward sweep that follows it and is dead before
+                              // the next predictor assembles (Wm, wb) again.
   Real vref;
 };
 
@@ -68,19 +69,23 @@ RDA_HD size_t su_work_layout(int T, int N, SuWork<Real>* w, char* base, bool hin
   };
 #define RDA_TAKE(field, n, type) { char* p_ = take((size_t)(n), sizeof(type)); if (w) w->field = (type*)p_; }
   RDA_TAKE(s, 3 * (T + 1), Real) RDA_TAKE(u, 2 * T, Real) RDA_TAKE(d, T, Real)
-  RDA_TAKE(ref, 3 * (T + 1), Real) RDA_TAKE(lins, 3 * (T + 1), Real) RDA_TAKE(linu, 2 * T, Real)
-  RDA_TAKE(cph, T, Real) RDA_TAKE(sph, T, Real)
-  RDA_TAKE(Aj, 2 * T, Real) RDA_TAKE(Bj, 6 * T, Real) RDA_TAKE(Cj, 3 * T, Real)
-  RDA_TAKE(Skk, T, Real) RDA_TAKE(Sgk, T, Real) RDA_TAKE(pref, 2 * T, Real)
+  RDA_TAKE(ref, 3 * (T + 1), float) RDA_TAKE(lins, 3 * (T + 1), float)
+  RDA_TAKE(Aj, 2 * T, Real) RDA_TAKE(Bj, 6 * T, Real)
+  RDA_TAKE(Skk, T, Real) RDA_TAKE(Sgk, T, Real) RDA_TAKE(pref, 2 * T, float)
   if (hinge_arrays) {
     RDA_TAKE(hx, N * T, float) RDA_TAKE(hy, N * T, float) RDA_TAKE(hc, N * T, float)
     RDA_TAKE(hs, N * T, Real) RDA_TAKE(hnu, N * T, Real)
   }
   RDA_TAKE(bs, 10 * T, Real) RDA_TAKE(bnu, 10 * T, Real)
-  RDA_TAKE(Wm, 6 * T, Real) RDA_TAKE(gw, 8 * T, Real) RDA_TAKE(wb, 5 * T, Real)
-  RDA_TAKE(K, 15 * T, Real) RDA_TAKE(Lc, 6 * T, Real) RDA_TAKE(kf, 3 * T, Real) RDA_TAKE(rw, 128, Real)
+  {
+    const int shared = 11 * T > 8 * T + 5 ? 11 * T : 8 * T + 5;     // (Wm, wb) | (dza, dva)
+    RDA_TAKE(Wm, shared, Real)
+    if (w) { w->wb = w->Wm + 6 * T; w->dza = w->Wm; w->dva = w->Wm + 5 * (T + 1); }
+  }
+  RDA_TAKE(gw, 8 * T, Real)
+  RDA_TAKE(K, 15 * T, Real) RDA_TAKE(Lc, 6 * T, Real) RDA_TAKE(kf, 3 * T, Real)
   RDA_TAKE(dz, 5 * (T + 1), Real) RDA_TAKE(dv, 3 * T, Real)
-  RDA_TAKE(dza, 5 * (T + 1), Real) RDA_TAKE(dva, 3 * T, Real)
+  if (w) { w->Cj = w->kf; w->linu = (float*)w->dv; }
 #undef RDA_TAKE
   return (off + 15) & ~(size_t)15;
 }
@@ -174,8 +179,6 @@ RDA_HD void su_riccati(const SuParams& P, SuWork<Real>& W, Ctx& ctx, bool factor
     const Real a02 = W.Aj[2 * t], a12 = W.Aj[2 * t + 1];
     const Real* Bt = W.Bj + 6 * t;
     const Real b00 = Bt[0], b01 = Bt[1], b10 = Bt[2], b11 = Bt[3], b20 = Bt[4], b21 = Bt[5];
-    const Real* wb = W.wb + 5 * t;
-    const Real wr0 = wb[3], wr1 = wb[4];
     // gradient in q-space (+ cost-to-go), pulled back through J
     const Real* gw = W.gw + 8 * t;
     const Real q0 = gw[0] + pv[0], q1 = gw[1] + pv[1], q2 = gw[2] + pv[2], q3 = gw[3] + pv[3],
@@ -187,6 +190,8 @@ RDA_HD void su_riccati(const SuParams& P, SuWork<Real>& W, Ctx& ctx, bool factor
     Real i00, L10, i11, L20, L21, i22;   // L D L' of Hvv: unit-lower entries and reciprocal pivots
     Real Kt[3][5];
     if (factor) {
+      const Real* wb = W.wb + 5 * t;
+      const Real wr0 = wb[3], wr1 = wb[4];
       Real Q[6][6];
       for (int a = 0; a < 5; ++a) { for (int b = 0; b < 5; ++b) Q[a][b] = Pm[a][b]; Q[a][5] = 0; Q[5][a] = 0; }
       const Real* M = W.Wm + 6 * t;
@@ -307,10 +312,11 @@ RDA_HD int su_solve(const SuParams& P, SuWork<Real>& W, Ctx& ctx, const float* g
   const bool acc = P.accelerated != 0;
   // ---- linearisation and aggregated rotation terms (lane-parallel over stages) ----
   for (int t = lane; t < T; t += nl) {
-    su_linearise<Real>(P, W.lins + 3 * t, W.linu + 2 * t, W.Aj + 2 * t, W.Bj + 6 * t, W.Cj + 3 * t);
-    Real phib = W.lins[3 * t + 2];
+    const Real st[3] = {(Real)W.lins[3 * t], (Real)W.lins[3 * t + 1], (Real)W.lins[3 * t + 2]};
+    const Real ut[2] = {(Real)W.linu[2 * t], (Real)W.linu[2 * t + 1]};
+    su_linearise<Real>(P, st, ut, W.Aj + 2 * t, W.Bj + 6 * t, W.Cj + 3 * t);
+    Real phib = st[2];
     Real c = cos(phib), s = sin(phib);
-    W.cph[t] = c; W.sph[t] = s;
     Real skk = 0, sgk = 0;
     for (int o = 0; o < N; ++o) {
       Real ax = W.hx[o * T + t], ay = W.hy[o * T + t];
@@ -321,7 +327,7 @@ RDA_HD int su_solve(const SuParams& P, SuWork<Real>& W, Ctx& ctx, const float* g
       sgk += g0 * k0 + g1 * k1;
     }
     W.Skk[t] = skk; W.Sgk[t] = sgk;
-    W.u[2 * t] = W.linu[2 * t]; W.u[2 * t + 1] = W.linu[2 * t + 1];
+    W.u[2 * t] = ut[0]; W.u[2 * t + 1] = ut[1];
   }
   ctx.sync();
   // ---- initial iterate: roll the linearised model out from s_0 ----
@@ -412,6 +418,7 @@ RDA_HD int su_solve(const SuParams& P, SuWork<Real>& W, Ctx& ctx, const float* g
         Real m0 = 0, m1 = 0, m2 = 0, m3 = 0, m4 = 0, m5 = 0;
         Real dx = sn[0] - W.pref[2 * t], dy = sn[1] - W.pref[2 * t + 1];
         Real dd = W.d[t];
+        Real g0 = gw[0], g1 = gw[1], g5 = gw[5];     // accumulated in registers: no store inside the hinge loop
         for (int o = 0; o < N; ++o) {
           Real ax = W.hx[o * T + t], ay = W.hy[o * T + t];
           Real l = ax * dx + ay * dy + (Real)W.hc[o * T + t] - dd;
@@ -437,12 +444,13 @@ RDA_HD int su_solve(const SuParams& P, SuWork<Real>& W, Ctx& ctx, const float* g
             om = ro1;               // plain quadratic 1/2 ro1 Im^2  (rda_solver.py:378-379)
             tk = -ro1 * l;
           }
-          gw[0] -= ax * tk; gw[1] -= ay * tk; gw[5] += tk;
+          g0 -= ax * tk; g1 -= ay * tk; g5 += tk;
           if (phase == 0) {
             m0 += om * ax * ax; m1 += om * ax * ay; m2 -= om * ax;
             m3 += om * ay * ay; m4 -= om * ay; m5 += om;
           }
         }
+        gw[0] = g0; gw[1] = g1; gw[5] = g5;
         if (phase == 0) {
           Real* M = W.Wm + 6 * t;
           M[0] = m0; M[1] = m1; M[2] = m2; M[3] = m3; M[4] = m4; M[5] = m5;
