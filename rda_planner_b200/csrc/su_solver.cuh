@@ -44,10 +44,12 @@ struct SuWork {
   Real *hs, *hnu;             // hinge slack / multiplier
   Real *bs, *bnu;             // 10T box/rate slack / multiplier
   Real *Wm;                   // 6T hinge Hessian (xx, xy, xd, yy, yd, dd)
-  Real *gw;                   // 8T gradient in stage coordinates
+  Real *gw;                   // 8T gradient in stage coordinates: right-hand side of a backward sweep
   Real *wb;                   // 5T barrier weights (u0, u1, d, rate0, rate1)
   Real *K, *Lc, *kf;          // 15T, 6T, 3T Riccati gains / L D L' of Hvv / feed-forward
-  Real *dz, *dv;              // 5(T+1), 3T Newton step
+  Real *dz, *dv;              // 5(T+1), 3T Newton step.  Shares the storage of gw: the corrector's forward
+                              // sweep writes it after the backward sweep has consumed gw, and it is dead
+                              // (iterate updated) before the next predictor assembles gw.
   Real *dza, *dva;            // affine (predictor) step.  Shares the storage of (Wm, wb): those are
                               // consumed by the factorising backward sweep of the predictor, the affine
                               // step is produced by the forward sweep that follows it and is dead before
@@ -82,9 +84,9 @@ RDA_HD size_t su_work_layout(int T, int N, SuWork<Real>* w, char* base, bool hin
     RDA_TAKE(Wm, shared, Real)
     if (w) { w->wb = w->Wm + 6 * T; w->dza = w->Wm; w->dva = w->Wm + 5 * (T + 1); }
   }
-  RDA_TAKE(gw, 8 * T, Real)
+  RDA_TAKE(gw, 8 * T + 5, Real)                                       // gw | (dz, dv)
+  if (w) { w->dz = w->gw; w->dv = w->gw + 5 * (T + 1); }
   RDA_TAKE(K, 15 * T, Real) RDA_TAKE(Lc, 6 * T, Real) RDA_TAKE(kf, 3 * T, Real)
-  RDA_TAKE(dz, 5 * (T + 1), Real) RDA_TAKE(dv, 3 * T, Real)
   if (w) { w->Cj = w->kf; w->linu = (float*)w->dv; }
 #undef RDA_TAKE
   return (off + 15) & ~(size_t)15;
