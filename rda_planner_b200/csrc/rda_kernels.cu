@@ -8,6 +8,7 @@
 // No host synchronisation, no allocation, CUDA-graph capturable.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <new>
 #include "rda_hd.h"
@@ -39,6 +40,13 @@ struct rda_handle {
   int launches;
   size_t su_smem;
   int began;
+  // rda_solve runs a large batch as `parts` contiguous sub-batches on as many streams (the caller's
+  // and `side[]`), so that the latency-bound worklist passes and the tail of the su-QP kernel of one
+  // sub-batch overlap the kernels of the others
+  cudaStream_t side[3];
+  cudaEvent_t ev_fork, ev_join[3];
+  int split_min;         // smallest batch that is split (RDA_B200_SPLIT_MIN, default 2048)
+  int parts;             // number of sub-batches, 1..4 (RDA_B200_SPLIT_PARTS, default 2)
 };
 
 #define RDA_CUDA(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return (int)e_; } while (0)
@@ -77,6 +85,7 @@ struct DevPtrs {
   float *lam, *mu, *z, *xi, *zeta, *dis, *coef, *pref, *cur_s, *cur_u, *ref_s, *ref_speed;
   float *resi_acc, *resi_pri, *resi_dual;
   int *status, *iters, *done, *counters, *worklist, *worklist2;
+  int* wl_count;         // lengths of the two worklists of this sub-batch
   double* su_scratch;
   const float *obs_A, *obs_b;
   const int *obs_kind, *obs_count;
@@ -340,7 +349,7 @@ __global__ void __launch_bounds__(128, (EC <= 4 ? 6 : 3)) k_cells_fast(DevPtrs d
     unsigned nm = __ballot_sync(0xffffffffu, need);
     if (nm) {
       int leader = __ffs(nm) - 1, pos = 0;
-      if (lane == leader) pos = atomicAdd(&d.counters[5], __popc(nm));
+      if (lane == leader) pos = atomicAdd(&d.wl_count[0], __popc(nm));
       pos = __shfl_sync(0xffffffffu, pos, leader);
       if (need) d.worklist[pos + __popc(nm & ((1u << lane) - 1))] = (int)idx;
     }
@@ -371,7 +380,7 @@ __global__ void __launch_bounds__(128, (EC <= 4 ? 6 : 3)) k_cells_fast(DevPtrs d
 // Second pass: the searched closed forms (vertex / edge contact, overlap cases) for the cells of the
 // first worklist, one thread per entry; what is still unresolved goes to the second worklist.
 __global__ void __launch_bounds__(128) k_cells_mid(DevPtrs d, RobotGeom rb, float ro2, float theta) {
-  const int count = d.counters[5];
+  const int count = d.wl_count[0];
   const int lane = threadIdx.x & 31;
   for (int base = blockIdx.x * blockDim.x; base < count; base += gridDim.x * blockDim.x) {
     const int wi = base + threadIdx.x;
@@ -397,7 +406,7 @@ __global__ void __launch_bounds__(128) k_cells_mid(DevPtrs d, RobotGeom rb, floa
     unsigned m = __ballot_sync(0xffffffffu, need);
     if (m) {
       int leader = __ffs(m) - 1, pos = 0;
-      if (lane == leader) pos = atomicAdd(&d.counters[6], __popc(m));
+      if (lane == leader) pos = atomicAdd(&d.wl_count[1], __popc(m));
       pos = __shfl_sync(0xffffffffu, pos, leader);
       if (need) d.worklist2[pos + __popc(m & ((1u << lane) - 1))] = (int)idx;
     }
@@ -411,7 +420,7 @@ __global__ void __launch_bounds__(128) k_cells_mid(DevPtrs d, RobotGeom rb, floa
 #define RDA_SLOW_MINBLOCKS 16
 #endif
 __global__ void __launch_bounds__(64, RDA_SLOW_MINBLOCKS) k_cells_slow(DevPtrs d, RobotGeom rb, float ro2, float theta) {
-  const int count = d.counters[6];
+  const int count = d.wl_count[1];
   for (int wi = blockIdx.x * blockDim.x + threadIdx.x; wi < count; wi += gridDim.x * blockDim.x) {
     const long long idx = d.worklist2[wi];
     CellIn c = cell_load(d, idx);
@@ -441,7 +450,7 @@ __global__ void __launch_bounds__(64, RDA_SLOW_MINBLOCKS) k_cells_slow(DevPtrs d
 // per instance: residuals (:688, :735-739), early stop (:594-596), empty-list quirk (:564-568)
 __global__ void k_finalize(DevPtrs d, RobotGeom rb, float thr) {
   int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b == 0) { d.counters[5] = 0; d.counters[6] = 0; }   // worklists consumed
+  if (b == 0) { d.wl_count[0] = 0; d.wl_count[1] = 0; }   // worklists consumed
   if (b >= d.B) return;
   if (d.done[b]) return;
   const int T = d.T, N = d.N, NT = N * T, R = d.R;
@@ -503,17 +512,30 @@ __global__ void k_fill(float* p, float v, size_t n) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
 }
 
-DevPtrs dev_ptrs(const rda_handle* h) {
+// pointers of the sub-batch [b0, b0 + nb) (part = 0, 1 selects its worklist counters)
+DevPtrs dev_ptrs(const rda_handle* h, int b0, int nb, int part) {
   DevPtrs d;
-  d.lam = h->lam; d.mu = h->mu; d.z = h->z; d.xi = h->xi; d.zeta = h->zeta; d.dis = h->dis;
-  d.coef = h->coef; d.pref = h->pref; d.cur_s = h->cur_s; d.cur_u = h->cur_u; d.ref_s = h->ref_s;
-  d.ref_speed = h->ref_speed; d.resi_acc = h->resi_acc; d.resi_pri = h->resi_pri; d.resi_dual = h->resi_dual;
-  d.status = h->status; d.iters = h->iters; d.done = h->done; d.counters = h->counters; d.worklist = h->worklist; d.worklist2 = h->worklist2; d.su_scratch = h->su_scratch;
-  d.obs_A = h->obs_A; d.obs_b = h->obs_b; d.obs_kind = h->obs_kind; d.obs_count = h->obs_count;
+  const size_t o = (size_t)b0, T = h->T, N = h->N, E = h->E, R = h->R, NT = N * T;
+  const size_t Tc = h->obs_tv ? T + 1 : 1;
+  d.lam = h->lam + o * N * E * T; d.mu = h->mu + o * N * R * T; d.z = h->z + o * NT; d.xi = h->xi + o * 2 * NT;
+  d.zeta = h->zeta + o * NT; d.dis = h->dis + o * T; d.coef = h->coef + o * 5 * NT; d.pref = h->pref + o * 2 * T;
+  d.cur_s = h->cur_s + o * 3 * (T + 1); d.cur_u = h->cur_u + o * 2 * T; d.ref_s = h->ref_s + o * 3 * (T + 1);
+  d.ref_speed = h->ref_speed + o; d.resi_acc = h->resi_acc + 2 * o; d.resi_pri = h->resi_pri + o;
+  d.resi_dual = h->resi_dual + o;
+  d.status = h->status + o; d.iters = h->iters + o; d.done = h->done + o;
+  d.counters = h->counters; d.wl_count = h->counters + 8 + 2 * part;     // part < 4
+  d.worklist = h->worklist + o * NT; d.worklist2 = h->worklist2 + o * NT;
+  d.su_scratch = h->su_scratch + o * 2 * NT;
+  d.obs_A = h->obs_A ? h->obs_A + o * N * Tc * E * 2 : nullptr;
+  d.obs_b = h->obs_b ? h->obs_b + o * N * Tc * E : nullptr;
+  d.obs_kind = h->obs_kind ? h->obs_kind + o * N : nullptr;
+  d.obs_count = h->obs_count ? h->obs_count + o : nullptr;
   d.obs_tv = h->obs_tv;
-  d.B = h->B; d.T = h->T; d.N = h->N; d.E = h->E; d.R = h->R;
+  d.B = nb; d.T = h->T; d.N = h->N; d.E = h->E; d.R = h->R;
   return d;
 }
+
+DevPtrs dev_ptrs(const rda_handle* h) { return dev_ptrs(h, 0, h->B, 0); }
 
 SuParams su_params(const rda_handle* h) {
   SuParams P;
@@ -568,7 +590,7 @@ int rda_create(const rda_config* cfg, const rda_tunables* tun, rda_handle** out)
   alloc(&h->cur_u, B * 2 * T); alloc(&h->ref_s, B * 3 * (T + 1)); alloc(&h->ref_speed, B);
   alloc(&h->resi_acc, B * 2); alloc(&h->resi_pri, B); alloc(&h->resi_dual, B);
   alloc((float**)&h->status, B); alloc((float**)&h->iters, B); alloc((float**)&h->done, B);
-  alloc((float**)&h->counters, 8);
+  alloc((float**)&h->counters, 16);     // [0..4] statistics, [8..11] worklist lengths of the two halves
   alloc((float**)&h->worklist, B * NT);
   alloc((float**)&h->worklist2, B * NT);
   alloc((float**)&h->su_scratch, B * 2 * NT * 2 * 2);      // doubles: 2 arrays x NT x (8/4 floats)
@@ -578,6 +600,16 @@ int rda_create(const rda_config* cfg, const rda_tunables* tun, rda_handle** out)
   if (cfg->su_fp64) e = cudaFuncSetAttribute(k_su<double, RDA_SU_GROUP>, cudaFuncAttributeMaxDynamicSharedMemorySize, su_cta_smem);
   else e = cudaFuncSetAttribute(k_su<float, RDA_SU_GROUP>, cudaFuncAttributeMaxDynamicSharedMemorySize, su_cta_smem);
   if (e != cudaSuccess) { rda_destroy(h); return (int)e; }
+  e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
+  for (int p = 0; p < 3; ++p) {
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->side[p], cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_join[p], cudaEventDisableTiming);
+  }
+  if (e != cudaSuccess) { rda_destroy(h); return (int)e; }
+  h->split_min = 2048;
+  h->parts = 2;
+  if (const char* sm = getenv("RDA_B200_SPLIT_MIN")) { int v = atoi(sm); if (v >= 2) h->split_min = v; }
+  if (const char* sp = getenv("RDA_B200_SPLIT_PARTS")) { int v = atoi(sp); if (v >= 1 && v <= 4) h->parts = v; }
   rc = rda_cold_start(h, nullptr);
   if (rc) { rda_destroy(h); return rc; }
   e = cudaDeviceSynchronize();
@@ -592,6 +624,11 @@ int rda_destroy(rda_handle* h) {
                    h->ref_s, h->ref_speed, h->resi_acc, h->resi_pri, h->resi_dual, (float*)h->status,
                    (float*)h->iters, (float*)h->done, (float*)h->counters, (float*)h->worklist, (float*)h->worklist2, (float*)h->su_scratch};
   for (float* p : bufs) if (p) cudaFree(p);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  for (int p = 0; p < 3; ++p) {
+    if (h->ev_join[p]) cudaEventDestroy(h->ev_join[p]);
+    if (h->side[p]) cudaStreamDestroy(h->side[p]);
+  }
   delete h;
   return 0;
 }
@@ -627,7 +664,7 @@ int rda_cold_start(rda_handle* h, void* stream) {
   RDA_CUDA(cudaMemsetAsync(h->status, 0, B * 4, s));
   RDA_CUDA(cudaMemsetAsync(h->iters, 0, B * 4, s));
   RDA_CUDA(cudaMemsetAsync(h->done, 0, B * 4, s));
-  RDA_CUDA(cudaMemsetAsync(h->counters, 0, 8 * 4, s));
+  RDA_CUDA(cudaMemsetAsync(h->counters, 0, 16 * 4, s));
   k_fill<<<grid_for((long long)(B * T), 256), 256, 0, s>>>(h->dis, 1.0f, B * T);   // para_dis = 1 (:119)
   RDA_CUDA(cudaGetLastError());
   h->launches = 1;
@@ -644,45 +681,39 @@ int rda_reset(rda_handle* h, void* stream) {
   return 0;
 }
 
-int rda_begin(rda_handle* h, const rda_inputs* in, float iter_threshold, void* stream) {
-  if (!h || !in || !in->nom_s || !in->nom_u || !in->ref_s || !in->ref_speed) return RDA_E_ARG;
-  if (h->N > 0 && (!in->obs_A || !in->obs_b || !in->obs_kind || !in->obs_count)) return RDA_E_ARG;
-  h->obs_A = in->obs_A; h->obs_b = in->obs_b; h->obs_kind = in->obs_kind; h->obs_count = in->obs_count;
-  h->obs_tv = in->obs_time_varying;
-  h->iter_threshold = iter_threshold;
-  DevPtrs d = dev_ptrs(h);
-  k_begin<<<grid_for((long long)h->B * 3 * (h->T + 1), 256), 256, 0, (cudaStream_t)stream>>>(
-      d, in->nom_s, in->nom_u, in->ref_s, in->ref_speed);
-  RDA_CUDA(cudaGetLastError());
-  h->began = 1;
-  h->launches = 1;
-  return 0;
-}
-
-int rda_step_su(rda_handle* h, void* stream) {
-  if (!h || !h->began) return RDA_E_ARG;
-  DevPtrs d = dev_ptrs(h);
-  SuParams P = su_params(h);
-  constexpr int per_warp = 32 / RDA_SU_GROUP;
-  const int grid = (h->B + per_warp - 1) / per_warp;
-  const size_t cta_smem = h->su_smem * per_warp;
-  if (h->cfg.su_fp64) k_su<double, RDA_SU_GROUP><<<grid, 32, cta_smem, (cudaStream_t)stream>>>(d, P, (int)h->su_smem);
-  else k_su<float, RDA_SU_GROUP><<<grid, 32, cta_smem, (cudaStream_t)stream>>>(d, P, (int)h->su_smem);
+// ---- the launches of one sub-batch [b0, b0 + nb) on stream s (part selects its worklist counters) ----
+static int begin_part(rda_handle* h, const rda_inputs* in, int b0, int nb, int part, cudaStream_t s) {
+  DevPtrs d = dev_ptrs(h, b0, nb, part);
+  const size_t o = (size_t)b0, T = h->T;
+  k_begin<<<grid_for((long long)nb * 3 * (h->T + 1), 256), 256, 0, s>>>(
+      d, (const float*)in->nom_s + o * 3 * (T + 1), (const float*)in->nom_u + o * 2 * T,
+      (const float*)in->ref_s + o * 3 * (T + 1), (const float*)in->ref_speed + o);
   RDA_CUDA(cudaGetLastError());
   h->launches += 1;
   return 0;
 }
 
-int rda_step_lammuz(rda_handle* h, void* stream) {
-  if (!h || !h->began) return RDA_E_ARG;
-  DevPtrs d = dev_ptrs(h);
-  cudaStream_t s = (cudaStream_t)stream;
+static int step_su_part(rda_handle* h, int b0, int nb, int part, cudaStream_t s) {
+  DevPtrs d = dev_ptrs(h, b0, nb, part);
+  SuParams P = su_params(h);
+  constexpr int per_warp = 32 / RDA_SU_GROUP;
+  const int grid = (nb + per_warp - 1) / per_warp;
+  const size_t cta_smem = h->su_smem * per_warp;
+  if (h->cfg.su_fp64) k_su<double, RDA_SU_GROUP><<<grid, 32, cta_smem, s>>>(d, P, (int)h->su_smem);
+  else k_su<float, RDA_SU_GROUP><<<grid, 32, cta_smem, s>>>(d, P, (int)h->su_smem);
+  RDA_CUDA(cudaGetLastError());
+  h->launches += 1;
+  return 0;
+}
+
+static int step_lammuz_part(rda_handle* h, int b0, int nb, int part, cudaStream_t s) {
+  DevPtrs d = dev_ptrs(h, b0, nb, part);
   if (h->N > 0) {
     const float theta = h->cfg.accelerated ? h->tun.z_theta : 1.0f;
     if (h->E <= 4 && h->R <= 4)
-      k_cells_fast<4, 4><<<grid_for((long long)h->B * h->N * h->T, 128), 128, 0, s>>>(d, h->rb, theta);
+      k_cells_fast<4, 4><<<grid_for((long long)nb * h->N * h->T, 128), 128, 0, s>>>(d, h->rb, theta);
     else
-      k_cells_fast<8, 8><<<grid_for((long long)h->B * h->N * h->T, 128), 128, 0, s>>>(d, h->rb, theta);
+      k_cells_fast<8, 8><<<grid_for((long long)nb * h->N * h->T, 128), 128, 0, s>>>(d, h->rb, theta);
     RDA_CUDA(cudaGetLastError());
     k_cells_mid<<<148 * 8, 128, 0, s>>>(d, h->rb, h->tun.ro2, theta);
     RDA_CUDA(cudaGetLastError());
@@ -690,34 +721,115 @@ int rda_step_lammuz(rda_handle* h, void* stream) {
     RDA_CUDA(cudaGetLastError());
     h->launches += 3;
   }
-  k_finalize<<<(h->B + 127) / 128, 128, 0, s>>>(d, h->rb, h->iter_threshold);
+  k_finalize<<<(nb + 127) / 128, 128, 0, s>>>(d, h->rb, h->iter_threshold);
   RDA_CUDA(cudaGetLastError());
   h->launches += 1;
   return 0;
 }
 
-int rda_finish(rda_handle* h, const rda_outputs* out, void* stream) {
-  if (!h || !out || !out->u_opt || !out->s_opt || !out->resi_pri || !out->resi_dual || !out->status || !out->iters)
-    return RDA_E_ARG;
-  DevPtrs d = dev_ptrs(h);
-  k_finish<<<grid_for((long long)h->B * 3 * (h->T + 1), 256), 256, 0, (cudaStream_t)stream>>>(d, *out);
+static int finish_part(rda_handle* h, const rda_outputs* out, int b0, int nb, int part, cudaStream_t s) {
+  DevPtrs d = dev_ptrs(h, b0, nb, part);
+  const size_t o = (size_t)b0, T = h->T;
+  rda_outputs po = *out;
+  po.u_opt = (float*)out->u_opt + o * 2 * T;
+  po.s_opt = (float*)out->s_opt + o * 3 * (T + 1);
+  po.resi_pri = (float*)out->resi_pri + o;
+  po.resi_dual = (float*)out->resi_dual + o;
+  po.status = (int*)out->status + o;
+  po.iters = (int*)out->iters + o;
+  k_finish<<<grid_for((long long)nb * 3 * (h->T + 1), 256), 256, 0, s>>>(d, po);
   RDA_CUDA(cudaGetLastError());
   h->launches += 1;
   return 0;
+}
+
+static int check_inputs(rda_handle* h, const rda_inputs* in, float iter_threshold) {
+  if (!h || !in || !in->nom_s || !in->nom_u || !in->ref_s || !in->ref_speed) return RDA_E_ARG;
+  if (h->N > 0 && (!in->obs_A || !in->obs_b || !in->obs_kind || !in->obs_count)) return RDA_E_ARG;
+  h->obs_A = (const float*)in->obs_A; h->obs_b = (const float*)in->obs_b;
+  h->obs_kind = (const int*)in->obs_kind; h->obs_count = (const int*)in->obs_count;
+  h->obs_tv = in->obs_time_varying;
+  h->iter_threshold = iter_threshold;
+  return 0;
+}
+
+static int check_outputs(const rda_handle* h, const rda_outputs* out) {
+  if (!h || !out || !out->u_opt || !out->s_opt || !out->resi_pri || !out->resi_dual || !out->status || !out->iters)
+    return RDA_E_ARG;
+  return 0;
+}
+
+int rda_begin(rda_handle* h, const rda_inputs* in, float iter_threshold, void* stream) {
+  int rc = check_inputs(h, in, iter_threshold);
+  if (rc) return rc;
+  h->launches = 0;
+  rc = begin_part(h, in, 0, h->B, 0, (cudaStream_t)stream);
+  if (rc) return rc;
+  h->began = 1;
+  return 0;
+}
+
+int rda_step_su(rda_handle* h, void* stream) {
+  if (!h || !h->began) return RDA_E_ARG;
+  return step_su_part(h, 0, h->B, 0, (cudaStream_t)stream);
+}
+
+int rda_step_lammuz(rda_handle* h, void* stream) {
+  if (!h || !h->began) return RDA_E_ARG;
+  return step_lammuz_part(h, 0, h->B, 0, (cudaStream_t)stream);
+}
+
+int rda_finish(rda_handle* h, const rda_outputs* out, void* stream) {
+  int rc = check_outputs(h, out);
+  if (rc) return rc;
+  return finish_part(h, out, 0, h->B, 0, (cudaStream_t)stream);
 }
 
 int rda_solve(rda_handle* h, const rda_inputs* in, const rda_outputs* out, int iter_num,
               float iter_threshold, void* stream) {
   if (iter_num < 1) return RDA_E_ARG;
-  int rc = rda_begin(h, in, iter_threshold, stream);
+  int rc = check_inputs(h, in, iter_threshold);
   if (rc) return rc;
-  for (int i = 0; i < iter_num; ++i) {
-    rc = rda_step_su(h, stream);
-    if (rc) return rc;
-    rc = rda_step_lammuz(h, stream);
-    if (rc) return rc;
+  rc = check_outputs(h, out);
+  if (rc) return rc;
+  cudaStream_t s0 = (cudaStream_t)stream;
+  h->launches = 0;
+  h->began = 1;
+  if (h->parts < 2 || h->B < h->split_min || h->B < h->parts) {
+    rc = begin_part(h, in, 0, h->B, 0, s0);
+    for (int i = 0; i < iter_num && !rc; ++i) {
+      rc = step_su_part(h, 0, h->B, 0, s0);
+      if (!rc) rc = step_lammuz_part(h, 0, h->B, 0, s0);
+    }
+    if (!rc) rc = finish_part(h, out, 0, h->B, 0, s0);
+    return rc;
   }
-  return rda_finish(h, out, stream);
+  // Contiguous sub-batches, each an independent chain of launches: fork the side streams from the
+  // caller's stream, enqueue the sub-batches alternately, join.  Instances never interact, so the
+  // results do not depend on the split; fork and join are events only (CUDA-graph capturable).
+  const int P = h->parts;
+  int b0[5];
+  for (int p = 0; p <= P; ++p) b0[p] = (int)((long long)h->B * p / P);
+  cudaStream_t st[4];
+  st[0] = s0;
+  for (int p = 1; p < P; ++p) st[p] = h->side[p - 1];
+  RDA_CUDA(cudaEventRecord(h->ev_fork, s0));
+  for (int p = 1; p < P; ++p) RDA_CUDA(cudaStreamWaitEvent(st[p], h->ev_fork, 0));
+  for (int p = 0; p < P && !rc; ++p) rc = begin_part(h, in, b0[p], b0[p + 1] - b0[p], p, st[p]);
+  for (int i = 0; i < iter_num && !rc; ++i) {
+    for (int p = 0; p < P && !rc; ++p) rc = step_su_part(h, b0[p], b0[p + 1] - b0[p], p, st[p]);
+    for (int p = 0; p < P && !rc; ++p) rc = step_lammuz_part(h, b0[p], b0[p + 1] - b0[p], p, st[p]);
+  }
+  for (int p = 0; p < P && !rc; ++p) rc = finish_part(h, out, b0[p], b0[p + 1] - b0[p], p, st[p]);
+  // always join, also on error, so that the caller's stream never outruns a side stream
+  cudaError_t ej = cudaSuccess;
+  for (int p = 1; p < P; ++p) {
+    cudaError_t e1 = cudaEventRecord(h->ev_join[p - 1], st[p]);
+    cudaError_t e2 = cudaStreamWaitEvent(s0, h->ev_join[p - 1], 0);
+    if (ej == cudaSuccess) ej = e1 != cudaSuccess ? e1 : e2;
+  }
+  if (rc) return rc;
+  return (int)ej;
 }
 
 int rda_get_buffer(rda_handle* h, int id, void** dev_ptr, size_t* count) {

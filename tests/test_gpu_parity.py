@@ -241,6 +241,53 @@ def test_cuda_graph_capture_replays_identically():
     assert torch.equal(out['u'], eager['u']) and torch.equal(out['s'], eager['s'])
 
 
+@pytest.mark.parametrize('kind,moving', [('polygon', False), ('circle', True)])
+def test_two_stream_split_is_invisible(monkeypatch, kind, moving):
+    """rda_solve runs large batches as two halves on two streams (fork/join by events).  Forced here
+    on a small odd batch (RDA_B200_SPLIT_MIN): outputs and persistent state must be bit-identical to
+    the single-stream order, eagerly and when captured in a CUDA graph."""
+    from rda_planner_b200.rda_solver import RDA_solver
+    from rda_planner_b200 import _cabi
+    T, N, B = 12, 6, 37
+    car = rectangle_robot()
+    insts, inp = _batch_inputs(B, T, N, 1500, lateral=(0.3, 3.5), kind=kind, moving=moving)
+    dev = {k: torch.as_tensor(v, device='cuda', dtype=torch.int32 if 'kind' in k or 'count' in k else torch.float32)
+           for k, v in inp.items()}
+    res = {}
+    for name, split_min, parts in (('whole', '1000000', '2'), ('split', '2', '2'), ('split3', '2', '3')):
+        monkeypatch.setenv('RDA_B200_SPLIT_MIN', split_min)
+        monkeypatch.setenv('RDA_B200_SPLIT_PARTS', parts)
+        g = RDA_solver(T, car, 4, N, iter_num=5, iter_threshold=0.0, time_print=False, batch=B)
+        out = {k: v.clone() for k, v in g.iterative_solve_batch(**dev, time_varying=moving).items()}
+        out2 = {k: v.clone() for k, v in g.iterative_solve_batch(**dev, time_varying=moving).items()}     # warm-started second call
+        state = {b: g.state_buffer(b).clone() for b in (_cabi.BUF_LAM, _cabi.BUF_MU, _cabi.BUF_Z, _cabi.BUF_XI,
+                                                        _cabi.BUF_ZETA, _cabi.BUF_DIS)}
+        res[name] = (out, out2, state, g)
+    assert res['split'][3].launch_count() > 1.9 * res['whole'][3].launch_count() - 4
+    for name in ('split', 'split3'):
+        for call in (0, 1):
+            w, sp = res['whole'][call], res[name][call]
+            for k in ('u', 's', 'status', 'iters'):
+                assert torch.equal(w[k], sp[k]), (name, call, k, float((w[k].float() - sp[k].float()).abs().max()))
+            for k in ('resi_pri', 'resi_dual'):     # float atomics: summation order is not fixed
+                assert torch.allclose(w[k], sp[k], rtol=1e-4, atol=1e-6), (name, call, k)
+        for b in res['whole'][2]:
+            assert torch.equal(res['whole'][2][b], res[name][2][b]), (name, b)
+    g = res['split'][3]
+    stream = torch.cuda.Stream()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(stream):
+        g.cold_start()
+        g.iterative_solve_batch(**dev, time_varying=moving)
+        stream.synchronize()
+        with torch.cuda.graph(graph, stream=stream):
+            g.cold_start()
+            out = g.iterative_solve_batch(**dev, time_varying=moving)
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out['u'], res['whole'][0]['u']) and torch.equal(out['s'], res['whole'][0]['s'])
+
+
 def test_float32_su_mode_and_residual_gap():
     """BASELINE configs[4] asks for a float32-vs-float64 comparison: su-QP interior point in float32
     (su_fp64=False) against the default float64 arithmetic on the same instances."""
