@@ -145,7 +145,7 @@ def main():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--batch', type=int, default=8192, help='instances per GPU per step')
+    ap.add_argument('--batch', type=int, default=16384, help='instances per GPU per step')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     if args.impl == 'reference':

@@ -126,6 +126,53 @@ int rda_copy_buffer(rda_handle *h, int id, void *user_dev_ptr, int to_handle, vo
 int rda_last_launch_count(const rda_handle *h);
 const char *rda_version(void);
 
+/* ------------------------------------------------------------------------------------------
+ * Front end: the steps either side of the solve, batched and stateless.
+ * All pointers are DEVICE pointers; every call only enqueues one kernel on cuda_stream.
+ * ------------------------------------------------------------------------------------------ */
+#define RDA_MAX_SHAPES 64     /* raw obstacles per instance handed to rda_convert_obstacles */
+
+/* MPC.pre_process (mpc.py:251-291) with closest_point :338-353, inter_point :355-383,
+ * range_cir_seg :385-423, wraptopi :431-438 and motion_predict_model_* :293-336, for B
+ * robots on ONE reference path.
+ *   state [B][3]; cur_vel [B][2][T] (the controls of the previous step, MPC.cur_vel_array);
+ *   ref_speed [B] (already multiplied by the gear); path [P][3] (x, y, heading);
+ *   start_index [B] (MPC.cur_index; NULL = 0); threshold / ind_range: closest_point kwargs
+ *   (0.1 / 10).  Out: nom_s, ref_s [B][3][T+1] (the solver's nom_s / ref_s), near_index [B]
+ *   (the new MPC.cur_index).                                                              */
+int rda_pre_process(int B, int T, int dynamics, float dt, float wheelbase, const float *state,
+                    const float *cur_vel, const float *ref_speed, const float *path, int P,
+                    const int32_t *start_index, float threshold, int ind_range, float *nom_s,
+                    float *ref_s, int32_t *near_index, void *cuda_stream);
+
+/* MPC.convert_rda_obstacle (mpc.py:189-218: conversion + optional distance sort) with
+ * convert_inequal_circle :440-458, convert_inequal_polygon :460-474, gen_inequal_global
+ * :476-510, is_convex_and_ordered :518-549, followed by RDA_solver.assign_obstacle_parameter
+ * (rda_solver.py:483-526: keep the first N, pad a short list by repeating its last element,
+ * zero rows beyond the shape's own).  Up to M <= RDA_MAX_SHAPES raw shapes per instance:
+ *   shape_kind [B][M] RDA_OBS_*; shape_nv [B][M] vertices of a polygon (3..E);
+ *   shape_xy [B][M][RDA_MAX_EDGE][2] polygon vertices, or the disc centre in entry 0;
+ *   shape_radius [B][M]; shape_vel [B][M][2]; shape_count [B]; state [B][3] (sort key origin,
+ *   may be NULL when order = 0).  time_varying selects the output layout (T+1 copies per
+ *   obstacle, moved by velocity * t * dt when |velocity| > 0.01, or one copy at t = 0).
+ * Out: obs_A, obs_b, obs_kind, obs_count exactly as rda_inputs expects them.              */
+int rda_convert_obstacles(int B, int M, int N, int T, int E, float dt, int time_varying, int order,
+                          const float *state, const int32_t *shape_kind, const int32_t *shape_nv,
+                          const float *shape_xy, const float *shape_radius, const float *shape_vel,
+                          const int32_t *shape_count, float *obs_A, float *obs_b, int32_t *obs_kind,
+                          int32_t *obs_count, void *cuda_stream);
+
+/* Arrive rule of MPC.control (mpc.py:170-185, single gear): instances whose near_index >=
+ * P - goal_index_threshold get u_opt = 0 and arrive = 1; cur_vel (may be NULL) receives the
+ * controls kept as the next step's nominal (mpc.py:186).  u_opt, cur_vel [B][2][T].        */
+int rda_post_process(int B, int T, int P, int goal_index_threshold, const int32_t *near_index,
+                     float *u_opt, float *cur_vel, int32_t *arrive, void *cuda_stream);
+
+/* state [B][3] advanced in place by one step of the nonlinear model with the first control of
+ * u_opt [B][2][T] (mpc.py:293-336; what the examples' simulator does between control calls). */
+int rda_motion_predict(int B, int T, int dynamics, float dt, float wheelbase, const float *u_opt,
+                       float *state, void *cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -205,3 +205,43 @@ extern "C" int port_solve_batch(const rda_config* cfg, const rda_tunables* tun, 
   }
   return 0;
 }
+
+// ---- front end cores (rda_planner_b200/csrc/frontend.cuh), one instance per call -----------------
+#include "../../rda_planner_b200/csrc/frontend.cuh"
+
+extern "C" int shim_pre_process(int dynamics, int T, double dt, double L, const float* state, const float* vel,
+                                double ref_speed, const float* path, int P, int start_index, double threshold,
+                                int ind_range, float* nom_s, float* ref_s) {
+  return rda::pre_process_one(dynamics, T, dt, L, state, vel, ref_speed, path, P, start_index, threshold, ind_range,
+                              nom_s, ref_s);
+}
+
+// Emulates k_convert_obstacles for one instance: M raw shapes -> N slots.
+extern "C" int shim_convert_obstacles(int M, int N, int T, int E, double dt, int time_varying, int order, const float* state,
+                                      const int* kind, const int* nv, const float* xy, const float* radius,
+                                      const float* vel, int count, float* obs_A, float* obs_b, int* obs_kind) {
+  if (count > M) count = M;
+  std::vector<double> keys(count > 0 ? count : 1);
+  for (int j = 0; j < count; ++j)
+    keys[j] = order ? rda::obstacle_key(kind[j], nv[j], xy + (size_t)j * RDA_MAX_EDGE * 2, state[0], state[1]) : (double)j;
+  const int Tc = time_varying ? T + 1 : 1;
+  for (int n = 0; n < N; ++n) {
+    float* A = obs_A + (size_t)n * Tc * E * 2;
+    float* b = obs_b + (size_t)n * Tc * E;
+    const int src = rda::obstacle_slot_source(n, count, 1, keys.data());
+    if (src < 0) {
+      for (int i = 0; i < Tc * E; ++i) { A[2 * i] = 0.f; A[2 * i + 1] = 0.f; b[i] = 0.f; }
+      obs_kind[n] = RDA_OBS_POLYGON;
+      continue;
+    }
+    obs_kind[n] = kind[src];
+    for (int t = 0; t < Tc; ++t)
+      rda::obstacle_rows(kind[src], nv[src], xy + (size_t)src * RDA_MAX_EDGE * 2, radius[src], vel[2 * src], vel[2 * src + 1], t,
+                         dt, E, A + (size_t)t * E * 2, b + (size_t)t * E);
+  }
+  return count;
+}
+
+extern "C" void shim_motion_predict(int dynamics, double dt, double L, const double* s, double v0, double v1, double* out) {
+  rda::motion_predict(dynamics, dt, L, s, v0, v1, out);
+}

@@ -44,7 +44,9 @@ class Outputs(C.Structure):
 
 EXPORTS = ['rda_create', 'rda_destroy', 'rda_set_tunables', 'rda_get_tunables', 'rda_reset',
            'rda_cold_start', 'rda_solve', 'rda_begin', 'rda_step_su', 'rda_step_lammuz', 'rda_finish',
-           'rda_get_buffer', 'rda_copy_buffer', 'rda_last_launch_count', 'rda_version']
+           'rda_get_buffer', 'rda_copy_buffer', 'rda_last_launch_count', 'rda_version',
+           'rda_pre_process', 'rda_convert_obstacles', 'rda_post_process', 'rda_motion_predict']
+MAX_SHAPES = 64
 
 _lib = None
 
@@ -76,6 +78,11 @@ def load():
     lib.rda_copy_buffer.argtypes = [vp, C.c_int, vp, C.c_int, vp]
     lib.rda_last_launch_count.argtypes = [vp]
     lib.rda_version.restype = C.c_char_p
+    i, f = C.c_int, C.c_float
+    lib.rda_pre_process.argtypes = [i, i, i, f, f, vp, vp, vp, vp, i, vp, f, i, vp, vp, vp, vp]
+    lib.rda_convert_obstacles.argtypes = [i, i, i, i, i, f, i, i] + [vp] * 12
+    lib.rda_post_process.argtypes = [i, i, i, i, vp, vp, vp, vp, vp]
+    lib.rda_motion_predict.argtypes = [i, i, i, f, f, vp, vp, vp]
     for name in EXPORTS:
         if name != 'rda_version':
             getattr(lib, name).restype = C.c_int

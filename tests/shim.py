@@ -75,3 +75,36 @@ def su(params, lins, linu, ref, vref, dis, hx, hy, hc, gx, gy, pref, prec='d'):
     st = fn(C.byref(params), _p(lins), _p(linu), _p(ref), C.c_double(vref), _p(dis), _p(hx), _p(hy), _p(hc),
             _p(gx), _p(gy), _p(pref), _p(s), _p(u), _p(d), C.byref(it))
     return s.T.copy(), u.T.copy(), d, st, it.value
+
+
+# ---- front end cores (frontend.cuh) ----
+def pre_process(dynamics, T, dt, L, state, vel, ref_speed, path, start_index, threshold=0.1, ind_range=10):
+    state, vel, path = _f32(np.ravel(state)[:3]), _f32(vel), _f32(path)
+    nom = np.zeros((3, T + 1), np.float32)
+    ref = np.zeros((3, T + 1), np.float32)
+    f = lib().shim_pre_process
+    f.restype = C.c_int
+    f.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_int,
+                  C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_void_p]
+    near = f(DYN[dynamics], T, dt, L, state.ctypes.data, vel.ctypes.data, ref_speed, path.ctypes.data, path.shape[0],
+             start_index, threshold, ind_range, nom.ctypes.data, ref.ctypes.data)
+    return nom, ref, near
+
+
+def convert_obstacles(shapes, N, T, E, dt, time_varying, order, state):
+    """shapes: dict of arrays kind [M], nv [M], xy [M,8,2], radius [M], vel [M,2], count."""
+    M = len(shapes['kind'])
+    Tc = T + 1 if time_varying else 1
+    A = np.zeros((N, Tc, E, 2), np.float32)
+    b = np.zeros((N, Tc, E), np.float32)
+    kind = np.zeros(N, np.int32)
+    st = _f32(np.ravel(state)[:3])
+    k = np.ascontiguousarray(shapes['kind'], np.int32)
+    nv = np.ascontiguousarray(shapes['nv'], np.int32)
+    xy, rad, vel = _f32(shapes['xy']), _f32(shapes['radius']), _f32(shapes['vel'])
+    f = lib().shim_convert_obstacles
+    f.restype = C.c_int
+    f.argtypes = [C.c_int] * 4 + [C.c_double, C.c_int, C.c_int] + [C.c_void_p] * 6 + [C.c_int] + [C.c_void_p] * 3
+    cnt = f(M, N, T, E, dt, int(time_varying), int(order), st.ctypes.data, k.ctypes.data, nv.ctypes.data, xy.ctypes.data,
+            rad.ctypes.data, vel.ctypes.data, int(shapes['count']), A.ctypes.data, b.ctypes.data, kind.ctypes.data)
+    return A, b, kind, cnt

@@ -1,0 +1,118 @@
+"""Front-end kernels (rda_frontend.cu) through the C ABI: against the g++ build of the same cores, and the
+closed loop of BatchedMPC against the host front end (rda_planner_b200/mpc.py) driving the same solver."""
+import copy
+import os
+from collections import namedtuple
+
+import numpy as np
+import pytest
+import torch
+
+import shim
+from rda_planner_b200.scenarios import rectangle_robot
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+PATH = list(np.load(os.path.join(HERE, 'golden', 'path_track_ref.npy'), allow_pickle=True))
+PATH_ARR = np.stack([np.asarray(p, float).reshape(-1)[:3] for p in PATH])
+Obs = namedtuple('Obs', 'center radius vertex cone_type velocity')
+
+
+def _random_obstacles(rng, count):
+    obs = []
+    for j in range(count):
+        c = PATH_ARR[int(rng.integers(0, len(PATH_ARR))), :2].reshape(2, 1) + rng.uniform(2.5, 6.0, (2, 1)) * rng.choice([-1, 1], (2, 1))
+        vel = rng.uniform(-0.5, 0.5, (2, 1)) if j % 2 else np.zeros((2, 1))
+        if j % 3 == 0:
+            obs.append(Obs(c, float(rng.uniform(0.3, 1.0)), None, 'norm2', vel))
+        else:
+            n = int(rng.integers(3, 5))
+            ang = np.sort(rng.uniform(0, 2 * np.pi, n))
+            if j % 2:
+                ang = ang[::-1]
+            obs.append(Obs(None, None, c + rng.uniform(0.5, 1.2) * np.vstack([np.cos(ang), np.sin(ang)]), 'Rpositive', vel))
+    return obs
+
+
+@pytest.mark.parametrize('dyn', ['acker', 'diff', 'omni'])
+def test_pre_process_kernel_matches_cpu_core(dyn):
+    from rda_planner_b200.frontend import pre_process_batch, path_tensor
+    rng = np.random.default_rng(3)
+    B, T = 96, 15
+    idx = rng.integers(0, len(PATH_ARR), B)
+    idx[:8] = len(PATH_ARR) - 1 - rng.integers(0, 5, 8)             # exhausted tail
+    start = np.maximum(0, idx - rng.integers(0, 8, B)).astype(np.int32)
+    state = (PATH_ARR[idx] + rng.normal(0, [0.3, 0.3, 0.2], (B, 3))).astype(np.float32)
+    vel = np.stack([rng.uniform(1, 5, (B, T)), rng.uniform(-0.3, 0.3, (B, T))], 1).astype(np.float32)
+    speed = rng.uniform(2, 5, B).astype(np.float32)
+    dev = torch.device('cuda:0')
+    nom, ref, near = pre_process_batch(torch.as_tensor(state, device=dev), torch.as_tensor(vel, device=dev),
+                                       torch.as_tensor(speed, device=dev), path_tensor(PATH, dev),
+                                       torch.as_tensor(start, device=dev), dyn, 0.1, 3.0, T)
+    nom, ref, near = nom.cpu().numpy(), ref.cpu().numpy(), near.cpu().numpy()
+    for b in range(B):
+        n1, r1, k1 = shim.pre_process(dyn, T, 0.1, 3.0, state[b], vel[b], float(speed[b]), PATH_ARR, int(start[b]))
+        assert near[b] == k1
+        np.testing.assert_allclose(nom[b], n1, atol=2e-5)
+        np.testing.assert_allclose(ref[b], r1, atol=2e-5)
+
+
+@pytest.mark.parametrize('tv,order', [(False, True), (True, True), (True, False)])
+def test_convert_obstacles_kernel_matches_cpu_core(tv, order):
+    from rda_planner_b200.frontend import convert_obstacles_batch, pack_shapes, shapes_to_device
+    rng = np.random.default_rng(11)
+    B, T, N, E, M = 33, 10, 6, 5, 16
+    lists = [_random_obstacles(rng, int(c)) for c in rng.integers(0, 14, B)]
+    lists[0] = []
+    state = (PATH_ARR[rng.integers(0, len(PATH_ARR), B)] + rng.normal(0, 0.3, (B, 3))).astype(np.float32)
+    shapes = pack_shapes(lists, M)
+    dev = torch.device('cuda:0')
+    A, b, kind, count = convert_obstacles_batch(shapes_to_device(shapes, dev), torch.as_tensor(state, device=dev), N, T, E, 0.1, tv, order)
+    A, b, kind, count = A.cpu().numpy(), b.cpu().numpy(), kind.cpu().numpy(), count.cpu().numpy()
+    for i in range(B):
+        one = {k: v[i] for k, v in shapes.items()}
+        A1, b1, k1, c1 = shim.convert_obstacles(one, N, T, E, 0.1, tv, order, state[i])
+        assert count[i] == c1 == len(lists[i])
+        assert list(kind[i]) == list(k1)
+        np.testing.assert_array_equal(A[i], A1)
+        np.testing.assert_allclose(b[i], b1, rtol=1e-6, atol=1e-6)
+
+
+def test_batched_mpc_closed_loop_matches_host_front_end():
+    """Three robots on the path_track reference with static and moving obstacles, 4 control steps:
+    BatchedMPC (everything on the device) against mpc.MPC (host front end) per robot, same solver."""
+    from rda_planner_b200.frontend import BatchedMPC, pack_shapes, shapes_to_device
+    from rda_planner_b200.mpc import MPC
+    car = rectangle_robot()
+    T, N, E, steps = 10, 4, 4, 4
+    obs = [Obs(np.array([[20.], [34.]]), 1.5, None, 'norm2', np.zeros((2, 1))),
+           Obs(np.array([[12.], [40.]]), 1.0, None, 'norm2', np.array([[0.3], [0.1]])),
+           Obs(None, None, np.array([[31., 33, 33, 31], [28, 28, 24, 24]]), 'Rpositive', np.zeros((2, 1))),
+           Obs(None, None, np.array([[11., 12, 12, 11], [44, 44, 45, 45]]), 'Rpositive', np.array([[0.0], [-0.5]]))]
+    starts = [0, 40, len(PATH) - 12]
+    B = len(starts)
+    states = np.stack([PATH_ARR[i] + np.array([0.2, -0.1, 0.05]) for i in starts]).astype(np.float32)
+    kw = dict(receding=T, sample_time=0.1, iter_num=3, max_edge_num=E, max_obs_num=N, iter_threshold=0.0)
+    bm = BatchedMPC(car, PATH, B, **kw)
+    bm.cur_index[:] = torch.as_tensor(starts, dtype=torch.int32)
+    hosts = []
+    for i in starts:
+        m = MPC(car, copy.deepcopy(PATH), time_print=False, **kw)
+        m.cur_index = i
+        hosts.append(m)
+    dev_state = torch.as_tensor(states, device='cuda:0')
+    host_state = [states[i].astype(float).reshape(3, 1) for i in range(B)]
+    shapes = shapes_to_device(pack_shapes([obs] * B, 8), 'cuda:0')
+    for k in range(steps):
+        u0, info = bm.control(dev_state, 4.0, shapes, time_varying=True)
+        u0 = u0.cpu().numpy()
+        arrive = info['arrive'].cpu().numpy()
+        for i, m in enumerate(hosts):
+            uh, ih = m.control(host_state[i], 4.0, obs)
+            assert bool(arrive[i]) == ih['arrive']
+            assert int(info['cur_index'][i]) == m.cur_index
+            np.testing.assert_allclose(u0[i], uh[:, 0], atol=2e-3)
+            s = host_state[i]
+            host_state[i] = s + 0.1 * np.array([[uh[0, 0] * np.cos(s[2, 0])], [uh[0, 0] * np.sin(s[2, 0])], [uh[0, 0] * np.tan(uh[1, 0]) / 3.0]])
+        bm.advance(dev_state)
+        np.testing.assert_allclose(dev_state.cpu().numpy(), np.hstack(host_state).T, atol=2e-3)
