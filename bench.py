@@ -113,6 +113,50 @@ def cpu_port_rate(inputs, sample, threads, iters=ITERS):
     return sample / dt, dt
 
 
+def closed_loop_probe(dev, B, steps=3):
+    """whole control steps on the device (pre_process -> obstacle conversion ->
+    50-iteration solve -> arrive rule -> state advance) for B robots on one 60 m reference line.
+    Reported next to the headline metric, not instead of it."""
+    import torch
+    from rda_planner_b200.frontend import BatchedMPC
+    from rda_planner_b200.scenarios import rectangle_robot
+    rng = np.random.default_rng(77)
+    path = np.stack([np.arange(0, 60, 0.1), np.zeros(600), np.zeros(600)], 1)
+    bm = BatchedMPC(rectangle_robot(), path, B, receding=T, sample_time=0.1, iter_num=ITERS, max_edge_num=E,
+                    max_obs_num=N, iter_threshold=0.0, device=dev)
+    idx = rng.integers(0, 480, B)
+    state = torch.as_tensor(path[idx] + rng.normal(0, [0.3, 0.3, 0.1], (B, 3)), dtype=torch.float32, device=dev)
+    bm.cur_index[:] = torch.as_tensor(np.maximum(idx - 3, 0), dtype=torch.int32)
+    bm.cur_vel[:, 0, :] = 4.0
+    # N boxes (2 x 1 m, random yaw) per robot, 2-8 m ahead and 1.5-5 m to either side
+    M = N
+    ctr = path[idx][:, None, :2] + np.stack([rng.uniform(2, 14, (B, M)), rng.uniform(1.8, 6, (B, M)) * rng.choice([-1, 1], (B, M))], -1)
+    yaw = rng.uniform(0, np.pi, (B, M))
+    corners = np.array([[-1, -0.5], [1, -0.5], [1, 0.5], [-1, 0.5]])
+    rot = np.stack([np.stack([np.cos(yaw), -np.sin(yaw)], -1), np.stack([np.sin(yaw), np.cos(yaw)], -1)], -2)
+    xy = np.zeros((B, M, 8, 2), np.float32)
+    xy[:, :, :4] = ctr[:, :, None, :] + np.einsum('bmij,kj->bmki', rot, corners)
+    shapes = {'kind': np.zeros((B, M), np.int32), 'nv': np.full((B, M), 4, np.int32), 'xy': xy,
+              'radius': np.zeros((B, M), np.float32), 'vel': np.zeros((B, M, 2), np.float32),
+              'count': np.full(B, M, np.int32)}
+    shapes = {k: torch.as_tensor(v, device=dev) for k, v in shapes.items()}
+    bm.control(state, 4.0, shapes)
+    bm.advance(state)
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        u0, info = bm.control(state, 4.0, shapes)
+        bm.advance(state)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / steps
+    ok = bool(torch.isfinite(u0).all()) and int((info['status'] & 6).sum()) == 0
+    return {'mpc_steps_per_s': B / (ms * 1e-3), 'ms_per_control_step': ms, 'robots': B, 'finite_and_converged': ok,
+            'what': 'BatchedMPC.control + advance: pre_process, obstacle conversion, 50 ADMM iterations (warm-started), '
+                    'arrive rule, model step; all on the device'}
+
+
 def run_reference(args):
     """CPU arm: the path on the host cores.  The reference's own implementation (cvxpy/ECOS/pathos) is
     not installable in this image, so this times the compiled port with all threads."""
@@ -295,6 +339,10 @@ def main():
         line['cpu_baseline'] = {'value': v, 'unit': 'solves/s', 'cores': cores, 'kind': 'port',
                                 'sample': f'{min(sample, B)} of the same instances x {ITERS} ADMM iterations, compiled C++ '
                                           f'port (oracle/cpu_port), OpenMP over instances, {dt:.1f} s'}
+    try:
+        line['closed_loop'] = closed_loop_probe(dev, B)
+    except Exception as ex:          # the probe must never cost the headline line
+        line['closed_loop'] = {'error': repr(ex)[:200]}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -1,7 +1,10 @@
-"""Short target for `ncu --set full`: one batched solve of a few ADMM iterations at the bench batch size."""
+"""Short target for `ncu --set full`: one batched solve of a few ADMM iterations at the bench batch size.
+The batch is kept whole (no two-stream split) so that each captured launch is the full-batch kernel."""
 import json
 import os
 import sys
+
+os.environ.setdefault('RDA_B200_SPLIT_MIN', '1000000000')
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.argv = ['bench']
@@ -10,7 +13,7 @@ import torch  # noqa: E402
 from rda_planner_b200.rda_solver import RDA_solver  # noqa: E402
 from rda_planner_b200.scenarios import rectangle_robot  # noqa: E402
 
-B = int(os.environ.get('PROF_BATCH', '8192'))
+B = int(os.environ.get('PROF_BATCH', '16384'))
 ITERS = 12
 host = bench.build_inputs(B, 9000)
 dev = torch.device('cuda:0')
