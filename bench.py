@@ -159,7 +159,7 @@ def closed_loop_probe(dev, B, steps=3):
 
 def run_reference(args):
     """CPU arm: the path on the host cores.  The reference's own implementation (cvxpy/ECOS/pathos) is
-    not installable in this image (DESIGN.md §7), so this times the compiled port with all threads."""
+    not installable in this image (DESIGN.md §0), so this times the compiled port with all threads."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
