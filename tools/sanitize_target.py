@@ -1,7 +1,10 @@
-"""Small target for compute-sanitizer (memcheck / racecheck): a short batched solve covering polygon and
-disc obstacles, static and moving."""
+"""Small target for compute-sanitizer (memcheck / racecheck): short batched solves covering polygon and
+disc obstacles, static and moving, the two-stream sub-batch path (forced on this small batch) and the
+front-end kernels through one closed-loop step of BatchedMPC."""
 import os
 import sys
+
+os.environ['RDA_B200_SPLIT_MIN'] = '2'
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np  # noqa: E402
@@ -25,3 +28,32 @@ for kind, moving in (('polygon', False), ('circle', True)):
                                   np.array([p[3] for p in packs]), tv)
     torch.cuda.synchronize()
     print(kind, 'ok', bool(torch.isfinite(out['u']).all()), int((out['status'] & 6).sum()))
+
+# front end: pre_process, obstacle conversion (sorted, padded, moving), arrive rule, model step
+from collections import namedtuple  # noqa: E402
+from rda_planner_b200.frontend import BatchedMPC, pack_shapes, shapes_to_device  # noqa: E402
+Obs = namedtuple('Obs', 'center radius vertex cone_type velocity')
+path = np.stack([np.arange(0, 20, 0.1), np.zeros(200), np.zeros(200)], 1)
+B, T, N = 33, 10, 5
+rng = np.random.default_rng(5)
+lists = []
+for b in range(B):
+    obs = []
+    for j in range(int(rng.integers(0, 9))):
+        c = np.array([[rng.uniform(2, 18)], [rng.uniform(2, 5) * rng.choice([-1, 1])]])
+        vel = rng.uniform(-0.4, 0.4, (2, 1)) if j % 2 else np.zeros((2, 1))
+        if j % 3 == 0:
+            obs.append(Obs(c, 0.6, None, 'norm2', vel))
+        else:
+            ang = np.sort(rng.uniform(0, 2 * np.pi, 4))[::(-1 if j % 2 else 1)]
+            obs.append(Obs(None, None, c + 0.8 * np.vstack([np.cos(ang), np.sin(ang)]), 'Rpositive', vel))
+    lists.append(obs)
+bm = BatchedMPC(rectangle_robot(), path, B, receding=T, iter_num=3, max_edge_num=4, max_obs_num=N, iter_threshold=0.0)
+state = torch.as_tensor(path[rng.integers(0, 199, B)] + rng.normal(0, 0.2, (B, 3)), dtype=torch.float32, device='cuda')
+bm.cur_index[:] = torch.as_tensor(rng.integers(150, 199, B), dtype=torch.int32)
+shapes = shapes_to_device(pack_shapes(lists, 10), 'cuda')
+for _ in range(2):
+    u0, info = bm.control(state, 4.0, shapes, time_varying=True)
+    bm.advance(state)
+torch.cuda.synchronize()
+print('front end ok', bool(torch.isfinite(u0).all()), int(info['arrive'].sum()))
