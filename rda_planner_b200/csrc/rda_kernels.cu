@@ -415,13 +415,23 @@ __global__ void __launch_bounds__(128) k_cells_mid(DevPtrs d, RobotGeom rb, floa
   }
 }
 
-// One thread per worklist entry (dense: no lane idles behind a closed-form neighbour).
+// One thread per worklist entry, RDA_SLOW_CPW entries per warp.  The pass is a latency tail (a few thousand
+// cells, each a serial interior point iteration with its own iteration count and fallbacks): fewer cells
+// per warp means less divergence to serialise and more warps to hide latency; the idle lanes cost nothing
+// because the SMs are otherwise empty.
 #ifndef RDA_SLOW_MINBLOCKS
 #define RDA_SLOW_MINBLOCKS 16
 #endif
+#ifndef RDA_SLOW_CPW
+#define RDA_SLOW_CPW 32
+#endif
 __global__ void __launch_bounds__(64, RDA_SLOW_MINBLOCKS) k_cells_slow(DevPtrs d, RobotGeom rb, float ro2, float theta) {
   const int count = d.wl_count[1];
-  for (int wi = blockIdx.x * blockDim.x + threadIdx.x; wi < count; wi += gridDim.x * blockDim.x) {
+  const int lane = threadIdx.x & 31;
+  if (lane >= RDA_SLOW_CPW) return;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int wi = warp * RDA_SLOW_CPW + lane; wi < count; wi += nwarps * RDA_SLOW_CPW) {
     const long long idx = d.worklist2[wi];
     CellIn c = cell_load(d, idx);
     CellWork<float> w;

@@ -35,10 +35,11 @@ def path_tensor(ref_path, device):
     return torch.as_tensor(arr, dtype=torch.float32, device=device).contiguous()
 
 
-def pack_shapes(obstacle_lists, max_shapes=None):
+def pack_shapes(obstacle_lists, max_shapes=None, max_edge_num=_cabi.MAX_EDGE):
     """Per-instance lists of simulator obstacles (attributes cone_type, center, radius, vertex,
     velocity — what MPC.convert_rda_obstacle reads, mpc.py:189-208) -> dict of host arrays in
-    the layout of rda_convert_obstacles."""
+    the layout of rda_convert_obstacles.  Polygons with more than `max_edge_num` vertices are
+    refused here (the kernel would write an all-zero obstacle for them)."""
     B = len(obstacle_lists)
     M = max_shapes or max(1, max(len(l) for l in obstacle_lists))
     if M > _cabi.MAX_SHAPES:
@@ -61,8 +62,8 @@ def pack_shapes(obstacle_lists, max_shapes=None):
             else:
                 v = np.asarray(o.vertex, float)
                 n = v.shape[1]
-                if n > _cabi.MAX_EDGE:
-                    raise ValueError(f'polygon with {n} vertices exceeds {_cabi.MAX_EDGE}')
+                if n > min(max_edge_num, _cabi.MAX_EDGE) or n < 3:
+                    raise ValueError(f'polygon with {n} vertices: 3..{min(max_edge_num, _cabi.MAX_EDGE)} supported')
                 out['kind'][b, j] = _cabi.OBS_POLYGON
                 out['nv'][b, j] = n
                 out['xy'][b, j, :n] = v[0:2].T
