@@ -245,3 +245,18 @@ extern "C" int shim_convert_obstacles(int M, int N, int T, int E, double dt, int
 extern "C" void shim_motion_predict(int dynamics, double dt, double L, const double* s, double v0, double v1, double* out) {
   rda::motion_predict(dynamics, dt, L, s, v0, v1, out);
 }
+
+// ---- statistics of the slow cell path (host analysis only; build with -DRDA_CELL_STATS) -------------
+#ifdef RDA_CELL_STATS
+namespace rda { long long g_cell_stats[8]; }     // which geometric situations reach the slow path (cell_solver.cuh)
+static long long g_stat_hist[3][512];
+extern "C" void rda_cell_stat(int what, int value) {
+  if (what < 0 || what > 2) return;
+  if (value < 0) value = 0;
+  if (value > 511) value = 511;
+#pragma omp atomic
+  g_stat_hist[what][value] += 1;
+}
+extern "C" void port_cell_stats(long long* out) { memcpy(out, g_stat_hist, sizeof(g_stat_hist)); }
+extern "C" void port_cell_situations(long long* out) { memcpy(out, rda::g_cell_stats, sizeof(rda::g_cell_stats)); }
+#endif
