@@ -157,6 +157,48 @@ def closed_loop_probe(dev, B, steps=3):
                     'arrive rule, model step; all on the device'}
 
 
+def extra_probes(dev, solver, devin, B):
+    """SURVEY.md §8(d) side measurements (never the headline): the same batch with the reference's
+    early-stop rule (iter_threshold 0.2, rda_solver.py:22,594-596) and the latency of ONE instance
+    (the reference's own use case)."""
+    import torch
+    from rda_planner_b200.rda_solver import RDA_solver
+    from rda_planner_b200.scenarios import rectangle_robot
+    out = {}
+
+    def timed(fn, reps):
+        fn()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            r = fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / reps, r
+
+    def early():
+        solver.cold_start()
+        return solver.iterative_solve_batch(devin['nom_s'], devin['nom_u'], devin['ref_s'], devin['ref_speed'],
+                                            devin['obs_A'], devin['obs_b'], devin['obs_kind'], devin['obs_count'], False,
+                                            iter_threshold=0.2)
+    ms, r = timed(early, 2)
+    out['early_stop'] = {'solves_per_s': B / (ms * 1e-3), 'iter_threshold': 0.2,
+                         'mean_iterations': float(r['iters'].float().mean()),
+                         'stopped_early_fraction': float((r['iters'] < ITERS).float().mean())}
+    one = RDA_solver(T, rectangle_robot(), max_edge_num=E, max_obs_num=N, iter_num=ITERS, iter_threshold=0.0,
+                     time_print=False, batch=1, device=dev)
+    d1 = {k: v[:1].contiguous() for k, v in devin.items()}
+
+    def single():
+        one.cold_start()
+        return one.iterative_solve_batch(d1['nom_s'], d1['nom_u'], d1['ref_s'], d1['ref_speed'], d1['obs_A'], d1['obs_b'],
+                                         d1['obs_kind'], d1['obs_count'], False)
+    ms1, _ = timed(single, 3)
+    out['single_instance'] = {'latency_ms': ms1, 'what': 'one instance, 50 iterations, cold start, inputs on the device'}
+    return out
+
+
 def run_reference(args):
     """CPU arm: the path on the host cores.  The reference's own implementation (cvxpy/ECOS/pathos) is
     not installable in this image, so this times the compiled port with all threads."""
@@ -339,6 +381,10 @@ def main():
         line['cpu_baseline'] = {'value': v, 'unit': 'solves/s', 'cores': cores, 'kind': 'port',
                                 'sample': f'{min(sample, B)} of the same instances x {ITERS} ADMM iterations, compiled C++ '
                                           f'port (oracle/cpu_port), OpenMP over instances, {dt:.1f} s'}
+    try:
+        line.update(extra_probes(dev, solver, devin, B))
+    except Exception as ex:
+        line['early_stop'] = {'error': repr(ex)[:200]}
     try:
         line['closed_loop'] = closed_loop_probe(dev, B)
     except Exception as ex:          # the probe must never cost the headline line
