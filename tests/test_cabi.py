@@ -49,3 +49,36 @@ def test_product_never_imports_oracle():
             if f.endswith('.py'):
                 src = open(os.path.join(ROOT, pkg, f)).read()
                 assert 'oracle' not in src.replace('# oracle', ''), f'{pkg}/{f} mentions oracle'
+
+
+def test_usage_errors_are_return_codes_not_exceptions():
+    """Error behaviour of the boundary (include/rda_b200.h): usage errors come back as negative codes
+    before any device work is attempted, so this runs without a GPU."""
+    lib = _cabi.load()
+    vp = ctypes.c_void_p
+    h = vp()
+    tun = _cabi.Tunables(8, 1.0, 0.1, 200, 1, 0.5)
+    cfg = _cabi.Config()
+    assert lib.rda_create(None, ctypes.byref(tun), ctypes.byref(h)) == -1
+    cfg.batch, cfg.receding, cfg.max_obs_num, cfg.max_edge_num, cfg.robot_edges = 0, 10, 4, 4, 4
+    assert lib.rda_create(ctypes.byref(cfg), ctypes.byref(tun), ctypes.byref(h)) == -1          # batch < 1
+    cfg.batch, cfg.max_edge_num = 1, 9
+    assert lib.rda_create(ctypes.byref(cfg), ctypes.byref(tun), ctypes.byref(h)) == -2          # > RDA_MAX_EDGE
+    cfg.max_edge_num, cfg.dynamics = 4, 7
+    assert lib.rda_create(ctypes.byref(cfg), ctypes.byref(tun), ctypes.byref(h)) == -1          # unknown dynamics
+    cfg.dynamics = 0                                                                              # G, h all zero:
+    assert lib.rda_create(ctypes.byref(cfg), ctypes.byref(tun), ctypes.byref(h)) == -2          # not a polygon
+    assert h.value is None
+    for f in (lib.rda_destroy, ):
+        assert f(None) == -1
+    assert lib.rda_solve(None, None, None, 1, 0.0, None) == -1
+    assert lib.rda_step_su(None, None) == -1 and lib.rda_step_lammuz(None, None) == -1
+    assert lib.rda_last_launch_count(None) == -1
+    # front end: sizes, missing pointers, more raw shapes than RDA_MAX_SHAPES
+    assert lib.rda_pre_process(0, 10, 0, 0.1, 3.0, None, None, None, None, 5, None, 0.1, 10, None, None, None, None) == -1
+    assert lib.rda_pre_process(4, 10, 0, 0.1, 3.0, None, None, None, None, 5, None, 0.1, 10, None, None, None, None) == -1
+    assert lib.rda_convert_obstacles(4, _cabi.MAX_SHAPES + 1, 5, 10, 4, 0.1, 0, 0, *([None] * 12)) == -2
+    assert lib.rda_convert_obstacles(4, 8, 5, 10, 2, 0.1, 0, 0, *([None] * 12)) == -2             # E < 3
+    assert lib.rda_convert_obstacles(4, 8, 5, 10, 4, 0.1, 0, 0, *([None] * 12)) == -1
+    assert lib.rda_post_process(4, 10, 100, 1, None, None, None, None, None) == -1
+    assert lib.rda_motion_predict(4, 10, 5, 0.1, 3.0, None, None, None) == -1
