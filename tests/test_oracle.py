@@ -139,3 +139,22 @@ def test_padding_invariance():
     ob = OracleRDA(6, car, 4, 3, iter_num=2, iter_threshold=0.0)
     ub, _ = ob.iterative_solve(inst['nom_s'], inst['nom_u'], ref, 4.0, list(inst['obstacles']) + [inst['obstacles'][-1]])
     np.testing.assert_allclose(ua, ub, atol=1e-12)
+
+
+def test_true_reference_harness_reports_unavailable_without_cvxpy():
+    """oracle/run_true_reference.py is the hook that pins the oracle where cvxpy/ECOS exist; here it must
+    say so in one JSON line and exit 0 (parity unpinned in this image)."""
+    import json
+    import subprocess
+    import sys
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    try:
+        import cvxpy  # noqa: F401
+        import ecos  # noqa: F401
+        pytest.skip('cvxpy present: run oracle/run_true_reference.py for the real comparison')
+    except ImportError:
+        pass
+    out = subprocess.run([sys.executable, os.path.join(root, 'oracle', 'run_true_reference.py')], capture_output=True, text=True)
+    assert out.returncode == 0
+    assert 'unavailable' in json.loads(out.stdout.strip().splitlines()[-1])
