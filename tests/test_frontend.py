@@ -130,3 +130,71 @@ def test_convert_obstacles_matches_host_front_end(order, count):
     assert list(kind) == list(kh)
     np.testing.assert_allclose(A, Ah, atol=1e-5)
     np.testing.assert_allclose(b, bh, atol=1e-4)
+
+
+# ---- size-independent properties of the front-end cores (hypothesis) ------------------------------------
+from hypothesis import given, settings, strategies as st  # noqa: E402
+
+
+@settings(max_examples=60, deadline=None)
+@given(n=st.integers(3, 8), cx=st.floats(-50, 50), cy=st.floats(-50, 50), rad=st.floats(0.3, 3.0),
+       clockwise=st.booleans(), vx=st.floats(-1, 1), vy=st.floats(-1, 1), seed=st.integers(0, 10 ** 6))
+def test_polygon_rows_contain_the_shape_and_follow_its_motion(n, cx, cy, rad, clockwise, vx, vy, seed):
+    """For any convex polygon, either orientation: every vertex satisfies A v <= b (tight on its two rows),
+    the centroid is strictly inside, rows turn counter-clockwise, and the copy at stage t is the shape moved
+    by velocity * t * dt (|velocity| > 0.01) or the same shape (slower)."""
+    rng = np.random.default_rng(seed)
+    ang = np.sort(rng.uniform(0, 2 * np.pi, n))
+    if np.min(np.diff(np.concatenate([ang, [ang[0] + 2 * np.pi]]))) < 0.15:
+        ang = np.linspace(0, 2 * np.pi, n, endpoint=False) + rng.uniform(0, 1)
+    v = np.array([[cx], [cy]]) + rad * np.vstack([np.cos(ang), np.sin(ang)])
+    if clockwise:
+        v = v[:, ::-1]
+    v = v.astype(np.float32).astype(float)
+    vel = np.array([[vx], [vy]], np.float32).astype(float)
+    T, dt = 6, 0.1
+    shapes = _shapes_from([Obs(None, None, v, 'Rpositive', vel)], 1)
+    A, b, kind, cnt = shim.convert_obstacles(shapes, 1, T, 8, dt, True, False, np.zeros(3))
+    moving = np.hypot(*vel[:, 0]) > 0.01
+    for t in (0, T):
+        off = vel * (t * dt) if moving else 0.0
+        vt = v + off
+        At, bt = A[0, t, :n].astype(float), b[0, t, :n].astype(float)
+        assert not A[0, t, n:].any() and not b[0, t, n:].any()
+        viol = At @ vt - bt[:, None]
+        scale = 1 + np.abs(bt).max()
+        assert viol.max() < 2e-5 * scale
+        assert np.all(At @ vt.mean(1) - bt < 0)
+        nxt = np.roll(At, -1, axis=0)
+        assert np.all(At[:, 0] * nxt[:, 1] - At[:, 1] * nxt[:, 0] > 0)          # rows counter-clockwise
+        assert np.sort(np.abs(viol), axis=1)[:, :2].max() < 2e-5 * scale         # each row tight on two vertices
+
+
+@settings(max_examples=40, deadline=None)
+@given(idx=st.integers(0, len(PATH_ARR) - 1), back=st.integers(0, 8), speed=st.floats(1.0, 6.0),
+       dyn=st.sampled_from(['acker', 'diff', 'omni']), seed=st.integers(0, 10 ** 6))
+def test_pre_process_properties(idx, back, speed, dyn, seed):
+    """The nominal columns are the model rolled out with the given controls; every reference point lies on
+    the path polyline; consecutive reference points are one arc step ref_speed * dt apart until the path
+    is exhausted, after which they sit on the last waypoint; headings are unwrapped around the prediction."""
+    from rda_planner_b200.scenarios import rollout
+    rng = np.random.default_rng(seed)
+    T, dt = 12, 0.1
+    start = max(0, idx - back)
+    state = (PATH_ARR[idx] + rng.normal(0, [0.2, 0.2, 0.1])).astype(np.float32)
+    vel = np.vstack([rng.uniform(0.5, 5, T), rng.uniform(-0.3, 0.3, T)]).astype(np.float32)
+    nom, ref, near = shim.pre_process(dyn, T, dt, 3.0, state, vel, float(speed), PATH_ARR, start)
+    assert start <= near < min(start + 10, len(PATH_ARR))
+    np.testing.assert_allclose(nom, rollout(state.astype(float), vel.astype(float), dt, 3.0, dyn), atol=2e-5)
+    P32 = PATH_ARR.astype(np.float32).astype(float)
+    seg_a, seg_b = P32[:-1, :2], P32[1:, :2]
+    for t in range(1, T + 1):
+        p = ref[:2, t].astype(float)
+        d = seg_b - seg_a
+        tt = np.clip(np.einsum('ij,ij->i', p - seg_a, d) / np.maximum(np.einsum('ij,ij->i', d, d), 1e-30), 0, 1)
+        assert np.min(np.linalg.norm(seg_a + tt[:, None] * d - p, axis=1)) < 2e-4      # on the polyline
+        stepped = np.linalg.norm(ref[:2, t].astype(float) - ref[:2, t - 1].astype(float))
+        at_end = np.linalg.norm(p - P32[-1, :2]) < 1e-6
+        if t >= 2:
+            assert at_end or abs(stepped - speed * dt) < 2e-4
+        assert abs(float(ref[2, t]) - float(nom[2, t])) <= np.pi + 1e-4                 # unwrapped around the prediction
