@@ -136,7 +136,7 @@ def test_convert_obstacles_matches_host_front_end(order, count):
 from hypothesis import given, settings, strategies as st  # noqa: E402
 
 
-@settings(max_examples=60, deadline=None)
+@settings(max_examples=60, deadline=None, derandomize=True, database=None)
 @given(n=st.integers(3, 8), cx=st.floats(-50, 50), cy=st.floats(-50, 50), rad=st.floats(0.3, 3.0),
        clockwise=st.booleans(), vx=st.floats(-1, 1), vy=st.floats(-1, 1), seed=st.integers(0, 10 ** 6))
 def test_polygon_rows_contain_the_shape_and_follow_its_motion(n, cx, cy, rad, clockwise, vx, vy, seed):
@@ -170,7 +170,7 @@ def test_polygon_rows_contain_the_shape_and_follow_its_motion(n, cx, cy, rad, cl
         assert np.sort(np.abs(viol), axis=1)[:, :2].max() < 2e-5 * scale         # each row tight on two vertices
 
 
-@settings(max_examples=40, deadline=None)
+@settings(max_examples=40, deadline=None, derandomize=True, database=None)
 @given(idx=st.integers(0, len(PATH_ARR) - 1), back=st.integers(0, 8), speed=st.floats(1.0, 6.0),
        dyn=st.sampled_from(['acker', 'diff', 'omni']), seed=st.integers(0, 10 ** 6))
 def test_pre_process_properties(idx, back, speed, dyn, seed):
