@@ -14,6 +14,7 @@
 #include "../../rda_planner_b200/csrc/cell_solver.cuh"
 #include "../../rda_planner_b200/csrc/su_solver.cuh"
 #include "../../rda_planner_b200/csrc/cell_lean.cuh"
+#include "../../rda_planner_b200/csrc/cell_lean2.cuh"
 
 using namespace rda;
 
@@ -74,7 +75,30 @@ static int lean_impl(const float* G, const float* h, int R, int kind, int E, con
   for (int i = 0; i < EC; ++i) out[i] = o.lam[i];
   for (int j = 0; j < RC; ++j) out[8 + j] = o.mu[j];
   out[16] = o.z; out[17] = o.zeta_new; out[18] = 0; out[19] = 0; out[20] = o.ax; out[21] = o.ay; out[22] = o.c0;
-  out[23] = o.gx; out[24] = o.gy; out[25] = 0; out[26] = 0;
+  out[23] = o.gx; out[24] = o.gy; out[25] = o.feat; out[26] = 0;
+  return 0;
+}
+
+// coherent first pass (cell_lean2.cuh): out as lean_impl, out[25] = new feature byte, out[27] = 6 when declined
+extern "C" int shim_cell_lean2_4(const float* G, const float* h, int R, int E, const float* A, const float* b, int feat,
+                                 double px, double py, double phi, double dbar, double zeta, double theta, double* out) {
+  RobotGeom rb;
+  int rc = robot_geom_from_halfspaces(G, h, R, &rb);
+  if (rc) return rc;
+  RobotAux ra;
+  robot_aux_from_geom(rb, &ra);
+  ObstacleGeom<4> og;
+  obstacle_geometry<4>(E, A, b, og);
+  LeanOut<4, 4> o;
+  int nf = cell_lean2<4, 4>(rb, ra, og, feat, (float)px, (float)py, (float)cos(phi), (float)sin(phi), (float)dbar,
+                            (float)zeta, (float)theta, o);
+  for (int i = 0; i < 28; ++i) out[i] = 0;
+  out[27] = nf >= 0 ? 0 : 6;
+  if (nf < 0) return 0;
+  for (int i = 0; i < 4; ++i) out[i] = o.lam[i];
+  for (int j = 0; j < 4; ++j) out[8 + j] = o.mu[j];
+  out[16] = o.z; out[17] = o.zeta_new; out[20] = o.ax; out[21] = o.ay; out[22] = o.c0;
+  out[23] = o.gx; out[24] = o.gy; out[25] = nf;
   return 0;
 }
 
