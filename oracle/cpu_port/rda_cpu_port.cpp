@@ -15,6 +15,9 @@
 #include "../../rda_planner_b200/csrc/su_solver.cuh"
 #include "../../rda_planner_b200/csrc/cell_lean.cuh"
 #include "../../rda_planner_b200/csrc/cell_lean2.cuh"
+#ifdef RDA_CELL_STATS
+static void rda_coh_stat(int it, int lean_ok, int coh_ok);
+#endif
 
 using namespace rda;
 
@@ -170,6 +173,9 @@ extern "C" int port_solve_batch(const rda_config* cfg, const rda_tunables* tun, 
     su_work_layout<double>(T, N, &W, base);
     std::vector<float> lam((size_t)N * E * T, 0.f), mu((size_t)N * R * T, 0.f), z(NT, 0.f), xi(2 * NT, 0.f),
         zeta(NT, 0.f), dis(T, 1.f), coef(5 * (size_t)NT, 0.f), pref(2 * T, 0.f);
+#ifdef RDA_CELL_STATS
+    std::vector<int> featv(NT > 0 ? NT : 1, 0);
+#endif
     std::vector<float> cs(nom_s + (size_t)b * 3 * (T + 1), nom_s + (size_t)(b + 1) * 3 * (T + 1));
     std::vector<float> cu(nom_u + (size_t)b * 2 * T, nom_u + (size_t)(b + 1) * 2 * T);
     const float* rf = ref_s + (size_t)b * 3 * (T + 1);
@@ -198,6 +204,26 @@ extern "C" int port_solve_batch(const rda_config* cfg, const rda_tunables* tun, 
             int tc = tv ? t + 1 : 0, Tc = tv ? T + 1 : 1;
             size_t ob = ((size_t)b * N + o) * Tc + tc;
             float ph = cs[2 * (T + 1) + t];
+#ifdef RDA_CELL_STATS
+            // emulation of the coherent first pass (cell_lean2.cuh): how often does the support-vertex pair of
+            // the previous ADMM iteration still certify the closest pair?  statistics only, results unused
+            if (E == 4 && R == 4 && !tv && obs_kind[(size_t)b * N + o] == RDA_OBS_POLYGON && xi[o * T + t] == 0.f && xi[NT + o * T + t] == 0.f) {
+              LeanOut<4, 4> l1, l2;
+              const bool ok1 = cell_lean<4, 4>(rb, RDA_OBS_POLYGON, E, obs_A + ob * E * 2, obs_b + ob * E, cs[t + 1], cs[(T + 1) + t + 1],
+                                               cosf(ph), sinf(ph), dis[t], zeta[o * T + t], 0.f, 0.f, theta, l1);
+              ObstacleGeom<4> og;
+              obstacle_geometry<4>(E, obs_A + ob * E * 2, obs_b + ob * E, og);
+              RobotAux ra;
+              robot_aux_from_geom(rb, &ra);
+              const int nf = cell_lean2<4, 4>(rb, ra, og, featv[o * T + t], cs[t + 1], cs[(T + 1) + t + 1], cosf(ph), sinf(ph), dis[t],
+                                              zeta[o * T + t], theta, l2);
+              rda_coh_stat(it, ok1 ? 1 : 0, nf >= 0 ? 1 : 0);
+              featv[o * T + t] = nf >= 0 ? nf : (ok1 ? l1.feat : 0);
+            } else {
+              rda_coh_stat(it, 0, 0);
+              featv[o * T + t] = 0;
+            }
+#endif
             CellOut<float> out;
             cell_solve<float>(rb, obs_kind[(size_t)b * N + o], E, obs_A + ob * E * 2, obs_b + ob * E, cs[t + 1],
                               cs[(T + 1) + t + 1], cosf(ph), sinf(ph), dis[t], zeta[o * T + t], xi[o * T + t],
@@ -281,6 +307,17 @@ extern "C" void rda_cell_stat(int what, int value) {
 #pragma omp atomic
   g_stat_hist[what][value] += 1;
 }
+static long long g_coh[64][3];
+static void rda_coh_stat(int it, int lean_ok, int coh_ok) {
+  if (it < 0 || it > 63) return;
+#pragma omp atomic
+  g_coh[it][0] += 1;
+#pragma omp atomic
+  g_coh[it][1] += lean_ok;
+#pragma omp atomic
+  g_coh[it][2] += coh_ok;
+}
+extern "C" void port_coh_stats(long long* out) { memcpy(out, g_coh, sizeof(g_coh)); }
 extern "C" void port_cell_stats(long long* out) { memcpy(out, g_stat_hist, sizeof(g_stat_hist)); }
 extern "C" void port_cell_situations(long long* out) { memcpy(out, rda::g_cell_stats, sizeof(rda::g_cell_stats)); }
 #endif
