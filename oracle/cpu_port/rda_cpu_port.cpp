@@ -307,6 +307,13 @@ extern "C" void rda_cell_stat(int what, int value) {
 #pragma omp atomic
   g_stat_hist[what][value] += 1;
 }
+static long long g_case[1024];
+extern "C" void rda_case_stat(int line) {
+  if (line < 0 || line > 1023) return;
+#pragma omp atomic
+  g_case[line] += 1;
+}
+extern "C" void port_case_stats(long long* out) { memcpy(out, g_case, sizeof(g_case)); }
 static long long g_coh[64][3];
 static void rda_coh_stat(int it, int lean_ok, int coh_ok) {
   if (it < 0 || it > 63) return;
