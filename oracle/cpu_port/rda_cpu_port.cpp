@@ -176,6 +176,14 @@ extern "C" int port_solve_batch(const rda_config* cfg, const rda_tunables* tun, 
 #ifdef RDA_CELL_STATS
     std::vector<int> featv(NT > 0 ? NT : 1, 0);
 #endif
+    const bool use_lean2 = getenv("RDA_PORT_LEAN2") && atoi(getenv("RDA_PORT_LEAN2")) != 0;
+    std::vector<int> feat2(NT > 0 ? NT : 1, 0);
+    std::vector<ObstacleGeom<4>> og2(N > 0 ? N : 1);
+    RobotAux ra2;
+    robot_aux_from_geom(rb, &ra2);
+    long long coh_hits = 0;
+    if (use_lean2 && E == 4 && !tv)
+      for (int o = 0; o < N; ++o) obstacle_geometry<4>(E, obs_A + ((size_t)b * N + o) * E * 2, obs_b + ((size_t)b * N + o) * E, og2[o]);
     std::vector<float> cs(nom_s + (size_t)b * 3 * (T + 1), nom_s + (size_t)(b + 1) * 3 * (T + 1));
     std::vector<float> cu(nom_u + (size_t)b * 2 * T, nom_u + (size_t)(b + 1) * 2 * T);
     const float* rf = ref_s + (size_t)b * 3 * (T + 1);
@@ -225,6 +233,28 @@ extern "C" int port_solve_batch(const rda_config* cfg, const rda_tunables* tun, 
             }
 #endif
             CellOut<float> out;
+            // emulation of the coherent pipeline (RDA_PORT_LEAN2=1): k_cells_coh -> listed cell_lean -> generic solver
+            bool lean_done = false;
+            if (use_lean2 && E == 4 && R == 4 && !tv && obs_kind[(size_t)b * N + o] == RDA_OBS_POLYGON) {
+              LeanOut<4, 4> lo;
+              int nf = -1;
+              if (xi[o * T + t] == 0.f && xi[NT + o * T + t] == 0.f)
+                nf = cell_lean2<4, 4>(rb, ra2, og2[o], feat2[o * T + t], cs[t + 1], cs[(T + 1) + t + 1], cosf(ph), sinf(ph), dis[t],
+                                      zeta[o * T + t], theta, lo);
+              if (nf < 0) {
+                const bool ok1 = cell_lean<4, 4>(rb, RDA_OBS_POLYGON, E, obs_A + ob * E * 2, obs_b + ob * E, cs[t + 1], cs[(T + 1) + t + 1],
+                                                 cosf(ph), sinf(ph), dis[t], zeta[o * T + t], xi[o * T + t], xi[NT + o * T + t], theta, lo);
+                nf = ok1 ? lo.feat : -1;
+              } else ++coh_hits;
+              feat2[o * T + t] = nf >= 0 ? nf : 0;
+              if (nf >= 0) {
+                lean_done = true;
+                for (int i = 0; i < 8; ++i) { out.lam[i] = i < 4 ? lo.lam[i] : 0.f; out.mu[i] = i < 4 ? lo.mu[i] : 0.f; }
+                out.z = lo.z; out.zeta_new = lo.zeta_new; out.xi0_new = 0.f; out.xi1_new = 0.f; out.ax = lo.ax; out.ay = lo.ay;
+                out.c0 = lo.c0; out.gx = lo.gx; out.gy = lo.gy; out.hm0 = 0.f; out.hm1 = 0.f; out.path = CELL_FAST_INACTIVE;
+              }
+            }
+            if (!lean_done)
             cell_solve<float>(rb, obs_kind[(size_t)b * N + o], E, obs_A + ob * E * 2, obs_b + ob * E, cs[t + 1],
                               cs[(T + 1) + t + 1], cosf(ph), sinf(ph), dis[t], zeta[o * T + t], xi[o * T + t],
                               xi[NT + o * T + t], (float)P.ro2, theta, out);
@@ -251,7 +281,7 @@ extern "C" int port_solve_batch(const rda_config* cfg, const rda_tunables* tun, 
     for (int i = 0; i < 2 * T; ++i) u_opt[(size_t)b * 2 * T + i] = cu[i];
     resi_pri[b] = rp; resi_dual[b] = rd;
     if (iters_out) iters_out[b] = it;
-    if (fails_out) { fails_out[4 * b] = nfail; fails_out[4 * b + 1] = first_fail; fails_out[4 * b + 2] = su_iters; fails_out[4 * b + 3] = su_bad; }
+    if (fails_out) { fails_out[4 * b] = nfail; fails_out[4 * b + 1] = first_fail; fails_out[4 * b + 2] = su_iters; fails_out[4 * b + 3] = su_bad; if (use_lean2) fails_out[4 * b + 1] = (int)coh_hits; }
   }
   return 0;
 }
