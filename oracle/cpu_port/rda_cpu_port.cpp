@@ -14,6 +14,10 @@
 #include "../../rda_planner_b200/csrc/cell_solver.cuh"
 #include "../../rda_planner_b200/csrc/su_solver.cuh"
 #include "../../rda_planner_b200/csrc/cell_lean.cuh"
+#include "../../rda_planner_b200/csrc/cell_lean2.cuh"
+#ifdef RDA_CELL_STATS
+static void rda_coh_stat(int it, int lean_ok, int coh_ok);
+#endif
 
 using namespace rda;
 
@@ -74,7 +78,30 @@ static int lean_impl(const float* G, const float* h, int R, int kind, int E, con
   for (int i = 0; i < EC; ++i) out[i] = o.lam[i];
   for (int j = 0; j < RC; ++j) out[8 + j] = o.mu[j];
   out[16] = o.z; out[17] = o.zeta_new; out[18] = 0; out[19] = 0; out[20] = o.ax; out[21] = o.ay; out[22] = o.c0;
-  out[23] = o.gx; out[24] = o.gy; out[25] = 0; out[26] = 0;
+  out[23] = o.gx; out[24] = o.gy; out[25] = o.feat; out[26] = 0;
+  return 0;
+}
+
+// coherent first pass (cell_lean2.cuh): out as lean_impl, out[25] = new feature byte, out[27] = 6 when declined
+extern "C" int shim_cell_lean2_4(const float* G, const float* h, int R, int E, const float* A, const float* b, int feat,
+                                 double px, double py, double phi, double dbar, double zeta, double theta, double* out) {
+  RobotGeom rb;
+  int rc = robot_geom_from_halfspaces(G, h, R, &rb);
+  if (rc) return rc;
+  RobotAux ra;
+  robot_aux_from_geom(rb, &ra);
+  ObstacleGeom<4> og;
+  obstacle_geometry<4>(E, A, b, og);
+  LeanOut<4, 4> o;
+  int nf = cell_lean2<4, 4>(rb, ra, og, feat, (float)px, (float)py, (float)cos(phi), (float)sin(phi), (float)dbar,
+                            (float)zeta, (float)theta, o);
+  for (int i = 0; i < 28; ++i) out[i] = 0;
+  out[27] = nf >= 0 ? 0 : 6;
+  if (nf < 0) return 0;
+  for (int i = 0; i < 4; ++i) out[i] = o.lam[i];
+  for (int j = 0; j < 4; ++j) out[8 + j] = o.mu[j];
+  out[16] = o.z; out[17] = o.zeta_new; out[20] = o.ax; out[21] = o.ay; out[22] = o.c0;
+  out[23] = o.gx; out[24] = o.gy; out[25] = nf;
   return 0;
 }
 
@@ -146,6 +173,17 @@ extern "C" int port_solve_batch(const rda_config* cfg, const rda_tunables* tun, 
     su_work_layout<double>(T, N, &W, base);
     std::vector<float> lam((size_t)N * E * T, 0.f), mu((size_t)N * R * T, 0.f), z(NT, 0.f), xi(2 * NT, 0.f),
         zeta(NT, 0.f), dis(T, 1.f), coef(5 * (size_t)NT, 0.f), pref(2 * T, 0.f);
+#ifdef RDA_CELL_STATS
+    std::vector<int> featv(NT > 0 ? NT : 1, 0);
+#endif
+    const bool use_lean2 = getenv("RDA_PORT_LEAN2") && atoi(getenv("RDA_PORT_LEAN2")) != 0;
+    std::vector<int> feat2(NT > 0 ? NT : 1, 0);
+    std::vector<ObstacleGeom<4>> og2(N > 0 ? N : 1);
+    RobotAux ra2;
+    robot_aux_from_geom(rb, &ra2);
+    long long coh_hits = 0;
+    if (use_lean2 && E == 4 && !tv)
+      for (int o = 0; o < N; ++o) obstacle_geometry<4>(E, obs_A + ((size_t)b * N + o) * E * 2, obs_b + ((size_t)b * N + o) * E, og2[o]);
     std::vector<float> cs(nom_s + (size_t)b * 3 * (T + 1), nom_s + (size_t)(b + 1) * 3 * (T + 1));
     std::vector<float> cu(nom_u + (size_t)b * 2 * T, nom_u + (size_t)(b + 1) * 2 * T);
     const float* rf = ref_s + (size_t)b * 3 * (T + 1);
@@ -174,7 +212,49 @@ extern "C" int port_solve_batch(const rda_config* cfg, const rda_tunables* tun, 
             int tc = tv ? t + 1 : 0, Tc = tv ? T + 1 : 1;
             size_t ob = ((size_t)b * N + o) * Tc + tc;
             float ph = cs[2 * (T + 1) + t];
+#ifdef RDA_CELL_STATS
+            // emulation of the coherent first pass (cell_lean2.cuh): how often does the support-vertex pair of
+            // the previous ADMM iteration still certify the closest pair?  statistics only, results unused
+            if (E == 4 && R == 4 && !tv && obs_kind[(size_t)b * N + o] == RDA_OBS_POLYGON && xi[o * T + t] == 0.f && xi[NT + o * T + t] == 0.f) {
+              LeanOut<4, 4> l1, l2;
+              const bool ok1 = cell_lean<4, 4>(rb, RDA_OBS_POLYGON, E, obs_A + ob * E * 2, obs_b + ob * E, cs[t + 1], cs[(T + 1) + t + 1],
+                                               cosf(ph), sinf(ph), dis[t], zeta[o * T + t], 0.f, 0.f, theta, l1);
+              ObstacleGeom<4> og;
+              obstacle_geometry<4>(E, obs_A + ob * E * 2, obs_b + ob * E, og);
+              RobotAux ra;
+              robot_aux_from_geom(rb, &ra);
+              const int nf = cell_lean2<4, 4>(rb, ra, og, featv[o * T + t], cs[t + 1], cs[(T + 1) + t + 1], cosf(ph), sinf(ph), dis[t],
+                                              zeta[o * T + t], theta, l2);
+              rda_coh_stat(it, ok1 ? 1 : 0, nf >= 0 ? 1 : 0);
+              featv[o * T + t] = nf >= 0 ? nf : (ok1 ? l1.feat : 0);
+            } else {
+              rda_coh_stat(it, 0, 0);
+              featv[o * T + t] = 0;
+            }
+#endif
             CellOut<float> out;
+            // emulation of the coherent pipeline (RDA_PORT_LEAN2=1): k_cells_coh -> listed cell_lean -> generic solver
+            bool lean_done = false;
+            if (use_lean2 && E == 4 && R == 4 && !tv && obs_kind[(size_t)b * N + o] == RDA_OBS_POLYGON) {
+              LeanOut<4, 4> lo;
+              int nf = -1;
+              if (xi[o * T + t] == 0.f && xi[NT + o * T + t] == 0.f)
+                nf = cell_lean2<4, 4>(rb, ra2, og2[o], feat2[o * T + t], cs[t + 1], cs[(T + 1) + t + 1], cosf(ph), sinf(ph), dis[t],
+                                      zeta[o * T + t], theta, lo);
+              if (nf < 0) {
+                const bool ok1 = cell_lean<4, 4>(rb, RDA_OBS_POLYGON, E, obs_A + ob * E * 2, obs_b + ob * E, cs[t + 1], cs[(T + 1) + t + 1],
+                                                 cosf(ph), sinf(ph), dis[t], zeta[o * T + t], xi[o * T + t], xi[NT + o * T + t], theta, lo);
+                nf = ok1 ? lo.feat : -1;
+              } else ++coh_hits;
+              feat2[o * T + t] = nf >= 0 ? nf : 0;
+              if (nf >= 0) {
+                lean_done = true;
+                for (int i = 0; i < 8; ++i) { out.lam[i] = i < 4 ? lo.lam[i] : 0.f; out.mu[i] = i < 4 ? lo.mu[i] : 0.f; }
+                out.z = lo.z; out.zeta_new = lo.zeta_new; out.xi0_new = 0.f; out.xi1_new = 0.f; out.ax = lo.ax; out.ay = lo.ay;
+                out.c0 = lo.c0; out.gx = lo.gx; out.gy = lo.gy; out.hm0 = 0.f; out.hm1 = 0.f; out.path = CELL_FAST_INACTIVE;
+              }
+            }
+            if (!lean_done)
             cell_solve<float>(rb, obs_kind[(size_t)b * N + o], E, obs_A + ob * E * 2, obs_b + ob * E, cs[t + 1],
                               cs[(T + 1) + t + 1], cosf(ph), sinf(ph), dis[t], zeta[o * T + t], xi[o * T + t],
                               xi[NT + o * T + t], (float)P.ro2, theta, out);
@@ -201,7 +281,7 @@ extern "C" int port_solve_batch(const rda_config* cfg, const rda_tunables* tun, 
     for (int i = 0; i < 2 * T; ++i) u_opt[(size_t)b * 2 * T + i] = cu[i];
     resi_pri[b] = rp; resi_dual[b] = rd;
     if (iters_out) iters_out[b] = it;
-    if (fails_out) { fails_out[4 * b] = nfail; fails_out[4 * b + 1] = first_fail; fails_out[4 * b + 2] = su_iters; fails_out[4 * b + 3] = su_bad; }
+    if (fails_out) { fails_out[4 * b] = nfail; fails_out[4 * b + 1] = first_fail; fails_out[4 * b + 2] = su_iters; fails_out[4 * b + 3] = su_bad; if (use_lean2) fails_out[4 * b + 1] = (int)coh_hits; }
   }
   return 0;
 }
@@ -257,6 +337,24 @@ extern "C" void rda_cell_stat(int what, int value) {
 #pragma omp atomic
   g_stat_hist[what][value] += 1;
 }
+static long long g_case[1024];
+extern "C" void rda_case_stat(int line) {
+  if (line < 0 || line > 1023) return;
+#pragma omp atomic
+  g_case[line] += 1;
+}
+extern "C" void port_case_stats(long long* out) { memcpy(out, g_case, sizeof(g_case)); }
+static long long g_coh[64][3];
+static void rda_coh_stat(int it, int lean_ok, int coh_ok) {
+  if (it < 0 || it > 63) return;
+#pragma omp atomic
+  g_coh[it][0] += 1;
+#pragma omp atomic
+  g_coh[it][1] += lean_ok;
+#pragma omp atomic
+  g_coh[it][2] += coh_ok;
+}
+extern "C" void port_coh_stats(long long* out) { memcpy(out, g_coh, sizeof(g_coh)); }
 extern "C" void port_cell_stats(long long* out) { memcpy(out, g_stat_hist, sizeof(g_stat_hist)); }
 extern "C" void port_cell_situations(long long* out) { memcpy(out, rda::g_cell_stats, sizeof(rda::g_cell_stats)); }
 #endif

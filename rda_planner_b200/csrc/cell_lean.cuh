@@ -13,11 +13,18 @@
 
 namespace rda {
 
+// A vertex-vertex pair and the neighbouring vertex-edge pair can tie in float32 when the foot of the
+// perpendicular lies within sqrt(2 eps) |d| of the edge's end; the vertex-vertex direction is then off by up
+// to 5e-4 rad and the margin by that times the edge length.  End-point candidates carry this relative
+// handicap so that such ties go to the edge-interior pair, whose direction is the edge normal.
+#define RDA_ENDPOINT_BIAS 1.0000006f
+
 template <int EC, int RC>
 struct LeanOut {
   float lam[EC];
   float mu[RC];
   float z, zeta_new, ax, ay, c0, gx, gy;
+  int feat;      // 0x40 | obstacle support vertex << 3 | robot support vertex of a separated polygon pair, else 0 (cell_lean2.cuh)
 };
 
 // returns true when the cell is resolved (outputs valid); false -> next pass
@@ -42,6 +49,7 @@ RDA_HD bool cell_lean(const RobotGeom& rb, int kind, int E, const float* A, cons
   float best = 1e30f, bdx = 0.f, bdy = 0.f;
   float sO = 0.f;                      // support of the obstacle in direction v (relative coordinates)
   float lamv[EC];
+  int fi = -1, fj = -1;
 #pragma unroll
   for (int i = 0; i < EC; ++i) lamv[i] = 0.f;
   if (kind == RDA_OBS_CIRCLE) {
@@ -126,7 +134,7 @@ RDA_HD bool cell_lean(const RobotGeom& rb, int kind, int E, const float* A, cons
             mins = rmin(mins, nx[i] * rx + ny[i] * ry);
             const float t = rclamp((rx * ex + ry * ey) * ie2, 0.f, 1.f);
             const float dx = rx - t * ex, dy = ry - t * ey;
-            const float d2 = dx * dx + dy * dy;
+            const float d2 = (dx * dx + dy * dy) * ((t > 0.f && t < 1.f) ? 1.f : RDA_ENDPOINT_BIAS);
             if (d2 < dj2[j]) { dj2[j] = d2; djx[j] = dx; djy[j] = dy; }
           }
         }
@@ -151,7 +159,7 @@ RDA_HD bool cell_lean(const RobotGeom& rb, int kind, int E, const float* A, cons
             mins = rmin(mins, Mx[j] * rx + My[j] * ry);
             const float t = rclamp((rx * fx + ry * fy) * if2, 0.f, 1.f);
             const float dx = -(rx - t * fx), dy = -(ry - t * fy);
-            const float d2 = dx * dx + dy * dy;
+            const float d2 = (dx * dx + dy * dy) * ((t > 0.f && t < 1.f) ? 1.f : RDA_ENDPOINT_BIAS);
             if (d2 < best) { best = d2; bdx = dx; bdy = dy; }
           }
         }
@@ -182,6 +190,7 @@ RDA_HD bool cell_lean(const RobotGeom& rb, int kind, int E, const float* A, cons
       for (int i = 0; i < EC; ++i)
         if (i == ia) ain = invn[i];
       sO = sb;
+      fi = ib;
       const float det = anx * bny - any * bnx;
       const float al = (v0 * bny - v1 * bnx) / det;
       const float be = (anx * v1 - any * v0) / det;
@@ -222,6 +231,7 @@ RDA_HD bool cell_lean(const RobotGeom& rb, int kind, int E, const float* A, cons
       }
     }
     sR = sb;
+    fj = jb;
     const float det = anx * bny - any * bnx;
     const float al = (g0 * bny - g1 * bnx) / det;
     const float be = (anx * g1 - any * g0) / det;
@@ -242,6 +252,7 @@ RDA_HD bool cell_lean(const RobotGeom& rb, int kind, int E, const float* A, cons
   out.ax = v0; out.ay = v1;
   out.c0 = marg - z + out.zeta_new;
   out.gx = g0; out.gy = g1;
+  out.feat = (fi >= 0 && fj >= 0) ? (0x40 | (fi << 3) | fj) : 0;
   return true;
 }
 

@@ -15,6 +15,7 @@
 #include "cell_solver.cuh"
 #include "su_solver.cuh"
 #include "cell_lean.cuh"
+#include "cell_lean2.cuh"
 
 using namespace rda;
 
@@ -33,6 +34,13 @@ struct rda_handle {
   float *resi_acc, *resi_pri, *resi_dual;
   int *status, *iters, *done, *counters, *worklist, *worklist2;
   double* su_scratch;    // [B][2][N*T] hinge slack / multiplier of the su-QP interior point iteration
+  // coherent first cell pass (cell_lean2.cuh; RDA_B200_LEAN2=1, E <= 4, R <= 4, static obstacles)
+  int lean2;
+  RobotAux ra;
+  ObstacleGeom<4>* ogeo; // [B][N] per-obstacle geometry, rebuilt by every rda_begin / rda_solve
+  unsigned char* feat;   // [B][N][T] support-vertex pair of the previous iteration (0: none)
+  int* worklist0;        // cells the coherent pass declined (run through the search pass)
+  float* rot;            // [B][2][T] cos / sin of the nominal headings of this iteration
   const float *obs_A, *obs_b;
   const int *obs_kind, *obs_count;
   int obs_tv;
@@ -85,7 +93,10 @@ struct DevPtrs {
   float *lam, *mu, *z, *xi, *zeta, *dis, *coef, *pref, *cur_s, *cur_u, *ref_s, *ref_speed;
   float *resi_acc, *resi_pri, *resi_dual;
   int *status, *iters, *done, *counters, *worklist, *worklist2;
-  int* wl_count;         // lengths of the two worklists of this sub-batch
+  int* wl_count;         // lengths of the worklists of this sub-batch ([2]: cells declined by the coherent pass)
+  const ObstacleGeom<4>* ogeo;
+  unsigned char* feat;
+  int* worklist0;
   double* su_scratch;
   const float *obs_A, *obs_b;
   const int *obs_kind, *obs_count;
@@ -265,15 +276,17 @@ __device__ __forceinline__ void cell_store(const DevPtrs& d, const CellIn& c, co
 }
 
 // First pass: compile-time specialised lean solver (cell_lean.cuh), geometry in registers.
-template <int EC, int RC>
+// LISTED: the cells come from worklist0 (what the coherent pass k_cells_coh declined) instead of the whole batch.
+template <int EC, int RC, bool LISTED>
 __global__ void __launch_bounds__(128, (EC <= 4 ? 6 : 3)) k_cells_fast(DevPtrs d, RobotGeom rb, float theta) {
   const int T = d.T, N = d.N, E = d.E, R = d.R;
   const int NT = N * T;
-  const long long total = (long long)d.B * NT;
+  const long long total = LISTED ? (long long)d.wl_count[2] : (long long)d.B * NT;
   const int lane = threadIdx.x & 31;
   for (long long base = (long long)blockIdx.x * blockDim.x; base < total; base += (long long)gridDim.x * blockDim.x) {
     long long idx = base + threadIdx.x;
     bool live = idx < total;
+    if (LISTED && live) idx = d.worklist0[idx];
     int b = live ? (int)(idx / NT) : -1;
     float dual = 0.f;
     bool need = false;
@@ -308,6 +321,7 @@ __global__ void __launch_bounds__(128, (EC <= 4 ? 6 : 3)) k_cells_fast(DevPtrs d
       LeanOut<EC, RC> o;
       const bool ok = cell_lean<EC, RC>(rb, c.kind, EC, Ar, br, c.px, c.py, c.cp, c.sp, c.dbar, c.zeta, c.xi0,
                                         c.xi1, theta, o);
+      if (d.feat) d.feat[c.cell] = (unsigned char)(ok ? o.feat : 0);
       if (ok) {
         // dual residual |lam - lam_prev|^2 + |mu - mu_prev|^2 + |z - z_prev|^2 (:783-787)
         float* lam = d.lam + ((size_t)c.b * N + c.o) * E * T + c.t;
@@ -356,6 +370,12 @@ __global__ void __launch_bounds__(128, (EC <= 4 ? 6 : 3)) k_cells_fast(DevPtrs d
     const bool solved = live && !need;
     // dual-residual partial sums (Hm = 0 for every cell solved here): a warp spans at most two
     // instances when N*T >= 32
+    if (LISTED) {            // listed cells are not contiguous: one atomic per cell
+      if (solved) atomicAdd(&d.resi_acc[2 * b + 1], dual);
+      unsigned fastl = __ballot_sync(0xffffffffu, solved);
+      if (lane == 0 && fastl) atomicAdd(&d.counters[0], __popc(fastl));
+      continue;
+    }
     int b0 = __shfl_sync(0xffffffffu, b, 0);
     for (int pass = 0; pass < 2; ++pass) {
       bool mine = solved && ((pass == 0) ? (b == b0) : (b != b0));
@@ -374,6 +394,116 @@ __global__ void __launch_bounds__(128, (EC <= 4 ? 6 : 3)) k_cells_fast(DevPtrs d
     }
     unsigned fast = __ballot_sync(0xffffffffu, solved);
     if (lane == 0 && fast) atomicAdd(&d.counters[0], __popc(fast));
+  }
+}
+
+// Per-obstacle geometry of the coherent pass, once per solve (static polygons; discs get ne = 0).
+__global__ void k_obstacle_geometry(DevPtrs d, ObstacleGeom<4>* og) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= d.B * d.N) return;
+  ObstacleGeom<4> g;
+  if (d.obs_kind[i] == RDA_OBS_POLYGON && d.E <= 4) obstacle_geometry<4>(d.E, d.obs_A + (size_t)i * d.E * 2, d.obs_b + (size_t)i * d.E, g);
+  else { obstacle_geometry<4>(0, nullptr, nullptr, g); }
+  og[i] = g;
+}
+
+// cos / sin of the nominal headings (column t of cur_s, rda_solver.py:457-460), once per iteration for the
+// coherent pass instead of one sincosf per cell
+__global__ void k_heading(DevPtrs d, float* rot) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int T = d.T;
+  if (i >= d.B * T) return;
+  const int b = i / T, t = i - b * T;
+  float sp, cp;
+  sincosf(d.cur_s[(size_t)b * 3 * (T + 1) + 2 * (T + 1) + t], &sp, &cp);
+  rot[(size_t)b * 2 * T + t] = cp;
+  rot[(size_t)b * 2 * T + T + t] = sp;
+}
+
+// Coherent first pass (cell_lean2.cuh): one thread per cell tries the support-vertex pair of the previous
+// iteration; what it declines goes to worklist0 and through k_cells_fast<.., LISTED>.  Grid: (cells of one
+// instance / 128, instances) — no 64-bit index arithmetic, one instance per CTA (uniform early exit, one
+// residual atomic per warp), 32-bit offsets inside the instance.
+__global__ void __launch_bounds__(128, 6) k_cells_coh(DevPtrs d, RobotGeom rb, RobotAux ra, const float* __restrict__ rot,
+                                                      float theta, float invT) {
+  constexpr int EC = 4, RC = 4;
+  const int T = d.T, N = d.N, E = d.E, R = d.R, NT = N * T;
+  const int b = blockIdx.y;
+  if (d.done[b] || d.obs_count[b] == 0) return;             // uniform for the CTA
+  const int rem = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const bool live = rem < NT;
+  float dual = 0.f;
+  bool need = false, solved = false;
+  if (live) {
+    int o = (int)(((float)rem + 0.5f) * invT);
+    int t = rem - o * T;
+    if (t < 0) { --o; t += T; } else if (t >= T) { ++o; t -= T; }
+    const size_t ib = (size_t)b;
+    const float* cs = d.cur_s + ib * 3 * (T + 1);
+    const float* xi = d.xi + ib * 2 * NT;
+    float* lamb = d.lam + ib * N * E * T;
+    float* mub = d.mu + ib * N * R * T;
+    float* zb = d.z + ib * NT;
+    float* zetab = d.zeta + ib * NT;
+    unsigned char* featb = d.feat + ib * NT;
+    const float xi0 = xi[rem], xi1 = xi[NT + rem];
+    const int f = featb[rem];
+    int nf = -1;
+    if (xi0 == 0.f && xi1 == 0.f && (f & RDA_FEAT_VALID)) {
+      const float px = cs[t + 1], py = cs[(T + 1) + t + 1];
+      const float cp = rot[ib * 2 * T + t], sp = rot[ib * 2 * T + T + t];
+      const float dbar = d.dis[ib * T + t], zeta = zetab[rem];
+      const int lo = o * E * T + t, mo = o * R * T + t;
+      float lamo[EC], muo[RC];
+#pragma unroll
+      for (int i = 0; i < EC; ++i) lamo[i] = (i < E) ? lamb[lo + i * T] : 0.f;
+#pragma unroll
+      for (int j = 0; j < RC; ++j) muo[j] = (j < R) ? mub[mo + j * T] : 0.f;
+      const float zo = zb[rem];
+      const ObstacleGeom<4>& og = d.ogeo[ib * N + o];         // same address for the T cells of an obstacle
+      LeanOut<EC, RC> r;
+      nf = cell_lean2<EC, RC>(rb, ra, og, f, px, py, cp, sp, dbar, zeta, theta, r);
+      if (nf >= 0) {
+        float acc = 0.f;
+#pragma unroll
+        for (int i = 0; i < EC; ++i) {
+          if (i < E) { const float df = r.lam[i] - lamo[i]; acc += df * df; lamb[lo + i * T] = r.lam[i]; }
+        }
+#pragma unroll
+        for (int j = 0; j < RC; ++j) {
+          if (j < R) { const float df = r.mu[j] - muo[j]; acc += df * df; mub[mo + j * T] = r.mu[j]; }
+        }
+        const float dz = r.z - zo;
+        acc += dz * dz;
+        zb[rem] = r.z;
+        dual = acc;
+        zetab[rem] = r.zeta_new;
+        float* cf = d.coef + ib * 5 * NT + rem;
+        cf[0] = r.ax; cf[NT] = r.ay; cf[2 * NT] = r.c0; cf[3 * NT] = r.gx; cf[4 * NT] = r.gy;
+        if (o == 0) {
+          d.pref[ib * 2 * T + t] = px;
+          d.pref[ib * 2 * T + T + t] = py;
+        }
+        if (nf != f) featb[rem] = (unsigned char)nf;
+        solved = true;
+      }
+    }
+    need = nf < 0;
+  }
+  const unsigned nm = __ballot_sync(0xffffffffu, need);
+  if (nm) {
+    const int leader = __ffs(nm) - 1;
+    int pos = 0;
+    if (lane == leader) pos = atomicAdd(&d.wl_count[2], __popc(nm));
+    pos = __shfl_sync(0xffffffffu, pos, leader);
+    if (need) d.worklist0[pos + __popc(nm & ((1u << lane) - 1))] = b * NT + rem;
+  }
+  const unsigned fast = __ballot_sync(0xffffffffu, solved);
+  if (fast) {
+    float q = dual;
+    for (int o2 = 16; o2 > 0; o2 >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o2);
+    if (lane == 0) { atomicAdd(&d.resi_acc[2 * b + 1], q); atomicAdd(&d.counters[0], __popc(fast)); }
   }
 }
 
@@ -460,7 +590,7 @@ __global__ void __launch_bounds__(64, RDA_SLOW_MINBLOCKS) k_cells_slow(DevPtrs d
 // per instance: residuals (:688, :735-739), early stop (:594-596), empty-list quirk (:564-568)
 __global__ void k_finalize(DevPtrs d, RobotGeom rb, float thr) {
   int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b == 0) { d.wl_count[0] = 0; d.wl_count[1] = 0; }   // worklists consumed
+  if (b == 0) { d.wl_count[0] = 0; d.wl_count[1] = 0; d.wl_count[2] = 0; }   // worklists consumed
   if (b >= d.B) return;
   if (d.done[b]) return;
   const int T = d.T, N = d.N, NT = N * T, R = d.R;
@@ -533,7 +663,10 @@ DevPtrs dev_ptrs(const rda_handle* h, int b0, int nb, int part) {
   d.ref_speed = h->ref_speed + o; d.resi_acc = h->resi_acc + 2 * o; d.resi_pri = h->resi_pri + o;
   d.resi_dual = h->resi_dual + o;
   d.status = h->status + o; d.iters = h->iters + o; d.done = h->done + o;
-  d.counters = h->counters; d.wl_count = h->counters + 8 + 2 * part;     // part < 4
+  d.counters = h->counters; d.wl_count = h->counters + 8 + 3 * part;     // part < 4
+  d.ogeo = h->ogeo ? h->ogeo + o * N : nullptr;
+  d.feat = h->feat ? h->feat + o * NT : nullptr;
+  d.worklist0 = h->worklist0 ? h->worklist0 + o * NT : nullptr;
   d.worklist = h->worklist + o * NT; d.worklist2 = h->worklist2 + o * NT;
   d.su_scratch = h->su_scratch + o * 2 * NT;
   d.obs_A = h->obs_A ? h->obs_A + o * N * Tc * E * 2 : nullptr;
@@ -600,7 +733,7 @@ int rda_create(const rda_config* cfg, const rda_tunables* tun, rda_handle** out)
   alloc(&h->cur_u, B * 2 * T); alloc(&h->ref_s, B * 3 * (T + 1)); alloc(&h->ref_speed, B);
   alloc(&h->resi_acc, B * 2); alloc(&h->resi_pri, B); alloc(&h->resi_dual, B);
   alloc((float**)&h->status, B); alloc((float**)&h->iters, B); alloc((float**)&h->done, B);
-  alloc((float**)&h->counters, 16);     // [0..4] statistics, [8..11] worklist lengths of the two halves
+  alloc((float**)&h->counters, 24);     // [0..4] statistics, [8..11] worklist lengths of the two halves
   alloc((float**)&h->worklist, B * NT);
   alloc((float**)&h->worklist2, B * NT);
   alloc((float**)&h->su_scratch, B * 2 * NT * 2 * 2);      // doubles: 2 arrays x NT x (8/4 floats)
@@ -616,6 +749,15 @@ int rda_create(const rda_config* cfg, const rda_tunables* tun, rda_handle** out)
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_join[p], cudaEventDisableTiming);
   }
   if (e != cudaSuccess) { rda_destroy(h); return (int)e; }
+  if (const char* l2 = getenv("RDA_B200_LEAN2")) h->lean2 = atoi(l2) != 0 && h->E <= 4 && h->R <= 4 && h->N > 0;
+  if (h->lean2) {
+    robot_aux_from_geom(h->rb, &h->ra);
+    e = cudaMalloc((void**)&h->ogeo, B * N * sizeof(ObstacleGeom<4>));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&h->feat, B * NT ? B * NT : 1);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&h->worklist0, (B * NT ? B * NT : 1) * sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&h->rot, B * 2 * T * sizeof(float));
+    if (e != cudaSuccess) { rda_destroy(h); return (int)e; }
+  }
   h->split_min = 2048;
   h->parts = 2;
   if (const char* sm = getenv("RDA_B200_SPLIT_MIN")) { int v = atoi(sm); if (v >= 2) h->split_min = v; }
@@ -634,6 +776,10 @@ int rda_destroy(rda_handle* h) {
                    h->ref_s, h->ref_speed, h->resi_acc, h->resi_pri, h->resi_dual, (float*)h->status,
                    (float*)h->iters, (float*)h->done, (float*)h->counters, (float*)h->worklist, (float*)h->worklist2, (float*)h->su_scratch};
   for (float* p : bufs) if (p) cudaFree(p);
+  if (h->ogeo) cudaFree(h->ogeo);
+  if (h->feat) cudaFree(h->feat);
+  if (h->worklist0) cudaFree(h->worklist0);
+  if (h->rot) cudaFree(h->rot);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   for (int p = 0; p < 3; ++p) {
     if (h->ev_join[p]) cudaEventDestroy(h->ev_join[p]);
@@ -674,7 +820,8 @@ int rda_cold_start(rda_handle* h, void* stream) {
   RDA_CUDA(cudaMemsetAsync(h->status, 0, B * 4, s));
   RDA_CUDA(cudaMemsetAsync(h->iters, 0, B * 4, s));
   RDA_CUDA(cudaMemsetAsync(h->done, 0, B * 4, s));
-  RDA_CUDA(cudaMemsetAsync(h->counters, 0, 16 * 4, s));
+  RDA_CUDA(cudaMemsetAsync(h->counters, 0, 24 * 4, s));
+  if (h->feat) RDA_CUDA(cudaMemsetAsync(h->feat, 0, B * NT, s));
   k_fill<<<grid_for((long long)(B * T), 256), 256, 0, s>>>(h->dis, 1.0f, B * T);   // para_dis = 1 (:119)
   RDA_CUDA(cudaGetLastError());
   h->launches = 1;
@@ -700,6 +847,11 @@ static int begin_part(rda_handle* h, const rda_inputs* in, int b0, int nb, int p
       (const float*)in->ref_s + o * 3 * (T + 1), (const float*)in->ref_speed + o);
   RDA_CUDA(cudaGetLastError());
   h->launches += 1;
+  if (h->lean2 && !h->obs_tv && h->E <= 4 && h->R <= 4 && h->N > 0) {
+    k_obstacle_geometry<<<(nb * h->N + 127) / 128, 128, 0, s>>>(d, h->ogeo + o * h->N);
+    RDA_CUDA(cudaGetLastError());
+    h->launches += 1;
+  }
   return 0;
 }
 
@@ -720,10 +872,19 @@ static int step_lammuz_part(rda_handle* h, int b0, int nb, int part, cudaStream_
   DevPtrs d = dev_ptrs(h, b0, nb, part);
   if (h->N > 0) {
     const float theta = h->cfg.accelerated ? h->tun.z_theta : 1.0f;
-    if (h->E <= 4 && h->R <= 4)
-      k_cells_fast<4, 4><<<grid_for((long long)nb * h->N * h->T, 128), 128, 0, s>>>(d, h->rb, theta);
+    if (h->lean2 && !h->obs_tv && h->E <= 4 && h->R <= 4) {
+      k_heading<<<(nb * h->T + 255) / 256, 256, 0, s>>>(d, h->rot + (size_t)b0 * 2 * h->T);
+      RDA_CUDA(cudaGetLastError());
+      k_cells_coh<<<dim3((h->N * h->T + 127) / 128, nb), 128, 0, s>>>(d, h->rb, h->ra, h->rot + (size_t)b0 * 2 * h->T, theta,
+                                                                       1.0f / (float)h->T);
+      h->launches += 1;
+      RDA_CUDA(cudaGetLastError());
+      k_cells_fast<4, 4, true><<<grid_for((long long)nb * h->N * h->T, 128), 128, 0, s>>>(d, h->rb, theta);
+      h->launches += 1;
+    } else if (h->E <= 4 && h->R <= 4)
+      k_cells_fast<4, 4, false><<<grid_for((long long)nb * h->N * h->T, 128), 128, 0, s>>>(d, h->rb, theta);
     else
-      k_cells_fast<8, 8><<<grid_for((long long)nb * h->N * h->T, 128), 128, 0, s>>>(d, h->rb, theta);
+      k_cells_fast<8, 8, false><<<grid_for((long long)nb * h->N * h->T, 128), 128, 0, s>>>(d, h->rb, theta);
     RDA_CUDA(cudaGetLastError());
     k_cells_mid<<<148 * 8, 128, 0, s>>>(d, h->rb, h->tun.ro2, theta);
     RDA_CUDA(cudaGetLastError());

@@ -108,3 +108,18 @@ def convert_obstacles(shapes, N, T, E, dt, time_varying, order, state):
     cnt = f(M, N, T, E, dt, int(time_varying), int(order), st.ctypes.data, k.ctypes.data, nv.ctypes.data, xy.ctypes.data,
             rad.ctypes.data, vel.ctypes.data, int(shapes['count']), A.ctypes.data, b.ctypes.data, kind.ctypes.data)
     return A, b, kind, cnt
+
+
+def cell_lean2(G, h, A, b, feat, p, phi, dbar, zeta, theta=0.5):
+    """Coherent first pass (cell_lean2.cuh, E = R = 4 build): dict like cell(), plus 'feat'; path 6 = declined."""
+    G = _f32(G); h = _f32(np.ravel(h)); A = _f32(A); b = _f32(np.ravel(b))
+    out = np.zeros(28)
+    fn = lib().shim_cell_lean2_4
+    fn.restype = C.c_int
+    rc = fn(_p(G), _p(h), C.c_int(G.shape[0]), C.c_int(A.shape[0]), _p(A), _p(b), C.c_int(int(feat)), C.c_double(p[0]),
+            C.c_double(p[1]), C.c_double(phi), C.c_double(dbar), C.c_double(zeta), C.c_double(theta), _p(out))
+    assert rc == 0, rc
+    E, R = A.shape[0], G.shape[0]
+    r = {'z': out[16], 'zeta_new': out[17], 'ax': out[20], 'ay': out[21], 'c0': out[22], 'gx': out[23], 'gy': out[24],
+         'feat': int(out[25]), 'path': int(out[27]), 'lam': out[:E].copy(), 'mu': out[8:8 + R].copy()}
+    return r

@@ -325,3 +325,24 @@ def test_large_polytopes_config():
     assert int((out['status'] & 6).sum()) == 0
     np.testing.assert_allclose(out['u'].cpu().numpy(), port['u'], atol=3 * TRAJ_TOL)
     np.testing.assert_allclose(out['s'].cpu().numpy(), port['s'], atol=3 * TRAJ_TOL)
+
+
+def test_coherent_first_pass_matches_the_search_pass(monkeypatch):
+    """RDA_B200_LEAN2=1 (cell_lean2.cuh: cached support-vertex pair + separating-slab certificate, per-obstacle
+    precomputed geometry) against the default search pass on the same batch.  The two differ at float
+    rounding level per cell, so the comparison is made after few iterations; the coherent pass must
+    actually resolve most cells from the second iteration on."""
+    from rda_planner_b200.rda_solver import RDA_solver
+    from rda_planner_b200 import _cabi
+    T, N, B, iters = 12, 6, 96, 4
+    car = rectangle_robot()
+    insts, inp = _batch_inputs(B, T, N, 2500, lateral=(1.0, 5.0))
+    res = {}
+    for flag in ('0', '1'):
+        monkeypatch.setenv('RDA_B200_LEAN2', flag)
+        g = RDA_solver(T, car, 4, N, iter_num=iters, iter_threshold=0.0, time_print=False, batch=B)
+        res[flag] = ({k: v.clone() for k, v in g.iterative_solve_batch(**inp).items()}, g.launch_count())
+    assert res['1'][1] > res['0'][1]                       # extra launches of the coherent pipeline
+    assert int((res['1'][0]['status'] & 7).sum()) == 0
+    du = (res['0'][0]['u'] - res['1'][0]['u']).abs().flatten(1).max(1).values
+    assert float(du.median()) < 2e-5 and float(du.max()) < 3 * TRAJ_TOL
