@@ -233,6 +233,8 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--batch', type=int, default=16384, help='instances per GPU per step')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--su-fp32', action='store_true', help='float32 su-QP arithmetic (lower bound probe, not the metric)')
+    ap.add_argument('--no-probes', action='store_true', help='skip early-stop / single-instance / closed-loop probes')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
@@ -260,7 +262,7 @@ def main():
     pinned = {k: torch.from_numpy(v).pin_memory() for k, v in host.items()}
     devin = {k: v.to(dev) for k, v in pinned.items()}
     solver = RDA_solver(T, rectangle_robot(), max_edge_num=E, max_obs_num=N, iter_num=ITERS, iter_threshold=0.0,
-                        time_print=False, batch=B, device=dev)
+                        time_print=False, batch=B, device=dev, su_fp64=not args.su_fp32)
 
     def step(inp):
         solver.cold_start()
@@ -368,6 +370,10 @@ def main():
         'counters': {'cells_fast': counters[0], 'cells_slow': counters[1], 'cells_failed': counters[2],
                      'su_ipm_iterations': counters[3], 'su_solves': counters[4]},
         'status_nonzero': int((status.cpu() != 0).sum()),
+        'status_bits': {'su_iteration_cap(1)': int(((status.cpu() & 1) != 0).sum()),
+                        'su_nonfinite_keep_previous(2)': int(((status.cpu() & 2) != 0).sum()),
+                        'cell_failed_keep_previous(4)': int(((status.cpu() & 4) != 0).sum()),
+                        'early_stop(8)': int(((status.cpu() & 8) != 0).sum())},
         'gathered_u_shape': list(full_u.shape),
     }
     if world == 1 and not args.no_cpu_baseline:
@@ -381,15 +387,19 @@ def main():
         line['cpu_baseline'] = {'value': v, 'unit': 'solves/s', 'cores': cores, 'kind': 'port',
                                 'sample': f'{min(sample, B)} of the same instances x {ITERS} ADMM iterations, compiled C++ '
                                           f'port (oracle/cpu_port), OpenMP over instances, {dt:.1f} s'}
-    try:
-        line.update(extra_probes(dev, solver, devin, B))
-    except Exception as ex:
-        line['early_stop'] = {'error': repr(ex)[:200]}
-    try:
-        line['closed_loop'] = closed_loop_probe(dev, B)
-    except Exception as ex:          # the probe must never cost the headline line
-        line['closed_loop'] = {'error': repr(ex)[:200]}
+    if not args.no_probes:
+        try:
+            line.update(extra_probes(dev, solver, devin, B))
+        except Exception as ex:
+            line['early_stop'] = {'error': repr(ex)[:200]}
+        try:
+            line['closed_loop'] = closed_loop_probe(dev, B)
+        except Exception as ex:          # the probe must never cost the headline line
+            line['closed_loop'] = {'error': repr(ex)[:200]}
     print(json.dumps(line), flush=True)
+    bad = line['status_bits']['su_nonfinite_keep_previous(2)'] + line['status_bits']['cell_failed_keep_previous(4)']
+    if bad:
+        raise SystemExit(f'bench: {bad} instances kept a previous iterate (status bits 2/4) — the metric is void')
     if world > 1:
         dist.destroy_process_group()
 

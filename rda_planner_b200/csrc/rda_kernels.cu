@@ -595,7 +595,7 @@ __global__ void k_finalize(DevPtrs d, RobotGeom rb, float thr) {
   if (d.done[b]) return;
   const int T = d.T, N = d.N, NT = N * T, R = d.R;
   float pri = 0.f, dual = 0.f;
-  if (d.obs_count[b] != 0 && N > 0) {
+  if (N > 0 && d.obs_count[b] != 0) {
     pri = sqrtf(d.resi_acc[2 * b]);
     dual = d.resi_acc[2 * b + 1] / (float)N;
   } else if (N > 0) {
