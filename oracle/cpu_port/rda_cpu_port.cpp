@@ -46,7 +46,7 @@ static int su_impl(const SuParams* P, const double* lins, const double* linu, co
                    const float* gy, const double* pref, double* s, double* u, double* d, int* iters) {
   const int T = P->T, N = P->N;
   SuWork<Real> W;
-  size_t bytes = su_work_layout<Real>(T, N, nullptr, nullptr);
+  size_t bytes = su_work_bytes<Real>(T, N);
   std::vector<char> buf(bytes + 64);
   char* base = (char*)(((uintptr_t)buf.data() + 63) & ~(uintptr_t)63);
   su_work_layout<Real>(T, N, &W, base);
@@ -56,7 +56,7 @@ static int su_impl(const SuParams* P, const double* lins, const double* linu, co
   for (int i = 0; i < N * T; ++i) { W.hx[i] = hx[i]; W.hy[i] = hy[i]; W.hc[i] = hc[i]; }
   W.vref = (Real)vref;
   SeqCtx ctx;
-  int st = su_solve<Real, SeqCtx>(*P, W, ctx, gx, gy, iters);
+  int st = su_solve<Real, Real, SeqCtx>(*P, W, ctx, gx, gy, iters);
   for (int i = 0; i < 3 * (T + 1); ++i) s[i] = W.s[i];
   for (int i = 0; i < 2 * T; ++i) u[i] = W.u[i];
   for (int i = 0; i < T; ++i) d[i] = W.d[i];
@@ -164,7 +164,7 @@ extern "C" int port_solve_batch(const rda_config* cfg, const rda_tunables* tun, 
   P.mu0 = getenv("RDA_PORT_MU0") ? (float)atof(getenv("RDA_PORT_MU0")) : 1.0f;
   const float theta = cfg->accelerated ? tun->z_theta : 1.0f;
   if (nthreads > 0) omp_set_num_threads(nthreads);
-  const size_t bytes = su_work_layout<double>(T, N, nullptr, nullptr);
+  const size_t bytes = su_work_bytes<double>(T, N);
 #pragma omp parallel for schedule(dynamic, 1)
   for (int b = 0; b < B; ++b) {
     std::vector<char> buf(bytes + 64);
@@ -197,7 +197,7 @@ extern "C" int port_solve_batch(const rda_config* cfg, const rda_tunables* tun, 
       W.vref = ref_speed[b];
       SeqCtx ctx;
       int nit = 0;
-      int st = su_solve<double, SeqCtx>(P, W, ctx, coef.data() + 3 * NT, coef.data() + 4 * NT, &nit);
+      int st = su_solve<double, double, SeqCtx>(P, W, ctx, coef.data() + 3 * NT, coef.data() + 4 * NT, &nit);
       su_iters += nit;
       if (st != 0) ++su_bad;
       if (st != 2) {

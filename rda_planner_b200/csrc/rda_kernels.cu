@@ -19,11 +19,11 @@
 
 using namespace rda;
 
-// lanes per planning instance in the su-QP kernel (32: one warp per instance; 16 / 8: 2 / 4 instances
-// share a warp and its FP64 issue slots)
-#ifndef RDA_SU_GROUP
-#define RDA_SU_GROUP 32
-#endif
+// Lanes per planning instance in the su-QP kernel: 32 = one warp per instance (lowest latency, everything in
+// shared memory); 16 / 8 = 2 / 4 instances share a warp.  The serial Riccati recursion is executed by every
+// lane of a group, so a narrower group wastes fewer issue slots on it; the kernel is latency bound at the
+// ~12 warps per SM that registers allow, so more instances per warp is more throughput once the batch is
+// large enough to fill the SMs (su_group_for).
 
 struct rda_handle {
   rda_config cfg;
@@ -33,7 +33,11 @@ struct rda_handle {
   float *lam, *mu, *z, *xi, *zeta, *dis, *coef, *pref, *cur_s, *cur_u, *ref_s, *ref_speed;
   float *resi_acc, *resi_pri, *resi_dual;
   int *status, *iters, *done, *counters, *worklist, *worklist2;
-  double* su_scratch;    // [B][2][N*T] hinge slack / multiplier of the su-QP interior point iteration
+  char* su_ws;           // [B][su_ws_stride] global workspace of the su-QP interior point iteration (hinge slacks /
+                         // multipliers; for sub-warp groups also the Riccati gains and the stage arrays)
+  size_t su_ws_stride;
+  int su_group;          // lanes per instance in k_su: 0 = by sub-batch size, else 32 / 16 / 8 (RDA_B200_SU_GROUP)
+  int su_level;          // workspace placement (su_work_layout): -1 = by group, else 0..2 (RDA_B200_SU_LEVEL)
   // coherent first cell pass (cell_lean2.cuh; RDA_B200_LEAN2=1, E <= 4, R <= 4, static obstacles)
   int lean2;
   RobotAux ra;
@@ -46,7 +50,6 @@ struct rda_handle {
   int obs_tv;
   float iter_threshold;
   int launches;
-  size_t su_smem;
   int began;
   // rda_solve runs a large batch as `parts` contiguous sub-batches on as many streams (the caller's
   // and `side[]`), so that the latency-bound worklist passes and the tail of the su-QP kernel of one
@@ -97,7 +100,8 @@ struct DevPtrs {
   const ObstacleGeom<4>* ogeo;
   unsigned char* feat;
   int* worklist0;
-  double* su_scratch;
+  char* su_ws;
+  size_t su_ws_stride;
   const float *obs_A, *obs_b;
   const int *obs_kind, *obs_count;
   int obs_tv;
@@ -127,7 +131,7 @@ __global__ void k_begin(DevPtrs d, const float* nom_s, const float* nom_u, const
 // K1: su-QP, one warp per instance.
 // ------------------------------------------------------------------------------------------------
 template <typename Real, int G>
-__global__ void __launch_bounds__(32) k_su(DevPtrs d, SuParams P, int smem_per_instance) {
+__global__ void __launch_bounds__(32) k_su(DevPtrs d, SuParams P, int smem_per_instance, int level) {
   extern __shared__ __align__(16) char smem[];
   constexpr int PER_WARP = 32 / G;
   const int grp = (threadIdx.x & 31) / G;
@@ -137,8 +141,13 @@ __global__ void __launch_bounds__(32) k_su(DevPtrs d, SuParams P, int smem_per_i
   GroupCtx<G> ctx;
   const int T = P.T, N = P.N, NT = N * T;
   const int lane = ctx.lane();
-  SuWork<Real> W;
-  su_work_layout<Real>(T, N, &W, smem + (size_t)grp * smem_per_instance, false);
+  SuWork<Real, float> W;
+  // per-hinge data stays in global memory (L2): every entry is touched only by the lane that owns
+  // its stage, consecutive lanes read consecutive addresses.  With sub-warp groups (level > 0) the
+  // Riccati gains / stage arrays live there too, so that shared memory does not limit the number of
+  // resident instances.
+  su_work_layout<Real, float>(T, N, &W, smem + (size_t)grp * smem_per_instance, false,
+                              d.su_ws + (size_t)b * d.su_ws_stride, level);
   const float* cs = d.cur_s + (size_t)b * 3 * (T + 1);   // [3][T+1]
   const float* cu = d.cur_u + (size_t)b * 2 * T;         // [2][T]
   const float* rf = d.ref_s + (size_t)b * 3 * (T + 1);
@@ -153,16 +162,12 @@ __global__ void __launch_bounds__(32) k_su(DevPtrs d, SuParams P, int smem_per_i
     W.pref[2 * t + r] = d.pref[(size_t)b * 2 * T + i];
   }
   for (int t = lane; t < T; t += G) W.d[t] = d.dis[(size_t)b * T + t];
-  // per-hinge data stays in global memory (L2): every entry is touched only by the lane that owns
-  // its stage, consecutive lanes read consecutive addresses
   float* cf = d.coef + (size_t)b * 5 * NT;
   W.hx = cf; W.hy = cf + NT; W.hc = cf + 2 * NT;
-  W.hs = (Real*)(d.su_scratch + (size_t)b * 2 * NT);
-  W.hnu = W.hs + NT;
   W.vref = d.ref_speed[b];
   ctx.sync();
   int iters = 0;
-  int st = su_solve<Real, GroupCtx<G>>(P, W, ctx, cf + 3 * NT, cf + 4 * NT, &iters);
+  int st = su_solve<Real, float, GroupCtx<G>>(P, W, ctx, cf + 3 * NT, cf + 4 * NT, &iters);
   ctx.sync();
   // accept OPTIMAL and OPTIMAL_INACCURATE (iteration cap), else keep the previous nominal
   // ("No update of state and control vector", rda_solver.py:696-700)
@@ -668,7 +673,7 @@ DevPtrs dev_ptrs(const rda_handle* h, int b0, int nb, int part) {
   d.feat = h->feat ? h->feat + o * NT : nullptr;
   d.worklist0 = h->worklist0 ? h->worklist0 + o * NT : nullptr;
   d.worklist = h->worklist + o * NT; d.worklist2 = h->worklist2 + o * NT;
-  d.su_scratch = h->su_scratch + o * 2 * NT;
+  d.su_ws = h->su_ws + o * h->su_ws_stride; d.su_ws_stride = h->su_ws_stride;
   d.obs_A = h->obs_A ? h->obs_A + o * N * Tc * E * 2 : nullptr;
   d.obs_b = h->obs_b ? h->obs_b + o * N * Tc * E : nullptr;
   d.obs_kind = h->obs_kind ? h->obs_kind + o * N : nullptr;
@@ -722,9 +727,18 @@ int rda_create(const rda_config* cfg, const rda_tunables* tun, rda_handle** out)
   h->B = cfg->batch; h->T = cfg->receding; h->N = cfg->max_obs_num; h->E = cfg->max_edge_num;
   h->R = cfg->robot_edges;
   const size_t B = h->B, T = h->T, N = h->N, E = h->E, R = h->R, NT = N * T;
-  h->su_smem = cfg->su_fp64 ? su_work_layout<double>((int)T, (int)N, nullptr, nullptr, false)
-                            : su_work_layout<float>((int)T, (int)N, nullptr, nullptr, false);
-  if (h->su_smem > 227 * 1024) { delete h; return RDA_E_UNSUPPORTED; }
+  {
+    // largest global slab any placement level needs, and the shared-memory footprints per level
+    size_t gmax = 0;
+    for (int lv = 0; lv < 3; ++lv) {
+      size_t g = 0;
+      const size_t sm = cfg->su_fp64 ? su_work_bytes<double, float>((int)T, (int)N, false, lv, &g)
+                                     : su_work_bytes<float, float>((int)T, (int)N, false, lv, &g);
+      if (g > gmax) gmax = g;
+      if (lv == 0 && sm > 227 * 1024) { delete h; return RDA_E_UNSUPPORTED; }
+    }
+    h->su_ws_stride = (gmax + 127) & ~(size_t)127;
+  }
   cudaError_t e = cudaSuccess;
   auto alloc = [&](float** p, size_t n) { if (e == cudaSuccess) e = cudaMalloc((void**)p, (n ? n : 1) * sizeof(float)); };
   alloc(&h->lam, B * N * E * T); alloc(&h->mu, B * N * R * T); alloc(&h->z, B * NT);
@@ -736,12 +750,23 @@ int rda_create(const rda_config* cfg, const rda_tunables* tun, rda_handle** out)
   alloc((float**)&h->counters, 24);     // [0..4] statistics, [8..11] worklist lengths of the two halves
   alloc((float**)&h->worklist, B * NT);
   alloc((float**)&h->worklist2, B * NT);
-  alloc((float**)&h->su_scratch, B * 2 * NT * 2 * 2);      // doubles: 2 arrays x NT x (8/4 floats)
+  alloc((float**)&h->su_ws, B * (h->su_ws_stride / 4));
   if (e != cudaSuccess) { rda_destroy(h); return (int)e; }
-  const int su_cta_smem = (int)h->su_smem * (32 / RDA_SU_GROUP);
-  if (su_cta_smem > 227 * 1024) { rda_destroy(h); return RDA_E_UNSUPPORTED; }
-  if (cfg->su_fp64) e = cudaFuncSetAttribute(k_su<double, RDA_SU_GROUP>, cudaFuncAttributeMaxDynamicSharedMemorySize, su_cta_smem);
-  else e = cudaFuncSetAttribute(k_su<float, RDA_SU_GROUP>, cudaFuncAttributeMaxDynamicSharedMemorySize, su_cta_smem);
+  {
+    const int cap = 227 * 1024;
+    if (cfg->su_fp64) {
+      e = cudaFuncSetAttribute(k_su<double, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(k_su<double, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(k_su<double, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+    } else {
+      e = cudaFuncSetAttribute(k_su<float, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(k_su<float, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(k_su<float, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+    }
+  }
+  h->su_group = 0; h->su_level = -1;
+  if (const char* g = getenv("RDA_B200_SU_GROUP")) { int v = atoi(g); if (v == 32 || v == 16 || v == 8) h->su_group = v; }
+  if (const char* g = getenv("RDA_B200_SU_LEVEL")) { int v = atoi(g); if (v >= 0 && v <= 2) h->su_level = v; }
   if (e != cudaSuccess) { rda_destroy(h); return (int)e; }
   e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
   for (int p = 0; p < 3; ++p) {
@@ -774,7 +799,7 @@ int rda_destroy(rda_handle* h) {
   if (!h) return RDA_E_ARG;
   float* bufs[] = {h->lam, h->mu, h->z, h->xi, h->zeta, h->dis, h->coef, h->pref, h->cur_s, h->cur_u,
                    h->ref_s, h->ref_speed, h->resi_acc, h->resi_pri, h->resi_dual, (float*)h->status,
-                   (float*)h->iters, (float*)h->done, (float*)h->counters, (float*)h->worklist, (float*)h->worklist2, (float*)h->su_scratch};
+                   (float*)h->iters, (float*)h->done, (float*)h->counters, (float*)h->worklist, (float*)h->worklist2, (float*)h->su_ws};
   for (float* p : bufs) if (p) cudaFree(p);
   if (h->ogeo) cudaFree(h->ogeo);
   if (h->feat) cudaFree(h->feat);
@@ -858,11 +883,29 @@ static int begin_part(rda_handle* h, const rda_inputs* in, int b0, int nb, int p
 static int step_su_part(rda_handle* h, int b0, int nb, int part, cudaStream_t s) {
   DevPtrs d = dev_ptrs(h, b0, nb, part);
   SuParams P = su_params(h);
-  constexpr int per_warp = 32 / RDA_SU_GROUP;
+  // group width: one warp per instance while the sub-batch does not fill the SMs (148 SMs x ~11 resident
+  // warps), narrower groups (more instances per warp) beyond
+  int G = h->su_group;
+  if (G == 0) G = nb <= 148 * 12 ? 32 : (nb <= 148 * 24 ? 16 : 8);
+  int level = h->su_level >= 0 ? h->su_level : (G == 32 ? 0 : (G == 16 ? 1 : 2));
+  const int per_warp = 32 / G;
+  size_t smem1 = h->cfg.su_fp64 ? su_work_bytes<double, float>(h->T, h->N, false, level)
+                                : su_work_bytes<float, float>(h->T, h->N, false, level);
+  while (smem1 * per_warp > 227 * 1024 && level < 2) {
+    ++level;
+    smem1 = h->cfg.su_fp64 ? su_work_bytes<double, float>(h->T, h->N, false, level)
+                           : su_work_bytes<float, float>(h->T, h->N, false, level);
+  }
+  if (smem1 * per_warp > 227 * 1024) return RDA_E_UNSUPPORTED;
   const int grid = (nb + per_warp - 1) / per_warp;
-  const size_t cta_smem = h->su_smem * per_warp;
-  if (h->cfg.su_fp64) k_su<double, RDA_SU_GROUP><<<grid, 32, cta_smem, s>>>(d, P, (int)h->su_smem);
-  else k_su<float, RDA_SU_GROUP><<<grid, 32, cta_smem, s>>>(d, P, (int)h->su_smem);
+  const size_t cta_smem = smem1 * per_warp;
+#define RDA_LAUNCH_SU(REAL, GG) k_su<REAL, GG><<<grid, 32, cta_smem, s>>>(d, P, (int)smem1, level)
+  if (h->cfg.su_fp64) {
+    if (G == 32) RDA_LAUNCH_SU(double, 32); else if (G == 16) RDA_LAUNCH_SU(double, 16); else RDA_LAUNCH_SU(double, 8);
+  } else {
+    if (G == 32) RDA_LAUNCH_SU(float, 32); else if (G == 16) RDA_LAUNCH_SU(float, 16); else RDA_LAUNCH_SU(float, 8);
+  }
+#undef RDA_LAUNCH_SU
   RDA_CUDA(cudaGetLastError());
   h->launches += 1;
   return 0;

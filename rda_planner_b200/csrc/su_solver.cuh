@@ -30,23 +30,27 @@ struct SuParams {
   float mu0;      // initial complementarity of the interior point iteration
 };
 
-// Per-instance workspace (shared memory on the GPU).  All arrays indexed by stage t (0..T-1)
-// unless noted; hinge arrays indexed [o*T + t].
-template <typename Real>
+// Per-instance workspace.  All arrays indexed by stage t (0..T-1) unless noted; hinge arrays indexed
+// [o*T + t].  Real: arithmetic / iterate type; Slk: storage type of the interior point slacks and
+// multipliers (float on the GPU: they are only ever used through ratios and products, the residuals are
+// recomputed from the double iterate every iteration).
+template <typename Real, typename Slk = Real>
 struct SuWork {
   Real *s, *u, *d;            // iterate: 3(T+1), 2T, T
   float *ref;                 // 3(T+1)   (inputs stay in the float32 they arrive in)
   float *lins, *linu;         // linearisation point 3(T+1), 2T; linu is dead after the setup (shares dv)
-  Real *Aj, *Bj, *Cj;         // 2T (A02, A12), 6T, 3T; Cj is dead after the initial rollout (shares kf)
+  Real *Aj, *Bj, *Cj;         // 2T (A02, A12), 6T, 3T; Cj is dead after the initial rollout (shares K)
   Real *Skk, *Sgk;            // aggregated rotation-consensus terms
   float *pref;                // 2T positions the hinge offsets refer to
   float *hx, *hy, *hc;        // hinge rows: lam'A (2) and offset
-  Real *hs, *hnu;             // hinge slack / multiplier
-  Real *bs, *bnu;             // 10T box/rate slack / multiplier
-  Real *Wm;                   // 6T hinge Hessian (xx, xy, xd, yy, yd, dd)
+  Slk *hs, *hnu;              // hinge slack / multiplier
+  Slk *bs, *bnu;              // 10T box/rate slack / multiplier
+  Real *Wm;                   // 3T hinge Hessian of the position block after the elimination of d_t (xx, xy, yy)
+  Real *Ed;                   // 3T elimination of d_t: (M_xd / Q_dd, M_yd / Q_dd, 1 / Q_dd)
+  Real *g5q;                  // T   reduced-out gradient of d_t: g_d / Q_dd (d step = -(g5q + Ed . dp))
   Real *gw;                   // 8T gradient in stage coordinates: right-hand side of a backward sweep
   Real *wb;                   // 5T barrier weights (u0, u1, d, rate0, rate1)
-  Real *K, *Lc, *kf;          // 15T, 6T, 3T Riccati gains / L D L' of Hvv / feed-forward
+  Real *K, *Lc, *kf;          // 10T, 3T, 2T Riccati gains / L D L' of Hvv / feed-forward (controls u_t; d_t eliminated)
   Real *dz, *dv;              // 5(T+1), 3T Newton step.  Shares the storage of gw: the corrector's forward
                               // sweep writes it after the backward sweep has consumed gw, and it is dead
                               // (iterate updated) before the next predictor assembles gw.
@@ -57,39 +61,52 @@ struct SuWork {
   Real vref;
 };
 
-template <typename Real>
-RDA_HD size_t su_work_layout(int T, int N, SuWork<Real>* w, char* base, bool hinge_arrays = true) {
-  // returns bytes used; if base != nullptr the pointers are set.  hinge_arrays = false leaves the
-  // per-hinge arrays (hx, hy, hc, hs, hnu: touched only by the lane that owns the stage) to the
-  // caller, who points them at global memory to keep the shared-memory footprint small.
-  size_t off = 0;
-  auto take = [&](size_t n, size_t elt) {
-    off = (off + 15) & ~(size_t)15;
-    char* p = base ? base + off : nullptr;
-    off += n * elt;
+// Workspace placement.  `base` is the fast memory of the instance (shared memory on the GPU), `gbase` an
+// optional per-instance slab of global memory (L2).  level 0: everything in `base`; level 1: the Riccati
+// gains and the box slacks / multipliers move to `gbase`; level 2: also the stage Hessian / gradient /
+// Newton step arrays.  With hinge_arrays = false the per-hinge arrays (hx, hy, hc: caller; hs, hnu: first
+// in `gbase`) are left out of `base` (each entry is touched only by the lane that owns its stage).
+// Returns the bytes of `base` used; *gbytes (if given) the bytes of `gbase` used.
+template <typename Real, typename Slk = Real>
+RDA_HD size_t su_work_layout(int T, int N, SuWork<Real, Slk>* w, char* base, bool hinge_arrays = true,
+                             char* gbase = nullptr, int level = 0, size_t* gbytes = nullptr) {
+  size_t off[2] = {0, 0};
+  char* bases[2] = {base, gbase};
+  auto take = [&](int where, size_t n, size_t elt) {
+    off[where] = (off[where] + 15) & ~(size_t)15;
+    char* p = bases[where] ? bases[where] + off[where] : nullptr;
+    off[where] += n * elt;
     return p;
   };
-#define RDA_TAKE(field, n, type) { char* p_ = take((size_t)(n), sizeof(type)); if (w) w->field = (type*)p_; }
-  RDA_TAKE(s, 3 * (T + 1), Real) RDA_TAKE(u, 2 * T, Real) RDA_TAKE(d, T, Real)
-  RDA_TAKE(ref, 3 * (T + 1), float) RDA_TAKE(lins, 3 * (T + 1), float)
-  RDA_TAKE(Aj, 2 * T, Real) RDA_TAKE(Bj, 6 * T, Real)
-  RDA_TAKE(Skk, T, Real) RDA_TAKE(Sgk, T, Real) RDA_TAKE(pref, 2 * T, float)
+#define RDA_TAKE(where, field, n, type) { char* p_ = take((where), (size_t)(n), sizeof(type)); if (w) w->field = (type*)p_; }
+  const int g1 = level >= 1 ? 1 : 0, g2 = level >= 2 ? 1 : 0;
+  RDA_TAKE(0, s, 3 * (T + 1), Real) RDA_TAKE(0, u, 2 * T, Real) RDA_TAKE(0, d, T, Real)
+  RDA_TAKE(0, ref, 3 * (T + 1), float) RDA_TAKE(0, lins, 3 * (T + 1), float)
+  RDA_TAKE(0, Aj, 2 * T, Real) RDA_TAKE(0, Bj, 6 * T, Real)
+  RDA_TAKE(0, Skk, T, Real) RDA_TAKE(0, Sgk, T, Real) RDA_TAKE(0, pref, 2 * T, float)
   if (hinge_arrays) {
-    RDA_TAKE(hx, N * T, float) RDA_TAKE(hy, N * T, float) RDA_TAKE(hc, N * T, float)
-    RDA_TAKE(hs, N * T, Real) RDA_TAKE(hnu, N * T, Real)
+    RDA_TAKE(0, hx, N * T, float) RDA_TAKE(0, hy, N * T, float) RDA_TAKE(0, hc, N * T, float)
+    RDA_TAKE(0, hs, N * T, Slk) RDA_TAKE(0, hnu, N * T, Slk)
+  } else {
+    RDA_TAKE(1, hs, N * T, Slk) RDA_TAKE(1, hnu, N * T, Slk)
   }
-  RDA_TAKE(bs, 10 * T, Real) RDA_TAKE(bnu, 10 * T, Real)
-  {
-    const int shared = 11 * T > 8 * T + 5 ? 11 * T : 8 * T + 5;     // (Wm, wb) | (dza, dva)
-    RDA_TAKE(Wm, shared, Real)
-    if (w) { w->wb = w->Wm + 6 * T; w->dza = w->Wm; w->dva = w->Wm + 5 * (T + 1); }
-  }
-  RDA_TAKE(gw, 8 * T + 5, Real)                                       // gw | (dz, dv)
+  RDA_TAKE(g1, bs, 10 * T, Slk) RDA_TAKE(g1, bnu, 10 * T, Slk)
+  RDA_TAKE(g2, Wm, 8 * T + 5, Real)                                   // (Wm, wb) | (dza, dva)
+  if (w) { w->wb = w->Wm + 3 * T; w->dza = w->Wm; w->dva = w->Wm + 5 * (T + 1); }
+  RDA_TAKE(g2, Ed, 3 * T, Real) RDA_TAKE(g2, g5q, T, Real)
+  RDA_TAKE(g2, gw, 8 * T + 5, Real)                                   // gw | (dz, dv)
   if (w) { w->dz = w->gw; w->dv = w->gw + 5 * (T + 1); }
-  RDA_TAKE(K, 15 * T, Real) RDA_TAKE(Lc, 6 * T, Real) RDA_TAKE(kf, 3 * T, Real)
-  if (w) { w->Cj = w->kf; w->linu = (float*)w->dv; }
+  RDA_TAKE(g1, K, 10 * T, Real) RDA_TAKE(g1, Lc, 3 * T, Real) RDA_TAKE(g1, kf, 2 * T, Real)
+  if (w) { w->Cj = w->K; w->linu = (float*)w->dv; }
 #undef RDA_TAKE
-  return (off + 15) & ~(size_t)15;
+  if (gbytes) *gbytes = (off[1] + 15) & ~(size_t)15;
+  return (off[0] + 15) & ~(size_t)15;
+}
+
+// size-only query of su_work_layout
+template <typename Real, typename Slk = Real>
+RDA_HD size_t su_work_bytes(int T, int N, bool hinge_arrays = true, int level = 0, size_t* gbytes = nullptr) {
+  return su_work_layout<Real, Slk>(T, N, (SuWork<Real, Slk>*)nullptr, nullptr, hinge_arrays, nullptr, level, gbytes);
 }
 
 // Jacobians of the discrete model about (s, u): linear_ackermann_model :949-963,
@@ -128,8 +145,8 @@ RDA_HD void su_linearise(const SuParams& P, const Real* st, const Real* ut, Real
 template <typename Real>
 struct Row { Real g; Real sgn; int comp; bool rate; bool live; };
 
-template <typename Real>
-RDA_HD Row<Real> su_row(const SuParams& P, const SuWork<Real>& W, int t, int c) {
+template <typename Real, typename Slk>
+RDA_HD Row<Real> su_row(const SuParams& P, const SuWork<Real, Slk>& W, int t, int c) {
   Row<Real> r;
   r.rate = c >= 6;
   r.live = true;
@@ -164,13 +181,16 @@ RDA_HD Real su_row_dir(const Row<Real>& r, const Real* dz_t, const Real* dv_t) {
   return r.sgn * x;
 }
 
-template <typename Real, typename Ctx>
-RDA_HD void su_riccati(const SuParams& P, SuWork<Real>& W, Ctx& ctx, bool factor, Real* dz, Real* dv) {
+template <typename Real, typename Slk, typename Ctx>
+RDA_HD void su_riccati(const SuParams& P, SuWork<Real, Slk>& W, Ctx& ctx, bool factor, Real* dz, Real* dv) {
   // Riccati recursion of the Newton step (banded KKT system).  Stage t: state z = (s_t, u_{t-1}),
-  // control v = (u_t, d_t); the stage cost is quadratic in q = (s_{t+1}, u_t, d_t) = J [z; v] with
-  // J = [[A 0 B 0], [0 0 I 0], [0 0 0 1]] plus the rate-limit coupling between u_t and u_{t-1}.
-  // The sparsity of J is written out by hand (about 300 multiply-adds per stage).  Every lane
-  // runs the same recursion (no broadcast needed); lane 0 stores the gains.
+  // control v = u_t.  The safety distance d_t appears in stage t only (hinges and its own bounds), so
+  // it has been eliminated from the stage cost by the assembly (Schur complement on Q_dd: W.Wm holds
+  // the reduced position block, W.gw[0..1] the reduced gradient) and is recovered after the forward
+  // sweep from W.Ed / W.g5q.  The stage cost is quadratic in q = (s_{t+1}, u_t) = J [z; v] with
+  // J = [[A 0 B], [0 0 I]] plus the rate-limit coupling between u_t and u_{t-1}; the sparsity of J is
+  // written out by hand.  Every lane runs the same recursion (no broadcast needed); lane 0 stores the
+  // gains.
   const int T = P.T;
   const Real reg = (Real)1e-9;
   const Real tw = 2 * (Real)P.ws, tw3 = (P.dynamics == RDA_DYN_OMNI ? (Real)0 : tw);
@@ -183,29 +203,25 @@ RDA_HD void su_riccati(const SuParams& P, SuWork<Real>& W, Ctx& ctx, bool factor
     const Real b00 = Bt[0], b01 = Bt[1], b10 = Bt[2], b11 = Bt[3], b20 = Bt[4], b21 = Bt[5];
     // gradient in q-space (+ cost-to-go), pulled back through J
     const Real* gw = W.gw + 8 * t;
-    const Real q0 = gw[0] + pv[0], q1 = gw[1] + pv[1], q2 = gw[2] + pv[2], q3 = gw[3] + pv[3],
-               q4 = gw[4] + pv[4], q5 = gw[5];
+    const Real q0 = gw[0] + pv[0], q1 = gw[1] + pv[1], q2 = gw[2] + pv[2], q3 = gw[3] + pv[3], q4 = gw[4] + pv[4];
     const Real gz0 = q0, gz1 = q1, gz2 = a02 * q0 + a12 * q1 + q2, gz3 = gw[6], gz4 = gw[7];
     const Real gv0 = b00 * q0 + b10 * q1 + b20 * q2 + q3;
     const Real gv1 = b01 * q0 + b11 * q1 + b21 * q2 + q4;
-    const Real gv2 = q5;
-    Real i00, L10, i11, L20, L21, i22;   // L D L' of Hvv: unit-lower entries and reciprocal pivots
-    Real Kt[3][5];
+    Real i00, L10, i11;   // L D L' of Hvv: unit-lower entry and reciprocal pivots
+    Real Kt[2][5];
     if (factor) {
       const Real* wb = W.wb + 5 * t;
       const Real wr0 = wb[3], wr1 = wb[4];
-      Real Q[6][6];
-      for (int a = 0; a < 5; ++a) { for (int b = 0; b < 5; ++b) Q[a][b] = Pm[a][b]; Q[a][5] = 0; Q[5][a] = 0; }
-      const Real* M = W.Wm + 6 * t;
-      Q[0][0] += tw + M[0]; Q[0][1] += M[1]; Q[1][0] += M[1]; Q[0][5] = M[2]; Q[5][0] = M[2];
-      Q[1][1] += tw + M[3]; Q[1][5] = M[4]; Q[5][1] = M[4];
+      Real Q[5][5];
+      for (int a = 0; a < 5; ++a) for (int b = 0; b < 5; ++b) Q[a][b] = Pm[a][b];
+      const Real* M = W.Wm + 3 * t;
+      Q[0][0] += tw + M[0]; Q[0][1] += M[1]; Q[1][0] += M[1]; Q[1][1] += tw + M[2];
       Q[2][2] += tw3 + (Real)P.ro2 * W.Skk[t];
       Q[3][3] += 2 * (Real)P.wu + reg + wb[0] + wr0;
       Q[4][4] += reg + wb[1] + wr1;
-      Q[5][5] = (P.N > 0 ? reg + wb[2] + M[5] : (Real)1);
       // T1 = Q J for the columns of J that are not unit vectors
-      Real t2[6], t5[6], t6[6];
-      for (int r = 0; r < 6; ++r) {
+      Real t2[5], t5[5], t6[5];
+      for (int r = 0; r < 5; ++r) {
         t2[r] = a02 * Q[r][0] + a12 * Q[r][1] + Q[r][2];
         t5[r] = b00 * Q[r][0] + b10 * Q[r][1] + b20 * Q[r][2] + Q[r][3];
         t6[r] = b01 * Q[r][0] + b11 * Q[r][1] + b21 * Q[r][2] + Q[r][4];
@@ -220,76 +236,67 @@ RDA_HD void su_riccati(const SuParams& P, SuWork<Real>& W, Ctx& ctx, bool factor
       Hzz[0][2] = t2[0]; Hzz[1][2] = t2[1]; Hzz[2][2] = RDA_J2(t2);
       Hzz[1][0] = Hzz[0][1]; Hzz[2][0] = Hzz[0][2]; Hzz[2][1] = Hzz[1][2];
       Hzz[3][3] = wr0; Hzz[4][4] = wr1;
-      // Hvz (3 x 5)
-      Real Hvz[3][5];
+      // Hvz (2 x 5)
+      Real Hvz[2][5];
       Hvz[0][0] = t5[0]; Hvz[0][1] = t5[1]; Hvz[0][2] = RDA_J2(t5); Hvz[0][3] = -wr0; Hvz[0][4] = 0;
       Hvz[1][0] = t6[0]; Hvz[1][1] = t6[1]; Hvz[1][2] = RDA_J2(t6); Hvz[1][3] = 0; Hvz[1][4] = -wr1;
-      Hvz[2][0] = Q[5][0]; Hvz[2][1] = Q[5][1]; Hvz[2][2] = RDA_J2(Q[5]); Hvz[2][3] = 0; Hvz[2][4] = 0;
-      // Hvv (3 x 3)
-      const Real h00 = RDA_J5(t5), h10 = RDA_J6(t5), h11 = RDA_J6(t6), h20 = t5[5], h21 = t6[5], h22 = Q[5][5];
+      // Hvv (2 x 2)
+      const Real h00 = RDA_J5(t5), h10 = RDA_J6(t5), h11 = RDA_J6(t6);
 #undef RDA_J2
 #undef RDA_J5
 #undef RDA_J6
-      // Hvv = L D L' (unit lower L: L10, L20, L21; reciprocal pivots i00, i11, i22) — no square roots
+      // Hvv = L D L' (unit lower L: L10; reciprocal pivots i00, i11) — no square roots
       i00 = rcp_(h00);
       L10 = h10 * i00;
       i11 = rcp_(h11 - L10 * h10);
-      L20 = h20 * i00;
-      const Real w21 = h21 - L20 * h10;          // = L21 * d1
-      L21 = w21 * i11;
-      i22 = rcp_(h22 - L20 * h20 - L21 * w21);
       for (int b = 0; b < 5; ++b) {
         Real y0 = -Hvz[0][b];
         Real y1 = -Hvz[1][b] - L10 * y0;
-        Real y2 = -Hvz[2][b] - L20 * y0 - L21 * y1;
-        Real x2 = y2 * i22;
-        Real x1 = y1 * i11 - L21 * x2;
-        Real x0 = y0 * i00 - L10 * x1 - L20 * x2;
-        Kt[0][b] = x0; Kt[1][b] = x1; Kt[2][b] = x2;
+        Real x1 = y1 * i11;
+        Real x0 = y0 * i00 - L10 * x1;
+        Kt[0][b] = x0; Kt[1][b] = x1;
       }
       for (int a = 0; a < 5; ++a)
         for (int b = a; b < 5; ++b) {
-          Real v = Hzz[a][b] + Hvz[0][a] * Kt[0][b] + Hvz[1][a] * Kt[1][b] + Hvz[2][a] * Kt[2][b];
+          Real v = Hzz[a][b] + Hvz[0][a] * Kt[0][b] + Hvz[1][a] * Kt[1][b];
           Pm[a][b] = v; Pm[b][a] = v;
         }
       if (writer) {
-        Real* Ls = W.Lc + 6 * t;
-        Ls[0] = i00; Ls[1] = L10; Ls[2] = i11; Ls[3] = L20; Ls[4] = L21; Ls[5] = i22;
-        for (int k = 0; k < 3; ++k) for (int b = 0; b < 5; ++b) W.K[15 * t + 5 * k + b] = Kt[k][b];
+        Real* Ls = W.Lc + 3 * t;
+        Ls[0] = i00; Ls[1] = L10; Ls[2] = i11;
+        for (int k = 0; k < 2; ++k) for (int b = 0; b < 5; ++b) W.K[10 * t + 5 * k + b] = Kt[k][b];
       }
     } else {
-      const Real* Ls = W.Lc + 6 * t;
-      i00 = Ls[0]; L10 = Ls[1]; i11 = Ls[2]; L20 = Ls[3]; L21 = Ls[4]; i22 = Ls[5];
-      for (int k = 0; k < 3; ++k) for (int b = 0; b < 5; ++b) Kt[k][b] = W.K[15 * t + 5 * k + b];
+      const Real* Ls = W.Lc + 3 * t;
+      i00 = Ls[0]; L10 = Ls[1]; i11 = Ls[2];
+      for (int k = 0; k < 2; ++k) for (int b = 0; b < 5; ++b) Kt[k][b] = W.K[10 * t + 5 * k + b];
     }
     {
       Real y0 = -gv0;
       Real y1 = -gv1 - L10 * y0;
-      Real y2 = -gv2 - L20 * y0 - L21 * y1;
-      Real x2 = y2 * i22;
-      Real x1 = y1 * i11 - L21 * x2;
-      Real x0 = y0 * i00 - L10 * x1 - L20 * x2;
-      if (writer) { W.kf[3 * t] = x0; W.kf[3 * t + 1] = x1; W.kf[3 * t + 2] = x2; }
-      pv[0] = gz0 + Kt[0][0] * gv0 + Kt[1][0] * gv1 + Kt[2][0] * gv2;
-      pv[1] = gz1 + Kt[0][1] * gv0 + Kt[1][1] * gv1 + Kt[2][1] * gv2;
-      pv[2] = gz2 + Kt[0][2] * gv0 + Kt[1][2] * gv1 + Kt[2][2] * gv2;
-      pv[3] = gz3 + Kt[0][3] * gv0 + Kt[1][3] * gv1 + Kt[2][3] * gv2;
-      pv[4] = gz4 + Kt[0][4] * gv0 + Kt[1][4] * gv1 + Kt[2][4] * gv2;
+      Real x1 = y1 * i11;
+      Real x0 = y0 * i00 - L10 * x1;
+      if (writer) { W.kf[2 * t] = x0; W.kf[2 * t + 1] = x1; }
+      pv[0] = gz0 + Kt[0][0] * gv0 + Kt[1][0] * gv1;
+      pv[1] = gz1 + Kt[0][1] * gv0 + Kt[1][1] * gv1;
+      pv[2] = gz2 + Kt[0][2] * gv0 + Kt[1][2] * gv1;
+      pv[3] = gz3 + Kt[0][3] * gv0 + Kt[1][3] * gv1;
+      pv[4] = gz4 + Kt[0][4] * gv0 + Kt[1][4] * gv1;
     }
   }
   ctx.sync();
   // forward sweep
   Real z[5] = {0, 0, 0, 0, 0};
   for (int t = 0; t < T; ++t) {
-    Real v[3];
-    for (int k = 0; k < 3; ++k) {
-      Real sacc = W.kf[3 * t + k];
-      for (int b = 0; b < 5; ++b) sacc += W.K[15 * t + 5 * k + b] * z[b];
+    Real v[2];
+    for (int k = 0; k < 2; ++k) {
+      Real sacc = W.kf[2 * t + k];
+      for (int b = 0; b < 5; ++b) sacc += W.K[10 * t + 5 * k + b] * z[b];
       v[k] = sacc;
     }
     if (writer) {
       for (int a = 0; a < 5; ++a) dz[5 * t + a] = z[a];
-      for (int k = 0; k < 3; ++k) dv[3 * t + k] = v[k];
+      dv[3 * t] = v[0]; dv[3 * t + 1] = v[1];
     }
     Real n0 = z[0] + W.Aj[2 * t] * z[2] + W.Bj[6 * t] * v[0] + W.Bj[6 * t + 1] * v[1];
     Real n1 = z[1] + W.Aj[2 * t + 1] * z[2] + W.Bj[6 * t + 2] * v[0] + W.Bj[6 * t + 3] * v[1];
@@ -298,14 +305,17 @@ RDA_HD void su_riccati(const SuParams& P, SuWork<Real>& W, Ctx& ctx, bool factor
   }
   if (writer) for (int a = 0; a < 5; ++a) dz[5 * T + a] = z[a];
   ctx.sync();
+  // recover the step of the eliminated safety distances (each lane its own stages)
+  for (int t = ctx.lane(); t < T; t += ctx.nlanes())
+    dv[3 * t + 2] = P.N > 0 ? -(W.g5q[t] + W.Ed[3 * t] * dz[5 * t + 5] + W.Ed[3 * t + 1] * dz[5 * t + 6]) : (Real)0;
 }
 
 // Solve the su-QP.  Inputs already staged in W: lins, linu, ref, vref, hx/hy/hc, pref, Skk/Sgk
 // are computed here from (gx, gy) planes passed as pointers (global or shared memory, [o*T+t]).
 // On entry W.d holds para_dis (initial guess of d).  Returns 0 (converged), 1 (iteration cap),
 // 2 (non-finite).  On return W.s, W.u, W.d hold the solution.
-template <typename Real, typename Ctx>
-RDA_HD int su_solve(const SuParams& P, SuWork<Real>& W, Ctx& ctx, const float* gx, const float* gy,
+template <typename Real, typename Slk, typename Ctx>
+RDA_HD int su_solve(const SuParams& P, SuWork<Real, Slk>& W, Ctx& ctx, const float* gx, const float* gy,
                     int* iters_out) {
   const int T = P.T, N = P.N;
   const int lane = ctx.lane(), nl = ctx.nlanes();
@@ -348,7 +358,7 @@ RDA_HD int su_solve(const SuParams& P, SuWork<Real>& W, Ctx& ctx, const float* g
   int nrows = 0;
   for (int t = lane; t < T; t += nl) {
     for (int c = 0; c < 10; ++c) {
-      Row<Real> r = su_row<Real>(P, W, t, c);
+      Row<Real> r = su_row<Real, Slk>(P, W, t, c);
       Real sv = r.live ? rmax(r.g, (Real)1e-2) : (Real)1;
       W.bs[10 * t + c] = sv;
       W.bnu[10 * t + c] = r.live ? mu0 / sv : (Real)0;
@@ -394,7 +404,7 @@ RDA_HD int su_solve(const SuParams& P, SuWork<Real>& W, Ctx& ctx, const float* g
         gw[6] = 0; gw[7] = 0;
         Real wb[5] = {0, 0, 0, 0, 0};
         for (int c = 0; c < 10; ++c) {
-          Row<Real> r = su_row<Real>(P, W, t, c);
+          Row<Real> r = su_row<Real, Slk>(P, W, t, c);
           if (!r.live) continue;
           Real sv = W.bs[10 * t + c], nu = W.bnu[10 * t + c];
           Real res = r.g - sv;
@@ -452,11 +462,16 @@ RDA_HD int su_solve(const SuParams& P, SuWork<Real>& W, Ctx& ctx, const float* g
             m3 += om * ay * ay; m4 -= om * ay; m5 += om;
           }
         }
-        gw[0] = g0; gw[1] = g1; gw[5] = g5;
+        // eliminate d_t (it enters stage t only): Schur complement on Q_dd = reg + barrier weights + sum om
         if (phase == 0) {
-          Real* M = W.Wm + 6 * t;
-          M[0] = m0; M[1] = m1; M[2] = m2; M[3] = m3; M[4] = m4; M[5] = m5;
+          const Real iq = N > 0 ? rcp_(reg + wb[2] + m5) : (Real)1;
+          const Real e0 = m2 * iq, e1 = m4 * iq;
+          Real* M = W.Wm + 3 * t;
+          M[0] = m0 - m2 * e0; M[1] = m1 - m2 * e1; M[2] = m3 - m4 * e1;
+          W.Ed[3 * t] = e0; W.Ed[3 * t + 1] = e1; W.Ed[3 * t + 2] = iq;
         }
+        W.g5q[t] = g5 * W.Ed[3 * t + 2];
+        gw[0] = g0 - W.Ed[3 * t] * g5; gw[1] = g1 - W.Ed[3 * t + 1] * g5; gw[5] = g5;
       }
       if (phase == 0) {
         mu = ctx.sum(acc_mu) / Mrows;
@@ -470,14 +485,14 @@ RDA_HD int su_solve(const SuParams& P, SuWork<Real>& W, Ctx& ctx, const float* g
         if (mu < tol_mu && rmx < tol_r && (last_step < tol_step || mu < tol_floor)) { status = 0; break; }
       }
       ctx.sync();
-      su_riccati<Real, Ctx>(P, W, ctx, phase == 0, phase == 0 ? W.dza : W.dz, phase == 0 ? W.dva : W.dv);
+      su_riccati<Real, Slk, Ctx>(P, W, ctx, phase == 0, phase == 0 ? W.dza : W.dz, phase == 0 ? W.dva : W.dv);
       // ---- step lengths ----
       const Real* dz = phase == 0 ? W.dza : W.dz;
       const Real* dv = phase == 0 ? W.dva : W.dv;
       Real rmaxr = 0, s0 = 0, s1 = 0, s2 = 0;   // rmaxr = max over rows of (-delta / value): 1 / max step
       for (int t = lane; t < T; t += nl) {
         for (int c = 0; c < 10; ++c) {
-          Row<Real> r = su_row<Real>(P, W, t, c);
+          Row<Real> r = su_row<Real, Slk>(P, W, t, c);
           if (!r.live) continue;
           Real sv = W.bs[10 * t + c], nu = W.bnu[10 * t + c];
           Real res = r.g - sv;
@@ -538,9 +553,9 @@ RDA_HD int su_solve(const SuParams& P, SuWork<Real>& W, Ctx& ctx, const float* g
         for (int t = lane; t < T; t += nl) {
           // rows first: they read the OLD iterate through su_row
           Real gsave[10];
-          for (int c = 0; c < 10; ++c) { Row<Real> r = su_row<Real>(P, W, t, c); gsave[c] = r.g; }
+          for (int c = 0; c < 10; ++c) { Row<Real> r = su_row<Real, Slk>(P, W, t, c); gsave[c] = r.g; }
           for (int c = 0; c < 10; ++c) {
-            Row<Real> r = su_row<Real>(P, W, t, c);
+            Row<Real> r = su_row<Real, Slk>(P, W, t, c);
             if (!r.live) continue;
             Real sv = W.bs[10 * t + c], nu = W.bnu[10 * t + c];
             Real res = gsave[c] - sv;
