@@ -141,6 +141,9 @@ int shim_su_f(const SuParams* P, const double* lins, const double* linu, const d
 }
 
 
+static long long g_su_hist[64];
+extern "C" void port_su_hist(long long* out, int reset) { for (int i = 0; i < 64; ++i) { out[i] = g_su_hist[i]; if (reset) g_su_hist[i] = 0; } }
+
 // ------------------------------------------------------------------------------------------------
 // Whole hot path on the CPU (mirrors rda_kernels.cu; see the kernel comments for reference lines).
 // Layouts as in include/rda_b200.h.  Every instance starts cold (constructor state).
@@ -199,6 +202,8 @@ extern "C" int port_solve_batch(const rda_config* cfg, const rda_tunables* tun, 
       int nit = 0;
       int st = su_solve<double, double, SeqCtx>(P, W, ctx, coef.data() + 3 * NT, coef.data() + 4 * NT, &nit);
       su_iters += nit;
+#pragma omp atomic
+      g_su_hist[nit < 63 ? nit : 63] += 1;
       if (st != 0) ++su_bad;
       if (st != 2) {
         for (int i = 0; i < 3 * (T + 1); ++i) { int r = i / (T + 1), t = i % (T + 1); cs[i] = (float)W.s[3 * t + r]; }

@@ -141,12 +141,12 @@ __global__ void __launch_bounds__(32) k_su(DevPtrs d, SuParams P, int smem_per_i
   GroupCtx<G> ctx;
   const int T = P.T, N = P.N, NT = N * T;
   const int lane = ctx.lane();
-  SuWork<Real, float> W;
+  SuWork<Real, Real> W;
   // per-hinge data stays in global memory (L2): every entry is touched only by the lane that owns
   // its stage, consecutive lanes read consecutive addresses.  With sub-warp groups (level > 0) the
   // Riccati gains / stage arrays live there too, so that shared memory does not limit the number of
   // resident instances.
-  su_work_layout<Real, float>(T, N, &W, smem + (size_t)grp * smem_per_instance, false,
+  su_work_layout<Real, Real>(T, N, &W, smem + (size_t)grp * smem_per_instance, false,
                               d.su_ws + (size_t)b * d.su_ws_stride, level);
   const float* cs = d.cur_s + (size_t)b * 3 * (T + 1);   // [3][T+1]
   const float* cu = d.cur_u + (size_t)b * 2 * T;         // [2][T]
@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(32) k_su(DevPtrs d, SuParams P, int smem_per_i
   W.vref = d.ref_speed[b];
   ctx.sync();
   int iters = 0;
-  int st = su_solve<Real, float, GroupCtx<G>>(P, W, ctx, cf + 3 * NT, cf + 4 * NT, &iters);
+  int st = su_solve<Real, Real, GroupCtx<G>>(P, W, ctx, cf + 3 * NT, cf + 4 * NT, &iters);
   ctx.sync();
   // accept OPTIMAL and OPTIMAL_INACCURATE (iteration cap), else keep the previous nominal
   // ("No update of state and control vector", rda_solver.py:696-700)
@@ -732,7 +732,7 @@ int rda_create(const rda_config* cfg, const rda_tunables* tun, rda_handle** out)
     size_t gmax = 0;
     for (int lv = 0; lv < 3; ++lv) {
       size_t g = 0;
-      const size_t sm = cfg->su_fp64 ? su_work_bytes<double, float>((int)T, (int)N, false, lv, &g)
+      const size_t sm = cfg->su_fp64 ? su_work_bytes<double, double>((int)T, (int)N, false, lv, &g)
                                      : su_work_bytes<float, float>((int)T, (int)N, false, lv, &g);
       if (g > gmax) gmax = g;
       if (lv == 0 && sm > 227 * 1024) { delete h; return RDA_E_UNSUPPORTED; }
@@ -883,17 +883,18 @@ static int begin_part(rda_handle* h, const rda_inputs* in, int b0, int nb, int p
 static int step_su_part(rda_handle* h, int b0, int nb, int part, cudaStream_t s) {
   DevPtrs d = dev_ptrs(h, b0, nb, part);
   SuParams P = su_params(h);
-  // group width: one warp per instance while the sub-batch does not fill the SMs (148 SMs x ~11 resident
-  // warps), narrower groups (more instances per warp) beyond
+  // group width: one warp per instance.  Narrower groups (RDA_B200_SU_GROUP=16/8: 2 / 4 instances per warp,
+  // workspace partly in global memory) were measured SLOWER on B200 (r02: 43 -> 54 -> 77 ms for the same
+  // work at B = 16384): the serial Riccati recursion then waits on L2 instead of shared memory every stage.
   int G = h->su_group;
-  if (G == 0) G = nb <= 148 * 12 ? 32 : (nb <= 148 * 24 ? 16 : 8);
+  if (G == 0) G = 32;
   int level = h->su_level >= 0 ? h->su_level : (G == 32 ? 0 : (G == 16 ? 1 : 2));
   const int per_warp = 32 / G;
-  size_t smem1 = h->cfg.su_fp64 ? su_work_bytes<double, float>(h->T, h->N, false, level)
+  size_t smem1 = h->cfg.su_fp64 ? su_work_bytes<double, double>(h->T, h->N, false, level)
                                 : su_work_bytes<float, float>(h->T, h->N, false, level);
   while (smem1 * per_warp > 227 * 1024 && level < 2) {
     ++level;
-    smem1 = h->cfg.su_fp64 ? su_work_bytes<double, float>(h->T, h->N, false, level)
+    smem1 = h->cfg.su_fp64 ? su_work_bytes<double, double>(h->T, h->N, false, level)
                            : su_work_bytes<float, float>(h->T, h->N, false, level);
   }
   if (smem1 * per_warp > 227 * 1024) return RDA_E_UNSUPPORTED;
