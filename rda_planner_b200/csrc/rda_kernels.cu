@@ -14,6 +14,7 @@
 #include "rda_hd.h"
 #include "cell_solver.cuh"
 #include "su_solver.cuh"
+#include "su_batched.cuh"
 #include "cell_lean.cuh"
 #include "cell_lean2.cuh"
 
@@ -36,6 +37,10 @@ struct rda_handle {
   char* su_ws;           // [B][su_ws_stride] global workspace of the su-QP interior point iteration (hinge slacks /
                          // multipliers; for sub-warp groups also the Riccati gains and the stage arrays)
   size_t su_ws_stride;
+  char* sb_ws;           // workspace of the batched su-QP pipeline (su_batched.cuh), allocated on first use
+  size_t sb_bytes, sb_slab;
+  int su_batched;        // -1: by sub-batch size (>= su_batched_min instances), 0: never, 1: always (RDA_B200_SU_BATCHED)
+  int su_batched_min;
   int su_group;          // lanes per instance in k_su: 0 = by sub-batch size, else 32 / 16 / 8 (RDA_B200_SU_GROUP)
   int su_level;          // workspace placement (su_work_layout): -1 = by group, else 0..2 (RDA_B200_SU_LEVEL)
   // coherent first cell pass (cell_lean2.cuh; RDA_B200_LEAN2=1, E <= 4, R <= 4, static obstacles)
@@ -767,6 +772,19 @@ int rda_create(const rda_config* cfg, const rda_tunables* tun, rda_handle** out)
   h->su_group = 0; h->su_level = -1;
   if (const char* g = getenv("RDA_B200_SU_GROUP")) { int v = atoi(g); if (v == 32 || v == 16 || v == 8) h->su_group = v; }
   if (const char* g = getenv("RDA_B200_SU_LEVEL")) { int v = atoi(g); if (v >= 0 && v <= 2) h->su_level = v; }
+  h->su_batched = -1; h->su_batched_min = 3072;
+  if (const char* g = getenv("RDA_B200_SU_BATCHED")) { int v = atoi(g); if (v >= -1 && v <= 1) h->su_batched = v; }
+  if (const char* g = getenv("RDA_B200_SU_BATCHED_MIN")) { int v = atoi(g); if (v >= 1) h->su_batched_min = v; }
+  if (cfg->su_fp64 && h->su_group == 0 && (h->su_batched == 1 || (h->su_batched < 0 && h->B >= h->su_batched_min))) {
+    int parts = 2;
+    if (const char* sp = getenv("RDA_B200_SPLIT_PARTS")) { int v = atoi(sp); if (v >= 1 && v <= 4) parts = v; }
+    const int nbmax = (h->B + parts - 1) / parts + 1;
+    h->sb_slab = (su_batch_layout(nbmax, (int)T, (int)N, nullptr, nullptr) + 4095) & ~(size_t)4095;
+    const size_t whole = su_batch_layout(h->B, (int)T, (int)N, nullptr, nullptr);
+    h->sb_bytes = (h->sb_slab * parts > whole ? h->sb_slab * parts : whole) + 4096;
+    e = cudaMalloc((void**)&h->sb_ws, h->sb_bytes);
+    if (e != cudaSuccess) { rda_destroy(h); return (int)e; }
+  }
   if (e != cudaSuccess) { rda_destroy(h); return (int)e; }
   e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
   for (int p = 0; p < 3; ++p) {
@@ -801,6 +819,7 @@ int rda_destroy(rda_handle* h) {
                    h->ref_s, h->ref_speed, h->resi_acc, h->resi_pri, h->resi_dual, (float*)h->status,
                    (float*)h->iters, (float*)h->done, (float*)h->counters, (float*)h->worklist, (float*)h->worklist2, (float*)h->su_ws};
   for (float* p : bufs) if (p) cudaFree(p);
+  if (h->sb_ws) cudaFree(h->sb_ws);
   if (h->ogeo) cudaFree(h->ogeo);
   if (h->feat) cudaFree(h->feat);
   if (h->worklist0) cudaFree(h->worklist0);
@@ -880,7 +899,47 @@ static int begin_part(rda_handle* h, const rda_inputs* in, int b0, int nb, int p
   return 0;
 }
 
+// The su-QP of a sub-batch as a pipeline of wide kernels (su_batched.cuh): chosen for large sub-batches in
+// float64, where one warp per instance leaves most of the machine idle.
+static int step_su_batched(rda_handle* h, int b0, int nb, int part, cudaStream_t s) {
+  DevPtrs d = dev_ptrs(h, b0, nb, part);
+  SuParams P = su_params(h);
+  P.max_iter = 28;
+  const int T = h->T, N = h->N;
+  // one slab per sub-batch (sb_slab bytes each); a whole-batch call (phase API) uses the workspace from 0
+  SuBatch W;
+  const size_t off = (size_t)part * h->sb_slab;
+  if (off + su_batch_layout(nb, T, N, nullptr, nullptr) > h->sb_bytes) return RDA_E_NOMEM;
+  su_batch_layout(nb, T, N, &W, h->sb_ws + off);
+  const bool acc = h->cfg.accelerated != 0;
+  const double Mrows = 4.0 * T + (N > 0 ? 2.0 * T : 0.0) + 4.0 * (T - 1) + (acc ? (double)N * T : 0.0);
+  SbOut out{d.cur_s, d.cur_u, d.dis, d.status, d.iters, d.counters};
+  RDA_CUDA(cudaMemsetAsync(W.n_active, 0, sizeof(int), s));
+  const dim3 gs((nb + 127) / 128, T);
+  const int gi = (nb + 31) / 32, gr = (nb + 127) / 128;
+  ksb_setup<<<gs, 128, 0, s>>>(W, P, d.cur_s, d.cur_u, d.ref_s, d.pref, d.coef, d.dis, d.ref_speed, d.done);
+  ksb_rollout<<<gi, 32, 0, s>>>(W);
+  h->launches += 2;
+  for (int it = 0; it <= P.max_iter; ++it) {
+    ksb_assemble<<<gs, 128, 0, s>>>(W, P, it);
+    ksb_riccati<true><<<gi, 32, 0, s>>>(W, P, it, Mrows, out);
+    h->launches += 2;
+    if (it == P.max_iter) break;
+    ksb_steplen<0><<<gs, 128, 0, s>>>(W, P, it);
+    ksb_reduce<0><<<gr, 128, 0, s>>>(W, Mrows);
+    ksb_corrector<<<gs, 128, 0, s>>>(W, P, it);
+    ksb_riccati<false><<<gi, 32, 0, s>>>(W, P, it, Mrows, out);
+    ksb_steplen<1><<<gs, 128, 0, s>>>(W, P, it);
+    ksb_reduce<1><<<gr, 128, 0, s>>>(W, Mrows);
+    h->launches += 6;
+  }
+  RDA_CUDA(cudaGetLastError());
+  return 0;
+}
+
 static int step_su_part(rda_handle* h, int b0, int nb, int part, cudaStream_t s) {
+  if (h->sb_ws && (h->su_batched == 1 || (h->su_batched < 0 && nb >= h->su_batched_min)))
+    return step_su_batched(h, b0, nb, part, s);
   DevPtrs d = dev_ptrs(h, b0, nb, part);
   SuParams P = su_params(h);
   // group width: one warp per instance.  Narrower groups (RDA_B200_SU_GROUP=16/8: 2 / 4 instances per warp,
