@@ -23,12 +23,46 @@ class _Tunables(C.Structure):
 
 
 _DYN = {'acker': 0, 'diff': 1, 'omni': 2}
+_LIB = None
+
+
+def _lib():
+    """Build (if stale) and load the port ONCE per process — never inside a timed loop."""
+    global _LIB
+    if _LIB is None:
+        _LIB = C.CDLL(build_port.build())
+        _LIB.port_solve_batch.restype = C.c_int
+    return _LIB
+
+
+def host_threads():
+    """Threads this process may really use: min(affinity mask, cgroup CPU quota), with the raw numbers.
+    os.cpu_count() reports the machine, not the lease: a 1-GPU lease of a 128-core box is typically pinned
+    or quota-limited to a fraction of it, and oversubscribing OpenMP threads makes the baseline noisy."""
+    import math
+    import os
+    aff = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
+    quota = None
+    try:
+        q, per = open('/sys/fs/cgroup/cpu.max').read().split()[:2]
+        if q != 'max':
+            quota = float(q) / float(per)
+    except Exception:
+        try:
+            q = int(open('/sys/fs/cgroup/cpu/cpu.cfs_quota_us').read())
+            per = int(open('/sys/fs/cgroup/cpu/cpu.cfs_period_us').read())
+            if q > 0:
+                quota = q / per
+        except Exception:
+            pass
+    eff = aff if quota is None else max(1, min(aff, int(math.floor(quota + 1e-9))))
+    return {'effective': eff, 'affinity': aff, 'cgroup_quota': quota, 'os_cpu_count': os.cpu_count()}
 
 
 def solve_batch(car, T, N, E, nom_s, nom_u, ref_s, ref_speed, obs_A, obs_b, obs_kind, obs_count,
                 time_varying=False, iter_num=50, iter_threshold=0.0, dt=0.1, accelerated=True, threads=0,
                 **kw):
-    lib = C.CDLL(build_port.build())
+    lib = _lib()
     G = np.asarray(car.G, float); h = np.asarray(car.h, float).ravel()
     cfg = _Config()
     B = int(np.asarray(nom_s).shape[0])
@@ -50,7 +84,6 @@ def solve_batch(car, T, N, E, nom_s, nom_u, ref_s, ref_speed, obs_A, obs_b, obs_
     rp = np.zeros(B, np.float32); rd = np.zeros(B, np.float32); it = np.zeros(B, np.int32)
     fails = np.zeros((B, 4), np.int32)
     p = lambda a: a.ctypes.data_as(C.c_void_p)
-    lib.port_solve_batch.restype = C.c_int
     rc = lib.port_solve_batch(C.byref(cfg), C.byref(tun), C.c_int(B), *[p(a) for a in arrs], C.c_int(int(time_varying)),
                               C.c_int(iter_num), C.c_float(iter_threshold), p(u), p(s), p(rp), p(rd), p(it), p(fails),
                               C.c_int(threads))

@@ -772,7 +772,7 @@ int rda_create(const rda_config* cfg, const rda_tunables* tun, rda_handle** out)
   h->su_group = 0; h->su_level = -1;
   if (const char* g = getenv("RDA_B200_SU_GROUP")) { int v = atoi(g); if (v == 32 || v == 16 || v == 8) h->su_group = v; }
   if (const char* g = getenv("RDA_B200_SU_LEVEL")) { int v = atoi(g); if (v >= 0 && v <= 2) h->su_level = v; }
-  h->su_batched = -1; h->su_batched_min = 3072;
+  h->su_batched = 0; h->su_batched_min = 3072;      // measured slower than k_su (r02): opt-in
   if (const char* g = getenv("RDA_B200_SU_BATCHED")) { int v = atoi(g); if (v >= -1 && v <= 1) h->su_batched = v; }
   if (const char* g = getenv("RDA_B200_SU_BATCHED_MIN")) { int v = atoi(g); if (v >= 1) h->su_batched_min = v; }
   if (cfg->su_fp64 && h->su_group == 0 && (h->su_batched == 1 || (h->su_batched < 0 && h->B >= h->su_batched_min))) {
@@ -792,6 +792,9 @@ int rda_create(const rda_config* cfg, const rda_tunables* tun, rda_handle** out)
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_join[p], cudaEventDisableTiming);
   }
   if (e != cudaSuccess) { rda_destroy(h); return (int)e; }
+  // coherent first cell pass: on for batches whose sub-batches reach 4096 instances (measured r02: -8 % of the cell
+  // passes at B = 16384, +15 % at B = 1024 where its two extra launches outweigh the saved work); RDA_B200_LEAN2=0/1 forces
+  h->lean2 = h->B >= 8192 && h->E <= 4 && h->R <= 4 && h->N > 0;
   if (const char* l2 = getenv("RDA_B200_LEAN2")) h->lean2 = atoi(l2) != 0 && h->E <= 4 && h->R <= 4 && h->N > 0;
   if (h->lean2) {
     robot_aux_from_geom(h->rb, &h->ra);

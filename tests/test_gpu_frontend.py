@@ -116,3 +116,91 @@ def test_batched_mpc_closed_loop_matches_host_front_end():
             host_state[i] = s + 0.1 * np.array([[uh[0, 0] * np.cos(s[2, 0])], [uh[0, 0] * np.sin(s[2, 0])], [uh[0, 0] * np.tan(uh[1, 0]) / 3.0]])
         bm.advance(dev_state)
         np.testing.assert_allclose(dev_state.cpu().numpy(), np.hstack(host_state).T, atol=2e-3)
+
+
+# ---- the kernels against the values produced by EXECUTING the reference's own helpers (no g++ twin in between) ----
+import json
+GOLD = json.load(open(os.path.join(HERE, 'golden', 'boundary_golden.json')))
+
+
+def test_pre_process_kernel_matches_reference_goldens():
+    """k_pre_process vs MPC.pre_process of the reference (mpc.py:251-291) run by oracle/gen_golden.py."""
+    from rda_planner_b200.frontend import pre_process_batch, path_tensor
+    dev = torch.device('cuda:0')
+    by_cfg = {}
+    for rec in GOLD['pre_process']:
+        by_cfg.setdefault((rec['dynamics'], rec['T']), []).append(rec)
+    assert by_cfg
+    for (dyn, T), recs in by_cfg.items():
+        state = torch.as_tensor(np.array([np.ravel(r['state'])[:3] for r in recs], np.float32), device=dev)
+        vel = torch.as_tensor(np.array([r['vel'] for r in recs], np.float32), device=dev)
+        start = torch.as_tensor(np.array([r['index'] for r in recs], np.int32), device=dev)
+        speed = torch.full((len(recs),), 4.0, dtype=torch.float32, device=dev)
+        nom, ref, near = pre_process_batch(state, vel, speed, path_tensor(PATH, dev), start, dyn, 0.1, 3.0, T)
+        for i, r in enumerate(recs):
+            assert int(near[i]) == r['new_index']
+            np.testing.assert_allclose(nom[i].cpu().numpy(), r['state_pre'], atol=3e-5)
+            np.testing.assert_allclose(ref[i].cpu().numpy(), r['ref'], atol=3e-5)
+
+
+def test_convert_obstacles_kernel_matches_reference_goldens():
+    """k_convert_obstacles vs convert_inequal_circle / convert_inequal_polygon / gen_inequal_global of the reference
+    (mpc.py:440-510): moving disc, moving square, and the CW / CCW polygons of the reference run."""
+    from rda_planner_b200.frontend import convert_obstacles_batch, pack_shapes, shapes_to_device
+    from rda_planner_b200 import _cabi
+    dev = torch.device('cuda:0')
+    sq = np.array([[0., 1, 1, 0], [0, 0, 1, 1]])
+    lst = [Obs(np.array([[20.], [34.]]), 1.5, None, 'norm2', np.array([[0.5], [-0.2]])),
+           Obs(None, None, sq, 'Rpositive', np.array([[1.0], [0.5]]))]
+    shapes = shapes_to_device(pack_shapes([lst], 4), dev)
+    A, b, kind, cnt = convert_obstacles_batch(shapes, torch.zeros((1, 3), device=dev), 2, 10, 4, 0.1, True, False)
+    A, b, kind = A[0].cpu().numpy(), b[0].cpu().numpy(), kind[0].cpu().numpy()
+    assert int(cnt[0]) == 2 and list(kind) == [_cabi.OBS_CIRCLE, _cabi.OBS_POLYGON]
+    np.testing.assert_allclose(A[0, :, :3], GOLD['circle_moving']['A'], atol=1e-6)
+    np.testing.assert_allclose(b[0, :, :3], np.array(GOLD['circle_moving']['b'])[:, :, 0], atol=1e-5)
+    np.testing.assert_allclose(A[1], GOLD['polygon_moving']['A'], atol=1e-6)
+    np.testing.assert_allclose(b[1], np.array(GOLD['polygon_moving']['b'])[:, :, 0], atol=1e-5)
+    n_checked = 0
+    for rec in GOLD['polygons']:
+        v = np.array(rec['vertex'])
+        if v.shape[1] > 8:
+            continue
+        shapes = shapes_to_device(pack_shapes([[Obs(None, None, v, 'Rpositive', np.zeros((2, 1)))]], 1), dev)
+        A, b, kind, cnt = convert_obstacles_batch(shapes, torch.zeros((1, 3), device=dev), 1, 5, 8, 0.1, False, False)
+        n = v.shape[1]
+        np.testing.assert_allclose(A[0, 0, 0, :n].cpu().numpy(), rec['A'], atol=1e-5)
+        np.testing.assert_allclose(b[0, 0, 0, :n].cpu().numpy(), np.array(rec['b'])[:, 0], atol=1e-4)
+        n_checked += 1
+    assert n_checked >= 2
+
+
+@pytest.mark.parametrize('nobs', [0, 3])
+def test_arrive_rule_and_free_space_match_reference_golden(nobs):
+    """End of the path, no obstacles (mpc.py:166-187 run by oracle/gen_golden.py): controls zeroed, arrive flag, index.
+    max_obs_num = 0 exercises the N == 0 paths of rda_create / k_finalize."""
+    from rda_planner_b200.frontend import BatchedMPC
+    g = GOLD['arrive']
+    bm = BatchedMPC(rectangle_robot(dynamics='diff'), PATH, 1, receding=10, sample_time=0.1, iter_num=2, max_obs_num=nobs)
+    bm.cur_index[:] = g['start_index']
+    u0, info = bm.control(np.ravel(g['state'])[:3][None].astype(np.float32), 4.0, None)
+    assert bool(info['arrive'][0]) == g['arrive'] and int(info['cur_index'][0]) == g['cur_index']
+    np.testing.assert_allclose(u0[0].cpu().numpy(), np.ravel(g['u']), atol=1e-6)
+    assert int(info['status'][0]) & 6 == 0
+
+
+def test_zero_obstacle_slots_single_instance_api():
+    """RDA_solver(max_obs_num=0).iterative_solve: pure tracking su-QP, no cell kernels, no NULL obs_count read."""
+    from rda_planner_b200.rda_solver import RDA_solver
+    from oracle.rda_oracle import OracleRDA
+    from rda_planner_b200.scenarios import make_instance
+    T = 8
+    car = rectangle_robot()
+    inst = make_instance(5, T=T, N=1, E=4)
+    ref = [inst['ref'][:, t:t + 1] for t in range(T + 1)]
+    g = RDA_solver(T, car, max_edge_num=4, max_obs_num=0, iter_num=3, iter_threshold=0.0, time_print=False)
+    o = OracleRDA(T, car, max_edge_num=4, max_obs_num=0, iter_num=3, iter_threshold=0.0)
+    ug, ig = g.iterative_solve(inst['nom_s'], inst['nom_u'], ref, 4.0, [])
+    uo, io = o.iterative_solve(inst['nom_s'], inst['nom_u'], ref, 4.0, [])
+    assert ig['status'] & 6 == 0
+    np.testing.assert_allclose(ug, uo, atol=1e-3)
+    np.testing.assert_allclose(np.hstack(ig['opt_state_list']), np.hstack(io['opt_state_list']), atol=1e-3)
