@@ -354,10 +354,12 @@ extern "C" int shim_su_batched(const SuParams* Pin, int nb, float* cur_s, float*
   SbOut out{cur_s, cur_u, dis, status, iters, counters};
   const int gs = (nb + 127) / 128, gi = (nb + 31) / 32;
   emu_launch(gs, T, 128, [&] { ksb_setup(W, P, cur_s, cur_u, ref_s, pref, coef, dis, ref_speed, done); });
+  emu_launch(1, 1, 1, [&] { ksb_compact(W); });
   emu_launch(gi, 1, 32, [&] { ksb_rollout(W); });
   for (int it = 0; it <= P.max_iter; ++it) {
     emu_launch(gs, T, 128, [&] { ksb_assemble(W, P, it); });
     emu_launch(gi, 1, 32, [&] { ksb_riccati<true>(W, P, it, Mrows, out); });
+    emu_launch(1, 1, 1, [&] { ksb_compact(W); });
     if (it == P.max_iter) break;
     emu_launch(gs, T, 128, [&] { ksb_steplen<0>(W, P, it); });
     emu_launch(gs, 1, 128, [&] { ksb_reduce<0>(W, Mrows); });

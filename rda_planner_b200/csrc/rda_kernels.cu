@@ -42,7 +42,6 @@ struct rda_handle {
   int su_batched;        // -1: by sub-batch size (>= su_batched_min instances), 0: never, 1: always (RDA_B200_SU_BATCHED)
   int su_batched_min;
   int su_group;          // lanes per instance in k_su: 0 = by sub-batch size, else 32 / 16 / 8 (RDA_B200_SU_GROUP)
-  int su_level;          // workspace placement (su_work_layout): -1 = by group, else 0..2 (RDA_B200_SU_LEVEL)
   // coherent first cell pass (cell_lean2.cuh; RDA_B200_LEAN2=1, E <= 4, R <= 4, static obstacles)
   int lean2;
   RobotAux ra;
@@ -136,7 +135,8 @@ __global__ void k_begin(DevPtrs d, const float* nom_s, const float* nom_u, const
 // K1: su-QP, one warp per instance.
 // ------------------------------------------------------------------------------------------------
 template <typename Real, int G>
-__global__ void __launch_bounds__(32) k_su(DevPtrs d, SuParams P, int smem_per_instance, int level) {
+__global__ void __launch_bounds__(32) k_su(DevPtrs d, SuParams P, int smem_per_instance) {
+  constexpr int LEVEL = G == 32 ? 0 : (G == 16 ? 1 : 2);      // workspace placement of sub-warp groups (su_work_layout)
   extern __shared__ __align__(16) char smem[];
   constexpr int PER_WARP = 32 / G;
   const int grp = (threadIdx.x & 31) / G;
@@ -151,8 +151,8 @@ __global__ void __launch_bounds__(32) k_su(DevPtrs d, SuParams P, int smem_per_i
   // its stage, consecutive lanes read consecutive addresses.  With sub-warp groups (level > 0) the
   // Riccati gains / stage arrays live there too, so that shared memory does not limit the number of
   // resident instances.
-  su_work_layout<Real, Real>(T, N, &W, smem + (size_t)grp * smem_per_instance, false,
-                              d.su_ws + (size_t)b * d.su_ws_stride, level);
+  su_work_layout<Real, Real, LEVEL>(T, N, &W, smem + (size_t)grp * smem_per_instance, false,
+                                    d.su_ws + (size_t)b * d.su_ws_stride);
   const float* cs = d.cur_s + (size_t)b * 3 * (T + 1);   // [3][T+1]
   const float* cu = d.cur_u + (size_t)b * 2 * T;         // [2][T]
   const float* rf = d.ref_s + (size_t)b * 3 * (T + 1);
@@ -733,15 +733,18 @@ int rda_create(const rda_config* cfg, const rda_tunables* tun, rda_handle** out)
   h->R = cfg->robot_edges;
   const size_t B = h->B, T = h->T, N = h->N, E = h->E, R = h->R, NT = N * T;
   {
-    // largest global slab any placement level needs, and the shared-memory footprints per level
-    size_t gmax = 0;
-    for (int lv = 0; lv < 3; ++lv) {
-      size_t g = 0;
-      const size_t sm = cfg->su_fp64 ? su_work_bytes<double, double>((int)T, (int)N, false, lv, &g)
-                                     : su_work_bytes<float, float>((int)T, (int)N, false, lv, &g);
-      if (g > gmax) gmax = g;
-      if (lv == 0 && sm > 227 * 1024) { delete h; return RDA_E_UNSUPPORTED; }
+    // largest global slab any placement level needs (sub-warp groups keep more of the workspace there)
+    size_t gmax = 0, g = 0, sm0;
+    if (cfg->su_fp64) {
+      sm0 = su_work_bytes<double, double, 0>((int)T, (int)N, false, &g); gmax = g;
+      su_work_bytes<double, double, 1>((int)T, (int)N, false, &g); if (g > gmax) gmax = g;
+      su_work_bytes<double, double, 2>((int)T, (int)N, false, &g); if (g > gmax) gmax = g;
+    } else {
+      sm0 = su_work_bytes<float, float, 0>((int)T, (int)N, false, &g); gmax = g;
+      su_work_bytes<float, float, 1>((int)T, (int)N, false, &g); if (g > gmax) gmax = g;
+      su_work_bytes<float, float, 2>((int)T, (int)N, false, &g); if (g > gmax) gmax = g;
     }
+    if (sm0 > 227 * 1024) { delete h; return RDA_E_UNSUPPORTED; }
     h->su_ws_stride = (gmax + 127) & ~(size_t)127;
   }
   cudaError_t e = cudaSuccess;
@@ -769,9 +772,8 @@ int rda_create(const rda_config* cfg, const rda_tunables* tun, rda_handle** out)
       if (e == cudaSuccess) e = cudaFuncSetAttribute(k_su<float, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
     }
   }
-  h->su_group = 0; h->su_level = -1;
+  h->su_group = 0;
   if (const char* g = getenv("RDA_B200_SU_GROUP")) { int v = atoi(g); if (v == 32 || v == 16 || v == 8) h->su_group = v; }
-  if (const char* g = getenv("RDA_B200_SU_LEVEL")) { int v = atoi(g); if (v >= 0 && v <= 2) h->su_level = v; }
   h->su_batched = 0; h->su_batched_min = 3072;      // measured slower than k_su (r02): opt-in
   if (const char* g = getenv("RDA_B200_SU_BATCHED")) { int v = atoi(g); if (v >= -1 && v <= 1) h->su_batched = v; }
   if (const char* g = getenv("RDA_B200_SU_BATCHED_MIN")) { int v = atoi(g); if (v >= 1) h->su_batched_min = v; }
@@ -917,16 +919,17 @@ static int step_su_batched(rda_handle* h, int b0, int nb, int part, cudaStream_t
   const bool acc = h->cfg.accelerated != 0;
   const double Mrows = 4.0 * T + (N > 0 ? 2.0 * T : 0.0) + 4.0 * (T - 1) + (acc ? (double)N * T : 0.0);
   SbOut out{d.cur_s, d.cur_u, d.dis, d.status, d.iters, d.counters};
-  RDA_CUDA(cudaMemsetAsync(W.n_active, 0, sizeof(int), s));
   const dim3 gs((nb + 127) / 128, T);
   const int gi = (nb + 31) / 32, gr = (nb + 127) / 128;
   ksb_setup<<<gs, 128, 0, s>>>(W, P, d.cur_s, d.cur_u, d.ref_s, d.pref, d.coef, d.dis, d.ref_speed, d.done);
+  ksb_compact<<<1, 1024, 0, s>>>(W);
   ksb_rollout<<<gi, 32, 0, s>>>(W);
-  h->launches += 2;
+  h->launches += 3;
   for (int it = 0; it <= P.max_iter; ++it) {
     ksb_assemble<<<gs, 128, 0, s>>>(W, P, it);
     ksb_riccati<true><<<gi, 32, 0, s>>>(W, P, it, Mrows, out);
-    h->launches += 2;
+    ksb_compact<<<1, 1024, 0, s>>>(W);
+    h->launches += 3;
     if (it == P.max_iter) break;
     ksb_steplen<0><<<gs, 128, 0, s>>>(W, P, it);
     ksb_reduce<0><<<gr, 128, 0, s>>>(W, Mrows);
@@ -950,19 +953,14 @@ static int step_su_part(rda_handle* h, int b0, int nb, int part, cudaStream_t s)
   // work at B = 16384): the serial Riccati recursion then waits on L2 instead of shared memory every stage.
   int G = h->su_group;
   if (G == 0) G = 32;
-  int level = h->su_level >= 0 ? h->su_level : (G == 32 ? 0 : (G == 16 ? 1 : 2));
   const int per_warp = 32 / G;
-  size_t smem1 = h->cfg.su_fp64 ? su_work_bytes<double, double>(h->T, h->N, false, level)
-                                : su_work_bytes<float, float>(h->T, h->N, false, level);
-  while (smem1 * per_warp > 227 * 1024 && level < 2) {
-    ++level;
-    smem1 = h->cfg.su_fp64 ? su_work_bytes<double, double>(h->T, h->N, false, level)
-                           : su_work_bytes<float, float>(h->T, h->N, false, level);
-  }
+  size_t smem1;
+  if (h->cfg.su_fp64) smem1 = G == 32 ? su_work_bytes<double, double, 0>(h->T, h->N, false) : (G == 16 ? su_work_bytes<double, double, 1>(h->T, h->N, false) : su_work_bytes<double, double, 2>(h->T, h->N, false));
+  else smem1 = G == 32 ? su_work_bytes<float, float, 0>(h->T, h->N, false) : (G == 16 ? su_work_bytes<float, float, 1>(h->T, h->N, false) : su_work_bytes<float, float, 2>(h->T, h->N, false));
   if (smem1 * per_warp > 227 * 1024) return RDA_E_UNSUPPORTED;
   const int grid = (nb + per_warp - 1) / per_warp;
   const size_t cta_smem = smem1 * per_warp;
-#define RDA_LAUNCH_SU(REAL, GG) k_su<REAL, GG><<<grid, 32, cta_smem, s>>>(d, P, (int)smem1, level)
+#define RDA_LAUNCH_SU(REAL, GG) k_su<REAL, GG><<<grid, 32, cta_smem, s>>>(d, P, (int)smem1)
   if (h->cfg.su_fp64) {
     if (G == 32) RDA_LAUNCH_SU(double, 32); else if (G == 16) RDA_LAUNCH_SU(double, 16); else RDA_LAUNCH_SU(double, 8);
   } else {

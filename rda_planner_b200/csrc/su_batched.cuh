@@ -42,7 +42,8 @@ struct SuBatch {
   double *p_mu, *p_r, *p_step, *p_rmax, *p_s0, *p_s1, *p_s2;   // per-stage partial reductions, T each
   double *mu, *sigma_mu, *alpha, *vref;
   int *active, *st, *its;
-  int *n_active;                    // one counter per sub-batch
+  int *list;                        // compact, ascending list of the active instances (ksb_compact)
+  int *n_active;                    // its length
 };
 
 // bytes of workspace for nb instances; if base != nullptr the pointers are set
@@ -75,7 +76,7 @@ inline size_t su_batch_layout(int nb, int T, int N, SuBatch* w, char* base) {
   W.p_mu = (double*)take(T, 8); W.p_r = (double*)take(T, 8); W.p_step = (double*)take(T, 8);
   W.p_rmax = (double*)take(T, 8); W.p_s0 = (double*)take(T, 8); W.p_s1 = (double*)take(T, 8); W.p_s2 = (double*)take(T, 8);
   W.mu = (double*)take(1, 8); W.sigma_mu = (double*)take(1, 8); W.alpha = (double*)take(1, 8); W.vref = (double*)take(1, 8);
-  W.active = (int*)take(1, 4); W.st = (int*)take(1, 4); W.its = (int*)take(1, 4);
+  W.active = (int*)take(1, 4); W.st = (int*)take(1, 4); W.its = (int*)take(1, 4); W.list = (int*)take(1, 4);
   off = (off + 255) & ~(size_t)255;
   W.n_active = (int*)(base ? base + off : nullptr);
   off += 256;
@@ -133,7 +134,6 @@ __global__ void ksb_setup(SuBatch W, SuParams P, const float* cur_s, const float
     W.active[b] = act; W.st[b] = 1; W.its[b] = 0;
     W.mu[b] = 0; W.sigma_mu[b] = 0; W.alpha[b] = 0;
     W.vref[b] = ref_speed[b];
-    if (act) atomicAdd(W.n_active, 1);
   }
   if (done[b]) return;
   const float* cs = cur_s + (size_t)b * 3 * (T + 1);
@@ -176,11 +176,52 @@ __global__ void ksb_setup(SuBatch W, SuParams P, const float* cur_s, const float
   SB_AT(W.dd[0], t) = (double)dis[(size_t)b * T + t];
 }
 
+
+// Rebuild the ascending list of active instances (after the set-up and after every convergence test): the
+// per-iteration kernels index through it, so their warps stay full while instances drop out.
+#if defined(RDA_SB_EMULATE)
+__global__ void ksb_compact(SuBatch W) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  int n = 0;
+  for (int b = 0; b < W.nb; ++b) if (W.active[b]) W.list[n++] = b;
+  *W.n_active = n;
+}
+#else
+__global__ void __launch_bounds__(1024) ksb_compact(SuBatch W) {
+  __shared__ int wcnt[32];
+  __shared__ int base, total;
+  const int nb = W.nb, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) base = 0;
+  __syncthreads();
+  for (int start = 0; start < nb; start += 1024) {
+    const int b = start + threadIdx.x;
+    const bool flag = b < nb && W.active[b] != 0;
+    const unsigned m = __ballot_sync(0xffffffffu, flag);
+    if (lane == 0) wcnt[warp] = __popc(m);
+    __syncthreads();
+    if (warp == 0) {
+      const int v = wcnt[lane];
+      int incl = v;
+      for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+      wcnt[lane] = incl - v;
+      if (lane == 31) total = incl;
+    }
+    __syncthreads();
+    if (flag) W.list[base + wcnt[warp] + __popc(m & ((1u << lane) - 1u))] = b;
+    __syncthreads();
+    if (threadIdx.x == 0) base += total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *W.n_active = base;
+}
+#endif
+
 // initial iterate: roll the linearised model out from s_0 (serial over the horizon)
 __global__ void ksb_rollout(SuBatch W) {
   const int nb = W.nb, T = W.T;
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= nb || !W.active[b]) return;
+  const int li = blockIdx.x * blockDim.x + threadIdx.x;
+  if (li >= *W.n_active) return;
+  const int b = W.list[li];
   double s0 = SB_AT(W.lins, 0), s1 = SB_AT(W.lins, 1), s2 = SB_AT(W.lins, 2);
   SB_AT(W.s[0], 0) = s0; SB_AT(W.s[0], 1) = s1; SB_AT(W.s[0], 2) = s2;
   SB_AT(W.s[1], 0) = s0; SB_AT(W.s[1], 1) = s1; SB_AT(W.s[1], 2) = s2;
@@ -197,9 +238,11 @@ __global__ void ksb_rollout(SuBatch W) {
 // ---- update of iteration it-1 fused with the predictor assembly of iteration it ------------------
 __global__ void __launch_bounds__(128) ksb_assemble(SuBatch W, SuParams P, int it) {
   const int nb = W.nb, T = W.T, N = W.N;
-  if (*W.n_active == 0) return;
-  const int b = blockIdx.x * blockDim.x + threadIdx.x, t = blockIdx.y;
-  if (b >= nb || !W.active[b]) return;
+  const int li = blockIdx.x * blockDim.x + threadIdx.x, t = blockIdx.y;
+  if (li >= *W.n_active) return;
+  const int b = W.list[li];
+  const float* __restrict__ hx_ = W.hx; const float* __restrict__ hy_ = W.hy; const float* __restrict__ hc_ = W.hc;
+  double* __restrict__ hs_ = W.hs; double* __restrict__ hnu_ = W.hnu;
   const bool accm = P.accelerated != 0;
   const double ro1 = P.ro1, ro2 = P.ro2, iro1 = 1.0 / ro1, reg = 1e-9;
   const int cur = it & 1, nxt = cur ^ 1;
@@ -245,6 +288,7 @@ __global__ void __launch_bounds__(128) ksb_assemble(SuBatch W, SuParams P, int i
   double wb[5] = {0, 0, 0, 0, 0};
   double acc_mu = 0, acc_r = 0;
   // ---- box / rate rows: update (old iterate), then predictor terms (new iterate) ----
+#pragma unroll
   for (int c = 0; c < 10; ++c) {
     const SbRow ro = sb_row(P, t, c, ut, up, dt_);
     double sv, nu;
@@ -283,7 +327,7 @@ __global__ void __launch_bounds__(128) ksb_assemble(SuBatch W, SuParams P, int i
 #pragma unroll 4
   for (int o = 0; o < N; ++o) {
     const size_t i = (size_t)o * T + t;
-    const double ax = SB_AT(W.hx, i), ay = SB_AT(W.hy, i), hc = SB_AT(W.hc, i);
+    const double ax = SB_AT(hx_, i), ay = SB_AT(hy_, i), hc = SB_AT(hc_, i);
     double tk, om;
     if (accm) {
       double sv, nu;
@@ -292,7 +336,7 @@ __global__ void __launch_bounds__(128) ksb_assemble(SuBatch W, SuParams P, int i
         sv = (l + sqrt(l * l + 4 * mu0 / ro1)) / 2;
         nu = mu0 / sv;
       } else {
-        sv = SB_AT(W.hs, i); nu = SB_AT(W.hnu, i);
+        sv = SB_AT(hs_, i); nu = SB_AT(hnu_, i);
         const double l = ax * dxo + ay * dyo + hc - dt_;
         const double nr = nu * iro1;
         const double res = l + nr - sv;
@@ -307,7 +351,7 @@ __global__ void __launch_bounds__(128) ksb_assemble(SuBatch W, SuParams P, int i
         const double ds = dir + dn * iro1 + res;
         sv += a * ds; nu += a * dn;
       }
-      SB_AT(W.hs, i) = sv; SB_AT(W.hnu, i) = nu;
+      SB_AT(hs_, i) = sv; SB_AT(hnu_, i) = nu;
       const double l = ax * dxn + ay * dyn + hc - dtn;
       const double nr = nu * iro1;
       const double res = l + nr - sv;
@@ -345,9 +389,9 @@ struct SbOut { float *cur_s, *cur_u, *dis; int *status, *iters, *counters; };
 template <bool FACTOR>
 __global__ void __launch_bounds__(64) ksb_riccati(SuBatch W, SuParams P, int it, double Mrows, SbOut out) {
   const int nb = W.nb, T = W.T;
-  if (*W.n_active == 0) return;
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= nb || !W.active[b]) return;
+  const int li = blockIdx.x * blockDim.x + threadIdx.x;
+  if (li >= *W.n_active) return;
+  const int b = W.list[li];
   const double reg = 1e-9;
   if (FACTOR) {
     // per-instance reductions over the horizon in a fixed order (deterministic)
@@ -390,8 +434,7 @@ __global__ void __launch_bounds__(64) ksb_riccati(SuBatch W, SuParams P, int it,
       out.iters[b] += 1;
       atomicAdd(&out.counters[3], it);
       atomicAdd(&out.counters[4], 1);
-      W.active[b] = 0; W.st[b] = fin; W.its[b] = it;
-      atomicSub(W.n_active, 1);
+      W.active[b] = 0; W.st[b] = fin; W.its[b] = it;        // ksb_compact drops it from the list
       return;
     }
   }
@@ -564,9 +607,11 @@ __global__ void __launch_bounds__(64) ksb_riccati(SuBatch W, SuParams P, int it,
 template <int PHASE>
 __global__ void __launch_bounds__(128) ksb_steplen(SuBatch W, SuParams P, int it) {
   const int nb = W.nb, T = W.T, N = W.N;
-  if (*W.n_active == 0) return;
-  const int b = blockIdx.x * blockDim.x + threadIdx.x, t = blockIdx.y;
-  if (b >= nb || !W.active[b]) return;
+  const int li = blockIdx.x * blockDim.x + threadIdx.x, t = blockIdx.y;
+  if (li >= *W.n_active) return;
+  const int b = W.list[li];
+  const float* __restrict__ hx_ = W.hx; const float* __restrict__ hy_ = W.hy; const float* __restrict__ hc_ = W.hc;
+  const double* __restrict__ hs_ = W.hs; const double* __restrict__ hnu_ = W.hnu;
   const bool accm = P.accelerated != 0;
   const double iro1 = 1.0 / (double)P.ro1;
   const int cb = (it + 1) & 1;
@@ -587,6 +632,7 @@ __global__ void __launch_bounds__(128) ksb_steplen(SuBatch W, SuParams P, int it
     sigma_mu = W.sigma_mu[b];
   }
   double rmaxr = 0, s0 = 0, s1 = 0, s2 = 0;
+#pragma unroll
   for (int c = 0; c < 10; ++c) {
     const SbRow r = sb_row(P, t, c, ut, up, dt_);
     if (!r.live) continue;
@@ -613,9 +659,9 @@ __global__ void __launch_bounds__(128) ksb_steplen(SuBatch W, SuParams P, int it
 #pragma unroll 4
     for (int o = 0; o < N; ++o) {
       const size_t i = (size_t)o * T + t;
-      const double ax = SB_AT(W.hx, i), ay = SB_AT(W.hy, i);
-      const double l = ax * dx + ay * dy + (double)SB_AT(W.hc, i) - dt_;
-      const double sv = SB_AT(W.hs, i), nu = SB_AT(W.hnu, i);
+      const double ax = SB_AT(hx_, i), ay = SB_AT(hy_, i);
+      const double l = ax * dx + ay * dy + (double)SB_AT(hc_, i) - dt_;
+      const double sv = SB_AT(hs_, i), nu = SB_AT(hnu_, i);
       const double nr = nu * iro1;
       const double res = l + nr - sv;
       const double iden = rcp_(sv + nr);
@@ -643,9 +689,9 @@ __global__ void __launch_bounds__(128) ksb_steplen(SuBatch W, SuParams P, int it
 template <int PHASE>
 __global__ void __launch_bounds__(128) ksb_reduce(SuBatch W, double Mrows) {
   const int nb = W.nb, T = W.T;
-  if (*W.n_active == 0) return;
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= nb || !W.active[b]) return;
+  const int li = blockIdx.x * blockDim.x + threadIdx.x;
+  if (li >= *W.n_active) return;
+  const int b = W.list[li];
   double rm = 0, s0 = 0, s1 = 0, s2 = 0;
   for (int t = 0; t < T; ++t) {
     rm = fmax(rm, SB_AT(W.p_rmax, t));
@@ -667,9 +713,11 @@ __global__ void __launch_bounds__(128) ksb_reduce(SuBatch W, double Mrows) {
 // ---- corrector right-hand side (needs sigma * mu of the instance) ----------------------------------
 __global__ void __launch_bounds__(128) ksb_corrector(SuBatch W, SuParams P, int it) {
   const int nb = W.nb, T = W.T, N = W.N;
-  if (*W.n_active == 0) return;
-  const int b = blockIdx.x * blockDim.x + threadIdx.x, t = blockIdx.y;
-  if (b >= nb || !W.active[b]) return;
+  const int li = blockIdx.x * blockDim.x + threadIdx.x, t = blockIdx.y;
+  if (li >= *W.n_active) return;
+  const int b = W.list[li];
+  const float* __restrict__ hx_ = W.hx; const float* __restrict__ hy_ = W.hy; const float* __restrict__ hc_ = W.hc;
+  const double* __restrict__ hs_ = W.hs; const double* __restrict__ hnu_ = W.hnu;
   const bool accm = P.accelerated != 0;
   const double ro2 = P.ro2, iro1 = 1.0 / (double)P.ro1, reg = 1e-9;
   const int cb = (it + 1) & 1;
@@ -692,6 +740,7 @@ __global__ void __launch_bounds__(128) ksb_corrector(SuBatch W, SuParams P, int 
   gw[4] = reg * ut[1];
   gw[5] = N > 0 ? -(double)P.slack_gain + reg * dt_ : 0.0;
   gw[6] = 0; gw[7] = 0;
+#pragma unroll
   for (int c = 0; c < 10; ++c) {
     const SbRow r = sb_row(P, t, c, ut, up, dt_);
     if (!r.live) continue;
@@ -709,11 +758,11 @@ __global__ void __launch_bounds__(128) ksb_corrector(SuBatch W, SuParams P, int 
 #pragma unroll 4
   for (int o = 0; o < N; ++o) {
     const size_t i = (size_t)o * T + t;
-    const double ax = SB_AT(W.hx, i), ay = SB_AT(W.hy, i);
-    const double l = ax * dx + ay * dy + (double)SB_AT(W.hc, i) - dt_;
+    const double ax = SB_AT(hx_, i), ay = SB_AT(hy_, i);
+    const double l = ax * dx + ay * dy + (double)SB_AT(hc_, i) - dt_;
     double tk;
     if (accm) {
-      const double sv = SB_AT(W.hs, i), nu = SB_AT(W.hnu, i);
+      const double sv = SB_AT(hs_, i), nu = SB_AT(hnu_, i);
       const double nr = nu * iro1;
       const double res = l + nr - sv;
       const double iden = rcp_(sv + nr);

@@ -62,51 +62,60 @@ struct SuWork {
 };
 
 // Workspace placement.  `base` is the fast memory of the instance (shared memory on the GPU), `gbase` an
-// optional per-instance slab of global memory (L2).  level 0: everything in `base`; level 1: the Riccati
-// gains and the box slacks / multipliers move to `gbase`; level 2: also the stage Hessian / gradient /
+// optional per-instance slab of global memory (L2).  LEVEL 0: everything in `base`; LEVEL 1: the Riccati
+// gains and the box slacks / multipliers move to `gbase`; LEVEL 2: also the stage Hessian / gradient /
 // Newton step arrays.  With hinge_arrays = false the per-hinge arrays (hx, hy, hc: caller; hs, hnu: first
 // in `gbase`) are left out of `base` (each entry is touched only by the lane that owns its stage).
-// Returns the bytes of `base` used; *gbytes (if given) the bytes of `gbase` used.
-template <typename Real, typename Slk = Real>
+// LEVEL is a compile-time constant so that every pointer keeps a single provenance (the compiler then
+// emits LDS / LDG instead of generic loads).  Returns the bytes of `base` used; *gbytes the bytes of `gbase`.
+template <typename Real, typename Slk = Real, int LEVEL = 0>
 RDA_HD size_t su_work_layout(int T, int N, SuWork<Real, Slk>* w, char* base, bool hinge_arrays = true,
-                             char* gbase = nullptr, int level = 0, size_t* gbytes = nullptr) {
-  size_t off[2] = {0, 0};
-  char* bases[2] = {base, gbase};
-  auto take = [&](int where, size_t n, size_t elt) {
-    off[where] = (off[where] + 15) & ~(size_t)15;
-    char* p = bases[where] ? bases[where] + off[where] : nullptr;
-    off[where] += n * elt;
+                             char* gbase = nullptr, size_t* gbytes = nullptr) {
+  size_t offs = 0, offg = 0;
+  auto takes = [&](size_t n, size_t elt) {
+    offs = (offs + 15) & ~(size_t)15;
+    char* p = base ? base + offs : nullptr;
+    offs += n * elt;
     return p;
   };
-#define RDA_TAKE(where, field, n, type) { char* p_ = take((where), (size_t)(n), sizeof(type)); if (w) w->field = (type*)p_; }
-  const int g1 = level >= 1 ? 1 : 0, g2 = level >= 2 ? 1 : 0;
-  RDA_TAKE(0, s, 3 * (T + 1), Real) RDA_TAKE(0, u, 2 * T, Real) RDA_TAKE(0, d, T, Real)
-  RDA_TAKE(0, ref, 3 * (T + 1), float) RDA_TAKE(0, lins, 3 * (T + 1), float)
-  RDA_TAKE(0, Aj, 2 * T, Real) RDA_TAKE(0, Bj, 6 * T, Real)
-  RDA_TAKE(0, Skk, T, Real) RDA_TAKE(0, Sgk, T, Real) RDA_TAKE(0, pref, 2 * T, float)
+  auto takeg = [&](size_t n, size_t elt) {
+    offg = (offg + 15) & ~(size_t)15;
+    char* p = gbase ? gbase + offg : nullptr;
+    offg += n * elt;
+    return p;
+  };
+#define RDA_TAKE_S(field, n, type) { char* p_ = takes((size_t)(n), sizeof(type)); if (w) w->field = (type*)p_; }
+#define RDA_TAKE_G(field, n, type) { char* p_ = takeg((size_t)(n), sizeof(type)); if (w) w->field = (type*)p_; }
+#define RDA_TAKE_L(lv, field, n, type) { if (LEVEL >= (lv)) RDA_TAKE_G(field, n, type) else RDA_TAKE_S(field, n, type) }
+  RDA_TAKE_S(s, 3 * (T + 1), Real) RDA_TAKE_S(u, 2 * T, Real) RDA_TAKE_S(d, T, Real)
+  RDA_TAKE_S(ref, 3 * (T + 1), float) RDA_TAKE_S(lins, 3 * (T + 1), float)
+  RDA_TAKE_S(Aj, 2 * T, Real) RDA_TAKE_S(Bj, 6 * T, Real)
+  RDA_TAKE_S(Skk, T, Real) RDA_TAKE_S(Sgk, T, Real) RDA_TAKE_S(pref, 2 * T, float)
   if (hinge_arrays) {
-    RDA_TAKE(0, hx, N * T, float) RDA_TAKE(0, hy, N * T, float) RDA_TAKE(0, hc, N * T, float)
-    RDA_TAKE(0, hs, N * T, Slk) RDA_TAKE(0, hnu, N * T, Slk)
+    RDA_TAKE_S(hx, N * T, float) RDA_TAKE_S(hy, N * T, float) RDA_TAKE_S(hc, N * T, float)
+    RDA_TAKE_S(hs, N * T, Slk) RDA_TAKE_S(hnu, N * T, Slk)
   } else {
-    RDA_TAKE(1, hs, N * T, Slk) RDA_TAKE(1, hnu, N * T, Slk)
+    RDA_TAKE_G(hs, N * T, Slk) RDA_TAKE_G(hnu, N * T, Slk)
   }
-  RDA_TAKE(g1, bs, 10 * T, Slk) RDA_TAKE(g1, bnu, 10 * T, Slk)
-  RDA_TAKE(g2, Wm, 8 * T + 5, Real)                                   // (Wm, wb) | (dza, dva)
+  RDA_TAKE_L(1, bs, 10 * T, Slk) RDA_TAKE_L(1, bnu, 10 * T, Slk)
+  RDA_TAKE_L(2, Wm, 8 * T + 5, Real)                                  // (Wm, wb) | (dza, dva)
   if (w) { w->wb = w->Wm + 3 * T; w->dza = w->Wm; w->dva = w->Wm + 5 * (T + 1); }
-  RDA_TAKE(g2, Ed, 3 * T, Real) RDA_TAKE(g2, g5q, T, Real)
-  RDA_TAKE(g2, gw, 8 * T + 5, Real)                                   // gw | (dz, dv)
+  RDA_TAKE_L(2, Ed, 3 * T, Real) RDA_TAKE_L(2, g5q, T, Real)
+  RDA_TAKE_L(2, gw, 8 * T + 5, Real)                                  // gw | (dz, dv)
   if (w) { w->dz = w->gw; w->dv = w->gw + 5 * (T + 1); }
-  RDA_TAKE(g1, K, 10 * T, Real) RDA_TAKE(g1, Lc, 3 * T, Real) RDA_TAKE(g1, kf, 2 * T, Real)
+  RDA_TAKE_L(1, K, 10 * T, Real) RDA_TAKE_L(1, Lc, 3 * T, Real) RDA_TAKE_L(1, kf, 2 * T, Real)
   if (w) { w->Cj = w->K; w->linu = (float*)w->dv; }
-#undef RDA_TAKE
-  if (gbytes) *gbytes = (off[1] + 15) & ~(size_t)15;
-  return (off[0] + 15) & ~(size_t)15;
+#undef RDA_TAKE_S
+#undef RDA_TAKE_G
+#undef RDA_TAKE_L
+  if (gbytes) *gbytes = (offg + 15) & ~(size_t)15;
+  return (offs + 15) & ~(size_t)15;
 }
 
 // size-only query of su_work_layout
-template <typename Real, typename Slk = Real>
-RDA_HD size_t su_work_bytes(int T, int N, bool hinge_arrays = true, int level = 0, size_t* gbytes = nullptr) {
-  return su_work_layout<Real, Slk>(T, N, (SuWork<Real, Slk>*)nullptr, nullptr, hinge_arrays, nullptr, level, gbytes);
+template <typename Real, typename Slk = Real, int LEVEL = 0>
+RDA_HD size_t su_work_bytes(int T, int N, bool hinge_arrays = true, size_t* gbytes = nullptr) {
+  return su_work_layout<Real, Slk, LEVEL>(T, N, (SuWork<Real, Slk>*)nullptr, nullptr, hinge_arrays, nullptr, gbytes);
 }
 
 // Jacobians of the discrete model about (s, u): linear_ackermann_model :949-963,
