@@ -35,12 +35,13 @@ def algorithmic_bytes():
     return k2, k1
 
 
-def build_inputs(batch, seed0):
-    from rda_planner_b200.scenarios import make_instance
+def build_inputs(batch, seed0, config='metric'):
+    from rda_planner_b200.scenarios import config_instance, CONFIGS
     from rda_planner_b200.rda_solver import pack_obstacles
-    uniq = min(batch, 1024)
-    insts = [make_instance(seed0 + i, T=T, N=N, E=E) for i in range(uniq)]
-    packs = [pack_obstacles(list(i['obstacles']), T, N, E) for i in insts]
+    c = CONFIGS[config]
+    uniq = min(batch, 1024 if config == 'metric' else 256)
+    insts = [config_instance(config, seed0 + i) for i in range(uniq)]
+    packs = [pack_obstacles(list(i['obstacles']), c['T'], c['N'], c['E']) for i in insts]
     rep = -(-batch // uniq)
 
     def tile(a):
@@ -55,6 +56,131 @@ def build_inputs(batch, seed0):
         'obs_kind': tile(np.stack([p[2] for p in packs])),
         'obs_count': tile(np.array([p[3] for p in packs], np.int32)),
     }
+
+
+def run_config(args):
+    """BASELINE.json configs B-E at their stated global batch (STRONG scaling: the global batch is fixed and split
+    over the ranks), 50 ADMM iterations, early stop disabled.  --scatter-from-rank0: rank 0 owns the whole batch; the
+    timed region then contains scatter_batch (NCCL) + solve + gather_batch of (u, s) — SURVEY.md §8e "report both".
+    Config E additionally runs the float32 su-QP and reports residual / trajectory gaps against float64 by iteration."""
+    import torch
+    import torch.distributed as dist
+    from rda_planner_b200.rda_solver import RDA_solver
+    from rda_planner_b200.scenarios import rectangle_robot, CONFIGS
+    from rda_planner_b200 import build as rbuild
+    from rda_planner_b200.sharding import gather_batch, scatter_batch, shard_bounds
+    cfg = CONFIGS[args.config]
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device(f'cuda:{local}')
+    if world > 1:
+        os.environ.setdefault('NCCL_DEBUG', 'WARN')
+        dist.init_process_group('nccl', device_id=dev)
+    rbuild.build()
+    G = args.global_batch or cfg['global_batch']
+    lo, hi = shard_bounds(G, world, rank)
+    nloc = hi - lo
+    car = rectangle_robot(dynamics=cfg['dynamics'])
+    Tc, Nc, Ec = cfg['T'], cfg['N'], cfg['E']
+    full = build_inputs(G, 1000 * 7, args.config) if (rank == 0 or not args.scatter_from_rank0) else None
+    tv = bool(full['obs_A'].shape[2] > 1) if full is not None else False
+    if world > 1:
+        flag = torch.tensor([int(tv)], device=dev)
+        dist.broadcast(flag, 0)
+        tv = bool(flag.item())
+    full_t = {k: torch.from_numpy(v) for k, v in full.items()} if full is not None else None
+
+    def mk(su_fp64=True):
+        return RDA_solver(Tc, car, max_edge_num=Ec, max_obs_num=Nc, iter_num=cfg['iter_num'], iter_threshold=0.0,
+                          time_print=False, batch=nloc, device=dev, su_fp64=su_fp64, **cfg['tun'])
+    solver = mk()
+    if args.scatter_from_rank0:
+        src = {k: v.to(dev) for k, v in full_t.items()} if rank == 0 else None      # resident on rank 0's GPU
+    else:
+        devin = {k: v[lo:hi].to(dev) for k, v in full_t.items()}
+
+    def step():
+        if args.scatter_from_rank0:
+            inp, n = scatter_batch(src, G, dev)
+        else:
+            inp = devin
+        solver.cold_start()
+        out = solver.iterative_solve_batch(inp['nom_s'], inp['nom_u'], inp['ref_s'], inp['ref_speed'], inp['obs_A'],
+                                           inp['obs_b'], inp['obs_kind'], inp['obs_count'], tv)
+        if args.scatter_from_rank0:
+            gu = gather_batch(out['u'], G)
+            gs = gather_batch(out['s'], G)
+            return out, (gu, gs)
+        return out, None
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        out, gathered = step()
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    st = out['status'].cpu()
+    bits = torch.tensor([int(((st & b) != 0).sum()) for b in (1, 2, 4)], device=dev)
+    if world > 1:
+        dist.all_reduce(bits)
+    line = {'metric': f'MPC solves/sec (config {args.config}: {cfg["what"]}, {cfg["iter_num"]} ADMM iterations)',
+            'value': G * args.steps / (ms * 1e-3), 'unit': 'solves/s', 'n_gpus': world, 'steps': args.steps,
+            'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'strong',
+            'vs_baseline': None, 'dtype': 'f32 state / f64 su-QP interior point', 'data': 'synthetic',
+            'config': {'workload': f'BASELINE config {args.config}', 'global_batch': G, 'batch_per_gpu': nloc,
+                       'T': Tc, 'N': Nc, 'E': Ec, 'time_varying_obstacles': tv,
+                       'inputs': 'scattered from rank 0 over NCCL inside the timed region, (u, s) gathered back'
+                       if args.scatter_from_rank0 else 'each rank generates its shard in place',
+                       'l2_policy': 'cold start every step; state of one step exceeds L2 only for configs D/E at full batch'},
+            'status_bits': {'su_iteration_cap(1)': int(bits[0]), 'su_nonfinite_keep_previous(2)': int(bits[1]),
+                            'cell_failed_keep_previous(4)': int(bits[2])},
+            'gpu_launches': (solver.launch_count() + 1) * args.steps}
+    if args.scatter_from_rank0 and rank == 0:
+        line['gathered_shapes'] = [list(gathered[0].shape), list(gathered[1].shape)]
+        line['scatter_bytes_per_step'] = int(sum(v.numel() * v.element_size() for v in src.values()))
+    if args.config == 'E' or args.precision_sweep:
+        # float32 vs float64 su-QP: residuals and trajectory gap by iteration (same inputs, phase API)
+        inp = scatter_batch(src, G, dev)[0] if args.scatter_from_rank0 else devin
+        s32 = mk(False)
+        rows = []
+        runs = {}
+        for name, sv in (('f64', solver), ('f32', s32)):
+            sv.cold_start()
+            sv.begin(inp['nom_s'], inp['nom_u'], inp['ref_s'], inp['ref_speed'], inp['obs_A'], inp['obs_b'], inp['obs_kind'],
+                     inp['obs_count'], tv, 0.0)
+            tr = {}
+            for it in range(1, cfg['iter_num'] + 1):
+                sv.step_su(); sv.step_lammuz()
+                if it in (1, 2, 4, 8, 16, 32, cfg['iter_num']):
+                    o = sv.finish()
+                    tr[it] = {k: o[k].clone() for k in ('s', 'u', 'resi_pri', 'resi_dual')}
+            runs[name] = tr
+        for it in sorted(runs['f64']):
+            a, b = runs['f64'][it], runs['f32'][it]
+            gap = (a['s'] - b['s']).abs().flatten(1).max(1).values
+            rows.append({'iteration': it,
+                         'resi_pri_f64_median': float(a['resi_pri'].median()), 'resi_pri_f32_median': float(b['resi_pri'].median()),
+                         'resi_dual_f64_median': float(a['resi_dual'].median()), 'resi_dual_f32_median': float(b['resi_dual'].median()),
+                         'state_gap_median': float(gap.median()), 'state_gap_p95': float(gap.quantile(0.95)), 'state_gap_max': float(gap.max())})
+        line['fp32_vs_fp64_su'] = rows
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
 
 
 class ClockSampler:
@@ -269,11 +395,19 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--batch', type=int, default=16384, help='instances per GPU per step')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--config', default='metric', choices=['metric', 'B', 'C', 'D', 'E'],
+                    help='BASELINE.json config (default: the metric row, the headline); B-E are strong-scaling side benches')
+    ap.add_argument('--global-batch', type=int, default=0, help='override the global batch of --config B..E')
+    ap.add_argument('--scatter-from-rank0', action='store_true',
+                    help='--config B..E: rank 0 owns the batch; scatter + solve + gather inside the timed region')
+    ap.add_argument('--precision-sweep', action='store_true', help='--config B..E: float32 vs float64 su-QP by iteration')
     ap.add_argument('--su-fp32', action='store_true', help='float32 su-QP arithmetic (lower bound probe, not the metric)')
     ap.add_argument('--no-probes', action='store_true', help='skip early-stop / single-instance / closed-loop probes')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
+    if args.config != 'metric':
+        return run_config(args)
 
     import torch
     import torch.distributed as dist

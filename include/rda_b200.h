@@ -168,6 +168,23 @@ int rda_convert_obstacles(int B, int M, int N, int T, int E, float dt, int time_
 int rda_post_process(int B, int T, int P, int goal_index_threshold, const int32_t *near_index,
                      float *u_opt, float *cur_vel, int32_t *arrive, void *cuda_stream);
 
+/* Gear changes (enable_reverse, mpc.py:139-144, :166-183, split_path :232-249).  The reference path is cut into
+ * n_curves single-gear curves, curve c = waypoints [curve_start[c], curve_start[c+1]) of `path`; every robot follows
+ * curve curve_index[b].  rda_pre_process_curves is rda_pre_process on the robot's current curve (near_index is
+ * relative to the curve).  rda_post_process_gear applies mpc.py:166-185: at the end of a curve the robot switches
+ * to the next one (cur_index back to 0, controls kept); past the last curve the controls are zeroed and arrive is
+ * set (curve_index then stays on the last curve: the reference would raise IndexError on the next call).
+ * gear [B] (output) is the gear flag (+1 / -1) of the robot's curve BEFORE the update; the caller multiplies the
+ * solver's reference speed with it (mpc.py:161). */
+int rda_pre_process_curves(int B, int T, int dynamics, float dt, float wheelbase, const float *state,
+                           const float *cur_vel, const float *ref_speed, const float *path, int n_curves,
+                           const int32_t *curve_start, const int32_t *curve_index, const int32_t *start_index,
+                           float threshold, int ind_range, float *nom_s, float *ref_s, int32_t *near_index,
+                           void *cuda_stream);
+int rda_post_process_gear(int B, int T, int n_curves, const int32_t *curve_start, int goal_index_threshold,
+                          int32_t *near_index, int32_t *curve_index, float *u_opt, float *cur_vel,
+                          int32_t *arrive, void *cuda_stream);
+
 /* state [B][3] advanced in place by one step of the nonlinear model with the first control of
  * u_opt [B][2][T] (mpc.py:293-336; what the examples' simulator does between control calls). */
 int rda_motion_predict(int B, int T, int dynamics, float dt, float wheelbase, const float *u_opt,

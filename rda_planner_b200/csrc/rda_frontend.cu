@@ -27,6 +27,23 @@ __global__ void k_pre_process(int B, int T, int dynamics, float dt, float L, con
   near_index[b] = near;
 }
 
+// the same on the single-gear curve the robot currently follows (enable_reverse, mpc.py:139-144)
+__global__ void k_pre_process_curves(int B, int T, int dynamics, float dt, float L, const float* state, const float* cur_vel,
+                                     const float* ref_speed, const float* path, int n_curves, const int* curve_start,
+                                     const int* curve_index, const int* start_index, float threshold, int ind_range,
+                                     float* nom_s, float* ref_s, int* near_index) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  int c = curve_index[b];
+  c = c < 0 ? 0 : (c >= n_curves ? n_curves - 1 : c);
+  const int p0 = curve_start[c], len = curve_start[c + 1] - p0;
+  const int near = pre_process_one(dynamics, T, (double)dt, (double)L, state + 3 * (size_t)b,
+                                   cur_vel + (size_t)b * 2 * T, (double)ref_speed[b], path + 3 * (size_t)p0, len,
+                                   start_index ? start_index[b] : 0, (double)threshold, ind_range,
+                                   nom_s + (size_t)b * 3 * (T + 1), ref_s + (size_t)b * 3 * (T + 1));
+  near_index[b] = near;
+}
+
 // one CTA per instance: keys -> stable ranks -> rows of the N slots
 __global__ void __launch_bounds__(RDA_MAX_SHAPES)
 k_convert_obstacles(int B, int M, int N, int T, int E, float dt, int time_varying, int order, const float* state,
@@ -86,6 +103,27 @@ __global__ void k_post_process(int B, int T, int P, int goal_index_threshold, co
   if (arrive && i == b * 2 * T) arrive[b] = arr ? 1 : 0;
 }
 
+// end-of-curve rule with gear changes (mpc.py:166-185), one thread per robot
+__global__ void k_post_process_gear(int B, int T, int n_curves, const int* curve_start, int goal_index_threshold,
+                                    int* near_index, int* curve_index, float* u_opt, float* cur_vel, int* arrive) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  int c = curve_index[b];
+  c = c < 0 ? 0 : (c >= n_curves ? n_curves - 1 : c);
+  const int len = curve_start[c + 1] - curve_start[c];
+  bool arr = false;
+  if (near_index[b] >= len - goal_index_threshold) {
+    if (c + 1 < n_curves) { curve_index[b] = c + 1; near_index[b] = 0; }     // next curve, controls kept
+    else arr = true;                                                            // past the last curve
+  }
+  float* u = u_opt + (size_t)b * 2 * T;
+  for (int i = 0; i < 2 * T; ++i) {
+    if (arr) u[i] = 0.f;
+    if (cur_vel) cur_vel[(size_t)b * 2 * T + i] = u[i];
+  }
+  if (arrive) arrive[b] = arr ? 1 : 0;
+}
+
 __global__ void k_motion_predict(int B, int T, int dynamics, float dt, float L, const float* u_opt, float* state) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
@@ -107,6 +145,30 @@ int rda_pre_process(int B, int T, int dynamics, float dt, float wheelbase, const
   k_pre_process<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(B, T, dynamics, dt, wheelbase, state, cur_vel, ref_speed,
                                                                    path, P, start_index, threshold, ind_range, nom_s,
                                                                    ref_s, near_index);
+  RDA_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int rda_pre_process_curves(int B, int T, int dynamics, float dt, float wheelbase, const float* state, const float* cur_vel,
+                           const float* ref_speed, const float* path, int n_curves, const int32_t* curve_start,
+                           const int32_t* curve_index, const int32_t* start_index, float threshold, int ind_range,
+                           float* nom_s, float* ref_s, int32_t* near_index, void* stream) {
+  if (B < 1 || T < 1 || n_curves < 1 || dynamics < 0 || dynamics > 2) return RDA_E_ARG;
+  if (!state || !cur_vel || !ref_speed || !path || !curve_start || !curve_index || !nom_s || !ref_s || !near_index) return RDA_E_ARG;
+  k_pre_process_curves<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(B, T, dynamics, dt, wheelbase, state, cur_vel,
+                                                                          ref_speed, path, n_curves, curve_start, curve_index,
+                                                                          start_index, threshold, ind_range, nom_s, ref_s,
+                                                                          near_index);
+  RDA_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int rda_post_process_gear(int B, int T, int n_curves, const int32_t* curve_start, int goal_index_threshold,
+                          int32_t* near_index, int32_t* curve_index, float* u_opt, float* cur_vel, int32_t* arrive,
+                          void* stream) {
+  if (B < 1 || T < 1 || n_curves < 1 || !curve_start || !near_index || !curve_index || !u_opt) return RDA_E_ARG;
+  k_post_process_gear<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(B, T, n_curves, curve_start, goal_index_threshold,
+                                                                         near_index, curve_index, u_opt, cur_vel, arrive);
   RDA_CUDA(cudaGetLastError());
   return 0;
 }

@@ -25,15 +25,19 @@ RDA_HD float sqrt_(float x) { return sqrtf(x); }
 RDA_HD double sqrt_(double x) { return sqrt(x); }
 RDA_HD float abs_(float x) { return fabsf(x); }
 RDA_HD double abs_(double x) { return fabs(x); }
-// reciprocal: on the device a float seed refined by two Newton steps (full double accuracy for
-// arguments inside the float range, which every caller guarantees) — shorter dependent chain than
-// the IEEE division sequence; plain division on the host.
+// reciprocal: on the device the hardware's double-precision reciprocal seed (MUFU.RCP64H, ~20 bits) refined by
+// two Newton steps — 5 dependent instructions, no float <-> double conversions (the float-seed variant of round
+// 1 spent 13 % of the su-QP kernel's stall samples on its two F2F conversions, profiles/ncu_r02_ksu_lines.md);
+// arguments are positive normal numbers at every call site.  Plain division on the host.
 RDA_HD float rcp_(float x) { return 1.0f / x; }
 RDA_HD double rcp_(double x) {
 #if defined(__CUDA_ARCH__)
-  double r = (double)__frcp_rn((float)x);
-  r = r * (2.0 - x * r);
-  r = r * (2.0 - x * r);
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
   return r;
 #else
   return 1.0 / x;

@@ -22,6 +22,10 @@
 
 namespace rda {
 
+#ifndef RDA_SU_CH
+#define RDA_SU_CH 4      // hinges per chunk of the su-QP hinge loops (loads grouped ahead of the arithmetic)
+#endif
+
 struct SuParams {
   int T, N, dynamics, accelerated;
   float dt, L, umax[2], ab[2], ws, wu;
@@ -440,35 +444,49 @@ RDA_HD int su_solve(const SuParams& P, SuWork<Real, Slk>& W, Ctx& ctx, const flo
         Real dx = sn[0] - W.pref[2 * t], dy = sn[1] - W.pref[2 * t + 1];
         Real dd = W.d[t];
         Real g0 = gw[0], g1 = gw[1], g5 = gw[5];     // accumulated in registers: no store inside the hinge loop
-        for (int o = 0; o < N; ++o) {
-          Real ax = W.hx[o * T + t], ay = W.hy[o * T + t];
-          Real l = ax * dx + ay * dy + (Real)W.hc[o * T + t] - dd;
-          Real tk, om;
-          if (acc) {
-            Real sv = W.hs[o * T + t], nu = W.hnu[o * T + t];
-            const Real nr = nu * iro1;
-            Real res = l + nr - sv;
-            const Real iden = rcp_(sv + nr);
-            om = nu * iden;
-            if (phase == 0) {
-              tk = om * (nr - res);
-              acc_mu += sv * nu;
-              acc_r = rmax(acc_r, abs_(res));
-            } else {
-              Real dir = ax * W.dza[5 * t + 5] + ay * W.dza[5 * t + 6] - W.dva[3 * t + 2];
-              Real dna = -om * (sv + res + dir);
-              Real dsa = dir + dna * iro1 + res;
-              Real cc = sv * nu - sigma_mu + dsa * dna;
-              tk = nu - (cc + nu * res) * iden;
-            }
-          } else {
-            om = ro1;               // plain quadratic 1/2 ro1 Im^2  (rda_solver.py:378-379)
-            tk = -ro1 * l;
+        // hinges in chunks of RDA_SU_CH: all (global-memory) loads of a chunk are issued before its arithmetic
+        const Real adx = phase == 1 ? W.dza[5 * t + 5] : (Real)0, ady = phase == 1 ? W.dza[5 * t + 6] : (Real)0;
+        const Real add = phase == 1 ? W.dva[3 * t + 2] : (Real)0;
+        for (int o0 = 0; o0 < N; o0 += RDA_SU_CH) {
+          Real axv[RDA_SU_CH], ayv[RDA_SU_CH], hcv[RDA_SU_CH], svv[RDA_SU_CH], nuv[RDA_SU_CH];
+#pragma unroll
+          for (int k = 0; k < RDA_SU_CH; ++k) {
+            const int i = (o0 + k < N ? o0 + k : N - 1) * T + t;
+            axv[k] = W.hx[i]; ayv[k] = W.hy[i]; hcv[k] = W.hc[i];
+            svv[k] = acc ? (Real)W.hs[i] : (Real)1; nuv[k] = acc ? (Real)W.hnu[i] : (Real)1;
           }
-          g0 -= ax * tk; g1 -= ay * tk; g5 += tk;
-          if (phase == 0) {
-            m0 += om * ax * ax; m1 += om * ax * ay; m2 -= om * ax;
-            m3 += om * ay * ay; m4 -= om * ay; m5 += om;
+#pragma unroll
+          for (int k = 0; k < RDA_SU_CH; ++k) {
+            if (o0 + k >= N) break;
+            const Real ax = axv[k], ay = ayv[k];
+            const Real l = ax * dx + ay * dy + hcv[k] - dd;
+            Real tk, om;
+            if (acc) {
+              const Real sv = svv[k], nu = nuv[k];
+              const Real nr = nu * iro1;
+              const Real res = l + nr - sv;
+              const Real iden = rcp_(sv + nr);
+              om = nu * iden;
+              if (phase == 0) {
+                tk = om * (nr - res);
+                acc_mu += sv * nu;
+                acc_r = rmax(acc_r, abs_(res));
+              } else {
+                const Real dir = ax * adx + ay * ady - add;
+                const Real dna = -om * (sv + res + dir);
+                const Real dsa = dir + dna * iro1 + res;
+                const Real cc = sv * nu - sigma_mu + dsa * dna;
+                tk = nu - (cc + nu * res) * iden;
+              }
+            } else {
+              om = ro1;               // plain quadratic 1/2 ro1 Im^2  (rda_solver.py:378-379)
+              tk = -ro1 * l;
+            }
+            g0 -= ax * tk; g1 -= ay * tk; g5 += tk;
+            if (phase == 0) {
+              m0 += om * ax * ax; m1 += om * ax * ay; m2 -= om * ax;
+              m3 += om * ay * ay; m4 -= om * ay; m5 += om;
+            }
           }
         }
         // eliminate d_t (it enters stage t only): Schur complement on Q_dd = reg + barrier weights + sum om
@@ -520,28 +538,39 @@ RDA_HD int su_solve(const SuParams& P, SuWork<Real, Slk>& W, Ctx& ctx, const flo
           s0 += sv * nu; s1 += sv * dn + nu * ds; s2 += ds * dn;
         }
         if (acc) {
-          Real dx = W.s[3 * t + 3] - W.pref[2 * t], dy = W.s[3 * t + 4] - W.pref[2 * t + 1];
-          for (int o = 0; o < N; ++o) {
-            Real ax = W.hx[o * T + t], ay = W.hy[o * T + t];
-            Real l = ax * dx + ay * dy + (Real)W.hc[o * T + t] - W.d[t];
-            Real sv = W.hs[o * T + t], nu = W.hnu[o * T + t];
-            const Real nr = nu * iro1;
-            Real res = l + nr - sv;
-            const Real iden = rcp_(sv + nr);
-            const Real om = nu * iden;
-            Real dir = ax * dz[5 * t + 5] + ay * dz[5 * t + 6] - dv[3 * t + 2];
-            Real cc = sv * nu;
-            if (phase == 1) {
-              Real dira = ax * W.dza[5 * t + 5] + ay * W.dza[5 * t + 6] - W.dva[3 * t + 2];
-              Real dna = -om * (sv + res + dira);
-              Real dsa = dira + dna * iro1 + res;
-              cc = sv * nu - sigma_mu + dsa * dna;
+          const Real dx = W.s[3 * t + 3] - W.pref[2 * t], dy = W.s[3 * t + 4] - W.pref[2 * t + 1], dd = W.d[t];
+          const Real zdx = dz[5 * t + 5], zdy = dz[5 * t + 6], zdd = dv[3 * t + 2];
+          const Real adx = W.dza[5 * t + 5], ady = W.dza[5 * t + 6], add = W.dva[3 * t + 2];
+          for (int o0 = 0; o0 < N; o0 += RDA_SU_CH) {
+            Real axv[RDA_SU_CH], ayv[RDA_SU_CH], hcv[RDA_SU_CH], svv[RDA_SU_CH], nuv[RDA_SU_CH];
+#pragma unroll
+            for (int k = 0; k < RDA_SU_CH; ++k) {
+              const int i = (o0 + k < N ? o0 + k : N - 1) * T + t;
+              axv[k] = W.hx[i]; ayv[k] = W.hy[i]; hcv[k] = W.hc[i]; svv[k] = W.hs[i]; nuv[k] = W.hnu[i];
             }
-            Real dn = -(cc + nu * res + nu * dir) * iden;
-            Real ds = dir + dn * iro1 + res;
-            const Real ip = rcp_(sv * nu);
-            rmaxr = rmax(rmaxr, rmax(-ds * nu * ip, -dn * sv * ip));
-            s0 += sv * nu; s1 += sv * dn + nu * ds; s2 += ds * dn;
+#pragma unroll
+            for (int k = 0; k < RDA_SU_CH; ++k) {
+              if (o0 + k >= N) break;
+              const Real ax = axv[k], ay = ayv[k], sv = svv[k], nu = nuv[k];
+              const Real l = ax * dx + ay * dy + hcv[k] - dd;
+              const Real nr = nu * iro1;
+              const Real res = l + nr - sv;
+              const Real iden = rcp_(sv + nr);
+              const Real om = nu * iden;
+              const Real dir = ax * zdx + ay * zdy - zdd;
+              Real cc = sv * nu;
+              if (phase == 1) {
+                const Real dira = ax * adx + ay * ady - add;
+                const Real dna = -om * (sv + res + dira);
+                const Real dsa = dira + dna * iro1 + res;
+                cc = sv * nu - sigma_mu + dsa * dna;
+              }
+              const Real dn = -(cc + nu * res + nu * dir) * iden;
+              const Real ds = dir + dn * iro1 + res;
+              const Real ip = rcp_(sv * nu);
+              rmaxr = rmax(rmaxr, rmax(-ds * nu * ip, -dn * sv * ip));
+              s0 += sv * nu; s1 += sv * dn + nu * ds; s2 += ds * dn;
+            }
           }
         }
       }
@@ -579,24 +608,35 @@ RDA_HD int su_solve(const SuParams& P, SuWork<Real, Slk>& W, Ctx& ctx, const flo
             W.bnu[10 * t + c] = nu + a * dn;
           }
           if (acc) {
-            Real dx = W.s[3 * t + 3] - W.pref[2 * t], dy = W.s[3 * t + 4] - W.pref[2 * t + 1];
-            for (int o = 0; o < N; ++o) {
-              Real ax = W.hx[o * T + t], ay = W.hy[o * T + t];
-              Real l = ax * dx + ay * dy + (Real)W.hc[o * T + t] - W.d[t];
-              Real sv = W.hs[o * T + t], nu = W.hnu[o * T + t];
-              const Real nr = nu * iro1;
-              Real res = l + nr - sv;
-              const Real iden = rcp_(sv + nr);
-              const Real om = nu * iden;
-              Real dir = ax * W.dz[5 * t + 5] + ay * W.dz[5 * t + 6] - W.dv[3 * t + 2];
-              Real dira = ax * W.dza[5 * t + 5] + ay * W.dza[5 * t + 6] - W.dva[3 * t + 2];
-              Real dna = -om * (sv + res + dira);
-              Real dsa = dira + dna * iro1 + res;
-              Real cc = sv * nu - sigma_mu + dsa * dna;
-              Real dn = -(cc + nu * res + nu * dir) * iden;
-              Real ds = dir + dn * iro1 + res;
-              W.hs[o * T + t] = sv + a * ds;
-              W.hnu[o * T + t] = nu + a * dn;
+            const Real dx = W.s[3 * t + 3] - W.pref[2 * t], dy = W.s[3 * t + 4] - W.pref[2 * t + 1], dd = W.d[t];
+            const Real zdx = W.dz[5 * t + 5], zdy = W.dz[5 * t + 6], zdd = W.dv[3 * t + 2];
+            const Real adx = W.dza[5 * t + 5], ady = W.dza[5 * t + 6], add = W.dva[3 * t + 2];
+            for (int o0 = 0; o0 < N; o0 += RDA_SU_CH) {
+              Real axv[RDA_SU_CH], ayv[RDA_SU_CH], hcv[RDA_SU_CH], svv[RDA_SU_CH], nuv[RDA_SU_CH];
+#pragma unroll
+              for (int k = 0; k < RDA_SU_CH; ++k) {
+                const int i = (o0 + k < N ? o0 + k : N - 1) * T + t;
+                axv[k] = W.hx[i]; ayv[k] = W.hy[i]; hcv[k] = W.hc[i]; svv[k] = W.hs[i]; nuv[k] = W.hnu[i];
+              }
+#pragma unroll
+              for (int k = 0; k < RDA_SU_CH; ++k) {
+                if (o0 + k >= N) break;
+                const Real ax = axv[k], ay = ayv[k], sv = svv[k], nu = nuv[k];
+                const Real l = ax * dx + ay * dy + hcv[k] - dd;
+                const Real nr = nu * iro1;
+                const Real res = l + nr - sv;
+                const Real iden = rcp_(sv + nr);
+                const Real om = nu * iden;
+                const Real dir = ax * zdx + ay * zdy - zdd;
+                const Real dira = ax * adx + ay * ady - add;
+                const Real dna = -om * (sv + res + dira);
+                const Real dsa = dira + dna * iro1 + res;
+                const Real cc = sv * nu - sigma_mu + dsa * dna;
+                const Real dn = -(cc + nu * res + nu * dir) * iden;
+                const Real ds = dir + dn * iro1 + res;
+                W.hs[(o0 + k) * T + t] = sv + a * ds;
+                W.hnu[(o0 + k) * T + t] = nu + a * dn;
+              }
             }
           }
         }

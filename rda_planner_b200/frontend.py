@@ -114,14 +114,16 @@ def shapes_to_device(shapes, device):
 class BatchedMPC:
     """MPC.control (mpc.py:127-187) for `batch` robots that follow one reference path, every step on
     the device: pre_process -> obstacle conversion -> ADMM solve -> arrive rule.  Keyword set of the
-    reference's MPC where it applies; `enable_reverse` (gear changes) is not supported here."""
+    reference's MPC where it applies.  With `enable_reverse` the path carries a gear flag in its 4th row
+    (+1 forward, -1 reverse; mpc.py:139-144): it is cut into single-gear curves (split_path, mpc.py:232-249),
+    every robot follows its own curve, the solver's reference speed carries the gear's sign and a robot moves on
+    to the next curve when it reaches the end of the current one (mpc.py:166-183)."""
 
     def __init__(self, car_tuple, ref_path, batch, receding=10, sample_time=0.1, iter_num=4,
                  enable_reverse=False, obstacle_order=True, max_edge_num=5, max_obs_num=5,
                  accelerated=True, goal_index_threshold=1, device=None, iter_threshold=0.2, **kwargs):
-        if enable_reverse:
-            raise NotImplementedError('BatchedMPC follows a single-gear path; use mpc.MPC for enable_reverse')
         self.lib = _cabi.load()
+        self.enable_reverse = bool(enable_reverse)
         self.rda = RDA_solver(receding, car_tuple, max_edge_num, max_obs_num, iter_num=iter_num,
                               step_time=sample_time, iter_threshold=iter_threshold, accelerated=accelerated,
                               time_print=False, batch=batch, device=device, **kwargs)
@@ -134,6 +136,14 @@ class BatchedMPC:
         self.goal_index_threshold = goal_index_threshold
         self.path = path_tensor(ref_path, self.device)
         self.cur_index = torch.zeros(batch, dtype=torch.int32, device=self.device)
+        if self.enable_reverse:
+            # split_path (mpc.py:232-249): a new curve starts wherever the gear flag changes
+            flags = np.array([float(np.asarray(p, float).reshape(-1)[-1]) for p in ref_path])
+            cuts = [0] + [i for i in range(1, len(flags)) if flags[i] != flags[i - 1]] + [len(flags)]
+            self.curve_start = torch.as_tensor(cuts, dtype=torch.int32, device=self.device)
+            self.curve_gear = torch.as_tensor([flags[c] for c in cuts[:-1]], dtype=torch.float32, device=self.device)
+            self.n_curves = len(cuts) - 1
+            self.curve_index = torch.zeros(batch, dtype=torch.int32, device=self.device)
         init_vel = kwargs.get('init_vel')
         self.cur_vel = torch.zeros((batch, 2, receding), dtype=torch.float32, device=self.device)
         if init_vel is not None:
@@ -160,8 +170,21 @@ class BatchedMPC:
             ref_speed = torch.full((B,), float(ref_speed), dtype=torch.float32, device=dev) if np.isscalar(ref_speed) \
                 else torch.as_tensor(ref_speed, dtype=torch.float32, device=dev)
         ref_speed = ref_speed.to(dtype=torch.float32).contiguous()
-        nom_s, ref_s, near = pre_process_batch(state, self.cur_vel, ref_speed, self.path, self.cur_index,
-                                               self.dynamics, self.dt, self.L, T)
+        solver_speed = ref_speed
+        if self.enable_reverse:
+            nom_s = torch.empty((B, 3, T + 1), dtype=torch.float32, device=dev)
+            ref_s = torch.empty((B, 3, T + 1), dtype=torch.float32, device=dev)
+            near = torch.empty(B, dtype=torch.int32, device=dev)
+            with torch.cuda.device(dev):
+                _cabi.check(self.lib.rda_pre_process_curves(
+                    B, T, _cabi.DYNAMICS[self.dynamics], self.dt, self.L, _ptr(state), _ptr(self.cur_vel), _ptr(ref_speed),
+                    _ptr(self.path), self.n_curves, _ptr(self.curve_start), _ptr(self.curve_index), _ptr(self.cur_index),
+                    0.1, 10, _ptr(nom_s), _ptr(ref_s), _ptr(near), _stream(dev)), 'rda_pre_process_curves')
+            gear = self.curve_gear[self.curve_index.long().clamp(max=self.n_curves - 1)]
+            solver_speed = (ref_speed * gear).contiguous()                      # gear_flag * ref_speed (mpc.py:161)
+        else:
+            nom_s, ref_s, near = pre_process_batch(state, self.cur_vel, ref_speed, self.path, self.cur_index,
+                                                   self.dynamics, self.dt, self.L, T)
         self.cur_index = near
         if shapes is None or self.N == 0:
             A, b, kind, count = self._no_obstacles()
@@ -169,13 +192,20 @@ class BatchedMPC:
         else:
             A, b, kind, count = convert_obstacles_batch(shapes, state, self.N, T, self.E, self.dt, time_varying,
                                                         self.obstacle_order)
-        out = self.rda.iterative_solve_batch(nom_s, self.cur_vel, ref_s, ref_speed, A, b, kind, count, time_varying)
+        out = self.rda.iterative_solve_batch(nom_s, self.cur_vel, ref_s, solver_speed, A, b, kind, count, time_varying)
         with torch.cuda.device(dev):
-            _cabi.check(self.lib.rda_post_process(B, T, self.path.shape[0], self.goal_index_threshold, _ptr(near),
-                                                  _ptr(out['u']), _ptr(self.cur_vel), _ptr(self.arrive), _stream(dev)),
-                        'rda_post_process')
+            if self.enable_reverse:
+                _cabi.check(self.lib.rda_post_process_gear(B, T, self.n_curves, _ptr(self.curve_start), self.goal_index_threshold,
+                                                           _ptr(near), _ptr(self.curve_index), _ptr(out['u']), _ptr(self.cur_vel),
+                                                           _ptr(self.arrive), _stream(dev)), 'rda_post_process_gear')
+            else:
+                _cabi.check(self.lib.rda_post_process(B, T, self.path.shape[0], self.goal_index_threshold, _ptr(near),
+                                                      _ptr(out['u']), _ptr(self.cur_vel), _ptr(self.arrive), _stream(dev)),
+                            'rda_post_process')
         info = dict(out)
         info.update(arrive=self.arrive, nom_s=nom_s, ref_s=ref_s, cur_index=near)
+        if self.enable_reverse:
+            info['curve_index'] = self.curve_index
         return out['u'][:, :, 0], info
 
     def advance(self, state):
@@ -190,3 +220,5 @@ class BatchedMPC:
         self.rda.reset()
         self.cur_index.zero_()
         self.cur_vel.zero_()
+        if self.enable_reverse:
+            self.curve_index.zero_()

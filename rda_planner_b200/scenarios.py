@@ -119,3 +119,76 @@ def make_instance(seed, T=30, N=20, E=4, dynamics='acker', dt=0.1, ref_speed=4.0
             obstacles.append(rdaobs(A, b, 'Rpositive', None, vert))
     return {'nom_s': nom_s, 'nom_u': nom_u, 'ref': ref, 'ref_speed': ref_speed,
             'obstacles': obstacles, 'state': state}
+
+
+# ---- BASELINE.json configs: seeded synthetic instances of the five named workloads --------------
+# name -> solver shape, tunables, global batch and GPU count the config is quoted on
+CONFIGS = {
+    'A': dict(what='path_track: acker, T=10, 4 static polygons, 1 instance', T=10, N=4, E=4, dynamics='acker', iter_num=2,
+              tun=dict(ro1=300), global_batch=1, gpus=1),
+    'B': dict(what='corridor: diff-drive, T=20, 10 polygon obstacles (two 70 x 2 m walls + 8 boxes), batch 64', T=20, N=10, E=4,
+              dynamics='diff', iter_num=50, tun={}, global_batch=64, gpus=1),
+    'C': dict(what='dynamic_obs: acker, T=30, 20 moving discs (per-stage copies), batch 512', T=30, N=20, E=3, dynamics='acker',
+              iter_num=50, tun=dict(min_sd=0.5, wu=0.2), global_batch=512, gpus=1),
+    'D': dict(what='lidar: acker, T=30, 64 convex hulls (3-8 vertices) within 10 m, batch 2048 over 4 GPUs', T=30, N=64, E=8,
+              dynamics='acker', iter_num=50, tun=dict(slack_gain=13), global_batch=2048, gpus=4),
+    'E': dict(what='stress: acker, T=40, 128 convex polytopes (<= 8 faces) in a 40 x 40 m field, batch 8192 over 8 GPUs', T=40,
+              N=128, E=8, dynamics='acker', iter_num=50, tun={}, global_batch=8192, gpus=8),
+    'metric': dict(what='metric row: acker, T=30, N=20 static polygons (E=4)', T=30, N=20, E=4, dynamics='acker', iter_num=50,
+                   tun={}, global_batch=None, gpus=None),
+}
+
+
+def config_instance(name, seed):
+    """One seeded instance of BASELINE config `name` (dict as make_instance)."""
+    cfg = CONFIGS[name]
+    T, N, E, dyn = cfg['T'], cfg['N'], cfg['E'], cfg['dynamics']
+    if name == 'metric':
+        return make_instance(seed, T=T, N=N, E=E)
+    if name == 'A':
+        return make_instance(seed, T=T, N=N, E=E, lateral=(1.5, 6.0))
+    if name == 'C':
+        return make_instance(seed, T=T, N=N, E=E, kind='circle', moving=True)
+    rng = np.random.default_rng(seed)
+    dt, ref_speed, L = 0.1, 4.0, 3.0
+    heading = rng.uniform(-np.pi, np.pi)
+    start = np.array([rng.uniform(5, 55), rng.uniform(5, 55)])
+    dirv = np.array([cos(heading), sin(heading)])
+    nrm = np.array([-dirv[1], dirv[0]])
+    state = np.array([start[0] + rng.normal(0, 0.3) * nrm[0], start[1] + rng.normal(0, 0.3) * nrm[1],
+                      heading + rng.normal(0, 0.1)])
+    nom_u = np.vstack([np.full(T, ref_speed), np.zeros(T)])
+    nom_s = rollout(state, nom_u, dt, L, dyn)
+    ref = np.zeros((3, T + 1))
+    for t in range(T + 1):
+        ref[0:2, t] = start + dirv * (ref_speed * dt * t)
+        ref[2, t] = heading
+    obstacles = []
+    if name == 'B':
+        # two 70 x 2 m walls at +-5 m from the line and 8 boxes 5 x 2 m beside it (corridor.yaml:23-33)
+        mid = start + dirv * 30.0
+        for side in (-1.0, 1.0):
+            c = mid + nrm * (5.0 * side)
+            obstacles.append(rect_vertices(c[0], c[1], 70.0, 2.0, heading))
+        for _ in range(N - 2):
+            c = start + dirv * rng.uniform(5, 55) + nrm * (rng.choice([-1.0, 1.0]) * rng.uniform(1.5, 3.5))
+            obstacles.append(rect_vertices(c[0], c[1], 5.0, 2.0, rng.uniform(0, np.pi)))
+    else:
+        clear = 3.2                       # keep the start pose free (robot half diagonal + margin)
+        while len(obstacles) < N:
+            if name == 'D':
+                r, a = 10.0 * np.sqrt(rng.uniform()), rng.uniform(0, 2 * np.pi)
+                c = state[:2] + r * np.array([cos(a), sin(a)])
+                rad = rng.uniform(0.3, 1.5)
+            else:
+                c = start + dirv * rng.uniform(-4, 36) + nrm * rng.uniform(-20, 20)
+                rad = rng.uniform(0.5, 2.0)
+            body = state[:2] + 1.5 * np.array([cos(state[2]), sin(state[2])])
+            if np.linalg.norm(c - body) < rad + clear:
+                continue
+            obstacles.append(random_convex_polygon(rng, c[0], c[1], rad, int(rng.integers(3, E + 1))))
+    obs = []
+    for vert in obstacles:
+        A, b = polygon_halfspaces(vert)
+        obs.append(rdaobs(A, b, 'Rpositive', None, vert))
+    return {'nom_s': nom_s, 'nom_u': nom_u, 'ref': ref, 'ref_speed': ref_speed, 'obstacles': obs, 'state': state}

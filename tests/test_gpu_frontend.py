@@ -204,3 +204,57 @@ def test_zero_obstacle_slots_single_instance_api():
     assert ig['status'] & 6 == 0
     np.testing.assert_allclose(ug, uo, atol=1e-3)
     np.testing.assert_allclose(np.hstack(ig['opt_state_list']), np.hstack(io['opt_state_list']), atol=1e-3)
+
+
+def test_batched_mpc_gear_changes_match_host_front_end():
+    """enable_reverse (mpc.py:139-144, :166-183, split_path :232-249): a path that drives 5 m forward, 4 m back and
+    forward again, gear flag in the 4th row.  Two robots at different places of it, closed loop over enough steps to
+    switch curves; BatchedMPC against mpc.MPC per robot (same solver): controls, arrive flag, curve and waypoint index."""
+    from rda_planner_b200.frontend import BatchedMPC
+    from rda_planner_b200.mpc import MPC
+    car = rectangle_robot()
+    pts = []
+    for i in range(26):                                   # forward along +x
+        pts.append(np.array([[0.2 * i], [0.0], [0.0], [1.0]]))
+    for i in range(1, 21):                                # reverse along -x (heading still 0)
+        pts.append(np.array([[5.0 - 0.2 * i], [0.0], [0.0], [-1.0]]))
+    for i in range(1, 16):                                # forward again
+        pts.append(np.array([[1.0 + 0.2 * i], [0.0], [0.0], [1.0]]))
+    T, steps = 8, 30
+    kw = dict(receding=T, sample_time=0.1, iter_num=2, max_edge_num=4, max_obs_num=2, iter_threshold=0.0, enable_reverse=True)
+    starts = [(0, 0), (1, 2)]                             # (curve, waypoint index inside the curve)
+    B = len(starts)
+    bm = BatchedMPC(car, pts, B, **kw)
+    assert bm.n_curves == 3 and bm.curve_gear.cpu().tolist() == [1.0, -1.0, 1.0]
+    hosts, host_state, st0 = [], [], []
+    for c, i in starts:
+        m = MPC(car, copy.deepcopy(pts), time_print=False, **kw)
+        assert [len(x) for x in m.curve_list] == [26, 20, 15]
+        m.curve_index, m.cur_index = c, i
+        hosts.append(m)
+        wp = np.asarray(m.curve_list[c][i], float).reshape(-1)[:3]
+        st0.append(wp + np.array([0.05, 0.03, 0.01]))
+        host_state.append(st0[-1].reshape(3, 1).copy())
+    bm.curve_index[:] = torch.as_tensor([c for c, _ in starts], dtype=torch.int32)
+    bm.cur_index[:] = torch.as_tensor([i for _, i in starts], dtype=torch.int32)
+    dev_state = torch.as_tensor(np.stack(st0).astype(np.float32), device='cuda:0')
+    switched = 0
+    for k in range(steps):
+        u0, info = bm.control(dev_state, 2.0, None)
+        u0 = u0.cpu().numpy()
+        for i, m in enumerate(hosts):
+            before = m.curve_index
+            uh, ih = m.control(host_state[i], 2.0, [])
+            switched += int(m.curve_index != before)
+            assert bool(info['arrive'][i]) == ih['arrive'], (k, i)
+            assert int(info['curve_index'][i]) == min(m.curve_index, 2), (k, i)
+            assert int(info['cur_index'][i]) == m.cur_index, (k, i)
+            np.testing.assert_allclose(u0[i], uh[:, 0], atol=3e-3)
+            s = host_state[i]
+            host_state[i] = s + 0.1 * np.array([[uh[0, 0] * np.cos(s[2, 0])], [uh[0, 0] * np.sin(s[2, 0])], [uh[0, 0] * np.tan(uh[1, 0]) / 3.0]])
+            if m.curve_index >= len(m.curve_list):
+                m.curve_index = len(m.curve_list) - 1      # the reference raises IndexError on its next call; stay arrived
+                m.cur_index = len(m.curve_list[-1]) - 1
+        bm.advance(dev_state)
+        np.testing.assert_allclose(dev_state.cpu().numpy(), np.hstack(host_state).T, atol=3e-3)
+    assert switched >= 2
