@@ -350,30 +350,57 @@ RDA_HD void cell_front(const RobotGeom& rb, int kind, int E, const float* A, con
       Real lo = 0, hi = 1;
       int dir = 0;                   // weighted stage: which side of sA the maximiser lies on
       bool bracket = true;
+      // h at the bracket ends (flo > 0 at lo, fhi < 0 at hi) where it was evaluated inside the region N > 0
+      Real flo = 0, fhi = 0;
+      bool vlo = false, vhi = false;
       if (!weighted) {
         eval((Real)0); const Real h0 = hv;
         eval((Real)1); const Real h1 = hv;
         if (!(h0 > 0 && h1 < 0)) bracket = false;      // N has no interior maximum on this edge
+        flo = h0; fhi = h1; vlo = vhi = true;
       } else {
         if (!(sA > 0)) { bracket = false; }
         else {
           eval(sA);
           if (!(Nv > 0)) bracket = false;              // hinge cannot be active with contact on this edge
-          else if (hv > 0) { dir = 1; lo = sA; hi = 1; eval((Real)1); if (Nv > 0 && hv > 0) bracket = false; }
-          else { dir = -1; lo = 0; hi = sA; eval((Real)0); if (Nv > 0 && hv < 0) bracket = false; }
+          else if (hv > 0) {
+            dir = 1; lo = sA; hi = 1; flo = hv; vlo = true;
+            eval((Real)1);
+            if (Nv > 0 && hv > 0) bracket = false;
+            fhi = hv; vhi = Nv > 0;
+          } else {
+            dir = -1; lo = 0; hi = sA; fhi = hv; vhi = true;
+            eval((Real)0);
+            if (Nv > 0 && hv < 0) bracket = false;
+            flo = hv; vlo = Nv > 0;
+          }
         }
       }
       if (bracket) {
-        for (int itn = 0; itn < 26; ++itn) {
-          const Real sc = (Real)0.5 * (lo + hi);
+        // Root of h on [lo, hi]: regula falsi with the Illinois modification where both end values are valid,
+        // plain bisection otherwise (outside the region N > 0 the ratio N/W is not quasi-concave: steer back
+        // towards sA).  Superlinear: ~6-8 evaluations instead of the 26 of pure bisection (ncu r02: the
+        // bisection was half of k_cells_mid's instructions).
+        const Real tol = sizeof(Real) == 4 ? (Real)2e-7 : (Real)1e-13;
+        Real sc = (Real)0.5 * (lo + hi), sprev = -1;
+        int side = 0;
+        for (int itn = 0; itn < 40; ++itn) {
+          const Real w = hi - lo;
+          if (vlo && vhi && flo > 0 && fhi < 0) {
+            sc = lo + w * (flo / (flo - fhi));
+            sc = rclamp(sc, lo + (Real)0.02 * w, hi - (Real)0.02 * w);
+          } else {
+            sc = (Real)0.5 * (lo + hi);
+          }
           eval(sc);
-          // outside the region N > 0 the ratio N/W is not quasi-concave: steer back towards sA
-          const bool pos = weighted ? (Nv > 0 ? hv > 0 : dir < 0) : hv > 0;
-          if (pos) lo = sc; else hi = sc;
-          if (hi - lo < (sizeof(Real) == 4 ? (Real)2e-7 : (Real)1e-13)) break;
+          const bool valid = !weighted || Nv > 0;
+          const bool pos = valid ? hv > 0 : dir < 0;
+          if (pos) { lo = sc; flo = hv; vlo = valid; if (side > 0 && vhi) fhi *= (Real)0.5; side = 1; }
+          else { hi = sc; fhi = hv; vhi = valid; if (side < 0 && vlo) flo *= (Real)0.5; side = -1; }
+          if (hi - lo < tol || abs_(sc - sprev) < tol || (valid && hv == (Real)0)) break;
+          sprev = sc;
         }
-        eval((Real)0.5 * (lo + hi));
-        if (!weighted) sA = (Real)0.5 * (lo + hi);
+        if (!weighted) sA = sc;
       }
       if (!bracket) continue;
       // KKT of the cell problem at this point
