@@ -149,6 +149,11 @@ def run_config(args):
             'status_bits': {'su_iteration_cap(1)': int(bits[0]), 'su_nonfinite_keep_previous(2)': int(bits[1]),
                             'cell_failed_keep_previous(4)': int(bits[2])},
             'gpu_launches': (solver.launch_count() + 1) * args.steps}
+    from rda_planner_b200 import _cabi
+    cnt = solver.state_buffer(_cabi.BUF_COUNTERS).cpu().numpy().tolist()
+    cells = max(nloc * Nc * Tc * cfg['iter_num'], 1)
+    line['counters_rank0_last_step'] = {'cells_closed_form_fraction': cnt[0] / cells, 'cells_interior_point_fraction': cnt[1] / cells,
+                                        'cells_failed': cnt[2], 'su_ipm_iterations_per_solve': cnt[3] / max(cnt[4], 1)}
     if args.scatter_from_rank0 and rank == 0:
         line['gathered_shapes'] = [list(gathered[0].shape), list(gathered[1].shape)]
         line['scatter_bytes_per_step'] = int(sum(v.numel() * v.element_size() for v in src.values()))

@@ -60,6 +60,7 @@ struct rda_handle {
   // sub-batch overlap the kernels of the others
   cudaStream_t side[3];
   cudaEvent_t ev_fork, ev_join[3];
+  int slow_cpw, slow_ctas;   // k_cells_slow: cells per warp, CTAs per SM (RDA_B200_SLOW_CPW / RDA_B200_SLOW_CTAS)
   int split_min;         // smallest batch that is split (RDA_B200_SPLIT_MIN, default 2048)
   int parts;             // number of sub-batches, 1..4 (RDA_B200_SPLIT_PARTS, default 2)
 };
@@ -565,13 +566,13 @@ __global__ void __launch_bounds__(128) k_cells_mid(DevPtrs d, RobotGeom rb, floa
 #ifndef RDA_SLOW_CPW
 #define RDA_SLOW_CPW 32
 #endif
-__global__ void __launch_bounds__(64, RDA_SLOW_MINBLOCKS) k_cells_slow(DevPtrs d, RobotGeom rb, float ro2, float theta) {
+__global__ void __launch_bounds__(64, RDA_SLOW_MINBLOCKS) k_cells_slow(DevPtrs d, RobotGeom rb, float ro2, float theta, int cpw) {
   const int count = d.wl_count[1];
   const int lane = threadIdx.x & 31;
-  if (lane >= RDA_SLOW_CPW) return;
+  if (lane >= cpw) return;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
-  for (int wi = warp * RDA_SLOW_CPW + lane; wi < count; wi += nwarps * RDA_SLOW_CPW) {
+  for (int wi = warp * cpw + lane; wi < count; wi += nwarps * cpw) {
     const long long idx = d.worklist2[wi];
     CellIn c = cell_load(d, idx);
     CellWork<float> w;
@@ -808,6 +809,9 @@ int rda_create(const rda_config* cfg, const rda_tunables* tun, rda_handle** out)
   }
   h->split_min = 2048;
   h->parts = 2;
+  h->slow_cpw = RDA_SLOW_CPW; h->slow_ctas = 16;
+  if (const char* v = getenv("RDA_B200_SLOW_CPW")) { int x = atoi(v); if (x >= 1 && x <= 32) h->slow_cpw = x; }
+  if (const char* v = getenv("RDA_B200_SLOW_CTAS")) { int x = atoi(v); if (x >= 1 && x <= 256) h->slow_ctas = x; }
   if (const char* sm = getenv("RDA_B200_SPLIT_MIN")) { int v = atoi(sm); if (v >= 2) h->split_min = v; }
   if (const char* sp = getenv("RDA_B200_SPLIT_PARTS")) { int v = atoi(sp); if (v >= 1 && v <= 4) h->parts = v; }
   rc = rda_cold_start(h, nullptr);
@@ -992,7 +996,7 @@ static int step_lammuz_part(rda_handle* h, int b0, int nb, int part, cudaStream_
     RDA_CUDA(cudaGetLastError());
     k_cells_mid<<<148 * 8, 128, 0, s>>>(d, h->rb, h->tun.ro2, theta);
     RDA_CUDA(cudaGetLastError());
-    k_cells_slow<<<148 * 16, 64, 0, s>>>(d, h->rb, h->tun.ro2, theta);
+    k_cells_slow<<<148 * h->slow_ctas, 64, 0, s>>>(d, h->rb, h->tun.ro2, theta, h->slow_cpw);
     RDA_CUDA(cudaGetLastError());
     h->launches += 3;
   }

@@ -77,9 +77,12 @@ def pack_obstacles(obstacle_list, T, N, E):
 class RDA_solver:
     def __init__(self, receding, car_tuple, max_edge_num=5, max_obs_num=5, iter_num=2, step_time=0.1,
                  iter_threshold=0.2, process_num=4, accelerated=True, time_print=True, batch=1,
-                 device=None, su_fp64=True, z_theta=0.5, **kwargs):
+                 device=None, su_fp64=True, z_theta=0.5, graph=False, **kwargs):
         """kwargs: slack_gain (8), max_sd (1.0), min_sd (0.1), ro1 (200), ro2 (1), ws (1), wu (1)
-        — rda_solver.py:24-31.  `process_num` is accepted for compatibility and ignored."""
+        — rda_solver.py:24-31.  `process_num` is accepted for compatibility and ignored.
+        graph=True replays the launches of a solve from a CUDA graph (captured on first use per set of input
+        buffers / iteration count): the single-instance API then copies its inputs into persistent device
+        buffers, so every control step after the first is one graph launch."""
         if not torch.cuda.is_available():
             raise RuntimeError('rda_planner_b200 needs a CUDA device (B200); there is no CPU fallback')
         self.lib = _cabi.load()
@@ -141,6 +144,9 @@ class RDA_solver:
         }
         self._keep = None
         self.obstacle_num = 0
+        self.use_graph = bool(graph)
+        self._graphs = {}
+        self._static = None
 
     def __del__(self):
         try:
@@ -243,6 +249,28 @@ class RDA_solver:
         out = self._outputs()
         it = self.iter_num if iter_num is None else iter_num
         thr = self.iter_threshold if iter_threshold is None else iter_threshold
+        if self.use_graph:
+            # one graph per (input buffers, iteration count, threshold): the launches read the inputs through
+            # their addresses, so a replay is valid exactly while the caller reuses the same tensors
+            key = (tuple(int(getattr(inp, k) or 0) for k in ('nom_s', 'nom_u', 'ref_s', 'ref_speed', 'obs_A', 'obs_b',
+                                                              'obs_kind', 'obs_count')), int(inp.obs_time_varying), int(it), float(thr))
+            g = self._graphs.get(key)
+            if g is None:
+                cur = torch.cuda.current_stream(self.device)
+                side = torch.cuda.Stream(self.device)
+                side.wait_stream(cur)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.stream(side):
+                    with torch.cuda.graph(g, stream=side):
+                        _cabi.check(self.lib.rda_solve(self._h, C.byref(inp), C.byref(out), int(it), float(thr),
+                                                       self._stream()), 'rda_solve (graph capture)')
+                cur.wait_stream(side)
+                if len(self._graphs) >= 8:
+                    self._graphs.pop(next(iter(self._graphs)))
+                self._graphs[key] = (g, self._keep)          # keep the captured input tensors alive
+                g = self._graphs[key]
+            g[0].replay()
+            return self._out
         with torch.cuda.device(self.device):
             _cabi.check(self.lib.rda_solve(self._h, C.byref(inp), C.byref(out), int(it), float(thr),
                                            self._stream()), 'rda_solve')
@@ -273,6 +301,31 @@ class RDA_solver:
     def launch_count(self):
         return self.lib.rda_last_launch_count(self._h)
 
+    def _solve_static(self, nom_s, nom_u, ref, ref_speed, A, b, kind, count, tv):
+        """graph=True, single instance: inputs are staged into persistent device buffers (one pinned host block, one
+        H2D copy each) so that the captured graph of the solve can be replayed every control step."""
+        T, N, E, dev = self.T, self.max_obs_num, self.max_edge_num, self.device
+        Tc = T + 1 if tv else 1
+        if self._static is None or self._static['Tc'] != Tc:
+            z = lambda *sh, dt=torch.float32: torch.zeros(sh, dtype=dt, device=dev)
+            self._static = {'Tc': Tc, 'nom_s': z(1, 3, T + 1), 'nom_u': z(1, 2, T), 'ref_s': z(1, 3, T + 1), 'ref_speed': z(1),
+                            'obs_A': z(1, max(N, 1), Tc, E, 2), 'obs_b': z(1, max(N, 1), Tc, E),
+                            'obs_kind': z(1, max(N, 1), dt=torch.int32), 'obs_count': z(1, dt=torch.int32)}
+            self._graphs.clear()
+        st = self._static
+        st['nom_s'].copy_(torch.as_tensor(nom_s, dtype=torch.float32)[None])
+        st['nom_u'].copy_(torch.as_tensor(nom_u, dtype=torch.float32)[None])
+        st['ref_s'].copy_(torch.as_tensor(ref, dtype=torch.float32)[None])
+        st['ref_speed'].fill_(ref_speed)
+        if N > 0:
+            st['obs_A'].copy_(torch.as_tensor(A, dtype=torch.float32)[None])
+            st['obs_b'].copy_(torch.as_tensor(b, dtype=torch.float32)[None])
+            st['obs_kind'].copy_(torch.as_tensor(kind, dtype=torch.int32)[None])
+        st['obs_count'].fill_(int(count))
+        return self.iterative_solve_batch(st['nom_s'], st['nom_u'], st['ref_s'], st['ref_speed'],
+                                          st['obs_A'] if N > 0 else None, st['obs_b'] if N > 0 else None,
+                                          st['obs_kind'] if N > 0 else None, st['obs_count'] if N > 0 else None, tv)
+
     def iterative_solve(self, nom_s, nom_u, ref_states, ref_speed, obstacle_list, **kwargs):
         """Reference signature (:573): numpy in, (u (2,T) ndarray, info dict) out."""
         if self.batch != 1:
@@ -286,10 +339,14 @@ class RDA_solver:
             A = b = kind = None
             count, tv = len(obstacle_list), False
         self.obstacle_num = len(obstacle_list)
-        res = self.iterative_solve_batch(np.asarray(nom_s, float)[None], np.asarray(nom_u, float)[None],
-                                         ref[None], np.array([ref_speed], float),
-                                         None if A is None else A[None], None if b is None else b[None],
-                                         None if kind is None else kind[None], np.array([count]), tv)
+        if self.use_graph:
+            res = self._solve_static(np.asarray(nom_s, float), np.asarray(nom_u, float), ref, float(ref_speed), A, b, kind,
+                                     count, tv)
+        else:
+            res = self.iterative_solve_batch(np.asarray(nom_s, float)[None], np.asarray(nom_u, float)[None],
+                                             ref[None], np.array([ref_speed], float),
+                                             None if A is None else A[None], None if b is None else b[None],
+                                             None if kind is None else kind[None], np.array([count]), tv)
         u = res['u'][0].double().cpu().numpy()
         s = res['s'][0].double().cpu().numpy()
         info = {'ref_traj_list': ref_states, 'opt_state_list': [s[:, t:t + 1] for t in range(T + 1)],

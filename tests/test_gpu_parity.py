@@ -381,3 +381,20 @@ def test_batched_su_pipeline_equals_one_warp_per_instance(monkeypatch, split):
             assert float((a[k] - b[k]).abs().max()) < 2e-5, (call, k, float((a[k] - b[k]).abs().max()))
     for k in res['0'][2]:
         assert float((res['0'][2][k] - res['1'][2][k]).abs().max()) < 1e-4, k
+
+
+def test_graph_replay_of_the_single_instance_api():
+    """RDA_solver(graph=True): the reference-signature call stages its inputs in persistent device buffers and replays
+    one CUDA graph per control step; results and warm-start evolution must be bit-identical to eager launches."""
+    from rda_planner_b200.rda_solver import RDA_solver
+    T, N = 10, 5
+    car = rectangle_robot()
+    gs = [RDA_solver(T, car, 4, N, iter_num=4, iter_threshold=0.0, time_print=False, graph=g) for g in (False, True)]
+    for k in range(4):
+        inst = make_instance(40 + k, T=T, N=N, E=4, lateral=(0.3, 3.0))
+        ref = [inst['ref'][:, t:t + 1] for t in range(T + 1)]
+        outs = [g.iterative_solve(inst['nom_s'], inst['nom_u'], ref, 4.0, list(inst['obstacles'])) for g in gs]
+        assert np.array_equal(outs[0][0], outs[1][0]), k
+        assert np.array_equal(np.hstack(outs[0][1]['opt_state_list']), np.hstack(outs[1][1]['opt_state_list']))
+        assert abs(outs[0][1]['resi_pri'] - outs[1][1]['resi_pri']) <= 1e-5 * (1 + outs[0][1]['resi_pri'])
+    assert len(gs[1]._graphs) == 1
