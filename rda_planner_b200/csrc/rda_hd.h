@@ -43,6 +43,14 @@ RDA_HD double rcp_(double x) {
   return 1.0 / x;
 #endif
 }
+// index of the lowest set bit (m != 0)
+RDA_HD int ctz_(unsigned m) {
+#if defined(__CUDA_ARCH__)
+  return __ffs((int)m) - 1;
+#else
+  return __builtin_ctz(m);
+#endif
+}
 RDA_HD bool finite_(float x) { return isfinite(x); }
 RDA_HD bool finite_(double x) { return isfinite(x); }
 

@@ -60,6 +60,7 @@ struct rda_handle {
   // sub-batch overlap the kernels of the others
   cudaStream_t side[3];
   cudaEvent_t ev_fork, ev_join[3];
+  float su_prune;        // hinge pruning margin of the su-QP (su_solver.cuh; RDA_B200_SU_PRUNE, 0 = off)
   int slow_cpw, slow_ctas;   // k_cells_slow: cells per warp, CTAs per SM (RDA_B200_SLOW_CPW / RDA_B200_SLOW_CTAS)
   int split_min;         // smallest batch that is split (RDA_B200_SPLIT_MIN, default 2048)
   int parts;             // number of sub-batches, 1..4 (RDA_B200_SPLIT_PARTS, default 2)
@@ -211,6 +212,7 @@ __global__ void __launch_bounds__(32) k_su(DevPtrs d, SuParams P, int smem_per_i
     if (flag) d.status[b] |= flag;
     atomicAdd(&d.counters[3], iters);
     atomicAdd(&d.counters[4], 1);
+    if (W.restarts) atomicAdd(&d.counters[5], 1);      // pruned solve repeated with all hinges
   }
 }
 
@@ -528,9 +530,11 @@ __global__ void __launch_bounds__(128) k_cells_mid(DevPtrs d, RobotGeom rb, floa
     const bool live = wi < count;
     bool need = false;
     long long idx = 0;
+    int kind_of = RDA_OBS_POLYGON;
     if (live) {
       idx = d.worklist[wi];
       CellIn c = cell_load(d, idx);
+      kind_of = c.kind;
       CellWork<float> w;
       cell_front<float, false>(rb, c.kind, d.E, c.A, c.bb, c.px, c.py, c.cp, c.sp, c.dbar, c.zeta, c.xi0, c.xi1, ro2, w);
       if (w.have) {
@@ -547,7 +551,8 @@ __global__ void __launch_bounds__(128) k_cells_mid(DevPtrs d, RobotGeom rb, floa
     unsigned m = __ballot_sync(0xffffffffu, need);
     if (m) {
       int leader = __ffs(m) - 1, pos = 0;
-      if (lane == leader) pos = atomicAdd(&d.wl_count[1], __popc(m));
+      const unsigned mc = __ballot_sync(m, need && kind_of == RDA_OBS_CIRCLE);
+      if (lane == leader) { pos = atomicAdd(&d.wl_count[1], __popc(m)); if (mc) atomicAdd(&d.wl_count[3], __popc(mc)); }
       pos = __shfl_sync(0xffffffffu, pos, leader);
       if (need) d.worklist2[pos + __popc(m & ((1u << lane) - 1))] = (int)idx;
     }
@@ -569,9 +574,12 @@ __global__ void __launch_bounds__(128) k_cells_mid(DevPtrs d, RobotGeom rb, floa
 __global__ void __launch_bounds__(64, RDA_SLOW_MINBLOCKS) k_cells_slow(DevPtrs d, RobotGeom rb, float ro2, float theta, int cpw) {
   const int count = d.wl_count[1];
   const int lane = threadIdx.x & 31;
-  if (lane >= cpw) return;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  // Disc cells run the (long, strongly divergent) barrier iteration: when the list is mostly discs and short enough, one
+  // cell per warp (r02: 6.5x on BASELINE config C at 128 instances); polygon lists are fastest packed 32 per warp.
+  if (2 * d.wl_count[3] > count && count <= nwarps) cpw = 1;
+  if (lane >= cpw) return;
   for (int wi = warp * cpw + lane; wi < count; wi += nwarps * cpw) {
     const long long idx = d.worklist2[wi];
     CellIn c = cell_load(d, idx);
@@ -601,7 +609,7 @@ __global__ void __launch_bounds__(64, RDA_SLOW_MINBLOCKS) k_cells_slow(DevPtrs d
 // per instance: residuals (:688, :735-739), early stop (:594-596), empty-list quirk (:564-568)
 __global__ void k_finalize(DevPtrs d, RobotGeom rb, float thr) {
   int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b == 0) { d.wl_count[0] = 0; d.wl_count[1] = 0; d.wl_count[2] = 0; }   // worklists consumed
+  if (b == 0) { d.wl_count[0] = 0; d.wl_count[1] = 0; d.wl_count[2] = 0; d.wl_count[3] = 0; }   // worklists consumed
   if (b >= d.B) return;
   if (d.done[b]) return;
   const int T = d.T, N = d.N, NT = N * T, R = d.R;
@@ -674,7 +682,7 @@ DevPtrs dev_ptrs(const rda_handle* h, int b0, int nb, int part) {
   d.ref_speed = h->ref_speed + o; d.resi_acc = h->resi_acc + 2 * o; d.resi_pri = h->resi_pri + o;
   d.resi_dual = h->resi_dual + o;
   d.status = h->status + o; d.iters = h->iters + o; d.done = h->done + o;
-  d.counters = h->counters; d.wl_count = h->counters + 8 + 3 * part;     // part < 4
+  d.counters = h->counters; d.wl_count = h->counters + 8 + 4 * part;     // part < 4
   d.ogeo = h->ogeo ? h->ogeo + o * N : nullptr;
   d.feat = h->feat ? h->feat + o * NT : nullptr;
   d.worklist0 = h->worklist0 ? h->worklist0 + o * NT : nullptr;
@@ -702,6 +710,7 @@ SuParams su_params(const rda_handle* h) {
   P.ro1 = h->tun.ro1; P.ro2 = h->tun.ro2;
   P.max_iter = 40;
   P.mu0 = 1.0f;
+  P.prune = h->su_prune;
   return P;
 }
 
@@ -756,7 +765,7 @@ int rda_create(const rda_config* cfg, const rda_tunables* tun, rda_handle** out)
   alloc(&h->cur_u, B * 2 * T); alloc(&h->ref_s, B * 3 * (T + 1)); alloc(&h->ref_speed, B);
   alloc(&h->resi_acc, B * 2); alloc(&h->resi_pri, B); alloc(&h->resi_dual, B);
   alloc((float**)&h->status, B); alloc((float**)&h->iters, B); alloc((float**)&h->done, B);
-  alloc((float**)&h->counters, 24);     // [0..4] statistics, [8..11] worklist lengths of the two halves
+  alloc((float**)&h->counters, 32);     // [0..4] statistics, [8..11] worklist lengths of the two halves
   alloc((float**)&h->worklist, B * NT);
   alloc((float**)&h->worklist2, B * NT);
   alloc((float**)&h->su_ws, B * (h->su_ws_stride / 4));
@@ -809,6 +818,8 @@ int rda_create(const rda_config* cfg, const rda_tunables* tun, rda_handle** out)
   }
   h->split_min = 2048;
   h->parts = 2;
+  h->su_prune = 1.0f;
+  if (const char* v = getenv("RDA_B200_SU_PRUNE")) { float x = (float)atof(v); if (x >= 0.f) h->su_prune = x; }
   h->slow_cpw = RDA_SLOW_CPW; h->slow_ctas = 16;
   if (const char* v = getenv("RDA_B200_SLOW_CPW")) { int x = atoi(v); if (x >= 1 && x <= 32) h->slow_cpw = x; }
   if (const char* v = getenv("RDA_B200_SLOW_CTAS")) { int x = atoi(v); if (x >= 1 && x <= 256) h->slow_ctas = x; }
@@ -873,7 +884,7 @@ int rda_cold_start(rda_handle* h, void* stream) {
   RDA_CUDA(cudaMemsetAsync(h->status, 0, B * 4, s));
   RDA_CUDA(cudaMemsetAsync(h->iters, 0, B * 4, s));
   RDA_CUDA(cudaMemsetAsync(h->done, 0, B * 4, s));
-  RDA_CUDA(cudaMemsetAsync(h->counters, 0, 24 * 4, s));
+  RDA_CUDA(cudaMemsetAsync(h->counters, 0, 32 * 4, s));
   if (h->feat) RDA_CUDA(cudaMemsetAsync(h->feat, 0, B * NT, s));
   k_fill<<<grid_for((long long)(B * T), 256), 256, 0, s>>>(h->dis, 1.0f, B * T);   // para_dis = 1 (:119)
   RDA_CUDA(cudaGetLastError());

@@ -32,6 +32,8 @@ struct SuParams {
   float slack_gain, dmin, dmax, ro1, ro2;
   int max_iter;
   float mu0;      // initial complementarity of the interior point iteration
+  float prune;    // > 0: hinges whose value at the nominal point exceeds it even for d = max_sd are left out of
+                  // the interior point iteration and verified afterwards (accelerated mode only); 0: keep all
 };
 
 // Per-instance workspace.  All arrays indexed by stage t (0..T-1) unless noted; hinge arrays indexed
@@ -48,6 +50,7 @@ struct SuWork {
   float *pref;                // 2T positions the hinge offsets refer to
   float *hx, *hy, *hc;        // hinge rows: lam'A (2) and offset
   Slk *hs, *hnu;              // hinge slack / multiplier
+  unsigned *hmask;            // T x ceil(N/32) words: hinges of stage t that take part in the interior point iteration
   Slk *bs, *bnu;              // 10T box/rate slack / multiplier
   Real *Wm;                   // 3T hinge Hessian of the position block after the elimination of d_t (xx, xy, yy)
   Real *Ed;                   // 3T elimination of d_t: (M_xd / Q_dd, M_yd / Q_dd, 1 / Q_dd)
@@ -63,6 +66,7 @@ struct SuWork {
                               // step is produced by the forward sweep that follows it and is dead before
                               // the next predictor assembles (Wm, wb) again.
   Real vref;
+  int restarts;               // out: 1 when the pruned solve failed its verification and was repeated with all hinges
 };
 
 // Workspace placement.  `base` is the fast memory of the instance (shared memory on the GPU), `gbase` an
@@ -95,6 +99,7 @@ RDA_HD size_t su_work_layout(int T, int N, SuWork<Real, Slk>* w, char* base, boo
   RDA_TAKE_S(ref, 3 * (T + 1), float) RDA_TAKE_S(lins, 3 * (T + 1), float)
   RDA_TAKE_S(Aj, 2 * T, Real) RDA_TAKE_S(Bj, 6 * T, Real)
   RDA_TAKE_S(Skk, T, Real) RDA_TAKE_S(Sgk, T, Real) RDA_TAKE_S(pref, 2 * T, float)
+  RDA_TAKE_S(hmask, T * ((N + 31) / 32 > 0 ? (N + 31) / 32 : 1), unsigned)
   if (hinge_arrays) {
     RDA_TAKE_S(hx, N * T, float) RDA_TAKE_S(hy, N * T, float) RDA_TAKE_S(hc, N * T, float)
     RDA_TAKE_S(hs, N * T, Slk) RDA_TAKE_S(hnu, N * T, Slk)
@@ -355,8 +360,21 @@ RDA_HD int su_solve(const SuParams& P, SuWork<Real, Slk>& W, Ctx& ctx, const flo
     W.u[2 * t] = ut[0]; W.u[2 * t + 1] = ut[1];
   }
   ctx.sync();
-  // ---- initial iterate: roll the linearised model out from s_0 ----
-  if (lane == 0) {
+  // Hinge pruning (accelerated mode).  A hinge 1/2 ro1 neg(l)^2 that is inactive at the minimiser changes neither the
+  // cost nor its gradient there, so the minimiser of the problem WITHOUT such hinges is the minimiser of the full
+  // problem provided every left-out hinge ends with l >= 0 — which is verified after convergence; a violation
+  // repeats the interior point iteration with all hinges, started from the (dynamically feasible) point reached.  Left out: hinges with l > prune at the nominal point even for d = max_sd
+  // (obstacles the robot is far from: ~3/4 of the hinges of the bench workload), so the per-hinge passes — about
+  // two thirds of this kernel's time (profiles/ncu_r02_ksu_lines_before.md) — run over the rest only.
+  const int NW = (N + 31) / 32 > 0 ? (N + 31) / 32 : 1;
+  const bool can_prune = acc && N > 0 && P.prune > 0;
+  int status = 1, it = 0, it_total = 0;
+  W.restarts = 0;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+  const bool full = !can_prune || attempt == 1;
+  W.restarts = attempt;
+  // ---- initial iterate: roll the linearised model out from s_0 (second attempt: continue from the point reached) ----
+  if (lane == 0 && attempt == 0) {
     W.s[0] = W.lins[0]; W.s[1] = W.lins[1]; W.s[2] = W.lins[2];
     for (int t = 0; t < T; ++t) {
       const Real* s0 = W.s + 3 * t;
@@ -379,13 +397,27 @@ RDA_HD int su_solve(const SuParams& P, SuWork<Real, Slk>& W, Ctx& ctx, const flo
     }
     if (acc) {
       Real dx = W.s[3 * t + 3] - W.pref[2 * t], dy = W.s[3 * t + 4] - W.pref[2 * t + 1];
+      for (int w = 0; w < NW; ++w) W.hmask[t * NW + w] = 0u;
+      // the two hinges nearest to activity always take part: they keep d_t's direction curved (a stage without any
+      // hinge leaves d_t to its bounds alone, on which Mehrotra's single step length was seen to cycle)
+      Real lmin1 = (Real)1e30, lmin2 = (Real)1e30;
+      if (!full)
+        for (int o = 0; o < N; ++o) {
+          const Real lp = (Real)W.hx[o * T + t] * dx + (Real)W.hy[o * T + t] * dy + (Real)W.hc[o * T + t];
+          if (lp < lmin1) { lmin2 = lmin1; lmin1 = lp; } else if (lp < lmin2) lmin2 = lp;
+        }
       for (int o = 0; o < N; ++o) {
-        Real l = (Real)W.hx[o * T + t] * dx + (Real)W.hy[o * T + t] * dy + (Real)W.hc[o * T + t] - W.d[t];
+        const Real lp = (Real)W.hx[o * T + t] * dx + (Real)W.hy[o * T + t] * dy + (Real)W.hc[o * T + t];
+        if (!full && lp - (Real)P.dmax > (Real)P.prune && lp > lmin2) continue;        // left out, verified after convergence
+        W.hmask[t * NW + (o >> 5)] |= 1u << (o & 31);
+        Real l = lp - W.d[t];
         Real sv = (l + sqrt_(l * l + 4 * mu0 / ro1)) / 2;
         W.hs[o * T + t] = sv;
         W.hnu[o * T + t] = mu0 / sv;
         ++nrows;
       }
+    } else {
+      for (int w = 0; w < NW; ++w) W.hmask[t * NW + w] = (N - 32 * w >= 32) ? 0xffffffffu : ((N - 32 * w > 0) ? ((1u << (N - 32 * w)) - 1u) : 0u);
     }
   }
   const Real Mrows = ctx.sum((Real)nrows);
@@ -396,8 +428,9 @@ RDA_HD int su_solve(const SuParams& P, SuWork<Real, Slk>& W, Ctx& ctx, const flo
   const Real tol_step = sizeof(Real) == 4 ? (Real)2e-4 : (Real)1e-6;
   const Real tol_floor = sizeof(Real) == 4 ? (Real)1e-7 : (Real)1e-13;
   Real last_step = 1e30f;       // size of the previous Newton update (stationarity proxy)
-  int status = 1, it = 0;
-  for (it = 0; it < P.max_iter; ++it) {
+  status = 1;
+  const int it_cap = full ? P.max_iter : (P.max_iter < 24 ? P.max_iter : 24);     // pruned attempt: give up earlier
+  for (it = 0; it < it_cap; ++it) {
     Real sigma_mu = 0;
     Real mu = 0;
     for (int phase = 0; phase < 2; ++phase) {
@@ -447,17 +480,21 @@ RDA_HD int su_solve(const SuParams& P, SuWork<Real, Slk>& W, Ctx& ctx, const flo
         // hinges in chunks of RDA_SU_CH: all (global-memory) loads of a chunk are issued before its arithmetic
         const Real adx = phase == 1 ? W.dza[5 * t + 5] : (Real)0, ady = phase == 1 ? W.dza[5 * t + 6] : (Real)0;
         const Real add = phase == 1 ? W.dva[3 * t + 2] : (Real)0;
-        for (int o0 = 0; o0 < N; o0 += RDA_SU_CH) {
+        for (int w_ = 0; w_ < NW; ++w_) {
+          unsigned m_ = W.hmask[t * NW + w_];
+          while (m_) {
+          int oi[RDA_SU_CH], cnt_ = 0;
           Real axv[RDA_SU_CH], ayv[RDA_SU_CH], hcv[RDA_SU_CH], svv[RDA_SU_CH], nuv[RDA_SU_CH];
 #pragma unroll
           for (int k = 0; k < RDA_SU_CH; ++k) {
-            const int i = (o0 + k < N ? o0 + k : N - 1) * T + t;
+            if (m_) { oi[k] = (32 * w_ + ctz_(m_)) * T + t; m_ &= m_ - 1u; cnt_ = k + 1; } else oi[k] = oi[0];
+            const int i = oi[k];
             axv[k] = W.hx[i]; ayv[k] = W.hy[i]; hcv[k] = W.hc[i];
             svv[k] = acc ? (Real)W.hs[i] : (Real)1; nuv[k] = acc ? (Real)W.hnu[i] : (Real)1;
           }
 #pragma unroll
           for (int k = 0; k < RDA_SU_CH; ++k) {
-            if (o0 + k >= N) break;
+            if (k >= cnt_) break;
             const Real ax = axv[k], ay = ayv[k];
             const Real l = ax * dx + ay * dy + hcv[k] - dd;
             Real tk, om;
@@ -487,6 +524,7 @@ RDA_HD int su_solve(const SuParams& P, SuWork<Real, Slk>& W, Ctx& ctx, const flo
               m0 += om * ax * ax; m1 += om * ax * ay; m2 -= om * ax;
               m3 += om * ay * ay; m4 -= om * ay; m5 += om;
             }
+          }
           }
         }
         // eliminate d_t (it enters stage t only): Schur complement on Q_dd = reg + barrier weights + sum om
@@ -541,16 +579,20 @@ RDA_HD int su_solve(const SuParams& P, SuWork<Real, Slk>& W, Ctx& ctx, const flo
           const Real dx = W.s[3 * t + 3] - W.pref[2 * t], dy = W.s[3 * t + 4] - W.pref[2 * t + 1], dd = W.d[t];
           const Real zdx = dz[5 * t + 5], zdy = dz[5 * t + 6], zdd = dv[3 * t + 2];
           const Real adx = W.dza[5 * t + 5], ady = W.dza[5 * t + 6], add = W.dva[3 * t + 2];
-          for (int o0 = 0; o0 < N; o0 += RDA_SU_CH) {
+          for (int w_ = 0; w_ < NW; ++w_) {
+            unsigned m_ = W.hmask[t * NW + w_];
+            while (m_) {
+            int oi[RDA_SU_CH], cnt_ = 0;
             Real axv[RDA_SU_CH], ayv[RDA_SU_CH], hcv[RDA_SU_CH], svv[RDA_SU_CH], nuv[RDA_SU_CH];
 #pragma unroll
             for (int k = 0; k < RDA_SU_CH; ++k) {
-              const int i = (o0 + k < N ? o0 + k : N - 1) * T + t;
+              if (m_) { oi[k] = (32 * w_ + ctz_(m_)) * T + t; m_ &= m_ - 1u; cnt_ = k + 1; } else oi[k] = oi[0];
+              const int i = oi[k];
               axv[k] = W.hx[i]; ayv[k] = W.hy[i]; hcv[k] = W.hc[i]; svv[k] = W.hs[i]; nuv[k] = W.hnu[i];
             }
 #pragma unroll
             for (int k = 0; k < RDA_SU_CH; ++k) {
-              if (o0 + k >= N) break;
+              if (k >= cnt_) break;
               const Real ax = axv[k], ay = ayv[k], sv = svv[k], nu = nuv[k];
               const Real l = ax * dx + ay * dy + hcv[k] - dd;
               const Real nr = nu * iro1;
@@ -570,6 +612,7 @@ RDA_HD int su_solve(const SuParams& P, SuWork<Real, Slk>& W, Ctx& ctx, const flo
               const Real ip = rcp_(sv * nu);
               rmaxr = rmax(rmaxr, rmax(-ds * nu * ip, -dn * sv * ip));
               s0 += sv * nu; s1 += sv * dn + nu * ds; s2 += ds * dn;
+            }
             }
           }
         }
@@ -611,16 +654,20 @@ RDA_HD int su_solve(const SuParams& P, SuWork<Real, Slk>& W, Ctx& ctx, const flo
             const Real dx = W.s[3 * t + 3] - W.pref[2 * t], dy = W.s[3 * t + 4] - W.pref[2 * t + 1], dd = W.d[t];
             const Real zdx = W.dz[5 * t + 5], zdy = W.dz[5 * t + 6], zdd = W.dv[3 * t + 2];
             const Real adx = W.dza[5 * t + 5], ady = W.dza[5 * t + 6], add = W.dva[3 * t + 2];
-            for (int o0 = 0; o0 < N; o0 += RDA_SU_CH) {
+            for (int w_ = 0; w_ < NW; ++w_) {
+              unsigned m_ = W.hmask[t * NW + w_];
+              while (m_) {
+              int oi[RDA_SU_CH], cnt_ = 0;
               Real axv[RDA_SU_CH], ayv[RDA_SU_CH], hcv[RDA_SU_CH], svv[RDA_SU_CH], nuv[RDA_SU_CH];
 #pragma unroll
               for (int k = 0; k < RDA_SU_CH; ++k) {
-                const int i = (o0 + k < N ? o0 + k : N - 1) * T + t;
+                if (m_) { oi[k] = (32 * w_ + ctz_(m_)) * T + t; m_ &= m_ - 1u; cnt_ = k + 1; } else oi[k] = oi[0];
+                const int i = oi[k];
                 axv[k] = W.hx[i]; ayv[k] = W.hy[i]; hcv[k] = W.hc[i]; svv[k] = W.hs[i]; nuv[k] = W.hnu[i];
               }
 #pragma unroll
               for (int k = 0; k < RDA_SU_CH; ++k) {
-                if (o0 + k >= N) break;
+                if (k >= cnt_) break;
                 const Real ax = axv[k], ay = ayv[k], sv = svv[k], nu = nuv[k];
                 const Real l = ax * dx + ay * dy + hcv[k] - dd;
                 const Real nr = nu * iro1;
@@ -634,8 +681,9 @@ RDA_HD int su_solve(const SuParams& P, SuWork<Real, Slk>& W, Ctx& ctx, const flo
                 const Real cc = sv * nu - sigma_mu + dsa * dna;
                 const Real dn = -(cc + nu * res + nu * dir) * iden;
                 const Real ds = dir + dn * iro1 + res;
-                W.hs[(o0 + k) * T + t] = sv + a * ds;
-                W.hnu[(o0 + k) * T + t] = nu + a * dn;
+                W.hs[oi[k]] = sv + a * ds;
+                W.hnu[oi[k]] = nu + a * dn;
+              }
               }
             }
           }
@@ -656,7 +704,26 @@ RDA_HD int su_solve(const SuParams& P, SuWork<Real, Slk>& W, Ctx& ctx, const flo
     }
     if (status != 1) break;
   }
-  if (iters_out) *iters_out = it;
+  it_total += it;
+  if (full || status == 2) break;
+  if (status == 1) continue;          // the pruned problem did not converge (iteration cap): repeat with all hinges
+  // verification of the left-out hinges at the solution: any l < 0 means the pruned problem was not equivalent
+  {
+    int viol = 0;
+    for (int t = lane; t < T; t += nl) {
+      const Real dx = W.s[3 * t + 3] - W.pref[2 * t], dy = W.s[3 * t + 4] - W.pref[2 * t + 1], dd = W.d[t];
+      for (int o = 0; o < N; ++o) {
+        if (W.hmask[t * NW + (o >> 5)] & (1u << (o & 31))) continue;
+        const Real l = (Real)W.hx[o * T + t] * dx + (Real)W.hy[o * T + t] * dy + (Real)W.hc[o * T + t] - dd;
+        if (l < (Real)0) viol = 1;
+      }
+    }
+    viol = ctx.max(viol);
+    if (!viol) break;
+  }
+  ctx.sync();
+  }   // attempt
+  if (iters_out) *iters_out = it_total;
   return status;
 }
 

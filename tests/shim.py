@@ -15,7 +15,7 @@ class SuParams(C.Structure):
                 ('dt', C.c_float), ('L', C.c_float), ('umax', C.c_float * 2), ('ab', C.c_float * 2),
                 ('ws', C.c_float), ('wu', C.c_float), ('slack_gain', C.c_float), ('dmin', C.c_float),
                 ('dmax', C.c_float), ('ro1', C.c_float), ('ro2', C.c_float), ('max_iter', C.c_int),
-                ('mu0', C.c_float)]
+                ('mu0', C.c_float), ('prune', C.c_float)]
 
 
 def build(force=False):
