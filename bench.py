@@ -326,7 +326,43 @@ def extra_probes(dev, solver, devin, B):
         return one.iterative_solve_batch(d1['nom_s'], d1['nom_u'], d1['ref_s'], d1['ref_speed'], d1['obs_A'], d1['obs_b'],
                                          d1['obs_kind'], d1['obs_count'], False)
     ms1, _ = timed(single, 3)
-    out['single_instance'] = {'latency_ms': ms1, 'what': 'one instance, 50 iterations, cold start, inputs on the device'}
+    out['single_instance'] = {'latency_ms': ms1, 'what': 'one instance, 50 iterations, cold start, inputs on the device '
+                                                         '(single-launch persistent kernel, SURVEY §8 f4)'}
+    # the reference's own use case (example/path_track/path_track.py:22): T=10, N=11, iter_num=2, one robot, warm-started
+    # control steps through the numpy-in / numpy-out API (host copies included), eager and with CUDA-graph replay
+    from rda_planner_b200.scenarios import make_instance, CONFIGS
+    inst = make_instance(4242, T=10, N=11, E=4, lateral=(1.5, 6.0))
+    ref = [inst['ref'][:, t:t + 1] for t in range(11)]
+    lat = {}
+    for name, graph in (('eager', False), ('graph', True)):
+        sv = RDA_solver(10, rectangle_robot(), max_edge_num=4, max_obs_num=11, iter_num=2, time_print=False, device=dev, graph=graph,
+                        ro1=300)
+        for _ in range(3):
+            sv.iterative_solve(inst['nom_s'], inst['nom_u'], ref, 4.0, list(inst['obstacles']))
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for _ in range(20):
+            sv.iterative_solve(inst['nom_s'], inst['nom_u'], ref, 4.0, list(inst['obstacles']))
+        torch.cuda.synchronize(dev)
+        lat[name] = (time.perf_counter() - t0) / 20 * 1e3
+    out['path_track_control_step'] = {'latency_ms': lat, 'what': 'T=10, N=11, iter_num=2, one instance, reference signature '
+                                      '(numpy in/out, host<->device copies and packing included), warm-started'}
+    # BASELINE configs B and C at their stated single-GPU batch (strong-scaling side benches: bench.py --config B|C|D|E)
+    for cname in ('B', 'C'):
+        c = CONFIGS[cname]
+        h = build_inputs(c['global_batch'], 7000, cname)
+        di = {k: torch.from_numpy(v).to(dev) for k, v in h.items()}
+        tv = h['obs_A'].shape[2] > 1
+        sv = RDA_solver(c['T'], rectangle_robot(dynamics=c['dynamics']), max_edge_num=c['E'], max_obs_num=c['N'], iter_num=c['iter_num'],
+                        iter_threshold=0.0, time_print=False, batch=c['global_batch'], device=dev, **c['tun'])
+
+        def cfg_step():
+            sv.cold_start()
+            return sv.iterative_solve_batch(di['nom_s'], di['nom_u'], di['ref_s'], di['ref_speed'], di['obs_A'], di['obs_b'],
+                                            di['obs_kind'], di['obs_count'], tv)
+        msc, r = timed(cfg_step, 2)
+        out[f'config_{cname}'] = {'solves_per_s': c['global_batch'] / (msc * 1e-3), 'batch': c['global_batch'], 'what': c['what'],
+                                  'kept_previous_iterate': int((r['status'] & 6).ne(0).sum())}
     return out
 
 
@@ -543,7 +579,7 @@ def main():
                      'k_cells': {'achieved': k2b * B / (t_cells * 1e-3) / 1e9, 'frac': k2b * B / (t_cells * 1e-3) / 1e9 / peak},
                      'k_su': {'achieved': k1b * B / (t_su * 1e-3) / 1e9, 'frac': k1b * B / (t_su * 1e-3) / 1e9 / peak}},
         'counters': {'cells_fast': counters[0], 'cells_slow': counters[1], 'cells_failed': counters[2],
-                     'su_ipm_iterations': counters[3], 'su_solves': counters[4]},
+                     'su_ipm_iterations': counters[3], 'su_solves': counters[4], 'su_pruned_solves_repeated': counters[5]},
         'status_nonzero': int((status.cpu() != 0).sum()),
         'status_bits': {'su_iteration_cap(1)': int(((status.cpu() & 1) != 0).sum()),
                         'su_nonfinite_keep_previous(2)': int(((status.cpu() & 2) != 0).sum()),

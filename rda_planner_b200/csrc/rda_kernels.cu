@@ -26,6 +26,11 @@ using namespace rda;
 // ~12 warps per SM that registers allow, so more instances per warp is more throughput once the batch is
 // large enough to fill the SMs (su_group_for).
 
+// byte offsets of the persistent kernel's shared-memory state (k_admm_small)
+struct SmallLayout {
+  int lam, mu, z, xi, zeta, dis, coef, pref, cur_s, cur_u, ref_s, misc, hs, su, total;
+};
+
 struct rda_handle {
   rda_config cfg;
   rda_tunables tun;
@@ -60,6 +65,10 @@ struct rda_handle {
   // sub-batch overlap the kernels of the others
   cudaStream_t side[3];
   cudaEvent_t ev_fork, ev_join[3];
+  // persistent single-launch ADMM for small batches (k_admm_small)
+  int small_mode;        // -1: batches up to small_max instances, 0: never, 1: always when the state fits (RDA_B200_SMALL)
+  int small_max, small_ok;
+  SmallLayout small_L;
   float su_prune;        // hinge pruning margin of the su-QP (su_solver.cuh; RDA_B200_SU_PRUNE, 0 = off)
   int slow_cpw, slow_ctas;   // k_cells_slow: cells per warp, CTAs per SM (RDA_B200_SLOW_CPW / RDA_B200_SLOW_CTAS)
   int split_min;         // smallest batch that is split (RDA_B200_SPLIT_MIN, default 2048)
@@ -133,28 +142,12 @@ __global__ void k_begin(DevPtrs d, const float* nom_s, const float* nom_u, const
   }
 }
 
-// ------------------------------------------------------------------------------------------------
-// K1: su-QP, one warp per instance.
-// ------------------------------------------------------------------------------------------------
+// The su-QP of instance b: inputs from the persistent state (d), solve (su_solver.cuh), accepted result back.
+// W is laid out by the caller (hs / hnu and the workspace may live in shared or global memory).
 template <typename Real, int G>
-__global__ void __launch_bounds__(32) k_su(DevPtrs d, SuParams P, int smem_per_instance) {
-  constexpr int LEVEL = G == 32 ? 0 : (G == 16 ? 1 : 2);      // workspace placement of sub-warp groups (su_work_layout)
-  extern __shared__ __align__(16) char smem[];
-  constexpr int PER_WARP = 32 / G;
-  const int grp = (threadIdx.x & 31) / G;
-  const int b = blockIdx.x * PER_WARP + grp;
-  if (b >= d.B) return;
-  if (d.done[b]) return;
-  GroupCtx<G> ctx;
+__device__ __forceinline__ void su_instance(const DevPtrs& d, const SuParams& P, int b, SuWork<Real, Real>& W, GroupCtx<G>& ctx) {
   const int T = P.T, N = P.N, NT = N * T;
   const int lane = ctx.lane();
-  SuWork<Real, Real> W;
-  // per-hinge data stays in global memory (L2): every entry is touched only by the lane that owns
-  // its stage, consecutive lanes read consecutive addresses.  With sub-warp groups (level > 0) the
-  // Riccati gains / stage arrays live there too, so that shared memory does not limit the number of
-  // resident instances.
-  su_work_layout<Real, Real, LEVEL>(T, N, &W, smem + (size_t)grp * smem_per_instance, false,
-                                    d.su_ws + (size_t)b * d.su_ws_stride);
   const float* cs = d.cur_s + (size_t)b * 3 * (T + 1);   // [3][T+1]
   const float* cu = d.cur_u + (size_t)b * 2 * T;         // [2][T]
   const float* rf = d.ref_s + (size_t)b * 3 * (T + 1);
@@ -214,6 +207,31 @@ __global__ void __launch_bounds__(32) k_su(DevPtrs d, SuParams P, int smem_per_i
     atomicAdd(&d.counters[4], 1);
     if (W.restarts) atomicAdd(&d.counters[5], 1);      // pruned solve repeated with all hinges
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1: su-QP, one warp per instance.
+// ------------------------------------------------------------------------------------------------
+template <typename Real, int G>
+__global__ void __launch_bounds__(32) k_su(DevPtrs d, SuParams P, int smem_per_instance) {
+  constexpr int LEVEL = G == 32 ? 0 : (G == 16 ? 1 : 2);      // workspace placement of sub-warp groups (su_work_layout)
+  extern __shared__ __align__(16) char smem[];
+  constexpr int PER_WARP = 32 / G;
+  const int grp = (threadIdx.x & 31) / G;
+  const int b = blockIdx.x * PER_WARP + grp;
+  if (b >= d.B) return;
+  if (d.done[b]) return;
+  GroupCtx<G> ctx;
+  const int T = P.T, N = P.N, NT = N * T;
+  const int lane = ctx.lane();
+  SuWork<Real, Real> W;
+  // per-hinge data stays in global memory (L2): every entry is touched only by the lane that owns
+  // its stage, consecutive lanes read consecutive addresses.  With sub-warp groups (level > 0) the
+  // Riccati gains / stage arrays live there too, so that shared memory does not limit the number of
+  // resident instances.
+  su_work_layout<Real, Real, LEVEL>(T, N, &W, smem + (size_t)grp * smem_per_instance, false,
+                                    d.su_ws + (size_t)b * d.su_ws_stride);
+  su_instance<Real, G>(d, P, b, W, ctx);
 }
 
 // inputs of one cell gathered from the persistent state
@@ -607,11 +625,7 @@ __global__ void __launch_bounds__(64, RDA_SLOW_MINBLOCKS) k_cells_slow(DevPtrs d
 }
 
 // per instance: residuals (:688, :735-739), early stop (:594-596), empty-list quirk (:564-568)
-__global__ void k_finalize(DevPtrs d, RobotGeom rb, float thr) {
-  int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b == 0) { d.wl_count[0] = 0; d.wl_count[1] = 0; d.wl_count[2] = 0; d.wl_count[3] = 0; }   // worklists consumed
-  if (b >= d.B) return;
-  if (d.done[b]) return;
+__device__ __forceinline__ void finalize_instance(const DevPtrs& d, const RobotGeom& rb, float thr, int b) {
   const int T = d.T, N = d.N, NT = N * T, R = d.R;
   float pri = 0.f, dual = 0.f;
   if (N > 0 && d.obs_count[b] != 0) {
@@ -633,6 +647,127 @@ __global__ void k_finalize(DevPtrs d, RobotGeom rb, float thr) {
   d.resi_acc[2 * b] = 0.f; d.resi_acc[2 * b + 1] = 0.f;
   d.resi_pri[b] = pri; d.resi_dual[b] = dual;
   if (dual < thr && pri < thr) { d.done[b] = 1; d.status[b] |= RDA_ST_EARLY_STOP; }
+}
+
+__global__ void k_finalize(DevPtrs d, RobotGeom rb, float thr) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b == 0) { d.wl_count[0] = 0; d.wl_count[1] = 0; d.wl_count[2] = 0; d.wl_count[3] = 0; }   // worklists consumed
+  if (b >= d.B) return;
+  if (d.done[b]) return;
+  finalize_instance(d, rb, thr, b);
+}
+
+// ------------------------------------------------------------------------------------------------
+// the whole ADMM loop of one (small) instance in ONE launch, one CTA per instance, every piece of
+// warm-start state staged in shared memory for the duration of the solve (HBM is touched once on the way in and
+// once on the way out).  Warp 0 runs the su-QP (same code as k_su), all warps the cells (first the lean closed
+// forms, then the searched ones and the interior point fall-back in the same thread), thread 0 the residual /
+// early-stop rule.  The kernel reuses the device functions of the streaming kernels through a DevPtrs whose
+// pointers address shared memory, so the arithmetic is identical; instances progress independently (no grid-wide
+// barrier between the ADMM phases).
+// ------------------------------------------------------------------------------------------------
+static SmallLayout small_layout(int T, int N, int E, int R, size_t su_bytes) {
+  SmallLayout L;
+  size_t o = 0;
+  auto take = [&](size_t bytes) { o = (o + 15) & ~(size_t)15; size_t r = o; o += bytes; return (int)r; };
+  const size_t NT = (size_t)N * T;
+  L.lam = take(4 * N * E * T); L.mu = take(4 * N * R * T); L.z = take(4 * NT); L.xi = take(8 * NT); L.zeta = take(4 * NT);
+  L.dis = take(4 * T); L.coef = take(20 * NT); L.pref = take(8 * T); L.cur_s = take(12 * (T + 1)); L.cur_u = take(8 * T);
+  L.ref_s = take(12 * (T + 1)); L.misc = take(64); L.hs = take(16 * NT); L.su = take(su_bytes);
+  L.total = (int)((o + 15) & ~(size_t)15);
+  return L;
+}
+
+template <typename Real>
+__global__ void __launch_bounds__(128) k_admm_small(DevPtrs d, SuParams P, RobotGeom rb, float ro2, float theta, float thr,
+                                                    int iter_num, SmallLayout L, const float* nom_s, const float* nom_u,
+                                                    const float* ref_s, const float* ref_speed, rda_outputs out) {
+  extern __shared__ __align__(16) char smem[];
+  const int b = blockIdx.x;
+  if (b >= d.B) return;
+  const int T = d.T, N = d.N, E = d.E, R = d.R, NT = N * T, tid = threadIdx.x, nth = blockDim.x;
+  // ---- a one-instance view of the persistent state in shared memory ----
+  DevPtrs ds = d;
+  ds.B = 1;
+  ds.lam = (float*)(smem + L.lam); ds.mu = (float*)(smem + L.mu); ds.z = (float*)(smem + L.z); ds.xi = (float*)(smem + L.xi);
+  ds.zeta = (float*)(smem + L.zeta); ds.dis = (float*)(smem + L.dis); ds.coef = (float*)(smem + L.coef);
+  ds.pref = (float*)(smem + L.pref); ds.cur_s = (float*)(smem + L.cur_s); ds.cur_u = (float*)(smem + L.cur_u);
+  ds.ref_s = (float*)(smem + L.ref_s);
+  float* misc = (float*)(smem + L.misc);
+  ds.resi_acc = misc; ds.resi_pri = misc + 2; ds.resi_dual = misc + 3; ds.ref_speed = misc + 4;
+  ds.status = (int*)(misc + 5); ds.iters = (int*)(misc + 6); ds.done = (int*)(misc + 7);
+  const size_t Tc = d.obs_tv ? T + 1 : 1;
+  ds.obs_A = d.obs_A ? d.obs_A + (size_t)b * N * Tc * E * 2 : nullptr;
+  ds.obs_b = d.obs_b ? d.obs_b + (size_t)b * N * Tc * E : nullptr;
+  ds.obs_kind = d.obs_kind ? d.obs_kind + (size_t)b * N : nullptr;
+  ds.obs_count = d.obs_count ? d.obs_count + b : nullptr;
+  auto copy_in = [&](float* dst, const float* src, int n) { for (int i = tid; i < n; i += nth) dst[i] = src[i]; };
+  auto copy_out = [&](float* dst, const float* src, int n) { for (int i = tid; i < n; i += nth) dst[i] = src[i]; };
+  copy_in(ds.lam, d.lam + (size_t)b * N * E * T, N * E * T); copy_in(ds.mu, d.mu + (size_t)b * N * R * T, N * R * T);
+  copy_in(ds.z, d.z + (size_t)b * NT, NT); copy_in(ds.xi, d.xi + (size_t)b * 2 * NT, 2 * NT);
+  copy_in(ds.zeta, d.zeta + (size_t)b * NT, NT); copy_in(ds.dis, d.dis + (size_t)b * T, T);
+  copy_in(ds.coef, d.coef + (size_t)b * 5 * NT, 5 * NT); copy_in(ds.pref, d.pref + (size_t)b * 2 * T, 2 * T);
+  copy_in(ds.cur_s, nom_s + (size_t)b * 3 * (T + 1), 3 * (T + 1)); copy_in(ds.cur_u, nom_u + (size_t)b * 2 * T, 2 * T);
+  copy_in(ds.ref_s, ref_s + (size_t)b * 3 * (T + 1), 3 * (T + 1));
+  if (tid == 0) {
+    misc[0] = 0.f; misc[1] = 0.f; misc[2] = 0.f; misc[3] = 0.f; misc[4] = ref_speed[b];
+    ds.status[0] = 0; ds.iters[0] = 0; ds.done[0] = 0;
+  }
+  __syncthreads();
+  const bool has_obs = N > 0 && ds.obs_count[0] != 0;
+  for (int it = 0; it < iter_num; ++it) {
+    if (tid < 32) {
+      GroupCtx<32> ctx;
+      SuWork<Real, Real> W;
+      su_work_layout<Real, Real, 0>(T, N, &W, smem + L.su, false, smem + L.hs);
+      su_instance<Real, 32>(ds, P, 0, W, ctx);
+    }
+    __syncthreads();
+    if (has_obs) {
+      for (int idx = tid; idx < NT; idx += nth) {
+        CellIn c = cell_load(ds, idx);
+        CellWork<float> w;
+        cell_front<float>(rb, c.kind, E, c.A, c.bb, c.px, c.py, c.cp, c.sp, c.dbar, c.zeta, c.xi0, c.xi1, ro2, w);
+        if (!w.have) {
+          CellSlowStore S;
+          SeqCtx sc;
+          cell_slow<float, SeqCtx>(rb, w, S, sc);
+        }
+        CellOut<float> o;
+        cell_back<float>(rb, w, c.zeta, theta, o);
+        float hm2 = 0.f, dual = 0.f;
+        if (o.path == CELL_FAILED) {
+          dual = INFINITY;
+          atomicOr(&ds.status[0], RDA_ST_CELL_FALLBACK);
+        } else {
+          cell_store(ds, c, o, &hm2, &dual);
+        }
+        atomicAdd(&ds.resi_acc[0], hm2);
+        atomicAdd(&ds.resi_acc[1], dual);
+        atomicAdd(&d.counters[o.path == CELL_FAILED ? 2 : ((o.path == CELL_SLOW_A || o.path == CELL_SLOW_B) ? 1 : 0)], 1);
+      }
+    }
+    __syncthreads();
+    if (tid == 0) finalize_instance(ds, rb, thr, 0);
+    __syncthreads();
+    if (ds.done[0]) break;
+  }
+  // ---- state and results back to HBM ----
+  copy_out(d.lam + (size_t)b * N * E * T, ds.lam, N * E * T); copy_out(d.mu + (size_t)b * N * R * T, ds.mu, N * R * T);
+  copy_out(d.z + (size_t)b * NT, ds.z, NT); copy_out(d.xi + (size_t)b * 2 * NT, ds.xi, 2 * NT);
+  copy_out(d.zeta + (size_t)b * NT, ds.zeta, NT); copy_out(d.dis + (size_t)b * T, ds.dis, T);
+  copy_out(d.coef + (size_t)b * 5 * NT, ds.coef, 5 * NT); copy_out(d.pref + (size_t)b * 2 * T, ds.pref, 2 * T);
+  copy_out(d.cur_s + (size_t)b * 3 * (T + 1), ds.cur_s, 3 * (T + 1)); copy_out(d.cur_u + (size_t)b * 2 * T, ds.cur_u, 2 * T);
+  copy_out(d.ref_s + (size_t)b * 3 * (T + 1), ds.ref_s, 3 * (T + 1));
+  copy_out((float*)out.s_opt + (size_t)b * 3 * (T + 1), ds.cur_s, 3 * (T + 1));
+  copy_out((float*)out.u_opt + (size_t)b * 2 * T, ds.cur_u, 2 * T);
+  if (tid == 0) {
+    d.ref_speed[b] = misc[4];
+    d.resi_pri[b] = misc[2]; d.resi_dual[b] = misc[3]; d.resi_acc[2 * b] = 0.f; d.resi_acc[2 * b + 1] = 0.f;
+    d.status[b] = ds.status[0]; d.iters[b] = ds.iters[0]; d.done[b] = ds.done[0];
+    ((float*)out.resi_pri)[b] = misc[2]; ((float*)out.resi_dual)[b] = misc[3];
+    ((int*)out.status)[b] = ds.status[0]; ((int*)out.iters)[b] = ds.iters[0];
+  }
 }
 
 __global__ void k_finish(DevPtrs d, rda_outputs o) {
@@ -819,6 +954,19 @@ int rda_create(const rda_config* cfg, const rda_tunables* tun, rda_handle** out)
   h->split_min = 2048;
   h->parts = 2;
   h->su_prune = 1.0f;
+  {
+    const size_t sub = cfg->su_fp64 ? su_work_bytes<double, double, 0>((int)T, (int)N, false) : su_work_bytes<float, float, 0>((int)T, (int)N, false);
+    h->small_L = small_layout((int)T, (int)N, (int)E, (int)R, sub);
+    h->small_ok = h->small_L.total <= 200 * 1024;
+    h->small_mode = -1; h->small_max = 296;
+    if (const char* v = getenv("RDA_B200_SMALL")) { int x = atoi(v); if (x >= -1 && x <= 1) h->small_mode = x; }
+    if (const char* v = getenv("RDA_B200_SMALL_MAX")) { int x = atoi(v); if (x >= 1) h->small_max = x; }
+    if (h->small_ok) {
+      if (cfg->su_fp64) e = cudaFuncSetAttribute(k_admm_small<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->small_L.total);
+      else e = cudaFuncSetAttribute(k_admm_small<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->small_L.total);
+      if (e != cudaSuccess) { rda_destroy(h); return (int)e; }
+    }
+  }
   if (const char* v = getenv("RDA_B200_SU_PRUNE")) { float x = (float)atof(v); if (x >= 0.f) h->su_prune = x; }
   h->slow_cpw = RDA_SLOW_CPW; h->slow_ctas = 16;
   if (const char* v = getenv("RDA_B200_SLOW_CPW")) { int x = atoi(v); if (x >= 1 && x <= 32) h->slow_cpw = x; }
@@ -1085,6 +1233,23 @@ int rda_solve(rda_handle* h, const rda_inputs* in, const rda_outputs* out, int i
   cudaStream_t s0 = (cudaStream_t)stream;
   h->launches = 0;
   h->began = 1;
+  if (h->small_ok && (h->small_mode == 1 || (h->small_mode < 0 && h->B <= h->small_max))) {
+    // the whole solve of every instance in one launch, state staged in shared memory (k_admm_small)
+    DevPtrs d = dev_ptrs(h);
+    SuParams P = su_params(h);
+    const float theta = h->cfg.accelerated ? h->tun.z_theta : 1.0f;
+    if (h->cfg.su_fp64)
+      k_admm_small<double><<<h->B, 128, h->small_L.total, s0>>>(d, P, h->rb, h->tun.ro2, theta, iter_threshold, iter_num, h->small_L,
+                                                              (const float*)in->nom_s, (const float*)in->nom_u, (const float*)in->ref_s,
+                                                              (const float*)in->ref_speed, *out);
+    else
+      k_admm_small<float><<<h->B, 128, h->small_L.total, s0>>>(d, P, h->rb, h->tun.ro2, theta, iter_threshold, iter_num, h->small_L,
+                                                             (const float*)in->nom_s, (const float*)in->nom_u, (const float*)in->ref_s,
+                                                             (const float*)in->ref_speed, *out);
+    RDA_CUDA(cudaGetLastError());
+    h->launches = 1;
+    return 0;
+  }
   if (h->parts < 2 || h->B < h->split_min || h->B < h->parts) {
     rc = begin_part(h, in, 0, h->B, 0, s0);
     for (int i = 0; i < iter_num && !rc; ++i) {

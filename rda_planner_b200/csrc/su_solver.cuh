@@ -23,7 +23,7 @@
 namespace rda {
 
 #ifndef RDA_SU_CH
-#define RDA_SU_CH 4      // hinges per chunk of the su-QP hinge loops (loads grouped ahead of the arithmetic)
+#define RDA_SU_CH 2      // hinges per chunk of the su-QP hinge loops (loads grouped ahead of the arithmetic)
 #endif
 
 struct SuParams {
@@ -388,7 +388,7 @@ RDA_HD int su_solve(const SuParams& P, SuWork<Real, Slk>& W, Ctx& ctx, const flo
   const Real mu0 = P.mu0 > 0 ? (Real)P.mu0 : (Real)1;
   int nrows = 0;
   for (int t = lane; t < T; t += nl) {
-    for (int c = 0; c < 10; ++c) {
+    _Pragma("unroll 1") for (int c = 0; c < 10; ++c) {
       Row<Real> r = su_row<Real, Slk>(P, W, t, c);
       Real sv = r.live ? rmax(r.g, (Real)1e-2) : (Real)1;
       W.bs[10 * t + c] = sv;
@@ -449,7 +449,7 @@ RDA_HD int su_solve(const SuParams& P, SuWork<Real, Slk>& W, Ctx& ctx, const flo
         gw[5] = N > 0 ? -(Real)P.slack_gain + reg * W.d[t] : (Real)0;
         gw[6] = 0; gw[7] = 0;
         Real wb[5] = {0, 0, 0, 0, 0};
-        for (int c = 0; c < 10; ++c) {
+        _Pragma("unroll 1") for (int c = 0; c < 10; ++c) {
           Row<Real> r = su_row<Real, Slk>(P, W, t, c);
           if (!r.live) continue;
           Real sv = W.bs[10 * t + c], nu = W.bnu[10 * t + c];
@@ -556,7 +556,7 @@ RDA_HD int su_solve(const SuParams& P, SuWork<Real, Slk>& W, Ctx& ctx, const flo
       const Real* dv = phase == 0 ? W.dva : W.dv;
       Real rmaxr = 0, s0 = 0, s1 = 0, s2 = 0;   // rmaxr = max over rows of (-delta / value): 1 / max step
       for (int t = lane; t < T; t += nl) {
-        for (int c = 0; c < 10; ++c) {
+        _Pragma("unroll 1") for (int c = 0; c < 10; ++c) {
           Row<Real> r = su_row<Real, Slk>(P, W, t, c);
           if (!r.live) continue;
           Real sv = W.bs[10 * t + c], nu = W.bnu[10 * t + c];
@@ -634,8 +634,8 @@ RDA_HD int su_solve(const SuParams& P, SuWork<Real, Slk>& W, Ctx& ctx, const flo
         for (int t = lane; t < T; t += nl) {
           // rows first: they read the OLD iterate through su_row
           Real gsave[10];
-          for (int c = 0; c < 10; ++c) { Row<Real> r = su_row<Real, Slk>(P, W, t, c); gsave[c] = r.g; }
-          for (int c = 0; c < 10; ++c) {
+          _Pragma("unroll 1") for (int c = 0; c < 10; ++c) { Row<Real> r = su_row<Real, Slk>(P, W, t, c); gsave[c] = r.g; }
+          _Pragma("unroll 1") for (int c = 0; c < 10; ++c) {
             Row<Real> r = su_row<Real, Slk>(P, W, t, c);
             if (!r.live) continue;
             Real sv = W.bs[10 * t + c], nu = W.bnu[10 * t + c];

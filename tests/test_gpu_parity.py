@@ -252,6 +252,7 @@ def test_two_stream_split_is_invisible(monkeypatch, kind, moving):
     from rda_planner_b200.rda_solver import RDA_solver
     from rda_planner_b200 import _cabi
     T, N, B = 12, 6, 37
+    monkeypatch.setenv('RDA_B200_SMALL', '0')          # the streaming kernels, not the single-launch path of small batches
     car = rectangle_robot()
     insts, inp = _batch_inputs(B, T, N, 1500, lateral=(0.3, 3.5), kind=kind, moving=moving)
     dev = {k: torch.as_tensor(v, device='cuda', dtype=torch.int32 if 'kind' in k or 'count' in k else torch.float32)
@@ -338,6 +339,7 @@ def test_coherent_first_pass_matches_the_search_pass(monkeypatch):
     from rda_planner_b200.rda_solver import RDA_solver
     from rda_planner_b200 import _cabi
     T, N, B, iters = 12, 6, 96, 4
+    monkeypatch.setenv('RDA_B200_SMALL', '0')
     car = rectangle_robot()
     insts, inp = _batch_inputs(B, T, N, 2500, lateral=(1.0, 5.0))
     res = {}
@@ -364,6 +366,8 @@ def test_batched_su_pipeline_equals_one_warp_per_instance(monkeypatch, split):
     dev = {k: torch.as_tensor(v, device='cuda', dtype=torch.int32 if 'kind' in k or 'count' in k else torch.float32)
            for k, v in inp.items()}
     monkeypatch.setenv('RDA_B200_SPLIT_MIN', '2' if split else '1000000')
+    monkeypatch.setenv('RDA_B200_SMALL', '0')
+    monkeypatch.setenv('RDA_B200_SU_PRUNE', '0')       # the pipeline keeps every hinge: compare like with like
     res = {}
     for mode in ('0', '1'):
         monkeypatch.setenv('RDA_B200_SU_BATCHED', mode)
@@ -398,3 +402,40 @@ def test_graph_replay_of_the_single_instance_api():
         assert np.array_equal(np.hstack(outs[0][1]['opt_state_list']), np.hstack(outs[1][1]['opt_state_list']))
         assert abs(outs[0][1]['resi_pri'] - outs[1][1]['resi_pri']) <= 1e-5 * (1 + outs[0][1]['resi_pri'])
     assert len(gs[1]._graphs) == 1
+
+
+@pytest.mark.parametrize('kind,moving,dyn,N', [('polygon', False, 'acker', 6), ('circle', True, 'diff', 5), ('polygon', False, 'omni', 0)])
+def test_persistent_small_kernel_equals_streaming_kernels(monkeypatch, kind, moving, dyn, N):
+    """small batches run the whole ADMM loop in ONE launch, one CTA per instance, state in shared memory
+    (k_admm_small).  Same device functions as the streaming kernels: trajectories, residuals, early stop and the
+    persistent warm-start state must agree to float32 rounding, cold and warm-started."""
+    from rda_planner_b200.rda_solver import RDA_solver
+    from rda_planner_b200 import _cabi
+    T, B = 10, 9
+    car = rectangle_robot(dynamics=dyn)
+    insts, inp = _batch_inputs(B, T, max(N, 1), 3100, lateral=(0.3, 3.5), kind=kind, moving=moving, dynamics=dyn)
+    dev = {k: torch.as_tensor(v, device='cuda', dtype=torch.int32 if 'kind' in k or 'count' in k else torch.float32)
+           for k, v in inp.items()}
+    if N == 0:
+        dev = {k: v for k, v in dev.items() if not k.startswith('obs_')}
+    res = {}
+    for mode in ('0', '1'):
+        monkeypatch.setenv('RDA_B200_SMALL', mode)
+        g = RDA_solver(T, car, 4, N, iter_num=6, iter_threshold=0.3, time_print=False, batch=B)
+        out = {k: v.clone() for k, v in g.iterative_solve_batch(**dev, time_varying=moving).items()}
+        out2 = {k: v.clone() for k, v in g.iterative_solve_batch(**dev, time_varying=moving).items()}
+        bufs = (_cabi.BUF_DIS, _cabi.BUF_CUR_S) if N == 0 else (_cabi.BUF_LAM, _cabi.BUF_MU, _cabi.BUF_Z, _cabi.BUF_XI, _cabi.BUF_ZETA,
+                                                               _cabi.BUF_DIS, _cabi.BUF_COEF)
+        state = {b: g.state_buffer(b).clone() for b in bufs}
+        res[mode] = (out, out2, state, g.launch_count())
+    assert res['1'][3] == 1 and res['0'][3] > 5
+    for call in (0, 1):
+        a, b = res['0'][call], res['1'][call]
+        assert torch.equal(a['iters'], b['iters']), (call, a['iters'], b['iters'])
+        assert torch.equal(a['status'], b['status'])
+        for k in ('u', 's'):
+            assert float((a[k] - b[k]).abs().max()) < 2e-5, (call, k, float((a[k] - b[k]).abs().max()))
+        for k in ('resi_pri', 'resi_dual'):
+            assert torch.allclose(a[k], b[k], rtol=1e-4, atol=1e-5), (call, k)
+    for k in res['0'][2]:
+        assert float((res['0'][2][k] - res['1'][2][k]).abs().max()) < 1e-4, k

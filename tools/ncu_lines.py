@@ -18,7 +18,7 @@ rep, mangled, pretty, out = sys.argv[1:5]
 page = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv', '--kernel-name', f'regex:{pretty.split("<")[0]}'],
                       capture_output=True, text=True).stdout
 with tempfile.TemporaryDirectory() as tmp:
-    subprocess.run(['cuobjdump', '-xelf', 'all', os.path.join(ROOT, 'rda_planner_b200', 'librda_b200.so')], cwd=tmp, check=True,
+    subprocess.run(['cuobjdump', '-xelf', 'all', os.environ.get('RDA_LINES_SO', os.path.join(ROOT, 'rda_planner_b200', 'librda_b200.so'))], cwd=tmp, check=True,
                    capture_output=True)
     cub = [f for f in os.listdir(tmp) if f.startswith('rda_kernels.') and f.endswith('.cubin')][0]
     dis = subprocess.run(['nvdisasm', '-g', '-c', os.path.join(tmp, cub)], capture_output=True, text=True).stdout.splitlines()
