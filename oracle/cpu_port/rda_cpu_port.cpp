@@ -169,7 +169,7 @@ extern "C" int port_solve_batch(const rda_config* cfg, const rda_tunables* tun, 
   P.ws = cfg->ws; P.wu = cfg->wu; P.slack_gain = tun->slack_gain; P.dmin = tun->min_sd; P.dmax = tun->max_sd;
   P.ro1 = tun->ro1; P.ro2 = tun->ro2; P.max_iter = 40;
   P.mu0 = getenv("RDA_PORT_MU0") ? (float)atof(getenv("RDA_PORT_MU0")) : 1.0f;
-  P.prune = getenv("RDA_PORT_PRUNE") ? (float)atof(getenv("RDA_PORT_PRUNE")) : 1.0f;      // as the library default
+  P.prune = getenv("RDA_PORT_PRUNE") ? (float)atof(getenv("RDA_PORT_PRUNE")) : 0.5f;      // as the library default
   const float theta = cfg->accelerated ? tun->z_theta : 1.0f;
   if (nthreads > 0) omp_set_num_threads(nthreads);
   const size_t bytes = su_work_bytes<double>(T, N);
