@@ -437,50 +437,6 @@ RDA_HD void cell_front(const RobotGeom& rb, int kind, int E, const float* A, con
       }
     }
   }
-  if (!have && sep && kind != RDA_OBS_CIRCLE) {
-    // Robot-EDGE against obstacle-EDGE contact (disjoint sets, active hinge): the optimal body point lies in the
-    // interior of body edge j and its nearest obstacle point in the interior of obstacle edge i, so v = n_i and the
-    // distance n_i.(R y - V_i) is LINEAR along the body edge: the weighted margin N/W has the closed-form stationary
-    // point s* = -(beta a + alpha b)/(beta b + alpha c) (as in the overlap cases below), accepted through the KKT
-    // conditions.  (With the unweighted margin N is linear in s: no interior maximum, those are vertex contacts.)
-    const Real tolc = sizeof(Real) == 4 ? (Real)1e-5 : (Real)1e-11;
-    const Real tole = sizeof(Real) == 4 ? (Real)3e-5 : (Real)1e-9;
-    for (int j = 0; j < R && !have; ++j) {
-      const int jn = (j + 1) % R;
-      const Real yjx = rb.yx[j], yjy = rb.yy[j];
-      const Real fx = (Real)rb.yx[jn] - yjx, fy = (Real)rb.yy[jn] - yjy;            // body frame
-      const Real wfx = cphi * fx - sphi * fy, wfy = sphi * fx + cphi * fy;          // R f
-      const Real a_ = (Real)1 + (yjx * yjx + yjy * yjy) / ro2, b_ = (yjx * fx + yjy * fy) / ro2;
-      const Real c_ = (fx * fx + fy * fy) / ro2;
-      for (int i = 0; i < ne && !have; ++i) {
-        const Real nix = g.nx[i], niy = g.ny[i];
-        const Real nf = nix * wfx + niy * wfy;                                         // n_i . R f
-        const Real rho0 = nix * (g.yx[j] - g.vx[i]) + niy * (g.yy[j] - g.vy[i]);       // distance of R y_j to the edge line
-        const Real al = k0 - (xi0 * yjx + xi1 * yjy) - rho0, be = (xi0 * fx + xi1 * fy) + nf;
-        const Real den = be * b_ + al * c_;
-        if (!(abs_(den) > (Real)1e-20)) continue;
-        const Real sst = -(be * a_ + al * b_) / den;
-        if (!(sst > tolc && sst < (Real)1 - tolc)) continue;
-        const Real yx = yjx + sst * fx, yy = yjy + sst * fy;
-        const Real rho = rho0 + sst * nf;
-        const Real Nv = al - be * sst;
-        if (!(rho > eps && Nv > 0)) continue;
-        // foot of the body point on obstacle edge i must lie strictly inside the edge
-        const int in = (i + 1) % ne;
-        const Real ex = g.vx[in] - g.vx[i], ey = g.vy[in] - g.vy[i];
-        const Real wx = (cphi * yx - sphi * yy) - rho * nix - g.vx[i], wy = (sphi * yx + cphi * yy) - rho * niy - g.vy[i];
-        const Real so_ = (wx * ex + wy * ey) / (ex * ex + ey * ey);
-        if (!(so_ > tolc && so_ < (Real)1 - tolc)) continue;
-        const Real tau = Nv / ((Real)1 + (yx * yx + yy * yy) / ro2);
-        const Real rvx = cphi * nix + sphi * niy, rvy = -sphi * nix + cphi * niy;      // R'v
-        const Real cgx = -tau * yx / ro2 - rvx - xi0, cgy = -tau * yy / ro2 - rvy - xi1;
-        const Real tang = abs_(cgx * fx + cgy * fy) * rsqrt_(fx * fx + fy * fy);
-        if (!(cgx * (Real)rb.nx[j] + cgy * (Real)rb.ny[j] >= -tolc && tang <= tole)) continue;
-        v0 = nix; v1 = niy; g0 = cgx; g1 = cgy;
-        have = true; RDA_CASE_STAT(__LINE__); path = CELL_FAST_VERTEX;
-      }
-    }
-  }
   if (!have && !sep && k0 > 0) {
     // Deep overlap: the optimal contact point y = -ro2 xi / k0 lies inside the robot AND inside the
     // obstacle; then v = 0, g = 0 (lam = mu = 0), tau = k0 and q = xi satisfy the KKT conditions.
