@@ -67,7 +67,7 @@ struct rda_handle {
   cudaEvent_t ev_fork, ev_join[3];
   // persistent single-launch ADMM for small batches (k_admm_small)
   int small_mode;        // -1: batches up to small_max instances, 0: never, 1: always when the state fits (RDA_B200_SMALL)
-  int small_max, small_ok;
+  int small_max, small_ok, small_bulk;
   SmallLayout small_L;
   float su_prune;        // hinge pruning margin of the su-QP (su_solver.cuh; RDA_B200_SU_PRUNE, 0 = off)
   int slow_cpw, slow_ctas;   // k_cells_slow: cells per warp, CTAs per SM (RDA_B200_SLOW_CPW / RDA_B200_SLOW_CTAS)
@@ -673,15 +673,47 @@ static SmallLayout small_layout(int T, int N, int E, int R, size_t su_bytes) {
   const size_t NT = (size_t)N * T;
   L.lam = take(4 * N * E * T); L.mu = take(4 * N * R * T); L.z = take(4 * NT); L.xi = take(8 * NT); L.zeta = take(4 * NT);
   L.dis = take(4 * T); L.coef = take(20 * NT); L.pref = take(8 * T); L.cur_s = take(12 * (T + 1)); L.cur_u = take(8 * T);
-  L.ref_s = take(12 * (T + 1)); L.misc = take(64); L.hs = take(16 * NT); L.su = take(su_bytes);
+  L.ref_s = take(12 * (T + 1)); L.misc = take(128); L.hs = take(16 * NT); L.su = take(su_bytes);
   L.total = (int)((o + 15) & ~(size_t)15);
   return L;
+}
+
+
+// ---- bulk asynchronous copies (TMA engine, 1-D: no tensor map) with mbarrier completion -----------------------
+// Used by the persistent kernel to stage an instance's warm-start state into shared memory and back: each array is one
+// contiguous, 16-byte aligned block per instance, which is exactly the shape cp.async.bulk moves without any thread
+// touching the data (SASS: UBLKCP).
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  unsigned ok = 0;
+  do {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void bulk_s2g(void* dst, const void* src, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit_wait() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 template <typename Real>
 __global__ void __launch_bounds__(128) k_admm_small(DevPtrs d, SuParams P, RobotGeom rb, float ro2, float theta, float thr,
                                                     int iter_num, SmallLayout L, const float* nom_s, const float* nom_u,
-                                                    const float* ref_s, const float* ref_speed, rda_outputs out) {
+                                                    const float* ref_s, const float* ref_speed, rda_outputs out, int use_bulk) {
   extern __shared__ __align__(16) char smem[];
   const int b = blockIdx.x;
   if (b >= d.B) return;
@@ -703,16 +735,34 @@ __global__ void __launch_bounds__(128) k_admm_small(DevPtrs d, SuParams P, Robot
   ds.obs_count = d.obs_count ? d.obs_count + b : nullptr;
   auto copy_in = [&](float* dst, const float* src, int n) { for (int i = tid; i < n; i += nth) dst[i] = src[i]; };
   auto copy_out = [&](float* dst, const float* src, int n) { for (int i = tid; i < n; i += nth) dst[i] = src[i]; };
-  copy_in(ds.lam, d.lam + (size_t)b * N * E * T, N * E * T); copy_in(ds.mu, d.mu + (size_t)b * N * R * T, N * R * T);
-  copy_in(ds.z, d.z + (size_t)b * NT, NT); copy_in(ds.xi, d.xi + (size_t)b * 2 * NT, 2 * NT);
-  copy_in(ds.zeta, d.zeta + (size_t)b * NT, NT); copy_in(ds.dis, d.dis + (size_t)b * T, T);
-  copy_in(ds.coef, d.coef + (size_t)b * 5 * NT, 5 * NT); copy_in(ds.pref, d.pref + (size_t)b * 2 * T, 2 * T);
+  unsigned long long* bar = (unsigned long long*)(misc + 8);
+  if (use_bulk) {
+    // the six per-cell arrays (16-byte multiples, checked on the host) through the TMA engine, the rest by the threads
+    if (tid == 0) mbar_init(bar, 1);
+    __syncthreads();
+    if (tid == 0) {
+      const unsigned nle = N * E * T * 4, nmu = N * R * T * 4, nc = NT * 4;
+      mbar_expect_tx(bar, nle + nmu + nc + 2 * nc + nc + 5 * nc);
+      bulk_g2s(ds.lam, d.lam + (size_t)b * N * E * T, nle, bar);
+      bulk_g2s(ds.mu, d.mu + (size_t)b * N * R * T, nmu, bar);
+      bulk_g2s(ds.z, d.z + (size_t)b * NT, nc, bar);
+      bulk_g2s(ds.xi, d.xi + (size_t)b * 2 * NT, 2 * nc, bar);
+      bulk_g2s(ds.zeta, d.zeta + (size_t)b * NT, nc, bar);
+      bulk_g2s(ds.coef, d.coef + (size_t)b * 5 * NT, 5 * nc, bar);
+    }
+  } else {
+    copy_in(ds.lam, d.lam + (size_t)b * N * E * T, N * E * T); copy_in(ds.mu, d.mu + (size_t)b * N * R * T, N * R * T);
+    copy_in(ds.z, d.z + (size_t)b * NT, NT); copy_in(ds.xi, d.xi + (size_t)b * 2 * NT, 2 * NT);
+    copy_in(ds.zeta, d.zeta + (size_t)b * NT, NT); copy_in(ds.coef, d.coef + (size_t)b * 5 * NT, 5 * NT);
+  }
+  copy_in(ds.dis, d.dis + (size_t)b * T, T); copy_in(ds.pref, d.pref + (size_t)b * 2 * T, 2 * T);
   copy_in(ds.cur_s, nom_s + (size_t)b * 3 * (T + 1), 3 * (T + 1)); copy_in(ds.cur_u, nom_u + (size_t)b * 2 * T, 2 * T);
   copy_in(ds.ref_s, ref_s + (size_t)b * 3 * (T + 1), 3 * (T + 1));
   if (tid == 0) {
     misc[0] = 0.f; misc[1] = 0.f; misc[2] = 0.f; misc[3] = 0.f; misc[4] = ref_speed[b];
     ds.status[0] = 0; ds.iters[0] = 0; ds.done[0] = 0;
   }
+  if (use_bulk) mbar_wait(bar, 0);
   __syncthreads();
   const bool has_obs = N > 0 && ds.obs_count[0] != 0;
   for (int it = 0; it < iter_num; ++it) {
@@ -753,10 +803,25 @@ __global__ void __launch_bounds__(128) k_admm_small(DevPtrs d, SuParams P, Robot
     if (ds.done[0]) break;
   }
   // ---- state and results back to HBM ----
-  copy_out(d.lam + (size_t)b * N * E * T, ds.lam, N * E * T); copy_out(d.mu + (size_t)b * N * R * T, ds.mu, N * R * T);
-  copy_out(d.z + (size_t)b * NT, ds.z, NT); copy_out(d.xi + (size_t)b * 2 * NT, ds.xi, 2 * NT);
-  copy_out(d.zeta + (size_t)b * NT, ds.zeta, NT); copy_out(d.dis + (size_t)b * T, ds.dis, T);
-  copy_out(d.coef + (size_t)b * 5 * NT, ds.coef, 5 * NT); copy_out(d.pref + (size_t)b * 2 * T, ds.pref, 2 * T);
+  if (use_bulk) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes visible to the copy engine
+    __syncthreads();
+    if (tid == 0) {
+      const unsigned nle = N * E * T * 4, nmu = N * R * T * 4, nc = NT * 4;
+      bulk_s2g(d.lam + (size_t)b * N * E * T, ds.lam, nle);
+      bulk_s2g(d.mu + (size_t)b * N * R * T, ds.mu, nmu);
+      bulk_s2g(d.z + (size_t)b * NT, ds.z, nc);
+      bulk_s2g(d.xi + (size_t)b * 2 * NT, ds.xi, 2 * nc);
+      bulk_s2g(d.zeta + (size_t)b * NT, ds.zeta, nc);
+      bulk_s2g(d.coef + (size_t)b * 5 * NT, ds.coef, 5 * nc);
+      bulk_commit_wait();
+    }
+  } else {
+    copy_out(d.lam + (size_t)b * N * E * T, ds.lam, N * E * T); copy_out(d.mu + (size_t)b * N * R * T, ds.mu, N * R * T);
+    copy_out(d.z + (size_t)b * NT, ds.z, NT); copy_out(d.xi + (size_t)b * 2 * NT, ds.xi, 2 * NT);
+    copy_out(d.zeta + (size_t)b * NT, ds.zeta, NT); copy_out(d.coef + (size_t)b * 5 * NT, ds.coef, 5 * NT);
+  }
+  copy_out(d.dis + (size_t)b * T, ds.dis, T); copy_out(d.pref + (size_t)b * 2 * T, ds.pref, 2 * T);
   copy_out(d.cur_s + (size_t)b * 3 * (T + 1), ds.cur_s, 3 * (T + 1)); copy_out(d.cur_u + (size_t)b * 2 * T, ds.cur_u, 2 * T);
   copy_out(d.ref_s + (size_t)b * 3 * (T + 1), ds.ref_s, 3 * (T + 1));
   copy_out((float*)out.s_opt + (size_t)b * 3 * (T + 1), ds.cur_s, 3 * (T + 1));
@@ -959,6 +1024,9 @@ int rda_create(const rda_config* cfg, const rda_tunables* tun, rda_handle** out)
     h->small_L = small_layout((int)T, (int)N, (int)E, (int)R, sub);
     h->small_ok = h->small_L.total <= 200 * 1024;
     h->small_mode = -1; h->small_max = 296;
+    // bulk (TMA) staging needs every staged block to be a multiple of 16 bytes: N*E*T, N*R*T and N*T multiples of 4
+    h->small_bulk = (N > 0) && ((N * E * T) % 4 == 0) && ((N * R * T) % 4 == 0) && ((N * T) % 4 == 0);
+    if (const char* v = getenv("RDA_B200_SMALL_BULK")) { if (atoi(v) == 0) h->small_bulk = 0; }
     if (const char* v = getenv("RDA_B200_SMALL")) { int x = atoi(v); if (x >= -1 && x <= 1) h->small_mode = x; }
     if (const char* v = getenv("RDA_B200_SMALL_MAX")) { int x = atoi(v); if (x >= 1) h->small_max = x; }
     if (h->small_ok) {
@@ -1241,11 +1309,11 @@ int rda_solve(rda_handle* h, const rda_inputs* in, const rda_outputs* out, int i
     if (h->cfg.su_fp64)
       k_admm_small<double><<<h->B, 128, h->small_L.total, s0>>>(d, P, h->rb, h->tun.ro2, theta, iter_threshold, iter_num, h->small_L,
                                                               (const float*)in->nom_s, (const float*)in->nom_u, (const float*)in->ref_s,
-                                                              (const float*)in->ref_speed, *out);
+                                                              (const float*)in->ref_speed, *out, h->small_bulk);
     else
       k_admm_small<float><<<h->B, 128, h->small_L.total, s0>>>(d, P, h->rb, h->tun.ro2, theta, iter_threshold, iter_num, h->small_L,
                                                              (const float*)in->nom_s, (const float*)in->nom_u, (const float*)in->ref_s,
-                                                             (const float*)in->ref_speed, *out);
+                                                             (const float*)in->ref_speed, *out, h->small_bulk);
     RDA_CUDA(cudaGetLastError());
     h->launches = 1;
     return 0;
