@@ -13,7 +13,7 @@ from rda_planner_b200.rda_solver import RDA_solver, pack_obstacles  # noqa: E402
 from rda_planner_b200.scenarios import rectangle_robot, make_instance  # noqa: E402
 
 for kind, moving in (('polygon', False), ('circle', True)):
-    T, N, B = 10, 5, 48
+    T, N, B = 10, 6, 48      # N*T multiple of 4: the persistent kernel stages its state with bulk (TMA) copies
     car = rectangle_robot()
     insts = [make_instance(40 + i, T=T, N=N, E=4, kind=kind, moving=moving, lateral=(0.3, 3.5)) for i in range(B)]
     packs = [pack_obstacles(list(i['obstacles']), T, N, 4) for i in insts]
