@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'librda_b200.so')
+LIB_PATH = os.environ.get('RDA_B200_LIB') or os.path.join(_HERE, 'librda_b200.so')      # override: tuning experiments only
 
 MAX_EDGE = 8
 MAX_ROBOT_EDGE = 8

@@ -24,7 +24,9 @@ def build(force=False, verbose=False):
     if not force and not needs_build():
         return OUT
     nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
-    cmd = [nvcc] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-o', OUT] + SRCS
+    out = os.environ.get('RDA_B200_BUILD_OUT', OUT)      # tuning experiments: variant libraries next to the default one
+    extra = os.environ.get('RDA_B200_NVCC_EXTRA', '').split()
+    cmd = [nvcc] + NVCC_FLAGS + extra + (['-Xptxas', '-v'] if verbose else []) + ['-o', out] + SRCS
     subprocess.check_call(cmd)
     return OUT
 

@@ -29,14 +29,20 @@ def canonical_polygon_rows(A, b):
     A = np.asarray(A, float)
     b = np.asarray(b, float).reshape(-1)
     n = A.shape[0]
-    det = A[np.arange(n) - 1, 0] * A[:, 1] - A[np.arange(n) - 1, 1] * A[:, 0]
-    if n >= 3 and np.all(det > 0):
+    def one_turn(M):
+        # consecutive normals turn left AND the turning angles add up to a single 2 pi (no double winding)
+        d = M[np.arange(n) - 1, 0] * M[:, 1] - M[np.arange(n) - 1, 1] * M[:, 0]
+        if n < 3 or not np.all(d > 0):
+            return False
+        a = np.arctan2(M[:, 1], M[:, 0])
+        turn = np.mod(a - np.roll(a, 1), 2 * np.pi)
+        return abs(turn.sum() - 2 * np.pi) < 1e-6
+    if one_turn(A):
         return A, b
     ang = np.arctan2(A[:, 1], A[:, 0])
     order = np.argsort(ang)
     A, b = A[order], b[order]
-    det = A[np.arange(n) - 1, 0] * A[:, 1] - A[np.arange(n) - 1, 1] * A[:, 0]
-    if n < 3 or not np.all(det > 0):
+    if not one_turn(A):
         raise ValueError('obstacle half-spaces must describe a closed convex polygon '
                          '(unbounded polyhedra are not supported by rda_planner_b200)')
     return A, b
@@ -128,6 +134,9 @@ class RDA_solver:
         self._tun = _cabi.Tunables(kwargs.get('slack_gain', 8), kwargs.get('max_sd', 1.0),
                                    kwargs.get('min_sd', 0.1), kwargs.get('ro1', 200),
                                    kwargs.get('ro2', 1), z_theta)
+        # the values as the caller gave them (the device copy is float32): get_adjust_parameter returns these
+        self._tun_py = {k: kwargs.get(k, dflt) for k, dflt in (('slack_gain', 8), ('max_sd', 1.0), ('min_sd', 0.1),
+                                                                ('ro1', 200), ('ro2', 1))}
         self._cfg = cfg
         self._h = C.c_void_p()
         with torch.cuda.device(self.device):
@@ -165,13 +174,20 @@ class RDA_solver:
         t.min_sd = kwargs.get('min_sd', t.min_sd)
         t.ro1 = kwargs.get('ro1', t.ro1)
         t.ro2 = kwargs.get('ro2', t.ro2)
+        for k in self._tun_py:
+            if k in kwargs:
+                self._tun_py[k] = kwargs[k]
         _cabi.check(self.lib.rda_set_tunables(self._h, C.byref(t)), 'rda_set_tunables')
 
     def get_adjust_parameter(self):
         t = _cabi.Tunables()
         _cabi.check(self.lib.rda_get_tunables(self._h, C.byref(t)), 'rda_get_tunables')
-        return {'slack_gain': t.slack_gain, 'max_sd': t.max_sd, 'min_sd': t.min_sd, 'ro1': t.ro1,
-                'ro2': t.ro2, 'ws': self.ws, 'wu': self.wu}
+        out = dict(self._tun_py)          # exact Python values, as the reference returns them (:1055-1056)
+        for k in out:                      # ... unless the handle was changed behind this object's back
+            if abs(float(getattr(t, k)) - float(out[k])) > 1e-6 * (1 + abs(float(out[k]))):
+                out[k] = float(getattr(t, k))
+        out.update(ws=self.ws, wu=self.wu)
+        return out
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)

@@ -75,9 +75,11 @@ if os.path.exists(rp):
             traffic[key] = gb('dram__bytes_read.sum') + gb('dram__bytes_write.sum')
     meta = {}
     mp = os.path.join(ROOT, 'gpurun_out', f'prof_{tag}_meta.json')
+    if not os.path.exists(mp):
+        mp = os.path.join(ROOT, 'gpurun_out', 'prof_r01_meta.json')      # written by tools/profile_target.py (same target every round)
     if os.path.exists(mp):
         meta = json.load(open(mp))
-    traffic['k_cells'] = traffic.get('k_cells_fast', 0) + traffic.get('k_cells_slow', 0)
+    traffic['k_cells'] = sum(v for k, v in traffic.items() if k.startswith('k_cells_'))      # all cell passes of one iteration
     traffic['_note'] = 'dram__bytes_read.sum + dram__bytes_write.sum per launch (bytes), ncu --set full, ' + json.dumps(meta)
     json.dump(traffic, open(os.path.join(out_dir, 'roofline_traffic.json'), 'w'), indent=1)
     print('wrote ncu summary + roofline_traffic.json', traffic)
