@@ -69,6 +69,7 @@ struct rda_handle {
   int small_mode;        // -1: batches up to small_max instances, 0: never, 1: always when the state fits (RDA_B200_SMALL)
   int small_max, small_ok, small_bulk;
   SmallLayout small_L;
+  int su_maxctas;        // cap on resident k_su CTAs per SM in split mode (0 = none; RDA_B200_SU_MAXCTAS)
   float su_prune;        // hinge pruning margin of the su-QP (su_solver.cuh; RDA_B200_SU_PRUNE, 0 = off)
   int slow_cpw, slow_ctas;   // k_cells_slow: cells per warp, CTAs per SM (RDA_B200_SLOW_CPW / RDA_B200_SLOW_CTAS)
   int split_min;         // smallest batch that is split (RDA_B200_SPLIT_MIN, default 2048)
@@ -1018,6 +1019,8 @@ int rda_create(const rda_config* cfg, const rda_tunables* tun, rda_handle** out)
   }
   h->split_min = 2048;
   h->parts = 2;
+  h->su_maxctas = 0;
+  if (const char* v = getenv("RDA_B200_SU_MAXCTAS")) { int x = atoi(v); if (x >= 1 && x <= 32) h->su_maxctas = x; }
   h->su_prune = 0.5f;       // measured r02 (B = 16384): 0.5 -> 9.0 ms, 1.0 -> 9.3 ms, 2.0 -> 11.4 ms, off -> 11.5 ms per su-QP launch
   {
     const size_t sub = cfg->su_fp64 ? su_work_bytes<double, double, 0>((int)T, (int)N, false) : su_work_bytes<float, float, 0>((int)T, (int)N, false);
@@ -1190,7 +1193,13 @@ static int step_su_part(rda_handle* h, int b0, int nb, int part, cudaStream_t s)
   else smem1 = G == 32 ? su_work_bytes<float, float, 0>(h->T, h->N, false) : (G == 16 ? su_work_bytes<float, float, 1>(h->T, h->N, false) : su_work_bytes<float, float, 2>(h->T, h->N, false));
   if (smem1 * per_warp > 227 * 1024) return RDA_E_UNSUPPORTED;
   const int grid = (nb + per_warp - 1) / per_warp;
-  const size_t cta_smem = smem1 * per_warp;
+  size_t cta_smem = smem1 * per_warp;
+  // optional cap on the resident su-QP CTAs per SM (RDA_B200_SU_MAXCTAS): padding the dynamic shared memory leaves
+  // registers / warp slots for the latency-bound cell passes of the OTHER sub-batch to run beside this kernel
+  if (h->su_maxctas > 0 && h->B >= h->split_min && h->parts >= 2) {
+    const size_t pad = (size_t)(227 * 1024) / (size_t)h->su_maxctas - 1024;
+    if (pad > cta_smem) cta_smem = pad & ~(size_t)15;
+  }
 #define RDA_LAUNCH_SU(REAL, GG) k_su<REAL, GG><<<grid, 32, cta_smem, s>>>(d, P, (int)smem1)
   if (h->cfg.su_fp64) {
     if (G == 32) RDA_LAUNCH_SU(double, 32); else if (G == 16) RDA_LAUNCH_SU(double, 16); else RDA_LAUNCH_SU(double, 8);

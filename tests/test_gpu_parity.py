@@ -404,8 +404,9 @@ def test_graph_replay_of_the_single_instance_api():
     assert len(gs[1]._graphs) == 1
 
 
-@pytest.mark.parametrize('kind,moving,dyn,N', [('polygon', False, 'acker', 6), ('circle', True, 'diff', 5), ('polygon', False, 'omni', 0)])
-def test_persistent_small_kernel_equals_streaming_kernels(monkeypatch, kind, moving, dyn, N):
+@pytest.mark.parametrize('kind,moving,dyn,N,fp64', [('polygon', False, 'acker', 6, True), ('circle', True, 'diff', 5, True),
+                                                     ('polygon', False, 'omni', 0, True), ('polygon', False, 'acker', 6, False)])
+def test_persistent_small_kernel_equals_streaming_kernels(monkeypatch, kind, moving, dyn, N, fp64):
     """small batches run the whole ADMM loop in ONE launch, one CTA per instance, state in shared memory
     (k_admm_small).  Same device functions as the streaming kernels: trajectories, residuals, early stop and the
     persistent warm-start state must agree to float32 rounding, cold and warm-started."""
@@ -421,7 +422,7 @@ def test_persistent_small_kernel_equals_streaming_kernels(monkeypatch, kind, mov
     res = {}
     for mode in ('0', '1'):
         monkeypatch.setenv('RDA_B200_SMALL', mode)
-        g = RDA_solver(T, car, 4, N, iter_num=6, iter_threshold=0.3, time_print=False, batch=B)
+        g = RDA_solver(T, car, 4, N, iter_num=6, iter_threshold=0.3, time_print=False, batch=B, su_fp64=fp64)
         out = {k: v.clone() for k, v in g.iterative_solve_batch(**dev, time_varying=moving).items()}
         out2 = {k: v.clone() for k, v in g.iterative_solve_batch(**dev, time_varying=moving).items()}
         bufs = (_cabi.BUF_DIS, _cabi.BUF_CUR_S) if N == 0 else (_cabi.BUF_LAM, _cabi.BUF_MU, _cabi.BUF_Z, _cabi.BUF_XI, _cabi.BUF_ZETA,
@@ -431,8 +432,12 @@ def test_persistent_small_kernel_equals_streaming_kernels(monkeypatch, kind, mov
     assert res['1'][3] == 1 and res['0'][3] > 5
     for call in (0, 1):
         a, b = res['0'][call], res['1'][call]
-        assert torch.equal(a['iters'], b['iters']), (call, a['iters'], b['iters'])
-        assert torch.equal(a['status'], b['status'])
+        if fp64:
+            assert torch.equal(a['iters'], b['iters']), (call, a['iters'], b['iters'])
+            assert torch.equal(a['status'], b['status'])
+        else:       # float32 su-QP (looser interior point tolerances): same code in both paths, only finiteness and closeness
+            assert float((a['u'] - b['u']).abs().max()) < 5e-3 and int((b['status'] & 6).sum()) == 0
+            continue
         # the streaming path resolves most cells in the lean first pass, the single-launch kernel in the general closed
         # forms: same arithmetic step by step but not the same rounding, amplified by the warm-started second call
         for k in ('u', 's'):
@@ -440,4 +445,4 @@ def test_persistent_small_kernel_equals_streaming_kernels(monkeypatch, kind, mov
         for k in ('resi_pri', 'resi_dual'):
             assert torch.allclose(a[k], b[k], rtol=1e-3, atol=1e-4), (call, k)
     for k in res['0'][2]:
-        assert float((res['0'][2][k] - res['1'][2][k]).abs().max()) < 1e-3, k
+        assert float((res['0'][2][k] - res['1'][2][k]).abs().max()) < (1e-3 if fp64 else 5e-2), k
