@@ -129,7 +129,9 @@ struct CellWork {
 // ---- stage 1: geometry relative to the robot reference point and the closed-form cases ----------
 // LEAN = true stops after the two cases that need no search (xi = 0 and a non-negative margin): the
 // first pass of the GPU pipeline, kept small so that its code stays resident in the instruction cache.
-template <typename Real, bool LEAN = false>
+// EXTRA: also try the candidates that only the (rare) cells of the last pass need: robot edge against obstacle edge.
+// The searched pass leaves them out (every one of its cells would pay for the extra candidates, r02 measurement).
+template <typename Real, bool LEAN = false, bool EXTRA = false>
 RDA_HD void cell_front(const RobotGeom& rb, int kind, int E, const float* A, const float* b, Real px, Real py,
                        Real cphi, Real sphi, Real dbar, Real zeta, Real xi0, Real xi1, Real ro2,
                        CellWork<Real>& w) {
@@ -353,13 +355,21 @@ RDA_HD void cell_front(const RobotGeom& rb, int kind, int E, const float* A, con
       // h at the bracket ends (flo > 0 at lo, fhi < 0 at hi) where it was evaluated inside the region N > 0
       Real flo = 0, fhi = 0;
       bool vlo = false, vhi = false;
+      bool conv = false;             // the root is bracketed by valid end values to the resolution of s
       if (!weighted) {
         eval((Real)0); const Real h0 = hv;
         eval((Real)1); const Real h1 = hv;
-        if (!(h0 > 0 && h1 < 0)) bracket = false;      // N has no interior maximum on this edge
+        if (!(h0 > 0 && h1 < 0)) {                     // N has no interior maximum on this edge:
+          bracket = false;                             // concave N, so it is largest at the end it increases towards
+          // the WEIGHTED margin may still peak inside the edge; rare (0.02 % of the cells), so only the last pass looks
+          // for it: the searched pass would pay a root search per candidate edge (r02: +1.8 ms per ADMM iteration)
+          sA = !EXTRA ? (Real)-1 : h1 >= 0 ? (Real)1 : (Real)0;
+        }
         flo = h0; fhi = h1; vlo = vhi = true;
       } else {
-        if (!(sA > 0)) { bracket = false; }
+        // sA: maximiser of the unweighted margin N on the edge (an end point when N is monotone there).  The WEIGHTED margin
+        // N/W is quasi-concave where N > 0, an interval that contains sA: its maximiser lies on the side of sA that h points to.
+        if (!(sA >= 0)) bracket = false;
         else {
           eval(sA);
           if (!(Nv > 0)) bracket = false;              // hinge cannot be active with contact on this edge
@@ -400,13 +410,17 @@ RDA_HD void cell_front(const RobotGeom& rb, int kind, int E, const float* A, con
           if (hi - lo < tol || abs_(sc - sprev) < tol || (valid && hv == (Real)0)) break;
           sprev = sc;
         }
+        conv = vlo && vhi && hi - lo < (Real)4 * tol;
         if (!weighted) sA = sc;
       }
       if (!bracket) continue;
       // KKT of the cell problem at this point
       const Real rvx = cphi * vx_ + sphi * vy_, rvy = -sphi * vx_ + cphi * vy_;   // R'v
       const Real tolc = sizeof(Real) == 4 ? (Real)1e-5 : (Real)1e-11;
-      const Real tole = sizeof(Real) == 4 ? (Real)3e-5 : (Real)1e-9;   // tangential residual of g on the edge
+      // tangential residual of g on the edge: h is the tangential component of the gradient scaled by W^2 |f| (steep: a
+      // slope of 1e4..1e5 per unit s with the metric's ro), so ONE float32 ulp of s leaves a residual of 1e-4; a root
+      // bracketed by valid end values to that resolution (conv) is accepted as it is
+      const Real tole = sizeof(Real) == 4 ? (Real)3e-5 : (Real)1e-9;
       bool cone_ok = true;
       if (kind != RDA_OBS_CIRCLE) {
         const int ip = (ce_i + ne - 1) % ne, inx = (ce_i + 1) % ne;
@@ -421,7 +435,7 @@ RDA_HD void cell_front(const RobotGeom& rb, int kind, int E, const float* A, con
           const Real cgx = -rvx - xi0, cgy = -rvy - xi1;
           // g must be a non-negative multiple of the edge normal: no tangential component left
           const Real tang = abs_(cgx * fx + cgy * fy) * rsqrt_(fx * fx + fy * fy);
-          if (cgx * (Real)rb.nx[j] + cgy * (Real)rb.ny[j] >= -tolc && tang <= tole) {
+          if (cgx * (Real)rb.nx[j] + cgy * (Real)rb.ny[j] >= -tolc && (tang <= tole || conv)) {
             v0 = vx_; v1 = vy_; g0 = cgx; g1 = cgy;
             exact_zero_q = true; have = true; RDA_CASE_STAT(__LINE__); path = CELL_FAST_VERTEX;
           }
@@ -430,10 +444,54 @@ RDA_HD void cell_front(const RobotGeom& rb, int kind, int E, const float* A, con
         const Real tau = Nv / W2;
         const Real cgx = -tau * yx / ro2 - rvx - xi0, cgy = -tau * yy / ro2 - rvy - xi1;
         const Real tang = abs_(cgx * fx + cgy * fy) * rsqrt_(fx * fx + fy * fy);
-        if (cgx * (Real)rb.nx[j] + cgy * (Real)rb.ny[j] >= -tolc && tang <= tole) {
+        if (cgx * (Real)rb.nx[j] + cgy * (Real)rb.ny[j] >= -tolc && (tang <= tole || conv)) {
           v0 = vx_; v1 = vy_; g0 = cgx; g1 = cgy;
           have = true; RDA_CASE_STAT(__LINE__); path = CELL_FAST_VERTEX;
         }
+      }
+    }
+  }
+  if (EXTRA && !have && sep && kind != RDA_OBS_CIRCLE) {
+    // Robot-EDGE against obstacle-EDGE contact (disjoint sets, active hinge): the optimal body point lies in the
+    // interior of body edge j and its nearest obstacle point in the interior of obstacle edge i, so v = n_i and the
+    // distance n_i.(R y - V_i) is LINEAR along the body edge: the weighted margin N/W has the closed-form stationary
+    // point s* = -(beta a + alpha b)/(beta b + alpha c) (as in the overlap cases below), accepted through the KKT
+    // conditions.  (With the unweighted margin N is linear in s: no interior maximum, those are vertex contacts.)
+    const Real tolc = sizeof(Real) == 4 ? (Real)1e-5 : (Real)1e-11;
+    for (int j = 0; j < R && !have; ++j) {
+      const int jn = (j + 1) % R;
+      const Real yjx = rb.yx[j], yjy = rb.yy[j];
+      const Real fx = (Real)rb.yx[jn] - yjx, fy = (Real)rb.yy[jn] - yjy;            // body frame
+      const Real wfx = cphi * fx - sphi * fy, wfy = sphi * fx + cphi * fy;          // R f
+      const Real a_ = (Real)1 + (yjx * yjx + yjy * yjy) / ro2, b_ = (yjx * fx + yjy * fy) / ro2;
+      const Real c_ = (fx * fx + fy * fy) / ro2;
+      for (int i = 0; i < ne && !have; ++i) {
+        const Real nix = g.nx[i], niy = g.ny[i];
+        const Real nf = nix * wfx + niy * wfy;                                         // n_i . R f
+        const Real rho0 = nix * (g.yx[j] - g.vx[i]) + niy * (g.yy[j] - g.vy[i]);       // distance of R y_j to the edge line
+        const Real al = k0 - (xi0 * yjx + xi1 * yjy) - rho0, be = (xi0 * fx + xi1 * fy) + nf;
+        const Real den = be * b_ + al * c_;
+        if (!(abs_(den) > (Real)1e-20)) continue;
+        const Real sst = -(be * a_ + al * b_) / den;
+        if (!(sst > tolc && sst < (Real)1 - tolc)) continue;
+        const Real yx = yjx + sst * fx, yy = yjy + sst * fy;
+        const Real rho = rho0 + sst * nf;
+        const Real Nv = al - be * sst;
+        if (!(rho > eps && Nv > 0)) continue;
+        // foot of the body point on obstacle edge i must lie strictly inside the edge
+        const int in = (i + 1) % ne;
+        const Real ex = g.vx[in] - g.vx[i], ey = g.vy[in] - g.vy[i];
+        const Real wx = (cphi * yx - sphi * yy) - rho * nix - g.vx[i], wy = (sphi * yx + cphi * yy) - rho * niy - g.vy[i];
+        const Real so_ = (wx * ex + wy * ey) / (ex * ex + ey * ey);
+        if (!(so_ > tolc && so_ < (Real)1 - tolc)) continue;
+        const Real tau = Nv / ((Real)1 + (yx * yx + yy * yy) / ro2);
+        const Real rvx = cphi * nix + sphi * niy, rvy = -sphi * nix + cphi * niy;      // R'v
+        const Real cgx = -tau * yx / ro2 - rvx - xi0, cgy = -tau * yy / ro2 - rvy - xi1;
+        // s* is a stationary point in closed form: the tangential component of g is rounding only (bounded loosely)
+        const Real tang = abs_(cgx * fx + cgy * fy) * rsqrt_(fx * fx + fy * fy);
+        if (!(cgx * (Real)rb.nx[j] + cgy * (Real)rb.ny[j] >= -tolc && tang <= (Real)1e-3)) continue;
+        v0 = nix; v1 = niy; g0 = cgx; g1 = cgy;
+        have = true; RDA_CASE_STAT(__LINE__); path = CELL_FAST_VERTEX;
       }
     }
   }
@@ -802,7 +860,7 @@ RDA_HD void cell_solve(const RobotGeom& rb, int kind, int E, const float* A, con
                        Real px, Real py, Real cphi, Real sphi, Real dbar, Real zeta, Real xi0,
                        Real xi1, Real ro2, Real theta, CellOut<Real>& out) {
   CellWork<Real> w;
-  cell_front<Real>(rb, kind, E, A, b, px, py, cphi, sphi, dbar, zeta, xi0, xi1, ro2, w);
+  cell_front<Real, false, true>(rb, kind, E, A, b, px, py, cphi, sphi, dbar, zeta, xi0, xi1, ro2, w);
   if (!w.have) {
     CellSlowStore S;
     SeqCtx ctx;

@@ -72,6 +72,7 @@ struct rda_handle {
   int su_maxctas;        // cap on resident k_su CTAs per SM in split mode (0 = none; RDA_B200_SU_MAXCTAS)
   float su_prune;        // hinge pruning margin of the su-QP (su_solver.cuh; RDA_B200_SU_PRUNE, 0 = off)
   int slow_cpw, slow_ctas;   // k_cells_slow: cells per warp, CTAs per SM (RDA_B200_SLOW_CPW / RDA_B200_SLOW_CTAS)
+  int slow_adapt;            // fewer cells per warp when the list fits one wave (RDA_B200_SLOW_ADAPT, default 0: measured slower)
   int split_min;         // smallest batch that is split (RDA_B200_SPLIT_MIN, default 2048)
   int parts;             // number of sub-batches, 1..4 (RDA_B200_SPLIT_PARTS, default 2)
 };
@@ -590,7 +591,7 @@ __global__ void __launch_bounds__(128) k_cells_mid(DevPtrs d, RobotGeom rb, floa
 #ifndef RDA_SLOW_CPW
 #define RDA_SLOW_CPW 32
 #endif
-__global__ void __launch_bounds__(64, RDA_SLOW_MINBLOCKS) k_cells_slow(DevPtrs d, RobotGeom rb, float ro2, float theta, int cpw) {
+__global__ void __launch_bounds__(64, RDA_SLOW_MINBLOCKS) k_cells_slow(DevPtrs d, RobotGeom rb, float ro2, float theta, int cpw, int adapt) {
   const int count = d.wl_count[1];
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -598,12 +599,15 @@ __global__ void __launch_bounds__(64, RDA_SLOW_MINBLOCKS) k_cells_slow(DevPtrs d
   // Disc cells run the (long, strongly divergent) barrier iteration: when the list is mostly discs and short enough, one
   // cell per warp (r02: 6.5x on BASELINE config C at 128 instances); polygon lists are fastest packed 32 per warp.
   if (2 * d.wl_count[3] > count && count <= nwarps) cpw = 1;
+  // optional: as few cells per warp as one wave of the grid allows.  r02 on B200: 5.8 ms instead of 4.1 ms per ADMM iteration
+  // at 16 384 instances — the pass is bound by issue slots and local-memory transactions, which full warps use 10x better.
+  if (adapt) cpw = min(cpw, max(1, (count + nwarps - 1) / nwarps));
   if (lane >= cpw) return;
   for (int wi = warp * cpw + lane; wi < count; wi += nwarps * cpw) {
     const long long idx = d.worklist2[wi];
     CellIn c = cell_load(d, idx);
     CellWork<float> w;
-    cell_front<float>(rb, c.kind, d.E, c.A, c.bb, c.px, c.py, c.cp, c.sp, c.dbar, c.zeta, c.xi0, c.xi1, ro2, w);
+    cell_front<float, false, true>(rb, c.kind, d.E, c.A, c.bb, c.px, c.py, c.cp, c.sp, c.dbar, c.zeta, c.xi0, c.xi1, ro2, w);
     if (!w.have) {
       CellSlowStore S;
       SeqCtx ctx;
@@ -778,7 +782,7 @@ __global__ void __launch_bounds__(128) k_admm_small(DevPtrs d, SuParams P, Robot
       for (int idx = tid; idx < NT; idx += nth) {
         CellIn c = cell_load(ds, idx);
         CellWork<float> w;
-        cell_front<float>(rb, c.kind, E, c.A, c.bb, c.px, c.py, c.cp, c.sp, c.dbar, c.zeta, c.xi0, c.xi1, ro2, w);
+        cell_front<float, false, true>(rb, c.kind, E, c.A, c.bb, c.px, c.py, c.cp, c.sp, c.dbar, c.zeta, c.xi0, c.xi1, ro2, w);
         if (!w.have) {
           CellSlowStore S;
           SeqCtx sc;
@@ -1040,6 +1044,8 @@ int rda_create(const rda_config* cfg, const rda_tunables* tun, rda_handle** out)
   }
   if (const char* v = getenv("RDA_B200_SU_PRUNE")) { float x = (float)atof(v); if (x >= 0.f) h->su_prune = x; }
   h->slow_cpw = RDA_SLOW_CPW; h->slow_ctas = 16;
+  h->slow_adapt = 0;
+  if (const char* v = getenv("RDA_B200_SLOW_ADAPT")) h->slow_adapt = atoi(v) != 0;
   if (const char* v = getenv("RDA_B200_SLOW_CPW")) { int x = atoi(v); if (x >= 1 && x <= 32) h->slow_cpw = x; }
   if (const char* v = getenv("RDA_B200_SLOW_CTAS")) { int x = atoi(v); if (x >= 1 && x <= 256) h->slow_ctas = x; }
   if (const char* sm = getenv("RDA_B200_SPLIT_MIN")) { int v = atoi(sm); if (v >= 2) h->split_min = v; }
@@ -1232,7 +1238,7 @@ static int step_lammuz_part(rda_handle* h, int b0, int nb, int part, cudaStream_
     RDA_CUDA(cudaGetLastError());
     k_cells_mid<<<148 * 8, 128, 0, s>>>(d, h->rb, h->tun.ro2, theta);
     RDA_CUDA(cudaGetLastError());
-    k_cells_slow<<<148 * h->slow_ctas, 64, 0, s>>>(d, h->rb, h->tun.ro2, theta, h->slow_cpw);
+    k_cells_slow<<<148 * h->slow_ctas, 64, 0, s>>>(d, h->rb, h->tun.ro2, theta, h->slow_cpw, h->slow_adapt);
     RDA_CUDA(cudaGetLastError());
     h->launches += 3;
   }

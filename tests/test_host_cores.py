@@ -49,6 +49,43 @@ def test_cell_core_matches_oracle(kind, seed):
     assert len(paths) >= 2
 
 
+def _rect_rows(cx, cy, w, h, ang):
+    c, s = np.cos(ang), np.sin(ang)
+    V = np.array([[-w / 2, -h / 2], [w / 2, -h / 2], [w / 2, h / 2], [-w / 2, h / 2]]) @ np.array([[c, s], [-s, c]]) + [cx, cy]
+    A, b = [], []
+    for i in range(4):
+        e = V[(i + 1) % 4] - V[i]
+        n = np.array([e[1], -e[0]])          # rows are NOT normalised (as the generator's and the reference's)
+        A.append(n)
+        b.append(n @ V[i])
+    return np.array(A, np.float32).astype(float), np.array(b, np.float32).astype(float)[:, None]
+
+
+def test_cell_edge_contacts_with_active_hinge_match_oracle():
+    """Active hinge, tilted xi, the car's long side nearly parallel to an obstacle edge: the contact configurations that
+    used to fall through to the interior point pass (robot edge x obstacle vertex with a steep stationarity function,
+    robot edge x obstacle edge).  Closed forms of cell_front (EXTRA candidates included) against the numpy cell oracle."""
+    car = rectangle_robot()
+    rng = np.random.default_rng(5)
+    closed_edge_edge = 0
+    for k in range(150):
+        phi = rng.uniform(-0.3, 0.3)
+        A, b = _rect_rows(rng.uniform(0, 3), rng.uniform(1.2, 2.2) + 1.0, 4.0, 2.0, phi + rng.uniform(-0.15, 0.15))
+        p = np.zeros(2)
+        dbar, zeta, xi = rng.uniform(0.3, 1.0), rng.uniform(-0.2, 0.2), rng.uniform(-0.2, 0.2, 2)
+        r = solve_cell_geo(A, b, False, car.G, car.h, p, phi, dbar, zeta, xi, 1.0)
+        nl, nm = int((np.asarray(r['lam']) > 1e-6).sum()), int((np.asarray(r['mu']) > 1e-6).sum())
+        for prec, tol in (('d', CELL_TOL_F64), ('f', CELL_TOL_F32)):
+            kk = shim.cell(car.G, car.h, 0, A, b, p, phi, dbar, zeta, xi, 1.0, prec=prec)
+            assert kk['path'] != 5
+            np.testing.assert_allclose(kk['lam'], r['lam'], atol=tol)
+            np.testing.assert_allclose(kk['mu'], r['mu'], atol=tol)
+            assert abs(kk['z'] - r['z']) < tol
+            if prec == 'f' and nl == 1 and nm == 1 and kk['path'] == 1:
+                closed_edge_edge += 1
+    assert closed_edge_edge >= 10
+
+
 @pytest.mark.parametrize('dyn', ['acker', 'diff', 'omni'])
 def test_su_core_matches_oracle(dyn):
     o, inst, car = oracle_state(43, 8, 3, 3, dyn=dyn)
