@@ -24,6 +24,7 @@ extern "C" {
 
 enum { RDA_DYN_ACKER = 0, RDA_DYN_DIFF = 1, RDA_DYN_OMNI = 2 };       /* rda_solver.py:446-451 */
 enum { RDA_OBS_POLYGON = 0, RDA_OBS_CIRCLE = 1 };                     /* cone flag :158,:512   */
+enum { RDA_ROBOT_POLYGON = 0, RDA_ROBOT_DISC = 1 };                   /* car_tuple.cone_type 'Rpositive' / 'norm2', :1034-1039 */
 enum { RDA_E_ARG = -1, RDA_E_UNSUPPORTED = -2, RDA_E_NOMEM = -3 };
 
 /* per-instance status bits (device word), mirroring the reference's keep-previous-iterate
@@ -36,7 +37,7 @@ typedef struct rda_config {
   int receding;       /* T   rda_solver.py:34                                            */
   int max_obs_num;    /* N   :38                                                         */
   int max_edge_num;   /* E   :39   (<= RDA_MAX_EDGE)                                      */
-  int robot_edges;    /* R = G.shape[0] (<= RDA_MAX_ROBOT_EDGE), Rpositive robot only     */
+  int robot_edges;    /* R = G.shape[0] (<= RDA_MAX_ROBOT_EDGE); 3 for a disc body          */
   int dynamics;       /* RDA_DYN_*  :40                                                  */
   int accelerated;    /* :47                                                             */
   int su_fp64;        /* 1: su-QP interior point arithmetic in float64 (default), 0: float32 */
@@ -47,6 +48,8 @@ typedef struct rda_config {
   float ws, wu;       /* :218-219 (fixed at construction, as in the reference)           */
   float G[RDA_MAX_ROBOT_EDGE * 2]; /* robot half-spaces, rows CCW (car_tuple.G)          */
   float h[RDA_MAX_ROBOT_EDGE];     /* car_tuple.h                                        */
+  int robot_cone;     /* RDA_ROBOT_*: polygon body (rows of G counter-clockwise) or the disc body
+                         G = [[1,0],[0,1],[0,0]], h = (cx, cy, -r) of cone_type 'norm2' (:1034-1039) */
 } rda_config;
 
 typedef struct rda_tunables {   /* rda_solver.py:185-201, :426-434 */

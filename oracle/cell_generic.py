@@ -51,8 +51,17 @@ def lam_from_v(A, b, is_circle, v):
     return lp_vertex_poly(A, b, v)
 
 
+def mu_from_g(G, h, g, robot_cone='Rpositive'):
+    """(L3) for the robot multipliers.  norm2 robot (rda_solver.py:1034-1039 with the ir-sim disc
+    G = [[1,0],[0,1],[0,0]], h = (cx, cy, -r)): G'mu = mu[0:2] = g and -mu in the cone means
+    |mu[0:2]| <= -mu[2]; min h'mu = g.c - r mu[2] is attained at mu[2] = -|g|."""
+    if robot_cone == 'norm2':
+        return np.array([g[0], g[1], -np.linalg.norm(g)])
+    return lp_vertex_poly(G, h, g)
+
+
 def solve_cell_generic(A, b, is_circle, G, h, p, phi, dbar, zeta, xi, ro2,
-                       theta=0.5):
+                       theta=0.5, robot_cone='Rpositive'):
     """Return dict(lam, mu, z, stuff, Hm, active).
 
     A (E,2), b (E,) obstacle copy t+1 (zero padded rows allowed); G (R,2), h (R,)
@@ -91,13 +100,23 @@ def solve_cell_generic(A, b, is_circle, G, h, p, phi, dbar, zeta, xi, ro2,
             bounds.append((None, None) if i < 3 else (0, 0))
         else:
             bounds.append((0, None) if np.linalg.norm(A[i]) > 0 else (0, 0))
-    bounds += [(0, None)] * R
+    disc_robot = robot_cone == 'norm2'
+    if disc_robot:
+        if R != 3 or np.abs(G - np.array([[1.0, 0], [0, 1], [0, 0]])).max() > 1e-12:
+            raise NotImplementedError('norm2 robot: G must be [[1,0],[0,1],[0,0]] (ir-sim disc)')
+        bounds += [(None, None)] * 3
+    else:
+        bounds += [(0, None)] * R
     cons = [{'type': 'ineq', 'fun': lambda th: 1.0 - np.sum((An.T @ th[:E]) ** 2),
              'jac': lambda th: np.concatenate([-2 * An @ (An.T @ th[:E]), np.zeros(R)])}]
     if is_circle:
         # -lam in norm2 cone: ||lam[0:2]|| + lam[2] <= 0   (rda_solver.py:1042-1050)
         cons.append({'type': 'ineq',
                      'fun': lambda th: -th[2] - np.sqrt(th[0] ** 2 + th[1] ** 2 + 1e-300)})
+    if disc_robot:
+        # -mu in norm2 cone: ||mu[0:2]|| + mu[2] <= 0   (rda_solver.py:1034-1039)
+        cons.append({'type': 'ineq',
+                     'fun': lambda th: -th[E + 2] - np.sqrt(th[E] ** 2 + th[E + 1] ** 2 + 1e-300)})
     # ---------- stage A: max margin with Hm + xi = 0 ----------
     consA = cons + [{'type': 'eq', 'fun': hm,
                      'jac': lambda th: np.hstack([AR.T, G.T])}]
@@ -108,10 +127,14 @@ def solve_cell_generic(A, b, is_circle, G, h, p, phi, dbar, zeta, xi, ro2,
         if is_circle:
             th0[2] = -1.0
             th0[3:E] = 0
+        if disc_robot:
+            th0[E + 2] = -1.0
         res = minimize(lambda th: -margin(th), th0, jac=lambda th: np.concatenate([bn, h]),
                        bounds=bounds, constraints=consA, method='SLSQP',
                        options={'ftol': 1e-14, 'maxiter': 400})
         viol = max(np.abs(hm(res.x)).max(), np.sum((An.T @ res.x[:E]) ** 2) - 1.0)
+        if disc_robot:
+            viol = max(viol, res.x[E + 2] + np.hypot(res.x[E], res.x[E + 1]))
         if viol < 1e-7 and (best is None or -res.fun > best[0]):
             best = (-res.fun, res.x)
         if fallback is None or viol < fallback[2]:
@@ -155,6 +178,8 @@ def solve_cell_generic(A, b, is_circle, G, h, p, phi, dbar, zeta, xi, ro2,
             else:
                 th0[:E] = 0.05 * np.maximum(An @ np.array([np.cos(ang), np.sin(ang)]), 0.0)
             th0[E:] = 0.01
+            if disc_robot:
+                th0[E:] = 0.01 * np.cos(ang + 1.0), 0.01 * np.sin(ang + 1.0), -0.02
             starts.append(th0)
         for th0 in starts:
             res = minimize(obj, th0, jac=jac, bounds=bounds, constraints=cons, method='SLSQP',
@@ -168,7 +193,7 @@ def solve_cell_generic(A, b, is_circle, G, h, p, phi, dbar, zeta, xi, ro2,
         stuff = None
     # ---------- (L3) LP-vertex multipliers ----------
     lam = lam_from_v(A, b, is_circle, v)
-    mu = lp_vertex_poly(G, h, g)
+    mu = mu_from_g(G, h, g, robot_cone)
     m_val = lam @ (A @ p - b) - mu @ h - k0
     if active:
         z = 0.0

@@ -12,7 +12,7 @@ tests/test_oracle_cell.py.  Cases solved here (all others -> generic solver):
 Follows /root/reference/RDA_planner/rda_solver.py:389-421, 874-909.
 """
 import numpy as np
-from .cell_generic import solve_cell_generic, lam_from_v, lp_vertex_poly
+from .cell_generic import solve_cell_generic, lam_from_v, lp_vertex_poly, mu_from_g
 
 
 def poly_vertices(A, b):
@@ -162,3 +162,42 @@ def solve_cell_geo(A, b, is_circle, G, h, p, phi, dbar, zeta, xi, ro2, theta=0.5
     if stats is not None:
         stats['generic'] = stats.get('generic', 0) + 1
     return solve_cell_generic(A, b, is_circle, G, h, p, phi, dbar, zeta, xi, ro2, theta)
+
+
+def solve_cell_geo_disc(A, b, is_circle, G, h, p, phi, dbar, zeta, xi, ro2, theta=0.5, stats=None):
+    """DISC body (cone_type 'norm2', rda_solver.py:1034-1039; G = [[1,0],[0,1],[0,0]], h = (cx, cy, -r)).
+    Closed form only for xi == 0, disjoint sets and an inactive hinge: the closest pair lies on the line from the
+    closest obstacle point to the disc centre, margin = dist(centre, O) - r.  Everything else -> generic solver."""
+    A = np.asarray(A, float)
+    b = np.asarray(b, float).ravel()
+    G = np.asarray(G, float)
+    h = np.asarray(h, float).ravel()
+    xi = np.asarray(xi, float).ravel()
+    c, s_ = np.cos(phi), np.sin(phi)
+    Rm = np.array([[c, -s_], [s_, c]])
+    k0 = dbar - zeta
+    ctr = p + Rm @ h[0:2]
+    rr = -h[2]
+    if not np.any(xi != 0):
+        if is_circle:
+            d = ctr - b[0:2]
+            dn = np.linalg.norm(d)
+            gap = dn - (-b[2]) - rr
+            vdir = d / dn if dn > 0 else None
+        else:
+            x, inside = _closest_on_poly(ctr, poly_vertices(A, b))
+            dn = np.linalg.norm(ctr - x)
+            gap = -1.0 if inside else dn - rr
+            vdir = (ctr - x) / dn if dn > 0 else None
+        if gap > 1e-9 and gap - k0 >= 0 and vdir is not None:
+            g = -Rm.T @ vdir
+            lam = lam_from_v(A, b, is_circle, vdir)
+            mu = mu_from_g(G, h, g, 'norm2')
+            stuff = lam @ (A @ p - b) - mu @ h - k0
+            if stats is not None:
+                stats['geo_disc_inactive'] = stats.get('geo_disc_inactive', 0) + 1
+            return {'lam': lam, 'mu': mu, 'z': theta * max(stuff, 0.0), 'stuff': stuff,
+                    'Hm': G.T @ mu + (A @ Rm).T @ lam, 'active': False, 'v': vdir, 'g': g}
+    if stats is not None:
+        stats['generic'] = stats.get('generic', 0) + 1
+    return solve_cell_generic(A, b, is_circle, G, h, p, phi, dbar, zeta, xi, ro2, theta, robot_cone='norm2')

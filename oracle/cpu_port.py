@@ -14,7 +14,8 @@ class _Config(C.Structure):
                 ('max_edge_num', C.c_int), ('robot_edges', C.c_int), ('dynamics', C.c_int),
                 ('accelerated', C.c_int), ('su_fp64', C.c_int), ('step_time', C.c_float),
                 ('wheelbase', C.c_float), ('max_speed', C.c_float * 2), ('acce_bound', C.c_float * 2),
-                ('ws', C.c_float), ('wu', C.c_float), ('G', C.c_float * 16), ('h', C.c_float * 8)]
+                ('ws', C.c_float), ('wu', C.c_float), ('G', C.c_float * 16), ('h', C.c_float * 8),
+                ('robot_cone', C.c_int)]
 
 
 class _Tunables(C.Structure):
@@ -75,6 +76,7 @@ def solve_batch(car, T, N, E, nom_s, nom_u, ref_s, ref_speed, obs_A, obs_b, obs_
     cfg.ws, cfg.wu = kw.get('ws', 1), kw.get('wu', 1)
     for j in range(G.shape[0]):
         cfg.G[2 * j], cfg.G[2 * j + 1], cfg.h[j] = G[j, 0], G[j, 1], h[j]
+    cfg.robot_cone = 1 if getattr(car, 'cone_type', 'Rpositive') == 'norm2' else 0
     tun = _Tunables(kw.get('slack_gain', 8), kw.get('max_sd', 1.0), kw.get('min_sd', 0.1), kw.get('ro1', 200),
                     kw.get('ro2', 1), kw.get('z_theta', 0.5))
     f32 = lambda a: np.ascontiguousarray(a, np.float32)

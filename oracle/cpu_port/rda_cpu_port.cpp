@@ -12,6 +12,7 @@
 #include <cstdlib>
 #include <omp.h>
 #include "../../rda_planner_b200/csrc/cell_solver.cuh"
+#include "../../rda_planner_b200/csrc/cell_disc_robot.cuh"
 #include "../../rda_planner_b200/csrc/su_solver.cuh"
 #include "../../rda_planner_b200/csrc/cell_lean.cuh"
 #include "../../rda_planner_b200/csrc/cell_lean2.cuh"
@@ -31,6 +32,26 @@ static int cell_impl(const float* G, const float* h, int R, int kind, int E, con
   CellOut<Real> o;
   cell_solve<Real>(rb, kind, E, A, b, (Real)px, (Real)py, (Real)cos(phi), (Real)sin(phi), (Real)dbar,
                    (Real)zeta, (Real)xi0, (Real)xi1, (Real)ro2, (Real)theta, o);
+  for (int i = 0; i < 8; ++i) out[i] = o.lam[i];
+  for (int i = 0; i < 8; ++i) out[8 + i] = o.mu[i];
+  double tail[] = {(double)o.z, (double)o.zeta_new, (double)o.xi0_new, (double)o.xi1_new, (double)o.ax,
+                   (double)o.ay, (double)o.c0, (double)o.gx, (double)o.gy, (double)o.hm0, (double)o.hm1,
+                   (double)o.path};
+  memcpy(out + 16, tail, sizeof(tail));
+  return 0;
+}
+
+// disc body (cone_type 'norm2'): h = (cx, cy, -r)
+template <typename Real>
+static int cell_dr_impl(const float* h, int kind, int E, const float* A, const float* b, double px, double py, double phi,
+                        double dbar, double zeta, double xi0, double xi1, double ro2, double theta, double* out) {
+  const float Gd[6] = {1.f, 0.f, 0.f, 1.f, 0.f, 0.f};
+  RobotGeom rb;
+  int rc = robot_geom_from_halfspaces(Gd, h, 3, &rb, RDA_ROBOT_DISC);
+  if (rc) return rc;
+  CellOut<Real> o;
+  cell_solve_dr<Real>(rb, kind, E, A, b, (Real)px, (Real)py, (Real)cos(phi), (Real)sin(phi), (Real)dbar,
+                      (Real)zeta, (Real)xi0, (Real)xi1, (Real)ro2, (Real)theta, o);
   for (int i = 0; i < 8; ++i) out[i] = o.lam[i];
   for (int i = 0; i < 8; ++i) out[8 + i] = o.mu[i];
   double tail[] = {(double)o.z, (double)o.zeta_new, (double)o.xi0_new, (double)o.xi1_new, (double)o.ax,
@@ -128,6 +149,14 @@ int shim_cell_f(const float* G, const float* h, int R, int kind, int E, const fl
                 double theta, double* out) {
   return cell_impl<float>(G, h, R, kind, E, A, b, px, py, phi, dbar, zeta, xi0, xi1, ro2, theta, out);
 }
+int shim_cell_dr_d(const float* h, int kind, int E, const float* A, const float* b, double px, double py, double phi,
+                   double dbar, double zeta, double xi0, double xi1, double ro2, double theta, double* out) {
+  return cell_dr_impl<double>(h, kind, E, A, b, px, py, phi, dbar, zeta, xi0, xi1, ro2, theta, out);
+}
+int shim_cell_dr_f(const float* h, int kind, int E, const float* A, const float* b, double px, double py, double phi,
+                   double dbar, double zeta, double xi0, double xi1, double ro2, double theta, double* out) {
+  return cell_dr_impl<float>(h, kind, E, A, b, px, py, phi, dbar, zeta, xi0, xi1, ro2, theta, out);
+}
 int shim_su_d(const SuParams* P, const double* lins, const double* linu, const double* ref, double vref,
               const double* dis, const float* hx, const float* hy, const float* hc, const float* gx,
               const float* gy, const double* pref, double* s, double* u, double* d, int* iters) {
@@ -158,7 +187,7 @@ extern "C" int port_solve_batch(const rda_config* cfg, const rda_tunables* tun, 
                                 const int* obs_count, int tv, int iter_num, float thr, float* u_opt,
                                 float* s_opt, float* resi_pri, float* resi_dual, int* iters_out, int* fails_out, int nthreads) {
   RobotGeom rb;
-  int rc = robot_geom_from_halfspaces(cfg->G, cfg->h, cfg->robot_edges, &rb);
+  int rc = robot_geom_from_halfspaces(cfg->G, cfg->h, cfg->robot_edges, &rb, cfg->robot_cone);
   if (rc) return rc;
   const int T = cfg->receding, N = cfg->max_obs_num, E = cfg->max_edge_num, R = cfg->robot_edges, NT = N * T;
   SuParams P;
@@ -191,7 +220,7 @@ extern "C" int port_solve_batch(const rda_config* cfg, const rda_tunables* tun, 
     RobotAux ra2;
     robot_aux_from_geom(rb, &ra2);
     long long coh_hits = 0;
-    if (use_lean2 && E == 4 && !tv)
+    if (use_lean2 && E == 4 && !tv && !rb.disc)
       for (int o = 0; o < N; ++o) obstacle_geometry<4>(E, obs_A + ((size_t)b * N + o) * E * 2, obs_b + ((size_t)b * N + o) * E, og2[o]);
     std::vector<float> cs(nom_s + (size_t)b * 3 * (T + 1), nom_s + (size_t)(b + 1) * 3 * (T + 1));
     std::vector<float> cu(nom_u + (size_t)b * 2 * T, nom_u + (size_t)(b + 1) * 2 * T);
@@ -261,7 +290,7 @@ extern "C" int port_solve_batch(const rda_config* cfg, const rda_tunables* tun, 
             CellOut<float> out;
             // emulation of the coherent pipeline (RDA_PORT_LEAN2=1): k_cells_coh -> listed cell_lean -> generic solver
             bool lean_done = false;
-            if (use_lean2 && E == 4 && R == 4 && !tv && obs_kind[(size_t)b * N + o] == RDA_OBS_POLYGON) {
+            if (use_lean2 && !rb.disc && E == 4 && R == 4 && !tv && obs_kind[(size_t)b * N + o] == RDA_OBS_POLYGON) {
               LeanOut<4, 4> lo;
               int nf = -1;
               if (xi[o * T + t] == 0.f && xi[NT + o * T + t] == 0.f)
@@ -280,7 +309,11 @@ extern "C" int port_solve_batch(const rda_config* cfg, const rda_tunables* tun, 
                 out.c0 = lo.c0; out.gx = lo.gx; out.gy = lo.gy; out.hm0 = 0.f; out.hm1 = 0.f; out.path = CELL_FAST_INACTIVE;
               }
             }
-            if (!lean_done)
+            if (rb.disc)
+              cell_solve_dr<float>(rb, obs_kind[(size_t)b * N + o], E, obs_A + ob * E * 2, obs_b + ob * E, cs[t + 1],
+                                   cs[(T + 1) + t + 1], cosf(ph), sinf(ph), dis[t], zeta[o * T + t], xi[o * T + t],
+                                   xi[NT + o * T + t], (float)P.ro2, theta, out);
+            else if (!lean_done)
             cell_solve<float>(rb, obs_kind[(size_t)b * N + o], E, obs_A + ob * E * 2, obs_b + ob * E, cs[t + 1],
                               cs[(T + 1) + t + 1], cosf(ph), sinf(ph), dis[t], zeta[o * T + t], xi[o * T + t],
                               xi[NT + o * T + t], (float)P.ro2, theta, out);

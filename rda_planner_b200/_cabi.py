@@ -12,6 +12,7 @@ MAX_EDGE = 8
 MAX_ROBOT_EDGE = 8
 DYNAMICS = {'acker': 0, 'diff': 1, 'omni': 2}
 OBS_POLYGON, OBS_CIRCLE = 0, 1
+ROBOT_POLYGON, ROBOT_DISC = 0, 1
 ST_SU_NOT_CONVERGED, ST_SU_NONFINITE, ST_CELL_FALLBACK, ST_EARLY_STOP = 1, 2, 4, 8
 (BUF_LAM, BUF_MU, BUF_Z, BUF_XI, BUF_ZETA, BUF_DIS, BUF_COEF, BUF_PREF, BUF_CUR_S, BUF_CUR_U,
  BUF_COUNTERS) = range(11)
@@ -23,7 +24,7 @@ class Config(C.Structure):
                 ('accelerated', C.c_int), ('su_fp64', C.c_int), ('step_time', C.c_float),
                 ('wheelbase', C.c_float), ('max_speed', C.c_float * 2), ('acce_bound', C.c_float * 2),
                 ('ws', C.c_float), ('wu', C.c_float), ('G', C.c_float * (MAX_ROBOT_EDGE * 2)),
-                ('h', C.c_float * MAX_ROBOT_EDGE)]
+                ('h', C.c_float * MAX_ROBOT_EDGE), ('robot_cone', C.c_int)]
 
 
 class Tunables(C.Structure):

@@ -1,0 +1,389 @@
+// cell_disc_robot.cuh — the (obstacle, stage) cell of the LamMuZ problem for a DISC robot.
+//
+// Reference: car_tuple.cone_type == 'norm2' — cone_cp_array(-indep_mu, 'norm2'), rda_solver.py:1034-1039, used by
+// LamMuZ_cost_cons :419 — with the ir-sim description of a circular body, G = [[1,0],[0,1],[0,0]], h = (cx, cy, -r):
+// mu has three rows, -mu in the second-order cone means |mu[0:2]| <= -mu[2], G'mu = mu[0:2] =: g and
+// mu'h = g.c - r mu[2] >= g.c + r|g|, so the body enters the cell problem of cell_solver.cuh through its support
+// function sigma_Rob(g) = g.c + r|g| only:
+//     min_{|v|<=1, g}  1/2 neg(stuff)^2 + ro2/2 |g + R'v + xi|^2,   stuff = v.p - sigma_O(v) - sigma_Rob(g) - d + zeta.
+// Closed forms (one thread per cell, Real): the two cases that cover the inactive hinges (xi = 0 and a non-negative
+// margin: closest point of the obstacle to the disc centre; overlap without tilt).  Everything else — active hinges,
+// tilted cells — is a small second-order cone programme with TWO cones (|v| <= 1 or the obstacle disc's cone, and the
+// body's |g| <= t_g), solved in float64 by the feasible log-barrier Newton method below.  Same tie-break as the polygon
+// body: max margin, mu[2] = -|g| (the LP-vertex analogue: smallest mu'h), z = theta * max(stuff, 0).
+#pragma once
+#include "cell_solver.cuh"
+
+namespace rda {
+
+// min 1/2 x'Qx + c'x  s.t.  a_i'x <= b_i (i < m)  and  |(x[ia_k] + sa_k, x[ib_k] + sb_k)| <= (it_k >= 0 ? x[it_k] : 1), k < nc
+template <int NV, int MC>
+struct SocQP {
+  double Q[NV][NV], c[NV], ad[MC][NV], b[MC];
+  int m, nc;
+  int ia[2], ib[2], it[2];
+  double sa[2], sb[2];
+  double x[NV];
+  RDA_HD void clear() {
+    for (int k = 0; k < NV; ++k) { c[k] = 0; for (int j = 0; j < NV; ++j) Q[k][j] = 0; }
+    m = 0; nc = 0;
+  }
+  RDA_HD int new_row(double rhs) {
+    for (int k = 0; k < NV; ++k) ad[m][k] = 0;
+    b[m] = rhs;
+    return m++;
+  }
+  RDA_HD void cone(int a, int b_, int t, double sha, double shb) { ia[nc] = a; ib[nc] = b_; it[nc] = t; sa[nc] = sha; sb[nc] = shb; ++nc; }
+};
+
+// value of t*f0 + barrier at y (1e300 outside the domain)
+template <int NV, int MC>
+RDA_HD double soc_value(const SocQP<NV, MC>& P, const double* y, double t) {
+  double f = 0;
+  for (int k = 0; k < NV; ++k) {
+    double qx = 0;
+    for (int j = 0; j < NV; ++j) qx += P.Q[k][j] * y[j];
+    f += t * y[k] * (0.5 * qx + P.c[k]);
+  }
+  for (int i = 0; i < P.m; ++i) {
+    double sl = P.b[i];
+    for (int k = 0; k < NV; ++k) sl -= P.ad[i][k] * y[k];
+    if (!(sl > 0)) return 1e300;
+    f -= log(sl);
+  }
+  for (int k = 0; k < P.nc; ++k) {
+    const double u = y[P.ia[k]] + P.sa[k], w = y[P.ib[k]] + P.sb[k];
+    const double tq = P.it[k] >= 0 ? y[P.it[k]] : 1.0;
+    const double psi = tq * tq - u * u - w * w;
+    if (!(psi > 0) || !(tq > 0)) return 1e300;
+    f -= log(psi);
+  }
+  return f;
+}
+
+// Feasible-start path following: damped Newton with backtracking on t*f0 + barrier, t = 1, 8, ..., 8^13
+// (duality gap (m + 2 nc)/t ~ 3e-11 at the end).  x must hold a strictly feasible point.
+template <int NV, int MC>
+RDA_HD bool soc_barrier(SocQP<NV, MC>& P) {
+  double H[NV][NV], L[NV][NV], gr[NV], dx[NV], xn[NV], w[MC];
+  double t = 1.0;
+  for (int outer = 0; outer < 14; ++outer, t *= 8.0) {
+    for (int itn = 0; itn < 30; ++itn) {
+      for (int i = 0; i < P.m; ++i) {
+        double sl = P.b[i];
+        for (int k = 0; k < NV; ++k) sl -= P.ad[i][k] * P.x[k];
+        w[i] = 1.0 / sl;
+      }
+      for (int k = 0; k < NV; ++k) {
+        double v = P.c[k];
+        for (int j = 0; j < NV; ++j) v += P.Q[k][j] * P.x[j];
+        v *= t;
+        for (int i = 0; i < P.m; ++i) v += P.ad[i][k] * w[i];
+        gr[k] = v;
+        for (int j = 0; j <= k; ++j) {
+          double hv = t * P.Q[k][j];
+          for (int i = 0; i < P.m; ++i) hv += w[i] * w[i] * P.ad[i][k] * P.ad[i][j];
+          H[k][j] = hv;
+        }
+      }
+      for (int k = 0; k < P.nc; ++k) {
+        const int a = P.ia[k], bq = P.ib[k], tt = P.it[k];
+        const double u = P.x[a] + P.sa[k], wv = P.x[bq] + P.sb[k];
+        const double tq = tt >= 0 ? P.x[tt] : 1.0;
+        const double ip = 1.0 / (tq * tq - u * u - wv * wv);
+        // -log psi: gradient -grad(psi)/psi, Hessian grad grad'/psi^2 - hess(psi)/psi
+        const double ga = -2 * u, gb = -2 * wv, gt = 2 * tq;
+        gr[a] -= ga * ip; gr[bq] -= gb * ip;
+        auto addh = [&](int r, int cidx, double v) { if (r >= cidx) H[r][cidx] += v; else H[cidx][r] += v; };
+        addh(a, a, ga * ga * ip * ip + 2 * ip);
+        addh(bq, bq, gb * gb * ip * ip + 2 * ip);
+        addh(a, bq, ga * gb * ip * ip);
+        if (tt >= 0) {
+          gr[tt] -= gt * ip;
+          addh(tt, tt, gt * gt * ip * ip - 2 * ip);
+          addh(tt, a, gt * ga * ip * ip);
+          addh(tt, bq, gt * gb * ip * ip);
+        }
+      }
+      for (int k = 0; k < NV; ++k) { H[k][k] += 1e-13 * (1.0 + H[k][k]); dx[k] = -gr[k]; }
+      // Cholesky (lower) and solve
+      for (int j = 0; j < NV; ++j) {
+        double d = H[j][j];
+        for (int k = 0; k < j; ++k) d -= L[j][k] * L[j][k];
+        if (!(d > 0)) return false;
+        L[j][j] = sqrt(d);
+        const double inv = 1.0 / L[j][j];
+        for (int r = j + 1; r < NV; ++r) {
+          double sacc = H[r][j];
+          for (int k = 0; k < j; ++k) sacc -= L[r][k] * L[j][k];
+          L[r][j] = sacc * inv;
+        }
+      }
+      for (int i = 0; i < NV; ++i) {
+        double sacc = dx[i];
+        for (int k = 0; k < i; ++k) sacc -= L[i][k] * dx[k];
+        dx[i] = sacc / L[i][i];
+      }
+      for (int i = NV - 1; i >= 0; --i) {
+        double sacc = dx[i];
+        for (int k = i + 1; k < NV; ++k) sacc -= L[k][i] * dx[k];
+        dx[i] = sacc / L[i][i];
+      }
+      double lam2 = 0;
+      for (int k = 0; k < NV; ++k) lam2 -= gr[k] * dx[k];
+      if (!(lam2 == lam2)) return false;
+      if (lam2 < 1e-9) break;
+      const double f0 = soc_value<NV, MC>(P, P.x, t);
+      double step = 1.0;
+      bool moved = false;
+      for (int bt = 0; bt < 50; ++bt, step *= 0.5) {
+        for (int k = 0; k < NV; ++k) xn[k] = P.x[k] + step * dx[k];
+        if (soc_value<NV, MC>(P, xn, t) <= f0 - 0.1 * step * lam2) { moved = true; break; }
+      }
+      if (!moved) break;
+      for (int k = 0; k < NV; ++k) P.x[k] = xn[k];
+    }
+  }
+  return true;
+}
+
+constexpr int DR_NVA = 5, DR_NVB = 8, DR_MC = RDA_MAX_EDGE + 3;
+struct DiscSlowStore {
+  union U {
+    SocQP<DR_NVA, DR_MC> a;
+    SocQP<DR_NVB, DR_MC> b;
+    RDA_HD U() {}
+  } u;
+};
+
+// ---- stage 1: geometry relative to the robot reference point and the closed forms of the inactive hinge ----------
+// Fills w.g (obstacle part), w.k0 ..., w.best (squared distance from the DISC CENTRE to the obstacle, 0 inside),
+// w.byx / w.byy (unit direction obstacle -> centre, world frame) and, when a closed form applies, the solution.
+template <typename Real>
+RDA_HD void cell_front_dr(const RobotGeom& rb, int kind, int E, const float* A, const float* b, Real px, Real py,
+                          Real cphi, Real sphi, Real dbar, Real zeta, Real xi0, Real xi1, Real ro2, CellWork<Real>& w) {
+  const Real k0 = dbar - zeta;
+  const Real eps = sizeof(Real) == 4 ? (Real)1e-5 : (Real)1e-11;
+  CellGeom<Real>& g = w.g;
+  w.k0 = k0; w.cphi = cphi; w.sphi = sphi; w.xi0 = xi0; w.xi1 = xi1; w.ro2 = ro2;
+  w.circ = (kind == RDA_OBS_CIRCLE);
+  g.kind = kind;
+  const Real rr = rb.rad;
+  const Real cwx = cphi * (Real)rb.cx - sphi * (Real)rb.cy, cwy = sphi * (Real)rb.cx + cphi * (Real)rb.cy;   // R c
+  Real dc = 0, dirx = 0, diry = 0;     // distance of the disc centre to the obstacle (0 inside), direction obstacle -> centre
+  bool sep;
+  if (kind == RDA_OBS_CIRCLE) {
+    g.cx = (Real)b[0] - px; g.cy = (Real)b[1] - py; g.rad = -(Real)b[2]; g.ne = 0;
+    const Real dx = cwx - g.cx, dy = cwy - g.cy;
+    const Real dn = sqrt_(dx * dx + dy * dy);
+    dc = rmax(dn - g.rad, (Real)0);
+    if (dn > eps) { dirx = dx / dn; diry = dy / dn; }
+    sep = dn > g.rad + rr + eps;
+  } else {
+    int ne = 0;
+    Real brel[RDA_MAX_EDGE];
+    for (int i = 0; i < E; ++i) {
+      const Real ax = A[2 * i], ay = A[2 * i + 1];
+      const Real n2 = ax * ax + ay * ay;
+      if (!(n2 > 0)) break;
+      const Real inv = rsqrt_(n2);
+      g.nx[i] = ax * inv; g.ny[i] = ay * inv; g.inv_norm[i] = inv;
+      brel[i] = ((Real)b[i] - ax * px - ay * py) * inv;
+      ne = i + 1;
+    }
+    g.ne = ne;
+    for (int i = 0; i < ne; ++i) {
+      const int a = (i + ne - 1) % ne;
+      const Real det = g.nx[a] * g.ny[i] - g.ny[a] * g.nx[i];
+      const Real inv = (Real)1 / det;
+      g.vx[i] = (brel[a] * g.ny[i] - brel[i] * g.ny[a]) * inv;
+      g.vy[i] = (g.nx[a] * brel[i] - g.nx[i] * brel[a]) * inv;
+    }
+    bool inside = true;
+    Real best = 1e30f, bdx = 0, bdy = 0;
+    for (int i = 0; i < ne; ++i) {
+      const int in = (i + 1) % ne;
+      const Real ex = g.vx[in] - g.vx[i], ey = g.vy[in] - g.vy[i];
+      const Real rx = cwx - g.vx[i], ry = cwy - g.vy[i];
+      if (g.nx[i] * rx + g.ny[i] * ry > 0) inside = false;
+      const Real t = rclamp((rx * ex + ry * ey) / (ex * ex + ey * ey), (Real)0, (Real)1);
+      const Real dx = rx - t * ex, dy = ry - t * ey;
+      const Real d2 = dx * dx + dy * dy;
+      if (d2 < best) { best = d2; bdx = dx; bdy = dy; }
+    }
+    if (ne == 0) { inside = false; best = 1e30f; }
+    const Real dn = sqrt_(best);
+    dc = inside ? (Real)0 : dn;
+    if (!inside && dn > eps) { dirx = bdx / dn; diry = bdy / dn; }
+    sep = !inside && dn > rr + eps;
+  }
+  w.sep = sep; w.best = dc * dc; w.byx = dirx; w.byy = diry;
+  Real v0 = 0, v1 = 0, g0 = 0, g1 = 0;
+  bool exact_zero_q = false, have = false;
+  int path = CELL_FAILED;
+  const bool xi_zero = (xi0 == (Real)0) && (xi1 == (Real)0);
+  w.xi_zero = xi_zero;
+  if (sep && xi_zero && dc - rr - k0 >= 0) {
+    // disjoint, no tilt, non-negative margin: unit normal of the closest pair (it lies on the line through the centre)
+    v0 = dirx; v1 = diry;
+    g0 = -(cphi * v0 + sphi * v1);
+    g1 = -(-sphi * v0 + cphi * v1);
+    exact_zero_q = true; have = true; path = CELL_FAST_INACTIVE;
+  } else if (!sep && xi_zero && k0 <= 0) {
+    // overlapping sets, no tilt: max margin 0 at v = 0 (stuff = -k0 >= 0)
+    exact_zero_q = true; have = true; path = CELL_OVERLAP_FREE;
+  }
+  w.v0 = v0; w.v1 = v1; w.g0 = g0; w.g1 = g1;
+  w.exact_zero_q = exact_zero_q; w.have = have; w.path = path;
+}
+
+// ---- stage 2: the two-cone programmes (float64) ---------------------------------------------------------------------
+template <typename Real>
+RDA_HD void cell_slow_dr(const RobotGeom& rb, CellWork<Real>& w, DiscSlowStore& S) {
+  const CellGeom<Real>& g = w.g;
+  const double x0 = w.xi0, x1 = w.xi1, k0d = (double)w.k0, c_ = w.cphi, s_ = w.sphi, r2 = w.ro2;
+  const double rr = rb.rad, bcx = rb.cx, bcy = rb.cy;
+  const double cwx = c_ * bcx - s_ * bcy, cwy = s_ * bcx + c_ * bcy;          // R c
+  const double ax_ = c_ * x0 - s_ * x1, ay_ = s_ * x0 + c_ * x1;                // R xi
+  const double xic = x0 * bcx + x1 * bcy;
+  const bool circ = w.circ;
+  const double radd = circ ? (double)g.rad : 0.0;
+  const int nv_o = circ ? 1 : g.ne;
+  if (!circ && g.ne < 3) { w.have = false; w.path = CELL_FAILED; return; }
+  // upper bound of the max margin from the closest pair: negative => the hinge is active for sure, stage A skipped
+  bool need_a = true;
+  if (w.sep) {
+    const double dirx = w.byx, diry = w.byy;
+    // body point of the closest pair, body frame: c - r R'dir
+    const double ybx = bcx - rr * (c_ * dirx + s_ * diry), yby = bcy - rr * (-s_ * dirx + c_ * diry);
+    const double ub = (sqrt((double)w.best) - rr) + x0 * ybx + x1 * yby - k0d;
+    if (ub < -1e-9) need_a = false;
+  }
+  bool ok = true, inactive = false;
+  if (need_a) {   // stage A: max margin with Hm + xi = 0 (g = -R'v - xi);  x = (v0, v1, so, tg, tv)
+    SocQP<DR_NVA, DR_MC>& P = S.u.a;
+    P.clear();
+    P.c[0] = -cwx; P.c[1] = -cwy; P.c[2] = 1; P.c[3] = rr;     // so + sigma_Rob(g) + xi.c = so + r tg - v.(R c)
+    for (int i = 0; i < nv_o; ++i) {
+      const int r = P.new_row(0.0);                            // v.x_i + rad tv <= so
+      P.ad[r][0] = circ ? (double)g.cx : (double)g.vx[i];
+      P.ad[r][1] = circ ? (double)g.cy : (double)g.vy[i];
+      P.ad[r][2] = -1.0; P.ad[r][4] = radd;
+    }
+    { const int r = P.new_row(1.0); P.ad[r][4] = 1.0; }        // tv <= 1
+    { const int r = P.new_row(0.0); P.ad[r][4] = -1.0; }       // tv >= 0
+    P.cone(0, 1, circ ? 4 : -1, 0.0, 0.0);                     // |v| <= 1  /  |v| <= tv
+    P.cone(0, 1, 3, ax_, ay_);                                 // |g| = |v + R xi| <= tg
+    P.x[0] = 0; P.x[1] = 0; P.x[2] = 1.0 + radd; P.x[3] = sqrt(ax_ * ax_ + ay_ * ay_) + 1.0; P.x[4] = 0.5;
+    ok = soc_barrier<DR_NVA, DR_MC>(P);
+    if (ok) {
+      const double va = P.x[0], vb = P.x[1];
+      const double gn = sqrt((va + ax_) * (va + ax_) + (vb + ay_) * (vb + ay_));
+      // margin at the barrier's v with the supports evaluated exactly (so, tg carry the barrier's 1/t slack)
+      double so = circ ? va * (double)g.cx + vb * (double)g.cy + radd * sqrt(va * va + vb * vb) : -1e300;
+      if (!circ) for (int i = 0; i < g.ne; ++i) so = rmax(so, va * (double)g.vx[i] + vb * (double)g.vy[i]);
+      const double cst = -(so + rr * gn - (va * cwx + vb * cwy) - xic) - k0d;
+      if (cst >= 0) {
+        inactive = true;
+        w.v0 = (Real)va; w.v1 = (Real)vb;
+        w.g0 = (Real)(-(c_ * va + s_ * vb) - x0);
+        w.g1 = (Real)(-(-s_ * va + c_ * vb) - x1);
+        w.exact_zero_q = true; w.have = true; w.path = CELL_SLOW_A;
+      }
+    }
+  }
+  if (ok && !inactive) {   // stage B: active hinge;  x = (v0, v1, g0, g1, so, tg, w, tv)
+    SocQP<DR_NVB, DR_MC>& P = S.u.b;
+    P.clear();
+    const double Mx[4] = {c_, s_, 1, 0}, My[4] = {-s_, c_, 0, 1};      // q = M (v, g) + xi, M = [R' I]
+    for (int k = 0; k < 4; ++k)
+      for (int j = 0; j < 4; ++j) P.Q[k][j] = r2 * (Mx[k] * Mx[j] + My[k] * My[j]);
+    for (int k = 0; k < 4; ++k) P.c[k] = r2 * (Mx[k] * x0 + My[k] * x1);
+    P.Q[6][6] = 1.0;                                                    // 1/2 w^2 (ro1 == 1 inside LamMuZ, rda_solver.py:257)
+    for (int i = 0; i < nv_o; ++i) {
+      const int r = P.new_row(0.0);
+      P.ad[r][0] = circ ? (double)g.cx : (double)g.vx[i];
+      P.ad[r][1] = circ ? (double)g.cy : (double)g.vy[i];
+      P.ad[r][4] = -1.0; P.ad[r][7] = radd;
+    }
+    { const int r = P.new_row(-k0d); P.ad[r][4] = 1.0; P.ad[r][2] = bcx; P.ad[r][3] = bcy; P.ad[r][5] = rr; P.ad[r][6] = -1.0; }   // so + sigma_Rob + k0 <= w
+    { const int r = P.new_row(1.0); P.ad[r][7] = 1.0; }
+    { const int r = P.new_row(0.0); P.ad[r][7] = -1.0; }
+    P.cone(0, 1, circ ? 7 : -1, 0.0, 0.0);
+    P.cone(2, 3, 5, 0.0, 0.0);                                          // |g| <= tg
+    const double so0 = 1.0 + radd;
+    const double xs[DR_NVB] = {0, 0, 0, 0, so0, 1.0, rmax(so0 + rr + k0d + 2.0, 1.0), 0.5};
+    for (int k = 0; k < DR_NVB; ++k) P.x[k] = xs[k];
+    ok = soc_barrier<DR_NVB, DR_MC>(P);
+    if (ok) {
+      w.v0 = (Real)P.x[0]; w.v1 = (Real)P.x[1]; w.g0 = (Real)P.x[2]; w.g1 = (Real)P.x[3];
+      w.exact_zero_q = false; w.have = true; w.path = CELL_SLOW_B;
+    }
+  }
+  if (!ok) { w.have = false; w.path = CELL_FAILED; }
+}
+
+// ---- stage 3: multipliers, updates, su-QP inputs (cell_back with the disc body's mu and support function) --------
+template <typename Real>
+RDA_HD void cell_back_dr(const RobotGeom& rb, const CellWork<Real>& w, Real zeta, Real theta, CellOut<Real>& out) {
+  const CellGeom<Real>& g = w.g;
+  const int ne = g.ne, kind = g.kind;
+  const Real v0 = w.v0, v1 = w.v1, g0 = w.g0, g1 = w.g1, cphi = w.cphi, sphi = w.sphi;
+  const Real xi0 = w.xi0, xi1 = w.xi1, k0 = w.k0;
+  for (int i = 0; i < RDA_MAX_EDGE; ++i) out.lam[i] = 0;
+  for (int j = 0; j < RDA_MAX_ROBOT_EDGE; ++j) out.mu[j] = 0;
+  out.path = w.path;
+  if (!w.have) {
+    out.z = 0; out.zeta_new = zeta; out.xi0_new = xi0; out.xi1_new = xi1;
+    out.ax = out.ay = out.c0 = out.gx = out.gy = out.hm0 = out.hm1 = 0;
+    return;
+  }
+  int io = 0;
+  const Real sO = support_obs<Real>(g, v0, v1, &io);
+  const Real vn = sqrt_(v0 * v0 + v1 * v1);
+  if (kind == RDA_OBS_CIRCLE) {
+    out.lam[0] = v0; out.lam[1] = v1; out.lam[2] = -vn;
+  } else if (vn > 0) {
+    const int a = (io + ne - 1) % ne, bb = io;
+    const Real det = g.nx[a] * g.ny[bb] - g.ny[a] * g.nx[bb];
+    const Real al = (v0 * g.ny[bb] - v1 * g.nx[bb]) / det;
+    const Real be = (g.nx[a] * v1 - g.ny[a] * v0) / det;
+    out.lam[a] = rmax(al, (Real)0) * g.inv_norm[a];
+    out.lam[bb] = rmax(be, (Real)0) * g.inv_norm[bb];
+  }
+  const Real gn = sqrt_(g0 * g0 + g1 * g1);
+  out.mu[0] = g0; out.mu[1] = g1; out.mu[2] = -gn;                       // (g, -|g|): smallest mu'h in the cone
+  const Real sR = g0 * (Real)rb.cx + g1 * (Real)rb.cy + (Real)rb.rad * gn;
+  const Real marg = -sO - sR;
+  const Real stuff = marg - k0;
+  const Real z = theta * rmax(stuff, (Real)0);
+  Real q0, q1;
+  if (w.exact_zero_q) { q0 = 0; q1 = 0; }
+  else {
+    q0 = g0 + (cphi * v0 + sphi * v1) + xi0;
+    q1 = g1 + (-sphi * v0 + cphi * v1) + xi1;
+  }
+  out.z = z;
+  out.zeta_new = stuff - z;
+  out.xi0_new = q0; out.xi1_new = q1;
+  out.hm0 = q0 - xi0; out.hm1 = q1 - xi1;
+  out.ax = v0; out.ay = v1;
+  out.c0 = marg - z + out.zeta_new;
+  out.gx = g0 + q0; out.gy = g1 + q1;
+}
+
+// One cell, one thread (CPU port, tests).
+template <typename Real>
+RDA_HD void cell_solve_dr(const RobotGeom& rb, int kind, int E, const float* A, const float* b, Real px, Real py,
+                          Real cphi, Real sphi, Real dbar, Real zeta, Real xi0, Real xi1, Real ro2, Real theta,
+                          CellOut<Real>& out) {
+  CellWork<Real> w;
+  cell_front_dr<Real>(rb, kind, E, A, b, px, py, cphi, sphi, dbar, zeta, xi0, xi1, ro2, w);
+  if (!w.have) {
+    DiscSlowStore S;
+    cell_slow_dr<Real>(rb, w, S);
+  }
+  cell_back_dr<Real>(rb, w, zeta, theta, out);
+}
+
+}  // namespace rda

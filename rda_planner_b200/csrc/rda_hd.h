@@ -69,6 +69,8 @@ struct SeqCtx {
 // unit outward normals and row norms.
 struct RobotGeom {
   int R;
+  int disc;                 // 1: disc body (car_tuple.cone_type 'norm2', rda_solver.py:1034-1039): centre (cx, cy), radius rad
+  float rad, cx, cy;
   float yx[RDA_MAX_ROBOT_EDGE], yy[RDA_MAX_ROBOT_EDGE];
   float nx[RDA_MAX_ROBOT_EDGE], ny[RDA_MAX_ROBOT_EDGE], gnorm[RDA_MAX_ROBOT_EDGE];
   float h[RDA_MAX_ROBOT_EDGE];
@@ -76,9 +78,21 @@ struct RobotGeom {
 
 // Fill RobotGeom from (G, h); returns 0 or RDA_E_UNSUPPORTED when the rows do not describe a
 // closed convex polygon listed counter-clockwise.
-inline int robot_geom_from_halfspaces(const float* G, const float* h, int R, RobotGeom* out) {
+inline int robot_geom_from_halfspaces(const float* G, const float* h, int R, RobotGeom* out, int cone = RDA_ROBOT_POLYGON) {
   if (R < 3 || R > RDA_MAX_ROBOT_EDGE) return RDA_E_UNSUPPORTED;
   out->R = R;
+  out->disc = 0; out->rad = 0.f; out->cx = 0.f; out->cy = 0.f;
+  if (cone == RDA_ROBOT_DISC) {
+    // ir-sim description of a circular body: G = [[1,0],[0,1],[0,0]], h = (cx, cy, -r); any other norm2 body is refused
+    const float Gd[6] = {1.f, 0.f, 0.f, 1.f, 0.f, 0.f};
+    if (R != 3) return RDA_E_UNSUPPORTED;
+    for (int k = 0; k < 6; ++k) if (fabsf(G[k] - Gd[k]) > 1e-6f) return RDA_E_UNSUPPORTED;
+    if (!(h[2] < 0.f)) return RDA_E_UNSUPPORTED;
+    out->disc = 1; out->cx = h[0]; out->cy = h[1]; out->rad = -h[2];
+    for (int j = 0; j < RDA_MAX_ROBOT_EDGE; ++j) { out->yx[j] = out->yy[j] = out->nx[j] = out->ny[j] = 0.f; out->gnorm[j] = 1.f; out->h[j] = j < 3 ? h[j] : 0.f; }
+    return 0;
+  }
+  if (cone != RDA_ROBOT_POLYGON) return RDA_E_UNSUPPORTED;
   for (int j = 0; j < R; ++j) {
     double gx = G[2 * j], gy = G[2 * j + 1];
     double n = sqrt(gx * gx + gy * gy);

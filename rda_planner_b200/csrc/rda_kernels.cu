@@ -17,6 +17,7 @@
 #include "su_batched.cuh"
 #include "cell_lean.cuh"
 #include "cell_lean2.cuh"
+#include "cell_disc_robot.cuh"
 
 using namespace rda;
 
@@ -629,6 +630,82 @@ __global__ void __launch_bounds__(64, RDA_SLOW_MINBLOCKS) k_cells_slow(DevPtrs d
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Disc body (car_tuple.cone_type 'norm2', rda_solver.py:1034-1039; cell_disc_robot.cuh).  Two passes over the
+// same worklist machinery: k_cells_dr solves every cell whose hinge is inactive in closed form (one thread per
+// cell, coalesced like the first polygon pass) and lists the rest; k_cells_dr_slow runs the two-cone barrier
+// programmes of the listed cells, one cell per thread.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_cells_dr(DevPtrs d, RobotGeom rb, float ro2, float theta) {
+  const int NT = d.N * d.T;
+  const long long total = (long long)d.B * NT;
+  const int lane = threadIdx.x & 31;
+  for (long long base = (long long)blockIdx.x * blockDim.x; base < total; base += (long long)gridDim.x * blockDim.x) {
+    const long long idx = base + threadIdx.x;
+    bool live = idx < total;
+    const int b = live ? (int)(idx / NT) : -1;
+    if (live && (d.done[b] || d.obs_count[b] == 0)) live = false;
+    bool need = false;
+    if (live) {
+      CellIn c = cell_load(d, idx);
+      CellWork<float> w;
+      cell_front_dr<float>(rb, c.kind, d.E, c.A, c.bb, c.px, c.py, c.cp, c.sp, c.dbar, c.zeta, c.xi0, c.xi1, ro2, w);
+      if (w.have) {
+        CellOut<float> out;
+        cell_back_dr<float>(rb, w, c.zeta, theta, out);
+        float hm2 = 0.f, dual = 0.f;
+        cell_store(d, c, out, &hm2, &dual);
+        atomicAdd(&d.resi_acc[2 * c.b], hm2);
+        atomicAdd(&d.resi_acc[2 * c.b + 1], dual);
+      } else {
+        need = true;
+      }
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, need);
+    if (m) {
+      int leader = __ffs(m) - 1, pos = 0;
+      if (lane == leader) pos = atomicAdd(&d.wl_count[1], __popc(m));
+      pos = __shfl_sync(0xffffffffu, pos, leader);
+      if (need) d.worklist2[pos + __popc(m & ((1u << lane) - 1))] = (int)idx;
+    }
+    const unsigned solved = __ballot_sync(0xffffffffu, live && !need);
+    if (lane == 0 && solved) atomicAdd(&d.counters[0], __popc(solved));
+  }
+}
+
+__global__ void __launch_bounds__(64) k_cells_dr_slow(DevPtrs d, RobotGeom rb, float ro2, float theta) {
+  const int count = d.wl_count[1];
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  // the barrier iteration is long and its length differs from cell to cell: one cell per warp while the list is
+  // short enough to give every cell its own warp, packed otherwise
+  const int cpw = count <= nwarps ? 1 : 32;
+  if (lane >= cpw) return;
+  for (int wi = warp * cpw + lane; wi < count; wi += nwarps * cpw) {
+    const long long idx = d.worklist2[wi];
+    CellIn c = cell_load(d, idx);
+    CellWork<float> w;
+    cell_front_dr<float>(rb, c.kind, d.E, c.A, c.bb, c.px, c.py, c.cp, c.sp, c.dbar, c.zeta, c.xi0, c.xi1, ro2, w);
+    if (!w.have) {
+      DiscSlowStore S;
+      cell_slow_dr<float>(rb, w, S);
+    }
+    CellOut<float> out;
+    cell_back_dr<float>(rb, w, c.zeta, theta, out);
+    float hm2 = 0.f, dual = 0.f;
+    if (out.path == CELL_FAILED) {
+      dual = INFINITY;                                   // "Update Lam Mu Fail": previous duals kept (:791-793)
+      atomicOr(&d.status[c.b], RDA_ST_CELL_FALLBACK);
+    } else {
+      cell_store(d, c, out, &hm2, &dual);
+    }
+    atomicAdd(&d.resi_acc[2 * c.b], hm2);
+    atomicAdd(&d.resi_acc[2 * c.b + 1], dual);
+    atomicAdd(&d.counters[out.path == CELL_FAILED ? 2 : 1], 1);
+  }
+}
+
 // per instance: residuals (:688, :735-739), early stop (:594-596), empty-list quirk (:564-568)
 __device__ __forceinline__ void finalize_instance(const DevPtrs& d, const RobotGeom& rb, float thr, int b) {
   const int T = d.T, N = d.N, NT = N * T, R = d.R;
@@ -942,7 +1019,7 @@ int rda_create(const rda_config* cfg, const rda_tunables* tun, rda_handle** out)
   if (!h) return RDA_E_NOMEM;
   memset(h, 0, sizeof(*h));
   h->cfg = *cfg; h->tun = *tun;
-  int rc = robot_geom_from_halfspaces(cfg->G, cfg->h, cfg->robot_edges, &h->rb);
+  int rc = robot_geom_from_halfspaces(cfg->G, cfg->h, cfg->robot_edges, &h->rb, cfg->robot_cone);
   if (rc) { delete h; return rc; }
   h->B = cfg->batch; h->T = cfg->receding; h->N = cfg->max_obs_num; h->E = cfg->max_edge_num;
   h->R = cfg->robot_edges;
@@ -1011,8 +1088,8 @@ int rda_create(const rda_config* cfg, const rda_tunables* tun, rda_handle** out)
   if (e != cudaSuccess) { rda_destroy(h); return (int)e; }
   // coherent first cell pass: on for batches whose sub-batches reach 4096 instances (measured r02: -8 % of the cell
   // passes at B = 16384, +15 % at B = 1024 where its two extra launches outweigh the saved work); RDA_B200_LEAN2=0/1 forces
-  h->lean2 = h->B >= 8192 && h->E <= 4 && h->R <= 4 && h->N > 0;
-  if (const char* l2 = getenv("RDA_B200_LEAN2")) h->lean2 = atoi(l2) != 0 && h->E <= 4 && h->R <= 4 && h->N > 0;
+  h->lean2 = h->B >= 8192 && h->E <= 4 && h->R <= 4 && h->N > 0 && !h->rb.disc;
+  if (const char* l2 = getenv("RDA_B200_LEAN2")) h->lean2 = atoi(l2) != 0 && h->E <= 4 && h->R <= 4 && h->N > 0 && !h->rb.disc;
   if (h->lean2) {
     robot_aux_from_geom(h->rb, &h->ra);
     e = cudaMalloc((void**)&h->ogeo, B * N * sizeof(ObstacleGeom<4>));
@@ -1029,7 +1106,7 @@ int rda_create(const rda_config* cfg, const rda_tunables* tun, rda_handle** out)
   {
     const size_t sub = cfg->su_fp64 ? su_work_bytes<double, double, 0>((int)T, (int)N, false) : su_work_bytes<float, float, 0>((int)T, (int)N, false);
     h->small_L = small_layout((int)T, (int)N, (int)E, (int)R, sub);
-    h->small_ok = h->small_L.total <= 200 * 1024;
+    h->small_ok = h->small_L.total <= 200 * 1024 && !h->rb.disc;      // the persistent kernel has the polygon body's cells only
     h->small_mode = -1; h->small_max = 296;
     // bulk (TMA) staging needs every staged block to be a multiple of 16 bytes: N*E*T, N*R*T and N*T multiples of 4
     h->small_bulk = (N > 0) && ((N * E * T) % 4 == 0) && ((N * R * T) % 4 == 0) && ((N * T) % 4 == 0);
@@ -1222,6 +1299,17 @@ static int step_lammuz_part(rda_handle* h, int b0, int nb, int part, cudaStream_
   DevPtrs d = dev_ptrs(h, b0, nb, part);
   if (h->N > 0) {
     const float theta = h->cfg.accelerated ? h->tun.z_theta : 1.0f;
+    if (h->rb.disc) {
+      k_cells_dr<<<grid_for((long long)nb * h->N * h->T, 128), 128, 0, s>>>(d, h->rb, h->tun.ro2, theta);
+      RDA_CUDA(cudaGetLastError());
+      k_cells_dr_slow<<<148 * 16, 64, 0, s>>>(d, h->rb, h->tun.ro2, theta);
+      RDA_CUDA(cudaGetLastError());
+      h->launches += 2;
+      k_finalize<<<(nb + 127) / 128, 128, 0, s>>>(d, h->rb, h->iter_threshold);
+      RDA_CUDA(cudaGetLastError());
+      h->launches += 1;
+      return 0;
+    }
     if (h->lean2 && !h->obs_tv && h->E <= 4 && h->R <= 4) {
       k_heading<<<(nb * h->T + 255) / 256, 256, 0, s>>>(d, h->rot + (size_t)b0 * 2 * h->T);
       RDA_CUDA(cudaGetLastError());

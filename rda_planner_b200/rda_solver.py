@@ -23,35 +23,105 @@ def _as_cuda_f32(x, device):
     return torch.as_tensor(x, dtype=torch.float32, device=device).contiguous()
 
 
-def canonical_polygon_rows(A, b):
-    """Order the rows of a closed convex polygon {x: Ax <= b} counter-clockwise by normal
-    angle (a no-op for the output of mpc.py:476-510) so that vertex i joins rows i-1 and i."""
+# Half-size [m] of the square (centred on the robot) that closes unbounded half-space sets in canonical_polygon_rows.
+# The kernels work in float32 relative to the robot: a vertex L metres away turns a direction error of one ulp into
+# L * 1e-7 m of margin, so the square is kept as small as a planning horizon allows and grown only when the set does
+# not reach into it (then the obstacle is too far to matter).
+HALFSPACE_BOUND = 100.0
+HALFSPACE_BOUND_MAX = 1.0e5
+
+
+def canonical_polygon_rows(A, b, bound=None, center=None):
+    """Rows of a convex set {x: Ax <= b} ordered counter-clockwise by normal angle so that vertex i joins rows i-1 and
+    i — the layout the kernels' closest-point geometry needs.  A no-op for the output of mpc.py:476-510 (closed convex
+    polygon, rows already in order).  Anything else the reference accepts through rda_obstacle=True (mpc.py:150-155:
+    the caller's own (A, b) tuples) is reduced to that case by clipping: rows in any order, redundant rows (dropped:
+    their multipliers are zero at every optimum), and UNBOUNDED sets (a wall, a wedge, a strip), which are closed by
+    the sides of the square |x - center|_inf <= bound (center: the robot position, default the origin; bound: default
+    HALFSPACE_BOUND, grown 4x until the set reaches into the square) — exact as long as the closest obstacle point to
+    the robot does not lie on one of those artificial sides.  Original rows keep their scaling.  Raises ValueError for
+    an empty set."""
     A = np.asarray(A, float)
     b = np.asarray(b, float).reshape(-1)
     n = A.shape[0]
     def one_turn(M):
         # consecutive normals turn left AND the turning angles add up to a single 2 pi (no double winding)
-        d = M[np.arange(n) - 1, 0] * M[:, 1] - M[np.arange(n) - 1, 1] * M[:, 0]
-        if n < 3 or not np.all(d > 0):
+        m = M.shape[0]
+        d = M[np.arange(m) - 1, 0] * M[:, 1] - M[np.arange(m) - 1, 1] * M[:, 0]
+        if m < 3 or not np.all(d > 0):
             return False
         a = np.arctan2(M[:, 1], M[:, 0])
         turn = np.mod(a - np.roll(a, 1), 2 * np.pi)
         return abs(turn.sum() - 2 * np.pi) < 1e-6
-    if one_turn(A):
+    def every_row_is_an_edge(M, c):
+        # vertex i = rows i-1 and i; every vertex must satisfy all rows, and consecutive vertices must differ
+        m = M.shape[0]
+        V = np.zeros((m, 2))
+        for i in range(m):
+            V[i] = np.linalg.solve(np.array([M[i - 1], M[i]]), np.array([c[i - 1], c[i]]))
+        slack = c[None, :] - V @ M.T
+        scale = np.linalg.norm(M, axis=1)[None, :] * (1.0 + np.abs(V).max())
+        if np.any(slack < -1e-9 * scale):
+            return False
+        return bool(np.all(np.linalg.norm(np.roll(V, -1, axis=0) - V, axis=1) > 1e-9 * (1.0 + np.abs(V).max())))
+    live = np.linalg.norm(A, axis=1) > 0
+    if live.all() and one_turn(A) and every_row_is_an_edge(A, b):
         return A, b
-    ang = np.arctan2(A[:, 1], A[:, 0])
-    order = np.argsort(ang)
-    A, b = A[order], b[order]
-    if not one_turn(A):
-        raise ValueError('obstacle half-spaces must describe a closed convex polygon '
-                         '(unbounded polyhedra are not supported by rda_planner_b200)')
-    return A, b
+    if np.any(b[~live] < 0):
+        raise ValueError('obstacle half-spaces describe an empty set (0 <= b violated by a zero row)')
+    ctr = np.zeros(2) if center is None else np.asarray(center, float).reshape(-1)[:2]
+    if bound is None or bound > 0:
+        # first square of half-size `bound` (default HALFSPACE_BOUND), grown 4x while the set does not reach into it
+        L = float(HALFSPACE_BOUND if bound is None else bound)
+        while True:
+            try:
+                return canonical_polygon_rows(A, b, bound=-L, center=ctr)
+            except ValueError:
+                if L >= HALFSPACE_BOUND_MAX:
+                    raise
+                L *= 4.0
+    L = -float(bound)            # negative: exactly this size, no growth (internal)
+    # Sutherland-Hodgman clipping of the square by every row; each vertex carries the row of the edge that STARTS there
+    # (-1..-4: the artificial sides of the square)
+    poly = [(ctr + np.array([-L, -L]), -1), (ctr + np.array([L, -L]), -2), (ctr + np.array([L, L]), -3),
+            (ctr + np.array([-L, L]), -4)]
+    for r in np.nonzero(live)[0]:
+        a, c = A[r], b[r]
+        tol = 1e-12 * np.linalg.norm(a) * (L + np.abs(ctr).max())
+        out = []
+        for k in range(len(poly)):
+            (P, tag), (Q, _) = poly[k], poly[(k + 1) % len(poly)]
+            sp, sq = a @ P - c, a @ Q - c
+            if sp <= tol:
+                out.append((P, tag))
+                if sq > tol:
+                    out.append((P + (Q - P) * (sp / (sp - sq)), int(r)))
+            elif sq <= tol:
+                out.append((P + (Q - P) * (sp / (sp - sq)), tag))
+        poly = out
+        if len(poly) < 3:
+            raise ValueError('obstacle half-spaces describe an empty set inside |x| <= %g' % L)
+    # drop zero-length edges (a row that only touches a vertex)
+    keep = [k for k in range(len(poly))
+            if np.linalg.norm(poly[(k + 1) % len(poly)][0] - poly[k][0]) > 1e-9 * (1.0 + 1e-4 * (L + np.abs(ctr).max()))]
+    poly = [poly[k] for k in keep]
+    if len(poly) < 3:
+        raise ValueError('obstacle half-spaces describe a set without interior')
+    box = {-1: (np.array([0.0, -1.0]), L - ctr[1]), -2: (np.array([1.0, 0.0]), L + ctr[0]),
+           -3: (np.array([0.0, 1.0]), L + ctr[1]), -4: (np.array([-1.0, 0.0]), L - ctr[0])}
+    rows = [(A[t], b[t]) if t >= 0 else box[t] for _, t in poly]
+    An = np.array([r[0] for r in rows], float)
+    bn = np.array([r[1] for r in rows], float)
+    if not one_turn(An):
+        raise ValueError('obstacle half-spaces could not be reduced to a closed convex polygon')
+    return An, bn
 
 
-def pack_obstacles(obstacle_list, T, N, E):
+def pack_obstacles(obstacle_list, T, N, E, center=None, bound=None):
     """assign_obstacle_parameter (rda_solver.py:483-526): pad a short list by repeating its
     last element (mutating the caller's list, as the reference does), truncate a long one,
-    zero-pad rows to E.  Returns (A [N,Tc,E,2], b [N,Tc,E], kind [N], count, time_varying)."""
+    zero-pad rows to E.  center: robot position, only used to close unbounded half-space sets
+    (canonical_polygon_rows).  Returns (A [N,Tc,E,2], b [N,Tc,E], kind [N], count, time_varying)."""
     count = len(obstacle_list)
     if 0 < count < N:
         obstacle_list += [obstacle_list[-1]] * (N - count)
@@ -71,10 +141,12 @@ def pack_obstacles(obstacle_list, T, N, E):
             At = np.asarray(At, float)
             bt = np.asarray(bt, float).reshape(-1)
             if not circle:
-                At, bt = canonical_polygon_rows(At, bt)
+                At, bt = canonical_polygon_rows(At, bt, bound=bound, center=center)
             en = At.shape[0]
             if en > E:
-                raise ValueError(f'obstacle with {en} edges exceeds max_edge_num={E}')
+                raise ValueError(f'obstacle with {en} edges exceeds max_edge_num={E}'
+                                 + (' (an unbounded half-space set is closed by up to four sides of a large square: '
+                                    'raise max_edge_num accordingly)' if en > np.asarray(o.A[t] if isinstance(o.A, list) else o.A).shape[0] else ''))
             A[i, t, :en] = At
             b[i, t, :en] = bt
     return A, b, kind, count, tv
@@ -108,11 +180,18 @@ class RDA_solver:
         self.batch = batch
         self.ws = kwargs.get('ws', 1)
         self.wu = kwargs.get('wu', 1)
-        if car_tuple.cone_type != 'Rpositive':
-            raise NotImplementedError('rda_planner_b200 supports polygon (Rpositive) robots')
         G = np.asarray(car_tuple.G, float)
         h = np.asarray(car_tuple.h, float).reshape(-1)
-        G, h = canonical_polygon_rows(G, h)
+        if car_tuple.cone_type == 'norm2':
+            # disc body (cone_cp_array(-mu, 'norm2'), :1034-1039) as ir-sim describes it: |y - (h0, h1)| <= -h2
+            if G.shape != (3, 2) or np.abs(G - np.array([[1.0, 0], [0, 1], [0, 0]])).max() > 1e-9 or not h[2] < 0:
+                raise NotImplementedError("norm2 robot: only the disc G = [[1,0],[0,1],[0,0]], h = (cx, cy, -r) is supported")
+            robot_cone = _cabi.ROBOT_DISC
+        elif car_tuple.cone_type == 'Rpositive':
+            G, h = canonical_polygon_rows(G, h)
+            robot_cone = _cabi.ROBOT_POLYGON
+        else:
+            raise ValueError(f'unknown robot cone type {car_tuple.cone_type!r}')
         R = G.shape[0]
         if R > _cabi.MAX_ROBOT_EDGE or self.max_edge_num > _cabi.MAX_EDGE:
             raise ValueError('at most 8 robot edges / obstacle edges are supported')
@@ -129,6 +208,7 @@ class RDA_solver:
             cfg.max_speed[k] = ms[k]
             cfg.acce_bound[k] = ma[k] * step_time                      # :44
         cfg.ws, cfg.wu = self.ws, self.wu
+        cfg.robot_cone = robot_cone
         for j in range(R):
             cfg.G[2 * j], cfg.G[2 * j + 1], cfg.h[j] = G[j, 0], G[j, 1], h[j]
         self._tun = _cabi.Tunables(kwargs.get('slack_gain', 8), kwargs.get('max_sd', 1.0),
@@ -137,6 +217,9 @@ class RDA_solver:
         # the values as the caller gave them (the device copy is float32): get_adjust_parameter returns these
         self._tun_py = {k: kwargs.get(k, dflt) for k, dflt in (('slack_gain', 8), ('max_sd', 1.0), ('min_sd', 0.1),
                                                                 ('ro1', 200), ('ro2', 1))}
+        # closing square of unbounded half-space obstacles (canonical_polygon_rows): 1.5 x what the robot can reach within the
+        # horizon plus body and safety distance, at least 30 m — small, because far vertices cost float32 precision
+        self._hs_bound = max(30.0, 1.5 * (receding * step_time * float(abs(ms[0])) + 8.0))
         self._cfg = cfg
         self._h = C.c_void_p()
         with torch.cuda.device(self.device):
@@ -350,7 +433,8 @@ class RDA_solver:
         start = time.time()
         ref = np.hstack(ref_states)[0:3, :]                                     # :580
         if N > 0:
-            A, b, kind, count, tv = pack_obstacles(obstacle_list, T, N, E)
+            A, b, kind, count, tv = pack_obstacles(obstacle_list, T, N, E, center=np.asarray(nom_s, float)[0:2, 0],
+                                                   bound=self._hs_bound)
         else:
             A = b = kind = None
             count, tv = len(obstacle_list), False

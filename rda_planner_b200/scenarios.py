@@ -25,6 +25,14 @@ def rectangle_robot(length=4.6, width=1.6, wheelbase=3.0, dynamics='acker',
     return car(G, h, 'Rpositive', wheelbase, list(max_speed), list(max_acce), dynamics)
 
 
+def disc_robot(radius=1.0, center=(0.0, 0.0), wheelbase=1.0, dynamics='diff', max_speed=(10, 1), max_acce=(10, 0.5)):
+    """Car tuple of a circular body as ir-sim describes it (cone_type 'norm2', rda_solver.py:1034-1039):
+    G = [[1,0],[0,1],[0,0]], h = (cx, cy, -r), i.e. |y - c| <= r in the body frame."""
+    G = np.array([[1.0, 0.0], [0.0, 1.0], [0.0, 0.0]])
+    h = np.array([[center[0]], [center[1]], [-radius]])
+    return car(G, h, 'norm2', wheelbase, list(max_speed), list(max_acce), dynamics)
+
+
 def rollout(state, u, dt, L, dynamics):
     """Nominal trajectory of the nonlinear model (mpc.py:293-336) for controls u (2,T)."""
     T = u.shape[1]

@@ -63,6 +63,22 @@ def cell(G, h, kind, A, b, p, phi, dbar, zeta, xi, ro2, theta=0.5, prec='d'):
     return r
 
 
+def cell_disc_robot(h, kind, A, b, p, phi, dbar, zeta, xi, ro2, theta=0.5, prec='d'):
+    """Cell of a DISC body (cone_type 'norm2', G = [[1,0],[0,1],[0,0]], h = (cx, cy, -r)): cell_disc_robot.cuh."""
+    h = _f32(np.ravel(h)); A = _f32(A); b = _f32(np.ravel(b))
+    out = np.zeros(28)
+    fn = getattr(lib(), 'shim_cell_dr_' + prec)
+    fn.restype = C.c_int
+    rc = fn(_p(h), C.c_int(kind), C.c_int(A.shape[0]), _p(A), _p(b), C.c_double(p[0]), C.c_double(p[1]), C.c_double(phi),
+            C.c_double(dbar), C.c_double(zeta), C.c_double(xi[0]), C.c_double(xi[1]), C.c_double(ro2), C.c_double(theta), _p(out))
+    assert rc == 0, rc
+    E = A.shape[0]
+    keys = ['z', 'zeta_new', 'xi0', 'xi1', 'ax', 'ay', 'c0', 'gx', 'gy', 'hm0', 'hm1', 'path']
+    r = {k: out[16 + i] for i, k in enumerate(keys)}
+    r['lam'] = out[:E].copy(); r['mu'] = out[8:11].copy(); r['path'] = int(r['path'])
+    return r
+
+
 def su(params, lins, linu, ref, vref, dis, hx, hy, hc, gx, gy, pref, prec='d'):
     T, N = params.T, params.N
     lins = _f64(np.asarray(lins).T); linu = _f64(np.asarray(linu).T); ref = _f64(np.asarray(ref).T)

@@ -26,7 +26,7 @@ def test_library_builds_and_exports_header_symbols():
 
 def test_struct_layouts_match_header():
     # sizes implied by the header (4-byte fields, no padding)
-    assert ctypes.sizeof(_cabi.Config) == 4 * (8 + 2 + 2 + 2 + 2 + 16 + 8)
+    assert ctypes.sizeof(_cabi.Config) == 4 * (8 + 2 + 2 + 2 + 2 + 16 + 8 + 1)      # ... + robot_cone
     assert ctypes.sizeof(_cabi.Tunables) == 24
     assert ctypes.sizeof(_cabi.Inputs) == 8 * 8 + 8
     assert ctypes.sizeof(_cabi.Outputs) == 6 * 8
@@ -68,6 +68,17 @@ def test_usage_errors_are_return_codes_not_exceptions():
     assert lib.rda_create(ctypes.byref(cfg), ctypes.byref(tun), ctypes.byref(h)) == -1          # unknown dynamics
     cfg.dynamics = 0                                                                              # G, h all zero:
     assert lib.rda_create(ctypes.byref(cfg), ctypes.byref(tun), ctypes.byref(h)) == -2          # not a polygon
+    # disc body (RDA_ROBOT_DISC, cone_type 'norm2'): only G = [[1,0],[0,1],[0,0]], h[2] < 0, three rows; unknown cone refused
+    cfg.robot_cone, cfg.robot_edges = _cabi.ROBOT_DISC, 3
+    assert lib.rda_create(ctypes.byref(cfg), ctypes.byref(tun), ctypes.byref(h)) == -2          # G all zero
+    for k, v in enumerate((1.0, 0.0, 0.0, 1.0, 0.0, 0.0)):
+        cfg.G[k] = v
+    cfg.h[2] = 0.5
+    assert lib.rda_create(ctypes.byref(cfg), ctypes.byref(tun), ctypes.byref(h)) == -2          # radius -h[2] <= 0
+    cfg.h[2], cfg.robot_edges = -0.5, 4
+    assert lib.rda_create(ctypes.byref(cfg), ctypes.byref(tun), ctypes.byref(h)) == -2          # a disc has three rows
+    cfg.robot_edges, cfg.robot_cone = 3, 5
+    assert lib.rda_create(ctypes.byref(cfg), ctypes.byref(tun), ctypes.byref(h)) == -2          # unknown cone
     assert h.value is None
     for f in (lib.rda_destroy, ):
         assert f(None) == -1
