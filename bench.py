@@ -363,6 +363,21 @@ def extra_probes(dev, solver, devin, B):
         msc, r = timed(cfg_step, 2)
         out[f'config_{cname}'] = {'solves_per_s': c['global_batch'] / (msc * 1e-3), 'batch': c['global_batch'], 'what': c['what'],
                                   'kept_previous_iterate': int((r['status'] & 6).ne(0).sum())}
+    # the metric shape with a DISC body (car_tuple.cone_type 'norm2', rda_solver.py:1034-1039): closed forms for the inactive
+    # hinges, two-cone barrier programmes for the rest (cell_disc_robot.cuh) — a coverage row, not tuned
+    from rda_planner_b200.scenarios import disc_robot
+    Bd = min(B, 2048)
+    dd = {k: v[:Bd].contiguous() for k, v in devin.items()}
+    svd = RDA_solver(T, disc_robot(radius=1.2, wheelbase=2.0, dynamics='diff'), max_edge_num=E, max_obs_num=N, iter_num=ITERS,
+                     iter_threshold=0.0, time_print=False, batch=Bd, device=dev)
+
+    def disc_step():
+        svd.cold_start()
+        return svd.iterative_solve_batch(dd['nom_s'], dd['nom_u'], dd['ref_s'], dd['ref_speed'], dd['obs_A'], dd['obs_b'],
+                                         dd['obs_kind'], dd['obs_count'], False)
+    msd, r = timed(disc_step, 2)
+    out['disc_robot'] = {'solves_per_s': Bd / (msd * 1e-3), 'batch': Bd, 'what': 'metric shape, disc body of radius 1.2 m, diff drive',
+                         'kept_previous_iterate': int((r['status'] & 6).ne(0).sum())}
     return out
 
 

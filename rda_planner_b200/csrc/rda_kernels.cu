@@ -73,6 +73,7 @@ struct rda_handle {
   int su_maxctas;        // cap on resident k_su CTAs per SM in split mode (0 = none; RDA_B200_SU_MAXCTAS)
   float su_prune;        // hinge pruning margin of the su-QP (su_solver.cuh; RDA_B200_SU_PRUNE, 0 = off)
   int slow_cpw, slow_ctas;   // k_cells_slow: cells per warp, CTAs per SM (RDA_B200_SLOW_CPW / RDA_B200_SLOW_CTAS)
+  int slow_coop;             // warp-cooperative last pass, one cell per warp (RDA_B200_SLOW_COOP, default 0)
   int slow_adapt;            // fewer cells per warp when the list fits one wave (RDA_B200_SLOW_ADAPT, default 0: measured slower)
   int split_min;         // smallest batch that is split (RDA_B200_SPLIT_MIN, default 2048)
   int parts;             // number of sub-batches, 1..4 (RDA_B200_SPLIT_PARTS, default 2)
@@ -706,6 +707,51 @@ __global__ void __launch_bounds__(64) k_cells_dr_slow(DevPtrs d, RobotGeom rb, f
   }
 }
 
+// Warp-cooperative variant of the last pass (RDA_B200_SLOW_COOP=1): ONE cell per warp, the interior point iteration of
+// coop_ipm.cuh spread over the lanes (rows, vector components and Newton-matrix entries), the problem in shared memory.
+// Round 1 measured it slower than one thread per cell — with 5 % of the cells in this pass; since the closed forms of
+// round 2 leave 0.1 % (~13 000 cells at 16 384 instances, three waves of warps) the pass is a pure latency tail, which is
+// what cooperation shortens.
+constexpr int SLOW_COOP_WARPS = 4;
+__global__ void __launch_bounds__(32 * SLOW_COOP_WARPS) k_cells_slow_coop(DevPtrs d, RobotGeom rb, float ro2, float theta) {
+  __shared__ CellSlowStore store[SLOW_COOP_WARPS];
+  const int count = d.wl_count[1];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  CellSlowStore& S = store[warp];
+  GroupCtx<32> ctx;
+  for (int wi = blockIdx.x * SLOW_COOP_WARPS + warp; wi < count; wi += gridDim.x * SLOW_COOP_WARPS) {
+    const long long idx = d.worklist2[wi];
+    CellIn c;
+    CellWork<float> w;
+    w.have = false;
+    if (lane == 0) {
+      c = cell_load(d, idx);
+      cell_front<float, false, true>(rb, c.kind, d.E, c.A, c.bb, c.px, c.py, c.cp, c.sp, c.dbar, c.zeta, c.xi0, c.xi1, ro2, w);
+    }
+    const int have = __shfl_sync(0xffffffffu, (int)w.have, 0);
+    if (!have) {
+      __syncwarp();
+      cell_slow<float, GroupCtx<32>>(rb, w, S, ctx);
+      __syncwarp();
+    }
+    if (lane == 0) {
+      CellOut<float> out;
+      cell_back<float>(rb, w, c.zeta, theta, out);
+      float hm2 = 0.f, dual = 0.f;
+      if (out.path == CELL_FAILED) {
+        dual = INFINITY;
+        atomicOr(&d.status[c.b], RDA_ST_CELL_FALLBACK);
+      } else {
+        cell_store(d, c, out, &hm2, &dual);
+      }
+      atomicAdd(&d.resi_acc[2 * c.b], hm2);
+      atomicAdd(&d.resi_acc[2 * c.b + 1], dual);
+      atomicAdd(&d.counters[out.path == CELL_FAILED ? 2 : 1], 1);
+    }
+    __syncwarp();
+  }
+}
+
 // per instance: residuals (:688, :735-739), early stop (:594-596), empty-list quirk (:564-568)
 __device__ __forceinline__ void finalize_instance(const DevPtrs& d, const RobotGeom& rb, float thr, int b) {
   const int T = d.T, N = d.N, NT = N * T, R = d.R;
@@ -1123,6 +1169,8 @@ int rda_create(const rda_config* cfg, const rda_tunables* tun, rda_handle** out)
   h->slow_cpw = RDA_SLOW_CPW; h->slow_ctas = 16;
   h->slow_adapt = 0;
   if (const char* v = getenv("RDA_B200_SLOW_ADAPT")) h->slow_adapt = atoi(v) != 0;
+  h->slow_coop = 0;
+  if (const char* v = getenv("RDA_B200_SLOW_COOP")) h->slow_coop = atoi(v) != 0;
   if (const char* v = getenv("RDA_B200_SLOW_CPW")) { int x = atoi(v); if (x >= 1 && x <= 32) h->slow_cpw = x; }
   if (const char* v = getenv("RDA_B200_SLOW_CTAS")) { int x = atoi(v); if (x >= 1 && x <= 256) h->slow_ctas = x; }
   if (const char* sm = getenv("RDA_B200_SPLIT_MIN")) { int v = atoi(sm); if (v >= 2) h->split_min = v; }
@@ -1326,7 +1374,8 @@ static int step_lammuz_part(rda_handle* h, int b0, int nb, int part, cudaStream_
     RDA_CUDA(cudaGetLastError());
     k_cells_mid<<<148 * 8, 128, 0, s>>>(d, h->rb, h->tun.ro2, theta);
     RDA_CUDA(cudaGetLastError());
-    k_cells_slow<<<148 * h->slow_ctas, 64, 0, s>>>(d, h->rb, h->tun.ro2, theta, h->slow_cpw, h->slow_adapt);
+    if (h->slow_coop) k_cells_slow_coop<<<148 * h->slow_ctas, 32 * SLOW_COOP_WARPS, 0, s>>>(d, h->rb, h->tun.ro2, theta);
+    else k_cells_slow<<<148 * h->slow_ctas, 64, 0, s>>>(d, h->rb, h->tun.ro2, theta, h->slow_cpw, h->slow_adapt);
     RDA_CUDA(cudaGetLastError());
     h->launches += 3;
   }

@@ -422,10 +422,17 @@ RDA_HD int su_solve(const SuParams& P, SuWork<Real, Slk>& W, Ctx& ctx, const flo
   }
   const Real Mrows = ctx.sum((Real)nrows);
   ctx.sync();
-  const Real tol_mu = sizeof(Real) == 4 ? (Real)1e-6 : (Real)1e-9;
-  const Real tol_r = sizeof(Real) == 4 ? (Real)1e-5 : (Real)1e-9;
+  // RDA_SU_TOL: complementarity / residual tolerance of the float64 iteration (default 1e-9; ECOS stops at 1e-8)
+#ifndef RDA_SU_TOL
+#define RDA_SU_TOL 1e-9
+#endif
+  const Real tol_mu = sizeof(Real) == 4 ? (Real)1e-6 : (Real)RDA_SU_TOL;
+  const Real tol_r = sizeof(Real) == 4 ? (Real)1e-5 : (Real)RDA_SU_TOL;
   const Real reg = (Real)1e-9;
-  const Real tol_step = sizeof(Real) == 4 ? (Real)2e-4 : (Real)1e-6;
+#ifndef RDA_SU_TOL_STEP
+#define RDA_SU_TOL_STEP 1e-6
+#endif
+  const Real tol_step = sizeof(Real) == 4 ? (Real)2e-4 : (Real)RDA_SU_TOL_STEP;
   const Real tol_floor = sizeof(Real) == 4 ? (Real)1e-7 : (Real)1e-13;
   Real last_step = 1e30f;       // size of the previous Newton update (stationarity proxy)
   status = 1;
