@@ -29,7 +29,7 @@ using namespace rda;
 
 // byte offsets of the persistent kernel's shared-memory state (k_admm_small)
 struct SmallLayout {
-  int lam, mu, z, xi, zeta, dis, coef, pref, cur_s, cur_u, ref_s, misc, hs, su, total;
+  int lam, mu, z, xi, zeta, dis, coef, pref, cur_s, cur_u, ref_s, misc, hs, su, wl, slow, total;
 };
 
 struct rda_handle {
@@ -69,11 +69,13 @@ struct rda_handle {
   // persistent single-launch ADMM for small batches (k_admm_small)
   int small_mode;        // -1: batches up to small_max instances, 0: never, 1: always when the state fits (RDA_B200_SMALL)
   int small_max, small_ok, small_bulk;
+  int small_coop;        // interior point cells of the persistent kernel one per warp (RDA_B200_SMALL_COOP, default 1)
   SmallLayout small_L;
   int su_maxctas;        // cap on resident k_su CTAs per SM in split mode (0 = none; RDA_B200_SU_MAXCTAS)
   float su_prune;        // hinge pruning margin of the su-QP (su_solver.cuh; RDA_B200_SU_PRUNE, 0 = off)
   int slow_cpw, slow_ctas;   // k_cells_slow: cells per warp, CTAs per SM (RDA_B200_SLOW_CPW / RDA_B200_SLOW_CTAS)
-  int slow_coop;             // warp-cooperative last pass, one cell per warp (RDA_B200_SLOW_COOP, default 0)
+  int slow_coop;             // warp-cooperative last pass, one cell per warp (RDA_B200_SLOW_COOP, default 1)
+  int mid_ctas;              // k_cells_mid CTAs per SM (RDA_B200_MID_CTAS)
   int slow_adapt;            // fewer cells per warp when the list fits one wave (RDA_B200_SLOW_ADAPT, default 0: measured slower)
   int split_min;         // smallest batch that is split (RDA_B200_SPLIT_MIN, default 2048)
   int parts;             // number of sub-batches, 1..4 (RDA_B200_SPLIT_PARTS, default 2)
@@ -544,7 +546,12 @@ __global__ void __launch_bounds__(128, 6) k_cells_coh(DevPtrs d, RobotGeom rb, R
 
 // Second pass: the searched closed forms (vertex / edge contact, overlap cases) for the cells of the
 // first worklist, one thread per entry; what is still unresolved goes to the second worklist.
-__global__ void __launch_bounds__(128) k_cells_mid(DevPtrs d, RobotGeom rb, float ro2, float theta) {
+#ifdef RDA_MID_MINBLOCKS
+#define RDA_MID_BOUNDS __launch_bounds__(128, RDA_MID_MINBLOCKS)
+#else
+#define RDA_MID_BOUNDS __launch_bounds__(128)
+#endif
+__global__ void RDA_MID_BOUNDS k_cells_mid(DevPtrs d, RobotGeom rb, float ro2, float theta) {
   const int count = d.wl_count[0];
   const int lane = threadIdx.x & 31;
   for (int base = blockIdx.x * blockDim.x; base < count; base += gridDim.x * blockDim.x) {
@@ -802,6 +809,8 @@ static SmallLayout small_layout(int T, int N, int E, int R, size_t su_bytes) {
   L.lam = take(4 * N * E * T); L.mu = take(4 * N * R * T); L.z = take(4 * NT); L.xi = take(8 * NT); L.zeta = take(4 * NT);
   L.dis = take(4 * T); L.coef = take(20 * NT); L.pref = take(8 * T); L.cur_s = take(12 * (T + 1)); L.cur_u = take(8 * T);
   L.ref_s = take(12 * (T + 1)); L.misc = take(128); L.hs = take(16 * NT); L.su = take(su_bytes);
+  // cells left over by the closed forms (indices) and one interior point problem per warp (cooperative pass)
+  L.wl = take(4 * (NT + 1)); L.slow = take(4 * sizeof(CellSlowStore));
   L.total = (int)((o + 15) & ~(size_t)15);
   return L;
 }
@@ -841,7 +850,7 @@ __device__ __forceinline__ void bulk_commit_wait() {
 template <typename Real>
 __global__ void __launch_bounds__(128) k_admm_small(DevPtrs d, SuParams P, RobotGeom rb, float ro2, float theta, float thr,
                                                     int iter_num, SmallLayout L, const float* nom_s, const float* nom_u,
-                                                    const float* ref_s, const float* ref_speed, rda_outputs out, int use_bulk) {
+                                                    const float* ref_s, const float* ref_speed, rda_outputs out, int use_bulk, int coop) {
   extern __shared__ __align__(16) char smem[];
   const int b = blockIdx.x;
   if (b >= d.B) return;
@@ -902,11 +911,15 @@ __global__ void __launch_bounds__(128) k_admm_small(DevPtrs d, SuParams P, Robot
     }
     __syncthreads();
     if (has_obs) {
+      int* wl = (int*)(smem + L.wl);                 // wl[0]: number of listed cells, wl[1..]: their indices
+      if (tid == 0) wl[0] = 0;
+      __syncthreads();
       for (int idx = tid; idx < NT; idx += nth) {
         CellIn c = cell_load(ds, idx);
         CellWork<float> w;
         cell_front<float, false, true>(rb, c.kind, E, c.A, c.bb, c.px, c.py, c.cp, c.sp, c.dbar, c.zeta, c.xi0, c.xi1, ro2, w);
         if (!w.have) {
+          if (coop) { wl[1 + atomicAdd(&wl[0], 1)] = idx; continue; }      // interior point pass below, one cell per warp
           CellSlowStore S;
           SeqCtx sc;
           cell_slow<float, SeqCtx>(rb, w, S, sc);
@@ -923,6 +936,42 @@ __global__ void __launch_bounds__(128) k_admm_small(DevPtrs d, SuParams P, Robot
         atomicAdd(&ds.resi_acc[0], hm2);
         atomicAdd(&ds.resi_acc[1], dual);
         atomicAdd(&d.counters[o.path == CELL_FAILED ? 2 : ((o.path == CELL_SLOW_A || o.path == CELL_SLOW_B) ? 1 : 0)], 1);
+      }
+      if (coop) {
+        // the cells the closed forms left: one per warp, interior point iteration spread over the lanes (coop_ipm.cuh),
+        // the problem in shared memory — as k_cells_slow_coop of the streaming path
+        __syncthreads();
+        const int nlist = wl[0], warp = tid >> 5, lane = tid & 31;
+        CellSlowStore& S = ((CellSlowStore*)(smem + L.slow))[warp];
+        GroupCtx<32> ctx;
+        for (int wi = warp; wi < nlist; wi += (nth >> 5)) {
+          const int idx = wl[1 + wi];
+          CellIn c;
+          CellWork<float> w;
+          w.have = false;
+          if (lane == 0) {
+            c = cell_load(ds, idx);
+            cell_front<float, false, true>(rb, c.kind, E, c.A, c.bb, c.px, c.py, c.cp, c.sp, c.dbar, c.zeta, c.xi0, c.xi1, ro2, w);
+          }
+          __syncwarp();
+          cell_slow<float, GroupCtx<32>>(rb, w, S, ctx);
+          __syncwarp();
+          if (lane == 0) {
+            CellOut<float> o;
+            cell_back<float>(rb, w, c.zeta, theta, o);
+            float hm2 = 0.f, dual = 0.f;
+            if (o.path == CELL_FAILED) {
+              dual = INFINITY;
+              atomicOr(&ds.status[0], RDA_ST_CELL_FALLBACK);
+            } else {
+              cell_store(ds, c, o, &hm2, &dual);
+            }
+            atomicAdd(&ds.resi_acc[0], hm2);
+            atomicAdd(&ds.resi_acc[1], dual);
+            atomicAdd(&d.counters[o.path == CELL_FAILED ? 2 : 1], 1);
+          }
+          __syncwarp();
+        }
       }
     }
     __syncthreads();
@@ -1157,6 +1206,8 @@ int rda_create(const rda_config* cfg, const rda_tunables* tun, rda_handle** out)
     // bulk (TMA) staging needs every staged block to be a multiple of 16 bytes: N*E*T, N*R*T and N*T multiples of 4
     h->small_bulk = (N > 0) && ((N * E * T) % 4 == 0) && ((N * R * T) % 4 == 0) && ((N * T) % 4 == 0);
     if (const char* v = getenv("RDA_B200_SMALL_BULK")) { if (atoi(v) == 0) h->small_bulk = 0; }
+    h->small_coop = 1;
+    if (const char* v = getenv("RDA_B200_SMALL_COOP")) h->small_coop = atoi(v) != 0;
     if (const char* v = getenv("RDA_B200_SMALL")) { int x = atoi(v); if (x >= -1 && x <= 1) h->small_mode = x; }
     if (const char* v = getenv("RDA_B200_SMALL_MAX")) { int x = atoi(v); if (x >= 1) h->small_max = x; }
     if (h->small_ok) {
@@ -1169,8 +1220,13 @@ int rda_create(const rda_config* cfg, const rda_tunables* tun, rda_handle** out)
   h->slow_cpw = RDA_SLOW_CPW; h->slow_ctas = 16;
   h->slow_adapt = 0;
   if (const char* v = getenv("RDA_B200_SLOW_ADAPT")) h->slow_adapt = atoi(v) != 0;
-  h->slow_coop = 0;
+  // measured r02 (B200): one cell per WARP beats one cell per thread at every batch size now that only 0.1 % of the cells reach
+  // this pass — all cell passes 4.15 -> 3.42 ms per ADMM iteration at 16 384 instances, 1.30 -> 0.48 ms at 1 024; BASELINE
+  // config C (disc cells on the barrier iteration) 467 -> 1 734 solves/s
+  h->slow_coop = 1;
   if (const char* v = getenv("RDA_B200_SLOW_COOP")) h->slow_coop = atoi(v) != 0;
+  h->mid_ctas = 8;
+  if (const char* v = getenv("RDA_B200_MID_CTAS")) { int x = atoi(v); if (x >= 1 && x <= 64) h->mid_ctas = x; }
   if (const char* v = getenv("RDA_B200_SLOW_CPW")) { int x = atoi(v); if (x >= 1 && x <= 32) h->slow_cpw = x; }
   if (const char* v = getenv("RDA_B200_SLOW_CTAS")) { int x = atoi(v); if (x >= 1 && x <= 256) h->slow_ctas = x; }
   if (const char* sm = getenv("RDA_B200_SPLIT_MIN")) { int v = atoi(sm); if (v >= 2) h->split_min = v; }
@@ -1372,7 +1428,7 @@ static int step_lammuz_part(rda_handle* h, int b0, int nb, int part, cudaStream_
     else
       k_cells_fast<8, 8, false><<<grid_for((long long)nb * h->N * h->T, 128), 128, 0, s>>>(d, h->rb, theta);
     RDA_CUDA(cudaGetLastError());
-    k_cells_mid<<<148 * 8, 128, 0, s>>>(d, h->rb, h->tun.ro2, theta);
+    k_cells_mid<<<148 * h->mid_ctas, 128, 0, s>>>(d, h->rb, h->tun.ro2, theta);
     RDA_CUDA(cudaGetLastError());
     if (h->slow_coop) k_cells_slow_coop<<<148 * h->slow_ctas, 32 * SLOW_COOP_WARPS, 0, s>>>(d, h->rb, h->tun.ro2, theta);
     else k_cells_slow<<<148 * h->slow_ctas, 64, 0, s>>>(d, h->rb, h->tun.ro2, theta, h->slow_cpw, h->slow_adapt);
@@ -1461,11 +1517,11 @@ int rda_solve(rda_handle* h, const rda_inputs* in, const rda_outputs* out, int i
     if (h->cfg.su_fp64)
       k_admm_small<double><<<h->B, 128, h->small_L.total, s0>>>(d, P, h->rb, h->tun.ro2, theta, iter_threshold, iter_num, h->small_L,
                                                               (const float*)in->nom_s, (const float*)in->nom_u, (const float*)in->ref_s,
-                                                              (const float*)in->ref_speed, *out, h->small_bulk);
+                                                              (const float*)in->ref_speed, *out, h->small_bulk, h->small_coop);
     else
       k_admm_small<float><<<h->B, 128, h->small_L.total, s0>>>(d, P, h->rb, h->tun.ro2, theta, iter_threshold, iter_num, h->small_L,
                                                              (const float*)in->nom_s, (const float*)in->nom_u, (const float*)in->ref_s,
-                                                             (const float*)in->ref_speed, *out, h->small_bulk);
+                                                             (const float*)in->ref_speed, *out, h->small_bulk, h->small_coop);
     RDA_CUDA(cudaGetLastError());
     h->launches = 1;
     return 0;
