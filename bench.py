@@ -35,13 +35,30 @@ def algorithmic_bytes():
     return k2, k1
 
 
-def build_inputs(batch, seed0, config='metric'):
-    from rda_planner_b200.scenarios import config_instance, CONFIGS
+def _one_instance(job):
+    """(config, seed, lateral) -> packed arrays of one seeded instance (worker of build_inputs; numpy only)."""
+    from rda_planner_b200.scenarios import config_instance, make_instance, CONFIGS
     from rda_planner_b200.rda_solver import pack_obstacles
+    config, seed, lateral = job
     c = CONFIGS[config]
-    uniq = min(batch, 1024 if config == 'metric' else 256)
-    insts = [config_instance(config, seed0 + i) for i in range(uniq)]
-    packs = [pack_obstacles(list(i['obstacles']), c['T'], c['N'], c['E']) for i in insts]
+    inst = config_instance(config, seed) if lateral is None else make_instance(seed, T=c['T'], N=c['N'], E=c['E'], lateral=lateral)
+    return inst, pack_obstacles(list(inst['obstacles']), c['T'], c['N'], c['E'])
+
+
+def build_inputs(batch, seed0, config='metric', lateral=None, unique=None):
+    """Host arrays of `batch` seeded instances.  The metric row is generated with EVERY instance unique (a process pool over
+    the leased host cores: call this before CUDA is initialised); the side configs keep 256 unique instances, tiled.
+    lateral: override of the obstacle band of the metric generator (the parity tests use the harsher (0.3, 3.5))."""
+    import multiprocessing as mp
+    uniq = min(batch, unique if unique is not None else (batch if config == 'metric' else 256))
+    jobs = [(config, seed0 + i, lateral) for i in range(uniq)]
+    workers = min(32, len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1))
+    if uniq >= 512 and workers > 1:
+        with mp.get_context('fork').Pool(workers) as pool:
+            res = pool.map(_one_instance, jobs, chunksize=max(1, uniq // (8 * workers)))
+    else:
+        res = [_one_instance(j) for j in jobs]
+    insts, packs = [r[0] for r in res], [r[1] for r in res]
     rep = -(-batch // uniq)
 
     def tile(a):
@@ -288,7 +305,7 @@ def closed_loop_probe(dev, B, steps=3):
                     'arrive rule, model step; all on the device'}
 
 
-def extra_probes(dev, solver, devin, B):
+def extra_probes(dev, solver, devin, B, host_harsh=None):
     """SURVEY.md §8(d) side measurements (never the headline): the same batch with the reference's
     early-stop rule (iter_threshold 0.2, rda_solver.py:22,594-596) and the latency of ONE instance
     (the reference's own use case)."""
@@ -363,6 +380,35 @@ def extra_probes(dev, solver, devin, B):
         msc, r = timed(cfg_step, 2)
         out[f'config_{cname}'] = {'solves_per_s': c['global_batch'] / (msc * 1e-3), 'batch': c['global_batch'], 'what': c['what'],
                                   'kept_previous_iterate': int((r['status'] & 6).ne(0).sum())}
+    # the metric shape on the HARSH obstacle band of the parity tests (lateral offsets 0.3-3.5 m instead of 1.8-6 m: more
+    # overlapping and active cells, i.e. more work for the searched closed forms and the interior point pass)
+    if host_harsh is not None:
+        Bh = host_harsh['nom_s'].shape[0]
+        dh = {k: torch.from_numpy(v).to(dev) for k, v in host_harsh.items()}
+        svh = RDA_solver(T, rectangle_robot(), max_edge_num=E, max_obs_num=N, iter_num=ITERS, iter_threshold=0.0, time_print=False,
+                         batch=Bh, device=dev)
+
+        def harsh_step():
+            svh.cold_start()
+            return svh.iterative_solve_batch(dh['nom_s'], dh['nom_u'], dh['ref_s'], dh['ref_speed'], dh['obs_A'], dh['obs_b'],
+                                             dh['obs_kind'], dh['obs_count'], False)
+        msh, r = timed(harsh_step, 2)
+        from rda_planner_b200 import _cabi as _c
+        cn = svh.state_buffer(_c.BUF_COUNTERS).cpu().tolist()
+        out['harsh_geometry'] = {'solves_per_s': Bh / (msh * 1e-3), 'batch': Bh, 'what': 'metric shape, obstacle band 0.3-3.5 m beside '
+                                 'the path (tests/test_gpu_parity.py) instead of 1.8-6 m', 'kept_previous_iterate': int((r['status'] & 6).ne(0).sum()),
+                                 'interior_point_cell_fraction': cn[1] / max(1, cn[0] + cn[1])}
+        # same batch size on the default band, for the ratio
+        dm = {k: v[:Bh].contiguous() for k, v in devin.items()}
+        svm = RDA_solver(T, rectangle_robot(), max_edge_num=E, max_obs_num=N, iter_num=ITERS, iter_threshold=0.0, time_print=False,
+                         batch=Bh, device=dev)
+
+        def mild_step():
+            svm.cold_start()
+            return svm.iterative_solve_batch(dm['nom_s'], dm['nom_u'], dm['ref_s'], dm['ref_speed'], dm['obs_A'], dm['obs_b'],
+                                             dm['obs_kind'], dm['obs_count'], False)
+        msm, _ = timed(mild_step, 2)
+        out['harsh_geometry']['default_band_same_batch_solves_per_s'] = Bh / (msm * 1e-3)
     # the metric shape with a DISC body (car_tuple.cone_type 'norm2', rda_solver.py:1034-1039): closed forms for the inactive
     # hinges, two-cone barrier programmes for the rest (cell_disc_robot.cuh) — a coverage row, not tuned
     from rda_planner_b200.scenarios import disc_robot
@@ -477,14 +523,18 @@ def main():
     local = int(os.environ.get('LOCAL_RANK', '0'))
     if args.warmup < 3:
         args.warmup = 3
+    B = args.batch
+    # host inputs first (process pool over the host cores: before CUDA / NCCL are initialised).  Every instance unique.
+    host = build_inputs(B, 1000 * 9 + rank * B)              # per-rank shard, generated in place (weak scaling)
+    host_harsh = None
+    if rank == 0 and not args.no_probes:
+        host_harsh = build_inputs(min(B, 2048), 5000 * 9, lateral=(0.3, 3.5))      # the parity tests' obstacle band
     torch.cuda.set_device(local)
     dev = torch.device(f'cuda:{local}')
     if world > 1:
         os.environ.setdefault('NCCL_DEBUG', 'WARN')      # keep stdout to the one JSON line
         dist.init_process_group('nccl', device_id=dev)
     rbuild.build()
-    B = args.batch
-    host = build_inputs(B, 1000 * 9 + rank * B)              # per-rank shard, generated in place (weak scaling)
     pinned = {k: torch.from_numpy(v).pin_memory() for k, v in host.items()}
     devin = {k: v.to(dev) for k, v in pinned.items()}
     solver = RDA_solver(T, rectangle_robot(), max_edge_num=E, max_obs_num=N, iter_num=ITERS, iter_threshold=0.0,
@@ -581,7 +631,7 @@ def main():
         'metric': METRIC, 'value': total / (ms * 1e-3), 'unit': 'solves/s', 'n_gpus': world, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32 state / f64 su-QP interior point', 'data': 'synthetic',
-        'config': {'workload': WORKLOAD, 'batch_per_gpu': B, 'global_batch': B * world,
+        'config': {'workload': WORKLOAD, 'batch_per_gpu': B, 'global_batch': B * world, 'unique_instances_per_gpu': B,
                    'parallelism': f'instances sharded over {world} GPU(s), no collective in the ADMM loop',
                    'l2_policy': f'per-step working set {41 * B // 1000} MB of warm-start state > 126 MB L2'
                    if B >= 3200 else 'working set below L2 size (small batch)'},
@@ -612,7 +662,7 @@ def main():
                                           f"instances, {info['cores']} pinned threads, {info['seconds']:.1f} s"}
     if not args.no_probes:
         try:
-            line.update(extra_probes(dev, solver, devin, B))
+            line.update(extra_probes(dev, solver, devin, B, host_harsh))
         except Exception as ex:
             line['early_stop'] = {'error': repr(ex)[:200]}
         try:

