@@ -32,6 +32,9 @@ extern "C" void rda_case_stat(int line);
 #ifndef RDA_CELL_ACCEPT_CONV
 #define RDA_CELL_ACCEPT_CONV 0
 #endif
+#ifndef RDA_CELL_POLISH
+#define RDA_CELL_POLISH 1      // float64 polish of float32 edge-contact roots in the last pass (edge_contact_polish)
+#endif
 #ifndef RDA_CELL_EE_TANG
 #define RDA_CELL_EE_TANG 1e-4
 #endif
@@ -136,6 +139,47 @@ struct CellWork {
   bool exact_zero_q, have;
   int path;
 };
+
+// ---- float64 polish of a robot-edge contact root (last pass only) ---------------------------------------------------
+// cell_front brackets the stationary point of the (weighted) margin along a body edge in the cell's own precision.  In
+// float32 that resolves the edge parameter to one ulp, which leaves a stationarity residual of up to 1e-4 when the
+// contact is close (the contact direction turns by |f|/distance per unit s) — more than the KKT acceptance allows, so
+// such cells used to go to the interior point iteration.  The last pass instead repeats the root search in float64 on
+// the float bracket (widened by a few ulps) and checks the KKT conditions in float64: same closed form, no loss of
+// parity.  Returns false when the bracket does not hold in float64 (the cell then goes to the interior point pass).
+struct EdgeRootD { double s, vx, vy, yx, yy, Nv, W2; };
+RDA_HD_NOINLINE bool edge_contact_polish(bool weighted, double lo, double hi, double yjx, double yjy, double fx, double fy,
+                                         double cphi, double sphi, double ox, double oy, double rad, double xi0, double xi1,
+                                         double k0, double ro2, EdgeRootD& r) {
+  const double wfx = cphi * fx - sphi * fy, wfy = sphi * fx + cphi * fy, xf = xi0 * fx + xi1 * fy;
+  double hv = 0;
+  auto eval = [&](double sc) {
+    r.s = sc;
+    r.yx = yjx + sc * fx; r.yy = yjy + sc * fy;
+    const double rx = (cphi * r.yx - sphi * r.yy) - ox, ry = (sphi * r.yx + cphi * r.yy) - oy;
+    const double rn = sqrt(rx * rx + ry * ry);
+    r.vx = rx / rn; r.vy = ry / rn;
+    r.Nv = k0 - (xi0 * r.yx + xi1 * r.yy) - (rn - rad);
+    const double Np = -xf - (r.vx * wfx + r.vy * wfy);
+    r.W2 = weighted ? 1.0 + (r.yx * r.yx + r.yy * r.yy) / ro2 : 1.0;
+    hv = weighted ? Np * r.W2 - r.Nv * (r.yx * fx + r.yy * fy) / ro2 : Np;
+  };
+  const double pad = 1e-6;
+  lo = rmax(lo - pad, 0.0); hi = rmin(hi + pad, 1.0);
+  eval(lo); double flo = hv; if (!(flo > 0) || (weighted && !(r.Nv > 0))) return false;
+  eval(hi); double fhi = hv; if (!(fhi < 0) || (weighted && !(r.Nv > 0))) return false;
+  int side = 0;
+  for (int itn = 0; itn < 60; ++itn) {
+    const double w = hi - lo;
+    double sc = lo + w * (flo / (flo - fhi));
+    sc = rclamp(sc, lo + 0.02 * w, hi - 0.02 * w);
+    eval(sc);
+    if (hv > 0) { lo = sc; flo = hv; if (side > 0) fhi *= 0.5; side = 1; }
+    else { hi = sc; fhi = hv; if (side < 0) flo *= 0.5; side = -1; }
+    if (hi - lo < 1e-14 || hv == 0) break;
+  }
+  return !weighted || r.Nv > 0;
+}
 
 // ---- stage 1: geometry relative to the robot reference point and the closed-form cases ----------
 // LEAN = true stops after the two cases that need no search (xi = 0 and a non-negative margin): the
@@ -367,6 +411,7 @@ RDA_HD void cell_front(const RobotGeom& rb, int kind, int E, const float* A, con
       Real flo = 0, fhi = 0;
       bool vlo = false, vhi = false;
       bool conv = false;             // the root is bracketed by valid end values to the resolution of s
+      bool convf = false;            // ... whether or not such a root is accepted as it is (RDA_CELL_ACCEPT_CONV)
       if (!weighted) {
         eval((Real)0); const Real h0 = hv;
         eval((Real)1); const Real h1 = hv;
@@ -422,6 +467,7 @@ RDA_HD void cell_front(const RobotGeom& rb, int kind, int E, const float* A, con
           sprev = sc;
         }
         conv = RDA_CELL_ACCEPT_CONV && vlo && vhi && hi - lo < (Real)4 * tol;
+        convf = vlo && vhi && hi - lo < (Real)4 * tol;
         if (!weighted) sA = sc;
       }
       if (!bracket) continue;
@@ -458,6 +504,31 @@ RDA_HD void cell_front(const RobotGeom& rb, int kind, int E, const float* A, con
         if (cgx * (Real)rb.nx[j] + cgy * (Real)rb.ny[j] >= -tolc && (tang <= tole || conv)) {
           v0 = vx_; v1 = vy_; g0 = cgx; g1 = cgy;
           have = true; RDA_CASE_STAT(__LINE__); path = CELL_FAST_VERTEX;
+        }
+      }
+      if (RDA_CELL_POLISH && EXTRA && sizeof(Real) == 4 && !have && convf) {
+        // float32 resolved the root to one ulp of s but not the KKT residual: polish in float64 (edge_contact_polish)
+        EdgeRootD rt;
+        if (edge_contact_polish(weighted, (double)lo, (double)hi, (double)yjx, (double)yjy, (double)fx, (double)fy, (double)cphi,
+                                (double)sphi, (double)ox, (double)oy, (double)rad, (double)xi0, (double)xi1, (double)k0, (double)ro2, rt)) {
+          const double c_ = cphi, s_ = sphi;
+          const double rvxd = c_ * rt.vx + s_ * rt.vy, rvyd = -s_ * rt.vx + c_ * rt.vy;
+          bool okd = true;
+          if (kind != RDA_OBS_CIRCLE) {
+            const int ip = (ce_i + ne - 1) % ne, inx = (ce_i + 1) % ne;
+            const double epx = (double)g.vx[ce_i] - (double)g.vx[ip], epy = (double)g.vy[ce_i] - (double)g.vy[ip];
+            const double enx = (double)g.vx[inx] - (double)g.vx[ce_i], eny = (double)g.vy[inx] - (double)g.vy[ce_i];
+            okd = (rt.vx * epx + rt.vy * epy >= -1e-9 * sqrt(epx * epx + epy * epy)) &&
+                  (rt.vx * enx + rt.vy * eny <= 1e-9 * sqrt(enx * enx + eny * eny));
+          }
+          const double tau = weighted ? rt.Nv / rt.W2 : 0.0;
+          const double cgx = -tau * rt.yx / (double)ro2 - rvxd - (double)xi0, cgy = -tau * rt.yy / (double)ro2 - rvyd - (double)xi1;
+          const double tang = fabs(cgx * (double)fx + cgy * (double)fy) / sqrt((double)fx * fx + (double)fy * fy);
+          okd = okd && (weighted ? rt.Nv > 0 : rt.Nv <= 0) && cgx * (double)rb.nx[j] + cgy * (double)rb.ny[j] >= -1e-9 && tang <= 1e-7;
+          if (okd) {
+            v0 = (Real)rt.vx; v1 = (Real)rt.vy; g0 = (Real)cgx; g1 = (Real)cgy;
+            exact_zero_q = !weighted; have = true; RDA_CASE_STAT(__LINE__); path = CELL_FAST_VERTEX;
+          }
         }
       }
     }

@@ -720,7 +720,7 @@ __global__ void __launch_bounds__(64) k_cells_dr_slow(DevPtrs d, RobotGeom rb, f
 // round 2 leave 0.1 % (~13 000 cells at 16 384 instances, three waves of warps) the pass is a pure latency tail, which is
 // what cooperation shortens.
 constexpr int SLOW_COOP_WARPS = 4;
-__global__ void __launch_bounds__(32 * SLOW_COOP_WARPS) k_cells_slow_coop(DevPtrs d, RobotGeom rb, float ro2, float theta) {
+__global__ void __launch_bounds__(32 * SLOW_COOP_WARPS, 5) k_cells_slow_coop(DevPtrs d, RobotGeom rb, float ro2, float theta) {
   __shared__ CellSlowStore store[SLOW_COOP_WARPS];
   const int count = d.wl_count[1];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

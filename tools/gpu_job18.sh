@@ -18,7 +18,8 @@ PY
 EXTRA=""
 run j18_base X=1
 run j18_conv1 RDA_B200_LIB=$PWD/rda_planner_b200/librda_b200_conv1.so
-EXTRA="--batch 1024"; run j18_b1024 X=1; run j18_b1024_conv1 RDA_B200_LIB=$PWD/rda_planner_b200/librda_b200_conv1.so
+EXTRA=""; run j18_nopolish RDA_B200_LIB=$PWD/rda_planner_b200/librda_b200_nopolish.so
+EXTRA="--batch 1024"; run j18_b1024 X=1; run j18_b1024_conv1 RDA_B200_LIB=$PWD/rda_planner_b200/librda_b200_conv1.so; run j18_b1024_nopolish RDA_B200_LIB=$PWD/rda_planner_b200/librda_b200_nopolish.so
 EXTRA="--batch 296"; run j18_b296 X=1
 ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip 60 -c 48 --csv --log-file gpurun_out/s2_launches_18.csv env RDA_B200_SPLIT_MIN=1000000 python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-probes > gpurun_out/s2_ncu_18.log 2>&1
 python - <<'PY'
