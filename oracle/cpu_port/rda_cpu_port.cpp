@@ -22,6 +22,17 @@ static void rda_coh_stat(int it, int lean_ok, int coh_ok);
 
 using namespace rda;
 
+#ifdef RDA_SOC_STATS
+static long long g_soc[2];
+extern "C" void rda_soc_stat(int newton) {
+#pragma omp atomic
+  g_soc[0] += 1;
+#pragma omp atomic
+  g_soc[1] += newton;
+}
+extern "C" void port_soc_stats(long long* out, int reset) { out[0] = g_soc[0]; out[1] = g_soc[1]; if (reset) g_soc[0] = g_soc[1] = 0; }
+#endif
+
 template <typename Real>
 static int cell_impl(const float* G, const float* h, int R, int kind, int E, const float* A, const float* b,
                      double px, double py, double phi, double dbar, double zeta, double xi0, double xi1,

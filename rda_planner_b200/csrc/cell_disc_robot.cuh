@@ -12,11 +12,18 @@
 // body's |g| <= t_g), solved in float64 by the feasible log-barrier Newton method below.  Same tie-break as the polygon
 // body: max margin, mu[2] = -|g| (the LP-vertex analogue: smallest mu'h), z = theta * max(stuff, 0).
 #pragma once
-#include "cell_solver.cuh"
+#include "cell_solver.cuh"      // includes coop_ipm.cuh: coop_chol, tri_solve, the cooperative context interface
+
+#if defined(RDA_SOC_STATS) && !defined(__CUDA_ARCH__)
+extern "C" void rda_soc_stat(int newton);      // host statistics build only
+#endif
 
 namespace rda {
 
 // min 1/2 x'Qx + c'x  s.t.  a_i'x <= b_i (i < m)  and  |(x[ia_k] + sa_k, x[ib_k] + sb_k)| <= (it_k >= 0 ? x[it_k] : 1), k < nc
+// Problem data and the work space of the barrier method in one block: shared memory when a warp solves the problem
+// cooperatively (one lane per row / vector component / Newton-matrix entry, as coop_ipm.cuh), local memory when one
+// thread does (SeqCtx: CPU port, tests).
 template <int NV, int MC>
 struct SocQP {
   double Q[NV][NV], c[NV], ad[MC][NV], b[MC];
@@ -24,6 +31,9 @@ struct SocQP {
   int ia[2], ib[2], it[2];
   double sa[2], sb[2];
   double x[NV];
+  double H[NV][NV], L[NV][NV], gr[NV], dx[NV], xn[NV], w[MC];
+  int flag;
+  int newton;                  // Newton steps of the last soc_barrier call (statistics)
   RDA_HD void clear() {
     for (int k = 0; k < NV; ++k) { c[k] = 0; for (int j = 0; j < NV; ++j) Q[k][j] = 0; }
     m = 0; nc = 0;
@@ -36,114 +46,133 @@ struct SocQP {
   RDA_HD void cone(int a, int b_, int t, double sha, double shb) { ia[nc] = a; ib[nc] = b_; it[nc] = t; sa[nc] = sha; sb[nc] = shb; ++nc; }
 };
 
-// value of t*f0 + barrier at y (1e300 outside the domain)
-template <int NV, int MC>
-RDA_HD double soc_value(const SocQP<NV, MC>& P, const double* y, double t) {
+// value of t*f0 + barrier at y (1e300 outside the domain); cooperative, the result is uniform over the lanes
+template <int NV, int MC, typename Ctx>
+RDA_HD double soc_value(const SocQP<NV, MC>& P, const double* y, double t, Ctx& ctx) {
+  const int lane = ctx.lane(), nl = ctx.nlanes();
   double f = 0;
-  for (int k = 0; k < NV; ++k) {
+  int bad = 0;
+  for (int k = lane; k < NV; k += nl) {
     double qx = 0;
     for (int j = 0; j < NV; ++j) qx += P.Q[k][j] * y[j];
     f += t * y[k] * (0.5 * qx + P.c[k]);
   }
-  for (int i = 0; i < P.m; ++i) {
+  for (int i = lane; i < P.m; i += nl) {
     double sl = P.b[i];
     for (int k = 0; k < NV; ++k) sl -= P.ad[i][k] * y[k];
-    if (!(sl > 0)) return 1e300;
-    f -= log(sl);
+    if (!(sl > 0)) bad = 1; else f -= log(sl);
   }
-  for (int k = 0; k < P.nc; ++k) {
+  for (int k = lane; k < P.nc; k += nl) {
     const double u = y[P.ia[k]] + P.sa[k], w = y[P.ib[k]] + P.sb[k];
     const double tq = P.it[k] >= 0 ? y[P.it[k]] : 1.0;
     const double psi = tq * tq - u * u - w * w;
-    if (!(psi > 0) || !(tq > 0)) return 1e300;
-    f -= log(psi);
+    if (!(psi > 0) || !(tq > 0)) bad = 1; else f -= log(psi);
   }
-  return f;
+  f = ctx.sum(f);
+  return ctx.max((double)bad) > 0 ? 1e300 : f;
 }
 
-// Feasible-start path following: damped Newton with backtracking on t*f0 + barrier, t = 1, 8, ..., 8^13
-// (duality gap (m + 2 nc)/t ~ 3e-11 at the end).  x must hold a strictly feasible point.
+// component r of grad(psi_k) / Hessian diagonal sign of cone k (0 when r is not one of its variables)
 template <int NV, int MC>
-RDA_HD bool soc_barrier(SocQP<NV, MC>& P) {
-  double H[NV][NV], L[NV][NV], gr[NV], dx[NV], xn[NV], w[MC];
+RDA_HD double soc_cone_grad(const SocQP<NV, MC>& P, int k, int r, double u, double wv, double tq) {
+  return r == P.ia[k] ? -2 * u : (r == P.ib[k] ? -2 * wv : (r == P.it[k] ? 2 * tq : 0.0));
+}
+
+// Feasible-start path following: damped Newton with backtracking on t*f0 + barrier, t = 1, MU, MU^2, ... up to TMAX
+// (duality gap (m + 2 nc)/t ~ 3e-11 at the end); intermediate centres only to a Newton decrement of RDA_SOC_CENTER (the
+// path is followed, not traced), the last one to 1e-9.  x must hold a strictly feasible point.  Measured on the committed
+// disc-body cases (CPU): MU 8 / centre 1e-9 -> 85 Newton steps per solve, MU 50 / 1e-2 -> 53, identical results.
+#ifndef RDA_SOC_MU
+#define RDA_SOC_MU 50.0
+#endif
+#ifndef RDA_SOC_TMAX
+#define RDA_SOC_TMAX 5.0e11
+#endif
+#ifndef RDA_SOC_CENTER
+#define RDA_SOC_CENTER 1e-2
+#endif
+template <int NV, int MC, typename Ctx>
+RDA_HD bool soc_barrier(SocQP<NV, MC>& P, Ctx& ctx) {
+  const int lane = ctx.lane(), nl = ctx.nlanes();
+  const int m = P.m;
   double t = 1.0;
-  for (int outer = 0; outer < 14; ++outer, t *= 8.0) {
+  int newton = 0;
+  for (int outer = 0; outer < 64; ++outer) {
+    const bool last = t >= RDA_SOC_TMAX;
     for (int itn = 0; itn < 30; ++itn) {
-      for (int i = 0; i < P.m; ++i) {
+      ++newton;
+      for (int i = lane; i < m; i += nl) {
         double sl = P.b[i];
         for (int k = 0; k < NV; ++k) sl -= P.ad[i][k] * P.x[k];
-        w[i] = 1.0 / sl;
+        P.w[i] = 1.0 / sl;
       }
-      for (int k = 0; k < NV; ++k) {
+      ctx.sync();
+      // the cones at the current point (every lane: two cones at most)
+      double cu[2] = {0, 0}, cw[2] = {0, 0}, ct[2] = {1, 1}, cip[2] = {0, 0};
+      for (int k = 0; k < P.nc; ++k) {
+        cu[k] = P.x[P.ia[k]] + P.sa[k]; cw[k] = P.x[P.ib[k]] + P.sb[k];
+        ct[k] = P.it[k] >= 0 ? P.x[P.it[k]] : 1.0;
+        cip[k] = 1.0 / (ct[k] * ct[k] - cu[k] * cu[k] - cw[k] * cw[k]);
+      }
+      for (int k = lane; k < NV; k += nl) {
         double v = P.c[k];
         for (int j = 0; j < NV; ++j) v += P.Q[k][j] * P.x[j];
         v *= t;
-        for (int i = 0; i < P.m; ++i) v += P.ad[i][k] * w[i];
-        gr[k] = v;
-        for (int j = 0; j <= k; ++j) {
-          double hv = t * P.Q[k][j];
-          for (int i = 0; i < P.m; ++i) hv += w[i] * w[i] * P.ad[i][k] * P.ad[i][j];
-          H[k][j] = hv;
+        for (int i = 0; i < m; ++i) v += P.ad[i][k] * P.w[i];
+        for (int q = 0; q < P.nc; ++q) v -= soc_cone_grad<NV, MC>(P, q, k, cu[q], cw[q], ct[q]) * cip[q];     // -grad(psi)/psi
+        P.gr[k] = v;
+        P.dx[k] = -v;
+      }
+      for (int e = lane; e < NV * (NV + 1) / 2; e += nl) {
+        int r = 0, rem = e;
+        while (rem > r) { rem -= r + 1; ++r; }
+        const int cidx = rem;               // r >= cidx
+        double h = t * P.Q[r][cidx];
+        for (int i = 0; i < m; ++i) h += P.w[i] * P.w[i] * P.ad[i][r] * P.ad[i][cidx];
+        for (int q = 0; q < P.nc; ++q) {
+          // -log psi: Hessian grad grad'/psi^2 - hess(psi)/psi, hess(psi) = diag(-2, -2, +2) on (ia, ib, it)
+          const double gr_ = soc_cone_grad<NV, MC>(P, q, r, cu[q], cw[q], ct[q]);
+          const double gc_ = soc_cone_grad<NV, MC>(P, q, cidx, cu[q], cw[q], ct[q]);
+          h += gr_ * gc_ * cip[q] * cip[q];
+          if (r == cidx) {
+            if (r == P.ia[q] || r == P.ib[q]) h += 2 * cip[q];
+            else if (r == P.it[q]) h -= 2 * cip[q];
+          }
         }
+        if (r == cidx) h += 1e-13 * (1.0 + h);
+        P.H[r][cidx] = h;
       }
-      for (int k = 0; k < P.nc; ++k) {
-        const int a = P.ia[k], bq = P.ib[k], tt = P.it[k];
-        const double u = P.x[a] + P.sa[k], wv = P.x[bq] + P.sb[k];
-        const double tq = tt >= 0 ? P.x[tt] : 1.0;
-        const double ip = 1.0 / (tq * tq - u * u - wv * wv);
-        // -log psi: gradient -grad(psi)/psi, Hessian grad grad'/psi^2 - hess(psi)/psi
-        const double ga = -2 * u, gb = -2 * wv, gt = 2 * tq;
-        gr[a] -= ga * ip; gr[bq] -= gb * ip;
-        auto addh = [&](int r, int cidx, double v) { if (r >= cidx) H[r][cidx] += v; else H[cidx][r] += v; };
-        addh(a, a, ga * ga * ip * ip + 2 * ip);
-        addh(bq, bq, gb * gb * ip * ip + 2 * ip);
-        addh(a, bq, ga * gb * ip * ip);
-        if (tt >= 0) {
-          gr[tt] -= gt * ip;
-          addh(tt, tt, gt * gt * ip * ip - 2 * ip);
-          addh(tt, a, gt * ga * ip * ip);
-          addh(tt, bq, gt * gb * ip * ip);
-        }
-      }
-      for (int k = 0; k < NV; ++k) { H[k][k] += 1e-13 * (1.0 + H[k][k]); dx[k] = -gr[k]; }
-      // Cholesky (lower) and solve
-      for (int j = 0; j < NV; ++j) {
-        double d = H[j][j];
-        for (int k = 0; k < j; ++k) d -= L[j][k] * L[j][k];
-        if (!(d > 0)) return false;
-        L[j][j] = sqrt(d);
-        const double inv = 1.0 / L[j][j];
-        for (int r = j + 1; r < NV; ++r) {
-          double sacc = H[r][j];
-          for (int k = 0; k < j; ++k) sacc -= L[r][k] * L[j][k];
-          L[r][j] = sacc * inv;
-        }
-      }
-      for (int i = 0; i < NV; ++i) {
-        double sacc = dx[i];
-        for (int k = 0; k < i; ++k) sacc -= L[i][k] * dx[k];
-        dx[i] = sacc / L[i][i];
-      }
-      for (int i = NV - 1; i >= 0; --i) {
-        double sacc = dx[i];
-        for (int k = i + 1; k < NV; ++k) sacc -= L[k][i] * dx[k];
-        dx[i] = sacc / L[i][i];
-      }
+      ctx.sync();
+      if (!coop_chol<NV, Ctx>(P.H, P.L, &P.flag, ctx)) return false;
+      if (lane == 0) tri_solve<NV>(P.L, P.dx);
+      ctx.sync();
       double lam2 = 0;
-      for (int k = 0; k < NV; ++k) lam2 -= gr[k] * dx[k];
+      for (int k = lane; k < NV; k += nl) lam2 -= P.gr[k] * P.dx[k];
+      lam2 = ctx.sum(lam2);
       if (!(lam2 == lam2)) return false;
-      if (lam2 < 1e-9) break;
-      const double f0 = soc_value<NV, MC>(P, P.x, t);
+      if (lam2 < (last ? 1e-9 : RDA_SOC_CENTER)) break;
+      const double f0 = soc_value<NV, MC, Ctx>(P, P.x, t, ctx);
       double step = 1.0;
       bool moved = false;
       for (int bt = 0; bt < 50; ++bt, step *= 0.5) {
-        for (int k = 0; k < NV; ++k) xn[k] = P.x[k] + step * dx[k];
-        if (soc_value<NV, MC>(P, xn, t) <= f0 - 0.1 * step * lam2) { moved = true; break; }
+        for (int k = lane; k < NV; k += nl) P.xn[k] = P.x[k] + step * P.dx[k];
+        ctx.sync();
+        const double f1 = soc_value<NV, MC, Ctx>(P, P.xn, t, ctx);
+        if (f1 <= f0 - 0.1 * step * lam2) { moved = true; break; }
+        ctx.sync();
       }
       if (!moved) break;
-      for (int k = 0; k < NV; ++k) P.x[k] = xn[k];
+      ctx.sync();
+      for (int k = lane; k < NV; k += nl) P.x[k] = P.xn[k];
+      ctx.sync();
     }
+    if (last) break;
+    t = rmin(t * RDA_SOC_MU, (double)RDA_SOC_TMAX);
   }
+  if (lane == 0) P.newton = newton;
+#if defined(RDA_SOC_STATS) && !defined(__CUDA_ARCH__)
+  rda_soc_stat(newton);
+#endif
   return true;
 }
 
@@ -154,6 +183,7 @@ struct DiscSlowStore {
     SocQP<DR_NVB, DR_MC> b;
     RDA_HD U() {}
   } u;
+  int need_a, ok, inactive, bad;      // control flow shared by the lanes of a cooperative solve
 };
 
 // ---- stage 1: geometry relative to the robot reference point and the closed forms of the inactive hinge ----------
@@ -238,89 +268,118 @@ RDA_HD void cell_front_dr(const RobotGeom& rb, int kind, int E, const float* A, 
 }
 
 // ---- stage 2: the two-cone programmes (float64) ---------------------------------------------------------------------
-template <typename Real>
-RDA_HD void cell_slow_dr(const RobotGeom& rb, CellWork<Real>& w, DiscSlowStore& S) {
-  const CellGeom<Real>& g = w.g;
-  const double x0 = w.xi0, x1 = w.xi1, k0d = (double)w.k0, c_ = w.cphi, s_ = w.sphi, r2 = w.ro2;
+// Lane 0 owns `w` and sets the problems up; all lanes of the context run the barrier iterations (cell_slow's pattern).
+template <typename Real, typename Ctx>
+RDA_HD void cell_slow_dr(const RobotGeom& rb, CellWork<Real>& w, DiscSlowStore& S, Ctx& ctx) {
+  const int lane = ctx.lane();
   const double rr = rb.rad, bcx = rb.cx, bcy = rb.cy;
-  const double cwx = c_ * bcx - s_ * bcy, cwy = s_ * bcx + c_ * bcy;          // R c
-  const double ax_ = c_ * x0 - s_ * x1, ay_ = s_ * x0 + c_ * x1;                // R xi
-  const double xic = x0 * bcx + x1 * bcy;
-  const bool circ = w.circ;
-  const double radd = circ ? (double)g.rad : 0.0;
-  const int nv_o = circ ? 1 : g.ne;
-  if (!circ && g.ne < 3) { w.have = false; w.path = CELL_FAILED; return; }
-  // upper bound of the max margin from the closest pair: negative => the hinge is active for sure, stage A skipped
-  bool need_a = true;
-  if (w.sep) {
-    const double dirx = w.byx, diry = w.byy;
-    // body point of the closest pair, body frame: c - r R'dir
-    const double ybx = bcx - rr * (c_ * dirx + s_ * diry), yby = bcy - rr * (-s_ * dirx + c_ * diry);
-    const double ub = (sqrt((double)w.best) - rr) + x0 * ybx + x1 * yby - k0d;
-    if (ub < -1e-9) need_a = false;
-  }
-  bool ok = true, inactive = false;
-  if (need_a) {   // stage A: max margin with Hm + xi = 0 (g = -R'v - xi);  x = (v0, v1, so, tg, tv)
-    SocQP<DR_NVA, DR_MC>& P = S.u.a;
-    P.clear();
-    P.c[0] = -cwx; P.c[1] = -cwy; P.c[2] = 1; P.c[3] = rr;     // so + sigma_Rob(g) + xi.c = so + r tg - v.(R c)
-    for (int i = 0; i < nv_o; ++i) {
-      const int r = P.new_row(0.0);                            // v.x_i + rad tv <= so
-      P.ad[r][0] = circ ? (double)g.cx : (double)g.vx[i];
-      P.ad[r][1] = circ ? (double)g.cy : (double)g.vy[i];
-      P.ad[r][2] = -1.0; P.ad[r][4] = radd;
+  if (lane == 0) {
+    const CellGeom<Real>& g = w.g;
+    const double x0 = w.xi0, x1 = w.xi1, k0d = (double)w.k0, c_ = w.cphi, s_ = w.sphi;
+    const double cwx = c_ * bcx - s_ * bcy, cwy = s_ * bcx + c_ * bcy;          // R c
+    const double ax_ = c_ * x0 - s_ * x1, ay_ = s_ * x0 + c_ * x1;                // R xi
+    const bool circ = w.circ;
+    const double radd = circ ? (double)g.rad : 0.0;
+    const int nv_o = circ ? 1 : g.ne;
+    S.bad = (!circ && g.ne < 3) ? 1 : 0;
+    // upper bound of the max margin from the closest pair: negative => the hinge is active for sure, stage A skipped
+    bool need_a = true;
+    if (w.sep) {
+      const double dirx = w.byx, diry = w.byy;
+      // body point of the closest pair, body frame: c - r R'dir
+      const double ybx = bcx - rr * (c_ * dirx + s_ * diry), yby = bcy - rr * (-s_ * dirx + c_ * diry);
+      const double ub = (sqrt((double)w.best) - rr) + x0 * ybx + x1 * yby - k0d;
+      if (ub < -1e-9) need_a = false;
     }
-    { const int r = P.new_row(1.0); P.ad[r][4] = 1.0; }        // tv <= 1
-    { const int r = P.new_row(0.0); P.ad[r][4] = -1.0; }       // tv >= 0
-    P.cone(0, 1, circ ? 4 : -1, 0.0, 0.0);                     // |v| <= 1  /  |v| <= tv
-    P.cone(0, 1, 3, ax_, ay_);                                 // |g| = |v + R xi| <= tg
-    P.x[0] = 0; P.x[1] = 0; P.x[2] = 1.0 + radd; P.x[3] = sqrt(ax_ * ax_ + ay_ * ay_) + 1.0; P.x[4] = 0.5;
-    ok = soc_barrier<DR_NVA, DR_MC>(P);
-    if (ok) {
-      const double va = P.x[0], vb = P.x[1];
-      const double gn = sqrt((va + ax_) * (va + ax_) + (vb + ay_) * (vb + ay_));
-      // margin at the barrier's v with the supports evaluated exactly (so, tg carry the barrier's 1/t slack)
-      double so = circ ? va * (double)g.cx + vb * (double)g.cy + radd * sqrt(va * va + vb * vb) : -1e300;
-      if (!circ) for (int i = 0; i < g.ne; ++i) so = rmax(so, va * (double)g.vx[i] + vb * (double)g.vy[i]);
-      const double cst = -(so + rr * gn - (va * cwx + vb * cwy) - xic) - k0d;
-      if (cst >= 0) {
-        inactive = true;
-        w.v0 = (Real)va; w.v1 = (Real)vb;
-        w.g0 = (Real)(-(c_ * va + s_ * vb) - x0);
-        w.g1 = (Real)(-(-s_ * va + c_ * vb) - x1);
-        w.exact_zero_q = true; w.have = true; w.path = CELL_SLOW_A;
+    S.need_a = need_a ? 1 : 0; S.ok = 1; S.inactive = 0;
+    if (need_a && !S.bad) {   // stage A: max margin with Hm + xi = 0 (g = -R'v - xi);  x = (v0, v1, so, tg, tv)
+      SocQP<DR_NVA, DR_MC>& P = S.u.a;
+      P.clear();
+      P.c[0] = -cwx; P.c[1] = -cwy; P.c[2] = 1; P.c[3] = rr;     // so + sigma_Rob(g) + xi.c = so + r tg - v.(R c)
+      for (int i = 0; i < nv_o; ++i) {
+        const int r = P.new_row(0.0);                            // v.x_i + rad tv <= so
+        P.ad[r][0] = circ ? (double)g.cx : (double)g.vx[i];
+        P.ad[r][1] = circ ? (double)g.cy : (double)g.vy[i];
+        P.ad[r][2] = -1.0; P.ad[r][4] = radd;
+      }
+      { const int r = P.new_row(1.0); P.ad[r][4] = 1.0; }        // tv <= 1
+      { const int r = P.new_row(0.0); P.ad[r][4] = -1.0; }       // tv >= 0
+      P.cone(0, 1, circ ? 4 : -1, 0.0, 0.0);                     // |v| <= 1  /  |v| <= tv
+      P.cone(0, 1, 3, ax_, ay_);                                 // |g| = |v + R xi| <= tg
+      P.x[0] = 0; P.x[1] = 0; P.x[2] = 1.0 + radd; P.x[3] = sqrt(ax_ * ax_ + ay_ * ay_) + 1.0; P.x[4] = 0.5;
+    }
+  }
+  ctx.sync();
+  if (S.bad) { if (lane == 0) { w.have = false; w.path = CELL_FAILED; } return; }
+  if (S.need_a) {
+    const bool ok = soc_barrier<DR_NVA, DR_MC, Ctx>(S.u.a, ctx);
+    ctx.sync();
+    if (lane == 0) {
+      S.ok = ok ? 1 : 0;
+      if (ok) {
+        const CellGeom<Real>& g = w.g;
+        const SocQP<DR_NVA, DR_MC>& P = S.u.a;
+        const double x0 = w.xi0, x1 = w.xi1, c_ = w.cphi, s_ = w.sphi;
+        const double cwx = c_ * bcx - s_ * bcy, cwy = s_ * bcx + c_ * bcy, ax_ = c_ * x0 - s_ * x1, ay_ = s_ * x0 + c_ * x1;
+        const double va = P.x[0], vb = P.x[1];
+        const double gn = sqrt((va + ax_) * (va + ax_) + (vb + ay_) * (vb + ay_));
+        // margin at the barrier's v with the supports evaluated exactly (so, tg carry the barrier's 1/t slack)
+        double so = w.circ ? va * (double)g.cx + vb * (double)g.cy + (double)g.rad * sqrt(va * va + vb * vb) : -1e300;
+        if (!w.circ) for (int i = 0; i < g.ne; ++i) so = rmax(so, va * (double)g.vx[i] + vb * (double)g.vy[i]);
+        const double cst = -(so + rr * gn - (va * cwx + vb * cwy) - (x0 * bcx + x1 * bcy)) - (double)w.k0;
+        if (cst >= 0) {
+          S.inactive = 1;
+          w.v0 = (Real)va; w.v1 = (Real)vb;
+          w.g0 = (Real)(-(c_ * va + s_ * vb) - x0);
+          w.g1 = (Real)(-(-s_ * va + c_ * vb) - x1);
+          w.exact_zero_q = true; w.have = true; w.path = CELL_SLOW_A;
+        }
       }
     }
+    ctx.sync();
   }
-  if (ok && !inactive) {   // stage B: active hinge;  x = (v0, v1, g0, g1, so, tg, w, tv)
+  if (S.ok && !S.inactive) {   // stage B: active hinge;  x = (v0, v1, g0, g1, so, tg, w, tv)
     SocQP<DR_NVB, DR_MC>& P = S.u.b;
-    P.clear();
-    const double Mx[4] = {c_, s_, 1, 0}, My[4] = {-s_, c_, 0, 1};      // q = M (v, g) + xi, M = [R' I]
-    for (int k = 0; k < 4; ++k)
-      for (int j = 0; j < 4; ++j) P.Q[k][j] = r2 * (Mx[k] * Mx[j] + My[k] * My[j]);
-    for (int k = 0; k < 4; ++k) P.c[k] = r2 * (Mx[k] * x0 + My[k] * x1);
-    P.Q[6][6] = 1.0;                                                    // 1/2 w^2 (ro1 == 1 inside LamMuZ, rda_solver.py:257)
-    for (int i = 0; i < nv_o; ++i) {
-      const int r = P.new_row(0.0);
-      P.ad[r][0] = circ ? (double)g.cx : (double)g.vx[i];
-      P.ad[r][1] = circ ? (double)g.cy : (double)g.vy[i];
-      P.ad[r][4] = -1.0; P.ad[r][7] = radd;
+    if (lane == 0) {
+      const CellGeom<Real>& g = w.g;
+      const double x0 = w.xi0, x1 = w.xi1, k0d = (double)w.k0, c_ = w.cphi, s_ = w.sphi, r2 = w.ro2;
+      const bool circ = w.circ;
+      const double radd = circ ? (double)g.rad : 0.0;
+      const int nv_o = circ ? 1 : g.ne;
+      P.clear();
+      const double Mx[4] = {c_, s_, 1, 0}, My[4] = {-s_, c_, 0, 1};      // q = M (v, g) + xi, M = [R' I]
+      for (int k = 0; k < 4; ++k)
+        for (int j = 0; j < 4; ++j) P.Q[k][j] = r2 * (Mx[k] * Mx[j] + My[k] * My[j]);
+      for (int k = 0; k < 4; ++k) P.c[k] = r2 * (Mx[k] * x0 + My[k] * x1);
+      P.Q[6][6] = 1.0;                                                    // 1/2 w^2 (ro1 == 1 inside LamMuZ, rda_solver.py:257)
+      for (int i = 0; i < nv_o; ++i) {
+        const int r = P.new_row(0.0);
+        P.ad[r][0] = circ ? (double)g.cx : (double)g.vx[i];
+        P.ad[r][1] = circ ? (double)g.cy : (double)g.vy[i];
+        P.ad[r][4] = -1.0; P.ad[r][7] = radd;
+      }
+      { const int r = P.new_row(-k0d); P.ad[r][4] = 1.0; P.ad[r][2] = bcx; P.ad[r][3] = bcy; P.ad[r][5] = rr; P.ad[r][6] = -1.0; }   // so + sigma_Rob + k0 <= w
+      { const int r = P.new_row(1.0); P.ad[r][7] = 1.0; }
+      { const int r = P.new_row(0.0); P.ad[r][7] = -1.0; }
+      P.cone(0, 1, circ ? 7 : -1, 0.0, 0.0);
+      P.cone(2, 3, 5, 0.0, 0.0);                                          // |g| <= tg
+      const double so0 = 1.0 + radd;
+      const double xs[DR_NVB] = {0, 0, 0, 0, so0, 1.0, rmax(so0 + rr + k0d + 2.0, 1.0), 0.5};
+      for (int k = 0; k < DR_NVB; ++k) P.x[k] = xs[k];
     }
-    { const int r = P.new_row(-k0d); P.ad[r][4] = 1.0; P.ad[r][2] = bcx; P.ad[r][3] = bcy; P.ad[r][5] = rr; P.ad[r][6] = -1.0; }   // so + sigma_Rob + k0 <= w
-    { const int r = P.new_row(1.0); P.ad[r][7] = 1.0; }
-    { const int r = P.new_row(0.0); P.ad[r][7] = -1.0; }
-    P.cone(0, 1, circ ? 7 : -1, 0.0, 0.0);
-    P.cone(2, 3, 5, 0.0, 0.0);                                          // |g| <= tg
-    const double so0 = 1.0 + radd;
-    const double xs[DR_NVB] = {0, 0, 0, 0, so0, 1.0, rmax(so0 + rr + k0d + 2.0, 1.0), 0.5};
-    for (int k = 0; k < DR_NVB; ++k) P.x[k] = xs[k];
-    ok = soc_barrier<DR_NVB, DR_MC>(P);
-    if (ok) {
-      w.v0 = (Real)P.x[0]; w.v1 = (Real)P.x[1]; w.g0 = (Real)P.x[2]; w.g1 = (Real)P.x[3];
-      w.exact_zero_q = false; w.have = true; w.path = CELL_SLOW_B;
+    ctx.sync();
+    const bool ok = soc_barrier<DR_NVB, DR_MC, Ctx>(P, ctx);
+    ctx.sync();
+    if (lane == 0) {
+      S.ok = ok ? 1 : 0;
+      if (ok) {
+        w.v0 = (Real)P.x[0]; w.v1 = (Real)P.x[1]; w.g0 = (Real)P.x[2]; w.g1 = (Real)P.x[3];
+        w.exact_zero_q = false; w.have = true; w.path = CELL_SLOW_B;
+      }
     }
+    ctx.sync();
   }
-  if (!ok) { w.have = false; w.path = CELL_FAILED; }
+  if (lane == 0 && !S.ok) { w.have = false; w.path = CELL_FAILED; }
 }
 
 // ---- stage 3: multipliers, updates, su-QP inputs (cell_back with the disc body's mu and support function) --------
@@ -381,7 +440,8 @@ RDA_HD void cell_solve_dr(const RobotGeom& rb, int kind, int E, const float* A, 
   cell_front_dr<Real>(rb, kind, E, A, b, px, py, cphi, sphi, dbar, zeta, xi0, xi1, ro2, w);
   if (!w.have) {
     DiscSlowStore S;
-    cell_slow_dr<Real>(rb, w, S);
+    SeqCtx ctx;
+    cell_slow_dr<Real, SeqCtx>(rb, w, S, ctx);
   }
   cell_back_dr<Real>(rb, w, zeta, theta, out);
 }

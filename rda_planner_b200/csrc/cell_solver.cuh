@@ -33,7 +33,9 @@ extern "C" void rda_case_stat(int line);
 #define RDA_CELL_ACCEPT_CONV 0
 #endif
 #ifndef RDA_CELL_POLISH
-#define RDA_CELL_POLISH 1      // float64 polish of float32 edge-contact roots in the last pass (edge_contact_polish)
+#define RDA_CELL_POLISH 0      // float64 polish of float32 edge-contact roots in the last pass (edge_contact_polish): halves the
+                               // interior point cells but measured SLOWER on B200 (r02: 4.07 vs 3.91 ms for all cell passes: the
+                               // kernel needs 168 registers with it, or spills when capped), so off
 #endif
 #ifndef RDA_CELL_EE_TANG
 #define RDA_CELL_EE_TANG 1e-4

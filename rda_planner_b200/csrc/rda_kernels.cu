@@ -76,6 +76,7 @@ struct rda_handle {
   int slow_cpw, slow_ctas;   // k_cells_slow: cells per warp, CTAs per SM (RDA_B200_SLOW_CPW / RDA_B200_SLOW_CTAS)
   int slow_coop;             // warp-cooperative last pass, one cell per warp (RDA_B200_SLOW_COOP, default 1)
   int mid_ctas;              // k_cells_mid CTAs per SM (RDA_B200_MID_CTAS)
+  int dr_coop;               // disc body: barrier cells one per warp (RDA_B200_DR_COOP, default 1)
   int slow_adapt;            // fewer cells per warp when the list fits one wave (RDA_B200_SLOW_ADAPT, default 0: measured slower)
   int split_min;         // smallest batch that is split (RDA_B200_SPLIT_MIN, default 2048)
   int parts;             // number of sub-batches, 1..4 (RDA_B200_SPLIT_PARTS, default 2)
@@ -697,7 +698,8 @@ __global__ void __launch_bounds__(64) k_cells_dr_slow(DevPtrs d, RobotGeom rb, f
     cell_front_dr<float>(rb, c.kind, d.E, c.A, c.bb, c.px, c.py, c.cp, c.sp, c.dbar, c.zeta, c.xi0, c.xi1, ro2, w);
     if (!w.have) {
       DiscSlowStore S;
-      cell_slow_dr<float>(rb, w, S);
+      SeqCtx ctx;
+      cell_slow_dr<float, SeqCtx>(rb, w, S, ctx);
     }
     CellOut<float> out;
     cell_back_dr<float>(rb, w, c.zeta, theta, out);
@@ -714,20 +716,101 @@ __global__ void __launch_bounds__(64) k_cells_dr_slow(DevPtrs d, RobotGeom rb, f
   }
 }
 
+// one cell per WARP: the two-cone barrier iterations spread over the lanes, the problem in shared memory
+constexpr int DR_COOP_WARPS = 4;
+__global__ void __launch_bounds__(32 * DR_COOP_WARPS) k_cells_dr_slow_coop(DevPtrs d, RobotGeom rb, float ro2, float theta) {
+  __shared__ DiscSlowStore store[DR_COOP_WARPS];
+  const int count = d.wl_count[1];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  DiscSlowStore& S = store[warp];
+  GroupCtx<32> ctx;
+  for (int wi = blockIdx.x * DR_COOP_WARPS + warp; wi < count; wi += gridDim.x * DR_COOP_WARPS) {
+    const long long idx = d.worklist2[wi];
+    CellIn c;
+    CellWork<float> w;
+    w.have = false;
+    if (lane == 0) {
+      c = cell_load(d, idx);
+      cell_front_dr<float>(rb, c.kind, d.E, c.A, c.bb, c.px, c.py, c.cp, c.sp, c.dbar, c.zeta, c.xi0, c.xi1, ro2, w);
+    }
+    const int have = __shfl_sync(0xffffffffu, (int)w.have, 0);
+    if (!have) {
+      __syncwarp();
+      cell_slow_dr<float, GroupCtx<32>>(rb, w, S, ctx);
+      __syncwarp();
+    }
+    if (lane == 0) {
+      CellOut<float> out;
+      cell_back_dr<float>(rb, w, c.zeta, theta, out);
+      float hm2 = 0.f, dual = 0.f;
+      if (out.path == CELL_FAILED) {
+        dual = INFINITY;
+        atomicOr(&d.status[c.b], RDA_ST_CELL_FALLBACK);
+      } else {
+        cell_store(d, c, out, &hm2, &dual);
+      }
+      atomicAdd(&d.resi_acc[2 * c.b], hm2);
+      atomicAdd(&d.resi_acc[2 * c.b + 1], dual);
+      atomicAdd(&d.counters[out.path == CELL_FAILED ? 2 : 1], 1);
+    }
+    __syncwarp();
+  }
+}
+
+// Last pass, first half (with the cooperative interior point pass): the closed forms only the rare cells need (robot edge x
+// obstacle edge, weighted maxima on monotone edges: cell_front<EXTRA>) for the cells the searched pass listed, one THREAD per
+// cell — they resolve ~90 % of that list; what is left (~0.01 % of all cells) goes to k_cells_slow_coop through d.worklist,
+// which the searched pass has consumed by now.  (Doing these closed forms in lane 0 of the cooperative kernel cost 1.7 ms per
+// ADMM iteration at 16 384 unique instances: ten thousand warps each waiting for one serial lane.)
+__global__ void __launch_bounds__(128) k_cells_extra(DevPtrs d, RobotGeom rb, float ro2, float theta) {
+  const int count = d.wl_count[1];
+  const int lane = threadIdx.x & 31;
+  for (int base = blockIdx.x * blockDim.x; base < count; base += gridDim.x * blockDim.x) {
+    const int wi = base + threadIdx.x;
+    bool need = false;
+    int idx = 0;
+    if (wi < count) {
+      idx = d.worklist2[wi];
+      CellIn c = cell_load(d, idx);
+      CellWork<float> w;
+      cell_front<float, false, true>(rb, c.kind, d.E, c.A, c.bb, c.px, c.py, c.cp, c.sp, c.dbar, c.zeta, c.xi0, c.xi1, ro2, w);
+      if (w.have) {
+        CellOut<float> out;
+        cell_back<float>(rb, w, c.zeta, theta, out);
+        float hm2 = 0.f, dual = 0.f;
+        cell_store(d, c, out, &hm2, &dual);
+        atomicAdd(&d.resi_acc[2 * c.b], hm2);
+        atomicAdd(&d.resi_acc[2 * c.b + 1], dual);
+        atomicAdd(&d.counters[1], 1);
+      } else {
+        need = true;
+      }
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, need);
+    if (m) {
+      int leader = __ffs(m) - 1, pos = 0;
+      if (lane == leader) pos = atomicAdd(&d.wl_count[4], __popc(m));
+      pos = __shfl_sync(0xffffffffu, pos, leader);
+      if (need) d.worklist[pos + __popc(m & ((1u << lane) - 1))] = idx;
+    }
+  }
+}
+
 // Warp-cooperative variant of the last pass (RDA_B200_SLOW_COOP=1): ONE cell per warp, the interior point iteration of
 // coop_ipm.cuh spread over the lanes (rows, vector components and Newton-matrix entries), the problem in shared memory.
 // Round 1 measured it slower than one thread per cell — with 5 % of the cells in this pass; since the closed forms of
 // round 2 leave 0.1 % (~13 000 cells at 16 384 instances, three waves of warps) the pass is a pure latency tail, which is
 // what cooperation shortens.
 constexpr int SLOW_COOP_WARPS = 4;
-__global__ void __launch_bounds__(32 * SLOW_COOP_WARPS, 5) k_cells_slow_coop(DevPtrs d, RobotGeom rb, float ro2, float theta) {
+__global__ void __launch_bounds__(32 * SLOW_COOP_WARPS) k_cells_slow_coop(DevPtrs d, RobotGeom rb, float ro2, float theta) {
   __shared__ CellSlowStore store[SLOW_COOP_WARPS];
-  const int count = d.wl_count[1];
+  // the list k_cells_extra left: d.worklist (the searched pass' list, consumed by now) with its own counter
+  const int count = d.wl_count[4];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   CellSlowStore& S = store[warp];
   GroupCtx<32> ctx;
   for (int wi = blockIdx.x * SLOW_COOP_WARPS + warp; wi < count; wi += gridDim.x * SLOW_COOP_WARPS) {
-    const long long idx = d.worklist2[wi];
+    const long long idx = d.worklist[wi];
     CellIn c;
     CellWork<float> w;
     w.have = false;
@@ -786,7 +869,7 @@ __device__ __forceinline__ void finalize_instance(const DevPtrs& d, const RobotG
 
 __global__ void k_finalize(DevPtrs d, RobotGeom rb, float thr) {
   int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b == 0) { d.wl_count[0] = 0; d.wl_count[1] = 0; d.wl_count[2] = 0; d.wl_count[3] = 0; }   // worklists consumed
+  if (b == 0) { d.wl_count[0] = 0; d.wl_count[1] = 0; d.wl_count[2] = 0; d.wl_count[3] = 0; d.wl_count[4] = 0; }   // worklists consumed
   if (b >= d.B) return;
   if (d.done[b]) return;
   finalize_instance(d, rb, thr, b);
@@ -1059,7 +1142,7 @@ DevPtrs dev_ptrs(const rda_handle* h, int b0, int nb, int part) {
   d.ref_speed = h->ref_speed + o; d.resi_acc = h->resi_acc + 2 * o; d.resi_pri = h->resi_pri + o;
   d.resi_dual = h->resi_dual + o;
   d.status = h->status + o; d.iters = h->iters + o; d.done = h->done + o;
-  d.counters = h->counters; d.wl_count = h->counters + 8 + 4 * part;     // part < 4
+  d.counters = h->counters; d.wl_count = h->counters + 8 + 8 * part;     // part < 4, 8 counters each
   d.ogeo = h->ogeo ? h->ogeo + o * N : nullptr;
   d.feat = h->feat ? h->feat + o * NT : nullptr;
   d.worklist0 = h->worklist0 ? h->worklist0 + o * NT : nullptr;
@@ -1142,7 +1225,7 @@ int rda_create(const rda_config* cfg, const rda_tunables* tun, rda_handle** out)
   alloc(&h->cur_u, B * 2 * T); alloc(&h->ref_s, B * 3 * (T + 1)); alloc(&h->ref_speed, B);
   alloc(&h->resi_acc, B * 2); alloc(&h->resi_pri, B); alloc(&h->resi_dual, B);
   alloc((float**)&h->status, B); alloc((float**)&h->iters, B); alloc((float**)&h->done, B);
-  alloc((float**)&h->counters, 32);     // [0..4] statistics, [8..11] worklist lengths of the two halves
+  alloc((float**)&h->counters, 64);     // [0..7] statistics, [8 + 8 part ..] worklist lengths of the sub-batches
   alloc((float**)&h->worklist, B * NT);
   alloc((float**)&h->worklist2, B * NT);
   alloc((float**)&h->su_ws, B * (h->su_ws_stride / 4));
@@ -1225,6 +1308,8 @@ int rda_create(const rda_config* cfg, const rda_tunables* tun, rda_handle** out)
   // config C (disc cells on the barrier iteration) 467 -> 1 734 solves/s
   h->slow_coop = 1;
   if (const char* v = getenv("RDA_B200_SLOW_COOP")) h->slow_coop = atoi(v) != 0;
+  h->dr_coop = 1;
+  if (const char* v = getenv("RDA_B200_DR_COOP")) h->dr_coop = atoi(v) != 0;
   h->mid_ctas = 16;     // measured r02: 8 / 12 / 18 CTAs per SM -> 3.42 / 3.32 / 3.28 ms for all cell passes (6 are resident)
   if (const char* v = getenv("RDA_B200_MID_CTAS")) { int x = atoi(v); if (x >= 1 && x <= 64) h->mid_ctas = x; }
   if (const char* v = getenv("RDA_B200_SLOW_CPW")) { int x = atoi(v); if (x >= 1 && x <= 32) h->slow_cpw = x; }
@@ -1290,7 +1375,7 @@ int rda_cold_start(rda_handle* h, void* stream) {
   RDA_CUDA(cudaMemsetAsync(h->status, 0, B * 4, s));
   RDA_CUDA(cudaMemsetAsync(h->iters, 0, B * 4, s));
   RDA_CUDA(cudaMemsetAsync(h->done, 0, B * 4, s));
-  RDA_CUDA(cudaMemsetAsync(h->counters, 0, 32 * 4, s));
+  RDA_CUDA(cudaMemsetAsync(h->counters, 0, 64 * 4, s));
   if (h->feat) RDA_CUDA(cudaMemsetAsync(h->feat, 0, B * NT, s));
   k_fill<<<grid_for((long long)(B * T), 256), 256, 0, s>>>(h->dis, 1.0f, B * T);   // para_dis = 1 (:119)
   RDA_CUDA(cudaGetLastError());
@@ -1406,7 +1491,8 @@ static int step_lammuz_part(rda_handle* h, int b0, int nb, int part, cudaStream_
     if (h->rb.disc) {
       k_cells_dr<<<grid_for((long long)nb * h->N * h->T, 128), 128, 0, s>>>(d, h->rb, h->tun.ro2, theta);
       RDA_CUDA(cudaGetLastError());
-      k_cells_dr_slow<<<148 * 16, 64, 0, s>>>(d, h->rb, h->tun.ro2, theta);
+      if (h->dr_coop) k_cells_dr_slow_coop<<<148 * 16, 32 * DR_COOP_WARPS, 0, s>>>(d, h->rb, h->tun.ro2, theta);
+      else k_cells_dr_slow<<<148 * 16, 64, 0, s>>>(d, h->rb, h->tun.ro2, theta);
       RDA_CUDA(cudaGetLastError());
       h->launches += 2;
       k_finalize<<<(nb + 127) / 128, 128, 0, s>>>(d, h->rb, h->iter_threshold);
@@ -1430,7 +1516,12 @@ static int step_lammuz_part(rda_handle* h, int b0, int nb, int part, cudaStream_
     RDA_CUDA(cudaGetLastError());
     k_cells_mid<<<148 * h->mid_ctas, 128, 0, s>>>(d, h->rb, h->tun.ro2, theta);
     RDA_CUDA(cudaGetLastError());
-    if (h->slow_coop) k_cells_slow_coop<<<148 * h->slow_ctas, 32 * SLOW_COOP_WARPS, 0, s>>>(d, h->rb, h->tun.ro2, theta);
+    if (h->slow_coop) {
+      k_cells_extra<<<148 * 4, 128, 0, s>>>(d, h->rb, h->tun.ro2, theta);
+      RDA_CUDA(cudaGetLastError());
+      h->launches += 1;
+      k_cells_slow_coop<<<148 * h->slow_ctas, 32 * SLOW_COOP_WARPS, 0, s>>>(d, h->rb, h->tun.ro2, theta);
+    }
     else k_cells_slow<<<148 * h->slow_ctas, 64, 0, s>>>(d, h->rb, h->tun.ro2, theta, h->slow_cpw, h->slow_adapt);
     RDA_CUDA(cudaGetLastError());
     h->launches += 3;

@@ -1,6 +1,6 @@
 """Small target for compute-sanitizer (memcheck / racecheck): short batched solves covering polygon and
-disc obstacles, static and moving, the two-stream sub-batch path (forced on this small batch) and the
-front-end kernels through one closed-loop step of BatchedMPC."""
+disc obstacles, static and moving, the two-stream sub-batch path (forced on this small batch; the interior point pass
+is the warp-cooperative one), a disc body, and the front-end kernels through one closed-loop step of BatchedMPC."""
 import os
 import sys
 
@@ -28,6 +28,19 @@ for kind, moving in (('polygon', False), ('circle', True)):
                                   np.array([p[3] for p in packs]), tv)
     torch.cuda.synchronize()
     print(kind, 'ok', bool(torch.isfinite(out['u']).all()), int((out['status'] & 6).sum()))
+
+# disc body (cone_type 'norm2'): k_cells_dr / k_cells_dr_slow
+from rda_planner_b200.scenarios import disc_robot  # noqa: E402
+T, N, B = 8, 4, 24
+insts = [make_instance(140 + i, T=T, N=N, E=4, kind='polygon' if i % 2 else 'circle', lateral=(0.3, 3.0), dynamics='diff') for i in range(B)]
+packs = [pack_obstacles(list(i['obstacles']), T, N, 4) for i in insts]
+g = RDA_solver(T, disc_robot(radius=1.1, center=(0.2, 0.0), wheelbase=2.0, dynamics='diff'), 4, N, iter_num=3, iter_threshold=0.0,
+               time_print=False, batch=B)
+out = g.iterative_solve_batch(np.stack([i['nom_s'] for i in insts]), np.stack([i['nom_u'] for i in insts]),
+                              np.stack([i['ref'] for i in insts]), np.array([4.0] * B), np.stack([p[0] for p in packs]),
+                              np.stack([p[1] for p in packs]), np.stack([p[2] for p in packs]), np.array([p[3] for p in packs]), False)
+torch.cuda.synchronize()
+print('disc body ok', bool(torch.isfinite(out['u']).all()), int((out['status'] & 6).sum()))
 
 # front end: pre_process, obstacle conversion (sorted, padded, moving), arrive rule, model step
 from collections import namedtuple  # noqa: E402
