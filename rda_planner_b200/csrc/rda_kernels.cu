@@ -76,6 +76,7 @@ struct rda_handle {
   int slow_cpw, slow_ctas;   // k_cells_slow: cells per warp, CTAs per SM (RDA_B200_SLOW_CPW / RDA_B200_SLOW_CTAS)
   int slow_coop;             // warp-cooperative last pass, one cell per warp (RDA_B200_SLOW_COOP, default 1)
   int mid_ctas;              // k_cells_mid CTAs per SM (RDA_B200_MID_CTAS)
+  int extra_min;             // sub-batches of at least this many instances run k_cells_extra before the cooperative pass (RDA_B200_EXTRA_MIN)
   int dr_coop;               // disc body: barrier cells one per warp (RDA_B200_DR_COOP, default 1)
   int slow_adapt;            // fewer cells per warp when the list fits one wave (RDA_B200_SLOW_ADAPT, default 0: measured slower)
   int split_min;         // smallest batch that is split (RDA_B200_SPLIT_MIN, default 2048)
@@ -802,15 +803,17 @@ __global__ void __launch_bounds__(128) k_cells_extra(DevPtrs d, RobotGeom rb, fl
 // round 2 leave 0.1 % (~13 000 cells at 16 384 instances, three waves of warps) the pass is a pure latency tail, which is
 // what cooperation shortens.
 constexpr int SLOW_COOP_WARPS = 4;
-__global__ void __launch_bounds__(32 * SLOW_COOP_WARPS) k_cells_slow_coop(DevPtrs d, RobotGeom rb, float ro2, float theta) {
+__global__ void __launch_bounds__(32 * SLOW_COOP_WARPS) k_cells_slow_coop(DevPtrs d, RobotGeom rb, float ro2, float theta, int from_extra) {
   __shared__ CellSlowStore store[SLOW_COOP_WARPS];
-  // the list k_cells_extra left: d.worklist (the searched pass' list, consumed by now) with its own counter
-  const int count = d.wl_count[4];
+  // from_extra: the list k_cells_extra left — d.worklist (the searched pass' list, consumed by now) with its own counter;
+  // otherwise the searched pass' own leftovers (small batches: one launch less, lane 0 runs the EXTRA closed forms)
+  const int count = from_extra ? d.wl_count[4] : d.wl_count[1];
+  const int* list = from_extra ? d.worklist : d.worklist2;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   CellSlowStore& S = store[warp];
   GroupCtx<32> ctx;
   for (int wi = blockIdx.x * SLOW_COOP_WARPS + warp; wi < count; wi += gridDim.x * SLOW_COOP_WARPS) {
-    const long long idx = d.worklist[wi];
+    const long long idx = list[wi];
     CellIn c;
     CellWork<float> w;
     w.have = false;
@@ -1310,6 +1313,8 @@ int rda_create(const rda_config* cfg, const rda_tunables* tun, rda_handle** out)
   if (const char* v = getenv("RDA_B200_SLOW_COOP")) h->slow_coop = atoi(v) != 0;
   h->dr_coop = 1;
   if (const char* v = getenv("RDA_B200_DR_COOP")) h->dr_coop = atoi(v) != 0;
+  h->extra_min = 3000;
+  if (const char* v = getenv("RDA_B200_EXTRA_MIN")) { int x = atoi(v); if (x >= 1) h->extra_min = x; }
   h->mid_ctas = 16;     // measured r02: 8 / 12 / 18 CTAs per SM -> 3.42 / 3.32 / 3.28 ms for all cell passes (6 are resident)
   if (const char* v = getenv("RDA_B200_MID_CTAS")) { int x = atoi(v); if (x >= 1 && x <= 64) h->mid_ctas = x; }
   if (const char* v = getenv("RDA_B200_SLOW_CPW")) { int x = atoi(v); if (x >= 1 && x <= 32) h->slow_cpw = x; }
@@ -1517,10 +1522,15 @@ static int step_lammuz_part(rda_handle* h, int b0, int nb, int part, cudaStream_
     k_cells_mid<<<148 * h->mid_ctas, 128, 0, s>>>(d, h->rb, h->tun.ro2, theta);
     RDA_CUDA(cudaGetLastError());
     if (h->slow_coop) {
-      k_cells_extra<<<148 * 4, 128, 0, s>>>(d, h->rb, h->tun.ro2, theta);
-      RDA_CUDA(cudaGetLastError());
-      h->launches += 1;
-      k_cells_slow_coop<<<148 * h->slow_ctas, 32 * SLOW_COOP_WARPS, 0, s>>>(d, h->rb, h->tun.ro2, theta);
+      // r02: the split costs a launch and pays from a few thousand instances on (cell passes at 16 384 unique instances 3.9 ->
+      // 3.2 ms per iteration, at 1 024 0.48 -> 0.56 ms)
+      const int split = nb >= h->extra_min;
+      if (split) {
+        k_cells_extra<<<148 * 4, 128, 0, s>>>(d, h->rb, h->tun.ro2, theta);
+        RDA_CUDA(cudaGetLastError());
+        h->launches += 1;
+      }
+      k_cells_slow_coop<<<148 * h->slow_ctas, 32 * SLOW_COOP_WARPS, 0, s>>>(d, h->rb, h->tun.ro2, theta, split);
     }
     else k_cells_slow<<<148 * h->slow_ctas, 64, 0, s>>>(d, h->rb, h->tun.ro2, theta, h->slow_cpw, h->slow_adapt);
     RDA_CUDA(cudaGetLastError());
