@@ -263,6 +263,57 @@ RDA_HD void cell_front_dr(const RobotGeom& rb, int kind, int E, const float* A, 
     // overlapping sets, no tilt: max margin 0 at v = 0 (stuff = -k0 >= 0)
     exact_zero_q = true; have = true; path = CELL_OVERLAP_FREE;
   }
+  if (!have && sep && kind != RDA_OBS_CIRCLE) {
+    // EDGE contact: the obstacle point nearest to the optimal body point y lies in the interior of obstacle edge i.  There the
+    // distance is the signed distance to the edge line, e_i(y) = n_i.(R y) - brel_i, LINEAR in y, so the numerator of the
+    // (weighted) margin is N_i(y) = alpha - beta.y with alpha = k0 + brel_i, beta = xi + R'n_i (body frame).  Since
+    // dist(P(y), O) >= e_i(y) everywhere, N_true <= N_i pointwise with equality where the feature holds: a maximiser of the
+    // edge problem whose foot lies inside the edge is the maximiser of the cell problem (tilted cells included).
+    //   max margin (stage A): max of N_i over the disc at y = c - r beta/|beta|; -N >= 0 there => inactive, v = n_i, g = -beta;
+    //   active hinge (N > 0), body centred on the reference point (c = 0): N_i/W with W^2 = 1 + |y|^2/ro2 peaks at
+    //   y = -t beta/|beta|, t = min(r, ro2 |beta|/alpha): inside the disc g = 0, on its rim g = -(|beta| - tau r/ro2) beta/|beta|.
+    const Real tolc = sizeof(Real) == 4 ? (Real)1e-5 : (Real)1e-11;
+    const Real bcx = rb.cx, bcy = rb.cy;
+    const bool centred = bcx == (Real)0 && bcy == (Real)0;
+    const int ne = g.ne;
+    for (int i = 0; i < ne && !have; ++i) {
+      const int in = (i + 1) % ne;
+      const Real nix = g.nx[i], niy = g.ny[i];
+      const Real bx_ = xi0 + (cphi * nix + sphi * niy), by_ = xi1 + (-sphi * nix + cphi * niy);      // beta = xi + R'n_i
+      const Real bn = sqrt_(bx_ * bx_ + by_ * by_);
+      if (!(bn > tolc)) continue;
+      const Real alpha = k0 - (nix * (-g.vx[i]) + niy * (-g.vy[i]));      // k0 + brel_i, brel_i = n_i.V_i (relative to p)
+      const Real ex = g.vx[in] - g.vx[i], ey = g.vy[in] - g.vy[i];
+      const Real ie2 = (Real)1 / (ex * ex + ey * ey);
+      for (int stage = 0; stage < 2 && !have; ++stage) {
+        Real yx, yy;
+        if (stage == 0) { yx = bcx - rr * bx_ / bn; yy = bcy - rr * by_ / bn; }
+        else {
+          if (!centred || !(alpha > 0)) break;
+          const Real t = rmin(rr, ro2 * bn / alpha);
+          yx = -t * bx_ / bn; yy = -t * by_ / bn;
+        }
+        const Real wx = cphi * yx - sphi * yy, wy = sphi * yx + cphi * yy;          // R y
+        const Real ed = nix * (wx - g.vx[i]) + niy * (wy - g.vy[i]);                  // distance of P(y) to the edge line
+        const Real so_ = ((wx - g.vx[i]) * ex + (wy - g.vy[i]) * ey) * ie2;          // foot along the edge
+        if (!(ed > eps && so_ > tolc && so_ < (Real)1 - tolc)) continue;
+        const Real Nv = alpha - (bx_ * yx + by_ * yy);
+        if (stage == 0) {
+          if (Nv <= 0) {
+            v0 = nix; v1 = niy; g0 = -bx_; g1 = -by_;
+            exact_zero_q = true; have = true; path = CELL_FAST_VERTEX;
+          }
+        } else if (Nv > 0) {
+          const Real tau = Nv / ((Real)1 + (yx * yx + yy * yy) / ro2);
+          v0 = nix; v1 = niy;
+          g0 = -tau * yx / ro2 - bx_; g1 = -tau * yy / ro2 - by_;
+          // interior of the disc: g vanishes up to rounding (stationary point); make it exact
+          if (ro2 * bn / alpha < rr) { g0 = 0; g1 = 0; }
+          have = true; path = CELL_FAST_VERTEX;
+        }
+      }
+    }
+  }
   w.v0 = v0; w.v1 = v1; w.g0 = g0; w.g1 = g1;
   w.exact_zero_q = exact_zero_q; w.have = have; w.path = path;
 }

@@ -546,6 +546,28 @@ __global__ void __launch_bounds__(128, 6) k_cells_coh(DevPtrs d, RobotGeom rb, R
   }
 }
 
+// The rows of an obstacle copy into local arrays BEFORE the geometry: cell_front walks the rows in a loop that ends at the
+// first zero row, so the compiler cannot hoist its loads — four dependent round trips to L2/HBM per cell.  With E == 4 (every
+// reference example) three 128-bit loads fetch all of them at once; other row counts are loaded row by row up front.
+struct RowsLocal { float A[2 * RDA_MAX_EDGE], b[RDA_MAX_EDGE]; };
+__device__ __forceinline__ void rows_preload(const DevPtrs& d, const CellIn& c, RowsLocal& r) {
+  if (d.E == 4) {
+    const float4 a0 = __ldg(reinterpret_cast<const float4*>(c.A));
+    const float4 a1 = __ldg(reinterpret_cast<const float4*>(c.A) + 1);
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(c.bb));
+    r.A[0] = a0.x; r.A[1] = a0.y; r.A[2] = a0.z; r.A[3] = a0.w; r.A[4] = a1.x; r.A[5] = a1.y; r.A[6] = a1.z; r.A[7] = a1.w;
+    r.b[0] = b0.x; r.b[1] = b0.y; r.b[2] = b0.z; r.b[3] = b0.w;
+  } else {
+#pragma unroll
+    for (int i = 0; i < RDA_MAX_EDGE; ++i) {
+      const bool in = i < d.E;
+      r.A[2 * i] = in ? __ldg(c.A + 2 * i) : 0.f;
+      r.A[2 * i + 1] = in ? __ldg(c.A + 2 * i + 1) : 0.f;
+      r.b[i] = in ? __ldg(c.bb + i) : 0.f;
+    }
+  }
+}
+
 // Second pass: the searched closed forms (vertex / edge contact, overlap cases) for the cells of the
 // first worklist, one thread per entry; what is still unresolved goes to the second worklist.
 #ifdef RDA_MID_MINBLOCKS
@@ -566,8 +588,10 @@ __global__ void RDA_MID_BOUNDS k_cells_mid(DevPtrs d, RobotGeom rb, float ro2, f
       idx = d.worklist[wi];
       CellIn c = cell_load(d, idx);
       kind_of = c.kind;
+      RowsLocal rows;
+      rows_preload(d, c, rows);
       CellWork<float> w;
-      cell_front<float, false>(rb, c.kind, d.E, c.A, c.bb, c.px, c.py, c.cp, c.sp, c.dbar, c.zeta, c.xi0, c.xi1, ro2, w);
+      cell_front<float, false>(rb, c.kind, d.E, rows.A, rows.b, c.px, c.py, c.cp, c.sp, c.dbar, c.zeta, c.xi0, c.xi1, ro2, w);
       if (w.have) {
         CellOut<float> out;
         cell_back<float>(rb, w, c.zeta, theta, out);
@@ -773,8 +797,10 @@ __global__ void __launch_bounds__(128) k_cells_extra(DevPtrs d, RobotGeom rb, fl
     if (wi < count) {
       idx = d.worklist2[wi];
       CellIn c = cell_load(d, idx);
+      RowsLocal rows;
+      rows_preload(d, c, rows);
       CellWork<float> w;
-      cell_front<float, false, true>(rb, c.kind, d.E, c.A, c.bb, c.px, c.py, c.cp, c.sp, c.dbar, c.zeta, c.xi0, c.xi1, ro2, w);
+      cell_front<float, false, true>(rb, c.kind, d.E, rows.A, rows.b, c.px, c.py, c.cp, c.sp, c.dbar, c.zeta, c.xi0, c.xi1, ro2, w);
       if (w.have) {
         CellOut<float> out;
         cell_back<float>(rb, w, c.zeta, theta, out);
