@@ -30,6 +30,12 @@ extern "C" void rda_soc_stat(int newton) {
 #pragma omp atomic
   g_soc[1] += newton;
 }
+static long long g_dr[4];
+extern "C" void rda_dr_stat(int what) {
+#pragma omp atomic
+  g_dr[what & 3] += 1;
+}
+extern "C" void port_dr_stats(long long* out) { for (int i = 0; i < 4; ++i) { out[i] = g_dr[i]; g_dr[i] = 0; } }
 extern "C" void port_soc_stats(long long* out, int reset) { out[0] = g_soc[0]; out[1] = g_soc[1]; if (reset) g_soc[0] = g_soc[1] = 0; }
 #endif
 
@@ -55,14 +61,14 @@ static int cell_impl(const float* G, const float* h, int R, int kind, int E, con
 // disc body (cone_type 'norm2'): h = (cx, cy, -r)
 template <typename Real>
 static int cell_dr_impl(const float* h, int kind, int E, const float* A, const float* b, double px, double py, double phi,
-                        double dbar, double zeta, double xi0, double xi1, double ro2, double theta, double* out) {
+                        double dbar, double zeta, double xi0, double xi1, double ro2, double theta, double* out, int forms = 1) {
   const float Gd[6] = {1.f, 0.f, 0.f, 1.f, 0.f, 0.f};
   RobotGeom rb;
   int rc = robot_geom_from_halfspaces(Gd, h, 3, &rb, RDA_ROBOT_DISC);
   if (rc) return rc;
   CellOut<Real> o;
   cell_solve_dr<Real>(rb, kind, E, A, b, (Real)px, (Real)py, (Real)cos(phi), (Real)sin(phi), (Real)dbar,
-                      (Real)zeta, (Real)xi0, (Real)xi1, (Real)ro2, (Real)theta, o);
+                      (Real)zeta, (Real)xi0, (Real)xi1, (Real)ro2, (Real)theta, o, forms != 0);
   for (int i = 0; i < 8; ++i) out[i] = o.lam[i];
   for (int i = 0; i < 8; ++i) out[8 + i] = o.mu[i];
   double tail[] = {(double)o.z, (double)o.zeta_new, (double)o.xi0_new, (double)o.xi1_new, (double)o.ax,
@@ -163,6 +169,11 @@ int shim_cell_f(const float* G, const float* h, int R, int kind, int E, const fl
 int shim_cell_dr_d(const float* h, int kind, int E, const float* A, const float* b, double px, double py, double phi,
                    double dbar, double zeta, double xi0, double xi1, double ro2, double theta, double* out) {
   return cell_dr_impl<double>(h, kind, E, A, b, px, py, phi, dbar, zeta, xi0, xi1, ro2, theta, out);
+}
+// searched closed forms off: every cell that is not a plain inactive one goes through the two-cone barrier programmes
+int shim_cell_dr_barrier_d(const float* h, int kind, int E, const float* A, const float* b, double px, double py, double phi,
+                           double dbar, double zeta, double xi0, double xi1, double ro2, double theta, double* out) {
+  return cell_dr_impl<double>(h, kind, E, A, b, px, py, phi, dbar, zeta, xi0, xi1, ro2, theta, out, 0);
 }
 int shim_cell_dr_f(const float* h, int kind, int E, const float* A, const float* b, double px, double py, double phi,
                    double dbar, double zeta, double xi0, double xi1, double ro2, double theta, double* out) {

@@ -16,6 +16,13 @@
 
 #if defined(RDA_SOC_STATS) && !defined(__CUDA_ARCH__)
 extern "C" void rda_soc_stat(int newton);      // host statistics build only
+extern "C" void rda_dr_stat(int what);         // which cells reach the barrier programmes: 0 disjoint, 1 overlapping, +2 tilted
+#endif
+#ifndef RDA_DR_OVERLAP_FORMS
+#define RDA_DR_OVERLAP_FORMS 1                 // closed forms of the disc body overlapping a polygon (cases ii-v)
+#endif
+#ifndef RDA_DR_POINT_CONTACT
+#define RDA_DR_POINT_CONTACT 1                 // float64 closed forms of the disc body's point contacts (disc_point_contact)
 #endif
 
 namespace rda {
@@ -176,6 +183,95 @@ RDA_HD bool soc_barrier(SocQP<NV, MC>& P, Ctx& ctx) {
   return true;
 }
 
+// ---- POINT contact of the disc body (float64): the obstacle point nearest to the optimal body point is a fixed point w --------
+// (a polygon vertex, or the centre of a disc obstacle of radius rho_o).  World frame relative to the robot reference point:
+// body disc of centre (cx, cy) and radius r, tilt xi' = R xi, numerator N(y) = k0 + rho_o - xi'.y - |y - w|, weight
+// W^2 = 1 + |y|^2/ro2.  Stage 0 maximises N over the disc (concave, optimum on the rim), stage 1 maximises N/W where N > 0
+// (quasi-concave: rim, or a stationary point inside the disc).  One-dimensional root search on the rim angle (Illinois) and
+// a two-dimensional Newton iteration inside, all in float64 — the contact direction turns by r/|y - w| per radian, so float32
+// cannot resolve the stationarity conditions of close contacts (the lesson of the polygon body's edge contacts).
+// The caller accepts the point through the KKT conditions of the convex cell problem (direction inside the vertex' normal cone).
+struct DiscContactD { double yx, yy, ux, uy, N, gam, tau; int rim; };
+RDA_HD_NOINLINE bool disc_point_contact(int weighted, double cx, double cy, double r, double wx, double wy, double rho_o,
+                                        double xix, double xiy, double k0, double ro2, DiscContactD& o) {
+  double h = 0;
+  auto eval = [&](double th) {
+    const double ux_ = cos(th), uy_ = sin(th);
+    o.yx = cx + r * ux_; o.yy = cy + r * uy_;
+    const double dx = o.yx - wx, dy = o.yy - wy, L = sqrt(dx * dx + dy * dy);
+    o.ux = dx / L; o.uy = dy / L;
+    o.N = k0 + rho_o - (xix * o.yx + xiy * o.yy) - L;
+    o.tau = weighted ? o.N / (1.0 + (o.yx * o.yx + o.yy * o.yy) / ro2) : 0.0;
+    const double gx = -xix - o.ux - o.tau * o.yx / ro2, gy = -xiy - o.uy - o.tau * o.yy / ro2;
+    h = -gx * uy_ + gy * ux_;            // tangential component of the gradient
+    o.gam = gx * ux_ + gy * uy_;         // outward component: multiplier of the rim
+  };
+  const double th0 = atan2(wy - cy, wx - cx);
+  double lo = th0 - 1.5, hi = th0 + 1.5;
+  eval(lo); double flo = h; if (!(flo > 0) || (weighted && !(o.N > 0))) {
+    // the region N > 0 may be a short arc around th0: shrink the bracket towards it
+    bool found = false;
+    for (int k = 0; k < 12 && !found; ++k) { lo = 0.5 * (lo + th0); eval(lo); flo = h; found = flo > 0 && (!weighted || o.N > 0); }
+    if (!found) return false;
+  }
+  eval(hi); double fhi = h; if (!(fhi < 0) || (weighted && !(o.N > 0))) {
+    bool found = false;
+    for (int k = 0; k < 12 && !found; ++k) { hi = 0.5 * (hi + th0); eval(hi); fhi = h; found = fhi < 0 && (!weighted || o.N > 0); }
+    if (!found) return false;
+  }
+  if (!(lo < hi)) return false;
+  int side = 0;
+  for (int itn = 0; itn < 80; ++itn) {
+    const double wdt = hi - lo;
+    double th = lo + wdt * (flo / (flo - fhi));
+    th = rclamp(th, lo + 0.02 * wdt, hi - 0.02 * wdt);
+    eval(th);
+    if (weighted && !(o.N > 0)) return false;
+    if (h > 0) { lo = th; flo = h; if (side > 0) fhi *= 0.5; side = 1; }
+    else { hi = th; fhi = h; if (side < 0) flo *= 0.5; side = -1; }
+    if (hi - lo < 1e-14 || h == 0) break;
+  }
+  o.rim = 1;
+  if (o.gam >= -1e-10) return true;
+  if (!weighted) return false;
+  // the rim is not where N/W peaks: stationary point inside the disc, xi' + u + tau y/ro2 = 0 (2 x 2 Newton, damped)
+  double yx = o.yx - 0.05 * r * cos(0.5 * (lo + hi)), yy = o.yy - 0.05 * r * sin(0.5 * (lo + hi));
+  for (int itn = 0; itn < 50; ++itn) {
+    const double dx = yx - wx, dy = yy - wy, L = sqrt(dx * dx + dy * dy);
+    if (!(L > 1e-12)) return false;
+    const double ux_ = dx / L, uy_ = dy / L;
+    const double W2 = 1.0 + (yx * yx + yy * yy) / ro2;
+    const double N = k0 + rho_o - (xix * yx + xiy * yy) - L;
+    if (!(N > 0)) return false;
+    const double tau = N / W2;
+    const double G0 = xix + ux_ + tau * yx / ro2, G1 = xiy + uy_ + tau * yy / ro2;
+    // grad tau = grad N / W2 - 2 N y / (ro2 W2^2)
+    const double tx = (-xix - ux_) / W2 - 2.0 * N * yx / (ro2 * W2 * W2), ty = (-xiy - uy_) / W2 - 2.0 * N * yy / (ro2 * W2 * W2);
+    const double J00 = (1.0 - ux_ * ux_) / L + tau / ro2 + yx * tx / ro2, J01 = -ux_ * uy_ / L + yx * ty / ro2;
+    const double J10 = -ux_ * uy_ / L + yy * tx / ro2, J11 = (1.0 - uy_ * uy_) / L + tau / ro2 + yy * ty / ro2;
+    const double det = J00 * J11 - J01 * J10;
+    if (!(fabs(det) > 1e-300)) return false;
+    double sx = -(J11 * G0 - J01 * G1) / det, sy = -(-J10 * G0 + J00 * G1) / det;
+    // damping: stay inside the disc and move at most half way to the point w
+    double a = 1.0;
+    for (int bt = 0; bt < 30; ++bt, a *= 0.5) {
+      const double nx_ = yx + a * sx, ny_ = yy + a * sy;
+      if ((nx_ - cx) * (nx_ - cx) + (ny_ - cy) * (ny_ - cy) < r * r && (nx_ - wx) * (nx_ - wx) + (ny_ - wy) * (ny_ - wy) > 0.25 * L * L) break;
+    }
+    yx += a * sx; yy += a * sy;
+    o.yx = yx; o.yy = yy; o.ux = ux_; o.uy = uy_; o.N = N; o.tau = tau; o.gam = 0; o.rim = 0;
+    if (sqrt(G0 * G0 + G1 * G1) < 1e-12 && a == 1.0) {
+      // re-evaluate at the final point
+      const double ex = yx - wx, ey = yy - wy, L2 = sqrt(ex * ex + ey * ey);
+      o.ux = ex / L2; o.uy = ey / L2;
+      o.N = k0 + rho_o - (xix * yx + xiy * yy) - L2;
+      o.tau = o.N / (1.0 + (yx * yx + yy * yy) / ro2);
+      return o.N > 0;
+    }
+  }
+  return false;
+}
+
 constexpr int DR_NVA = 5, DR_NVB = 8, DR_MC = RDA_MAX_EDGE + 3;
 struct DiscSlowStore {
   union U {
@@ -191,7 +287,8 @@ struct DiscSlowStore {
 // w.byx / w.byy (unit direction obstacle -> centre, world frame) and, when a closed form applies, the solution.
 template <typename Real>
 RDA_HD void cell_front_dr(const RobotGeom& rb, int kind, int E, const float* A, const float* b, Real px, Real py,
-                          Real cphi, Real sphi, Real dbar, Real zeta, Real xi0, Real xi1, Real ro2, CellWork<Real>& w) {
+                          Real cphi, Real sphi, Real dbar, Real zeta, Real xi0, Real xi1, Real ro2, CellWork<Real>& w,
+                          bool searched_forms = true) {
   const Real k0 = dbar - zeta;
   const Real eps = sizeof(Real) == 4 ? (Real)1e-5 : (Real)1e-11;
   CellGeom<Real>& g = w.g;
@@ -263,7 +360,7 @@ RDA_HD void cell_front_dr(const RobotGeom& rb, int kind, int E, const float* A, 
     // overlapping sets, no tilt: max margin 0 at v = 0 (stuff = -k0 >= 0)
     exact_zero_q = true; have = true; path = CELL_OVERLAP_FREE;
   }
-  if (!have && sep && kind != RDA_OBS_CIRCLE) {
+  if (searched_forms && !have && sep && kind != RDA_OBS_CIRCLE) {
     // EDGE contact: the obstacle point nearest to the optimal body point y lies in the interior of obstacle edge i.  There the
     // distance is the signed distance to the edge line, e_i(y) = n_i.(R y) - brel_i, LINEAR in y, so the numerator of the
     // (weighted) margin is N_i(y) = alpha - beta.y with alpha = k0 + brel_i, beta = xi + R'n_i (body frame).  Since
@@ -271,7 +368,7 @@ RDA_HD void cell_front_dr(const RobotGeom& rb, int kind, int E, const float* A, 
     // edge problem whose foot lies inside the edge is the maximiser of the cell problem (tilted cells included).
     //   max margin (stage A): max of N_i over the disc at y = c - r beta/|beta|; -N >= 0 there => inactive, v = n_i, g = -beta;
     //   active hinge (N > 0), body centred on the reference point (c = 0): N_i/W with W^2 = 1 + |y|^2/ro2 peaks at
-    //   y = -t beta/|beta|, t = min(r, ro2 |beta|/alpha): inside the disc g = 0, on its rim g = -(|beta| - tau r/ro2) beta/|beta|.
+    //   y = -t beta/|beta|, t = min(r, ro2 |beta|/alpha) (t = r when alpha <= 0): inside the disc g = 0, on its rim g = -(|beta| - tau r/ro2) beta/|beta|.
     const Real tolc = sizeof(Real) == 4 ? (Real)1e-5 : (Real)1e-11;
     const Real bcx = rb.cx, bcy = rb.cy;
     const bool centred = bcx == (Real)0 && bcy == (Real)0;
@@ -289,8 +386,9 @@ RDA_HD void cell_front_dr(const RobotGeom& rb, int kind, int E, const float* A, 
         Real yx, yy;
         if (stage == 0) { yx = bcx - rr * bx_ / bn; yy = bcy - rr * by_ / bn; }
         else {
-          if (!centred || !(alpha > 0)) break;
-          const Real t = rmin(rr, ro2 * bn / alpha);
+          if (!centred) break;
+          // f(t) = (alpha + t |beta|)/sqrt(1 + t^2/ro2) along y = -t beta/|beta|: increasing for every t when alpha <= 0
+          const Real t = alpha > 0 ? rmin(rr, ro2 * bn / alpha) : rr;
           yx = -t * bx_ / bn; yy = -t * by_ / bn;
         }
         const Real wx = cphi * yx - sphi * yy, wy = sphi * yx + cphi * yy;          // R y
@@ -308,8 +406,170 @@ RDA_HD void cell_front_dr(const RobotGeom& rb, int kind, int E, const float* A, 
           v0 = nix; v1 = niy;
           g0 = -tau * yx / ro2 - bx_; g1 = -tau * yy / ro2 - by_;
           // interior of the disc: g vanishes up to rounding (stationary point); make it exact
-          if (ro2 * bn / alpha < rr) { g0 = 0; g1 = 0; }
+          if (alpha > 0 && ro2 * bn / alpha < rr) { g0 = 0; g1 = 0; }
           have = true; path = CELL_FAST_VERTEX;
+        }
+      }
+    }
+  }
+  if (RDA_DR_POINT_CONTACT && searched_forms && !have && sep) {
+    // POINT contacts (float64, disc_point_contact): each obstacle vertex whose normal cone can hold the contact direction,
+    // or the centre of a disc obstacle
+    const double c_ = cphi, s_ = sphi;
+    const double cwxd = c_ * (double)rb.cx - s_ * (double)rb.cy, cwyd = s_ * (double)rb.cx + c_ * (double)rb.cy;
+    const double xwx = c_ * (double)xi0 - s_ * (double)xi1, xwy = s_ * (double)xi0 + c_ * (double)xi1;      // R xi
+    const int npt = kind == RDA_OBS_CIRCLE ? 1 : g.ne;
+    for (int stage = 0; stage < 2 && !have; ++stage) {
+      for (int i = 0; i < npt && !have; ++i) {
+        const double wxd = kind == RDA_OBS_CIRCLE ? (double)g.cx : (double)g.vx[i], wyd = kind == RDA_OBS_CIRCLE ? (double)g.cy : (double)g.vy[i];
+        const double rho_o = kind == RDA_OBS_CIRCLE ? (double)g.rad : 0.0;
+        DiscContactD o;
+        if (!disc_point_contact(stage, cwxd, cwyd, (double)rr, wxd, wyd, rho_o, xwx, xwy, (double)k0, (double)ro2, o)) continue;
+        if (kind != RDA_OBS_CIRCLE) {
+          // the nearest obstacle point is vertex i only while the direction lies strictly inside its normal cone
+          const int ne = g.ne, ip = (i + ne - 1) % ne, inx = (i + 1) % ne;
+          const double epx = (double)g.vx[i] - (double)g.vx[ip], epy = (double)g.vy[i] - (double)g.vy[ip];
+          const double enx = (double)g.vx[inx] - (double)g.vx[i], eny = (double)g.vy[inx] - (double)g.vy[i];
+          if (!(o.ux * epx + o.uy * epy >= 1e-7 * sqrt(epx * epx + epy * epy) && o.ux * enx + o.uy * eny <= -1e-7 * sqrt(enx * enx + eny * eny)))
+            continue;
+        }
+        if (stage == 0) {
+          if (o.N <= 0) {      // max margin -N >= 0: inactive, Hm + xi = 0
+            v0 = (Real)o.ux; v1 = (Real)o.uy;
+            g0 = (Real)(-(c_ * o.ux + s_ * o.uy) - (double)xi0);
+            g1 = (Real)(-(-s_ * o.ux + c_ * o.uy) - (double)xi1);
+            exact_zero_q = true; have = true; path = CELL_FAST_VERTEX;
+          }
+        } else if (o.N > 0) {
+          v0 = (Real)o.ux; v1 = (Real)o.uy;
+          if (o.rim) {
+            // g = gamma * (outward unit normal of the rim at y), body frame
+            const double nxw = (o.yx - cwxd) / (double)rr, nyw = (o.yy - cwyd) / (double)rr;
+            g0 = (Real)(o.gam * (c_ * nxw + s_ * nyw)); g1 = (Real)(o.gam * (-s_ * nxw + c_ * nyw));
+          } else { g0 = 0; g1 = 0; }
+          exact_zero_q = false; have = true; path = CELL_FAST_VERTEX;
+        }
+      }
+    }
+  }
+  if (RDA_DR_OVERLAP_FORMS && searched_forms && !have && !sep) {
+    // OVERLAPPING sets: the contact distance is zero, the numerator of the weighted margin is k0 - xi.y and the optimum sits
+    // (ii) at a body point whose image lies strictly inside the obstacle (v = 0), (iii) on an obstacle edge strictly inside the
+    // body (g = 0), (iv) at an obstacle vertex strictly inside the body, or (v) where the body's rim crosses an obstacle edge —
+    // the disc body's versions of cell_front's overlap cases, each accepted through the KKT conditions of the cell problem.
+    const Real tolc = sizeof(Real) == 4 ? (Real)1e-5 : (Real)1e-11;
+    const Real bcx = rb.cx, bcy = rb.cy;
+    const bool centred = bcx == (Real)0 && bcy == (Real)0;
+    const int ne = g.ne;
+    auto inside_obstacle = [&](Real wx, Real wy) {
+      if (kind == RDA_OBS_CIRCLE) {
+        const Real ex = wx - g.cx, ey = wy - g.cy;
+        return g.rad > eps && ex * ex + ey * ey < (g.rad - eps) * (g.rad - eps);
+      }
+      for (int i = 0; i < ne; ++i)
+        if (g.nx[i] * (wx - g.vx[i]) + g.ny[i] * (wy - g.vy[i]) > -eps) return false;
+      return ne >= 3;
+    };
+    // (ii) v = 0: maximise (k0 - xi.y)/W over the disc
+    {
+      const Real xn = sqrt_(xi0 * xi0 + xi1 * xi1);
+      Real yx = 0, yy = 0;
+      bool cand = false, interior = true;
+      if (centred) {
+        const Real t = xn > 0 ? (k0 > 0 ? rmin(rr, ro2 * xn / k0) : rr) : (Real)0;
+        if (xn > 0) { yx = -t * xi0 / xn; yy = -t * xi1 / xn; }
+        interior = !(xn > 0) || (k0 > 0 && ro2 * xn / k0 < rr);
+        cand = true;
+      } else if (k0 > 0) {
+        yx = -ro2 * xi0 / k0; yy = -ro2 * xi1 / k0;      // stationary point; only valid strictly inside the disc
+        cand = (yx - bcx) * (yx - bcx) + (yy - bcy) * (yy - bcy) < (rr - eps) * (rr - eps);
+      }
+      if (cand) {
+        const Real Nv = k0 - (xi0 * yx + xi1 * yy);
+        if (Nv > 0 && inside_obstacle(cphi * yx - sphi * yy, sphi * yx + cphi * yy)) {
+          const Real tau = Nv / ((Real)1 + (yx * yx + yy * yy) / ro2);
+          v0 = 0; v1 = 0;
+          if (interior) { g0 = 0; g1 = 0; } else { g0 = -tau * yx / ro2 - xi0; g1 = -tau * yy / ro2 - xi1; }
+          exact_zero_q = false; have = true; path = CELL_OVERLAP_FREE;
+        }
+      }
+    }
+    if (kind != RDA_OBS_CIRCLE) {
+      // (iii) P(y) on obstacle edge i, y strictly inside the body: g = 0, v = a n_i, 0 <= a <= 1 (closed-form stationary point
+      //       of (k0 - xi.y)/W on the edge line, as cell_front's case iii)
+      for (int i = 0; i < ne && !have; ++i) {
+        const int in = (i + 1) % ne;
+        const Real px_ = cphi * g.vx[i] + sphi * g.vy[i], py_ = -sphi * g.vx[i] + cphi * g.vy[i];   // R'V_i
+        const Real ex = g.vx[in] - g.vx[i], ey = g.vy[in] - g.vy[i];
+        const Real dx_ = cphi * ex + sphi * ey, dy_ = -sphi * ex + cphi * ey;
+        const Real al = k0 - (xi0 * px_ + xi1 * py_), be = xi0 * dx_ + xi1 * dy_;
+        const Real a_ = (Real)1 + (px_ * px_ + py_ * py_) / ro2, b_ = (px_ * dx_ + py_ * dy_) / ro2;
+        const Real c_ = (dx_ * dx_ + dy_ * dy_) / ro2;
+        const Real den = be * b_ + al * c_;
+        if (!(abs_(den) > (Real)1e-20)) continue;
+        const Real sst = -(be * a_ + al * b_) / den;
+        if (!(sst > tolc && sst < (Real)1 - tolc)) continue;
+        const Real yx = px_ + sst * dx_, yy = py_ + sst * dy_;
+        const Real Nv = k0 - (xi0 * yx + xi1 * yy);
+        if (!(Nv > 0)) continue;
+        if (!((yx - bcx) * (yx - bcx) + (yy - bcy) * (yy - bcy) < (rr - eps) * (rr - eps))) continue;
+        const Real tau = Nv / ((Real)1 + (yx * yx + yy * yy) / ro2);
+        const Real rx = -tau * yx / ro2 - xi0, ry = -tau * yy / ro2 - xi1;      // must equal R'v
+        const Real nbx = cphi * g.nx[i] + sphi * g.ny[i], nby = -sphi * g.nx[i] + cphi * g.ny[i];
+        const Real alpha = rx * nbx + ry * nby;
+        if (!(alpha >= -tolc && alpha <= (Real)1 + tolc)) continue;
+        const Real ac = rclamp(alpha, (Real)0, (Real)1);
+        v0 = ac * g.nx[i]; v1 = ac * g.ny[i]; g0 = 0; g1 = 0;
+        exact_zero_q = false; have = true; path = CELL_OVERLAP_FREE;
+      }
+      // (iv) obstacle vertex i strictly inside the body: y = R'V_i, g = 0, v = R(-tau y/ro2 - xi) in the vertex' normal cone, |v| <= 1
+      for (int i = 0; i < ne && !have; ++i) {
+        const Real yx = cphi * g.vx[i] + sphi * g.vy[i], yy = -sphi * g.vx[i] + cphi * g.vy[i];
+        if (!((yx - bcx) * (yx - bcx) + (yy - bcy) * (yy - bcy) < (rr - eps) * (rr - eps))) continue;
+        const Real Nv = k0 - (xi0 * yx + xi1 * yy);
+        if (!(Nv > 0)) continue;
+        const Real tau = Nv / ((Real)1 + (yx * yx + yy * yy) / ro2);
+        const Real rx = -tau * yx / ro2 - xi0, ry = -tau * yy / ro2 - xi1;
+        const Real vx_ = cphi * rx - sphi * ry, vy_ = sphi * rx + cphi * ry;          // v = R r
+        if (vx_ * vx_ + vy_ * vy_ > (Real)1 + tolc) continue;
+        const int ip = (i + ne - 1) % ne, in = (i + 1) % ne;
+        const Real epx = g.vx[i] - g.vx[ip], epy = g.vy[i] - g.vy[ip];
+        const Real enx = g.vx[in] - g.vx[i], eny = g.vy[in] - g.vy[i];
+        if (vx_ * epx + vy_ * epy < -tolc * sqrt_(epx * epx + epy * epy)) continue;
+        if (vx_ * enx + vy_ * eny > tolc * sqrt_(enx * enx + eny * eny)) continue;
+        v0 = vx_; v1 = vy_; g0 = 0; g1 = 0;
+        exact_zero_q = false; have = true; path = CELL_OVERLAP_FREE;
+      }
+      // (v) the body's rim crosses obstacle edge i: y fixed, g = gamma u (u: outward unit normal of the rim at y, body frame),
+      //     v = a n_i with gamma u + a R'n_i = -tau y/ro2 - xi (2 x 2), gamma >= 0, 0 <= a <= 1
+      const Real cwx_ = cphi * bcx - sphi * bcy, cwy_ = sphi * bcx + cphi * bcy;      // R c
+      for (int i = 0; i < ne && !have; ++i) {
+        const int in = (i + 1) % ne;
+        const Real ex = g.vx[in] - g.vx[i], ey = g.vy[in] - g.vy[i];
+        const Real fx = g.vx[i] - cwx_, fy = g.vy[i] - cwy_;
+        const Real qa = ex * ex + ey * ey, qb = (Real)2 * (fx * ex + fy * ey), qc = fx * fx + fy * fy - rr * rr;
+        const Real disc = qb * qb - (Real)4 * qa * qc;
+        if (!(disc > 0)) continue;
+        const Real sq = sqrt_(disc);
+        for (int root = 0; root < 2 && !have; ++root) {
+          const Real so_ = (-qb + (root ? sq : -sq)) / ((Real)2 * qa);
+          if (!(so_ > tolc && so_ < (Real)1 - tolc)) continue;
+          const Real wx = g.vx[i] + so_ * ex, wy = g.vy[i] + so_ * ey;               // crossing point, world
+          const Real yx = cphi * wx + sphi * wy, yy = -sphi * wx + cphi * wy;
+          const Real Nv = k0 - (xi0 * yx + xi1 * yy);
+          if (!(Nv > 0)) continue;
+          const Real tau = Nv / ((Real)1 + (yx * yx + yy * yy) / ro2);
+          const Real rx = -tau * yx / ro2 - xi0, ry = -tau * yy / ro2 - xi1;
+          const Real ux_ = (yx - bcx) / rr, uy_ = (yy - bcy) / rr;
+          const Real nbx = cphi * g.nx[i] + sphi * g.ny[i], nby = -sphi * g.nx[i] + cphi * g.ny[i];
+          const Real d2 = ux_ * nby - uy_ * nbx;
+          if (!(abs_(d2) > (Real)1e-9)) continue;
+          const Real gam = (rx * nby - ry * nbx) / d2;
+          const Real alp = (ux_ * ry - uy_ * rx) / d2;
+          if (!(gam >= -tolc && alp >= -tolc && alp <= (Real)1 + tolc)) continue;
+          const Real ac = rclamp(alp, (Real)0, (Real)1), gc = rmax(gam, (Real)0);
+          v0 = ac * g.nx[i]; v1 = ac * g.ny[i]; g0 = gc * ux_; g1 = gc * uy_;
+          exact_zero_q = false; have = true; path = CELL_OVERLAP_FREE;
         }
       }
     }
@@ -324,6 +584,19 @@ template <typename Real, typename Ctx>
 RDA_HD void cell_slow_dr(const RobotGeom& rb, CellWork<Real>& w, DiscSlowStore& S, Ctx& ctx) {
   const int lane = ctx.lane();
   const double rr = rb.rad, bcx = rb.cx, bcy = rb.cy;
+#if defined(RDA_SOC_STATS) && !defined(__CUDA_ARCH__)
+  rda_dr_stat((w.sep ? 0 : 1) + (w.xi_zero ? 0 : 2));
+#ifdef RDA_DR_DUMP
+  if (w.sep && !w.xi_zero) {
+    static int dumped = 0;
+    if (dumped < 12) { ++dumped;
+      fprintf(stderr, "DRCELL kind %d ne %d k0 %.9g cphi %.9g sphi %.9g xi %.9g %.9g ro2 %g r %g c %g %g best %.9g", w.g.kind, w.g.ne, (double)w.k0, (double)w.cphi, (double)w.sphi, (double)w.xi0, (double)w.xi1, (double)w.ro2, (double)rb.rad, (double)rb.cx, (double)rb.cy, (double)w.best);
+      for (int i = 0; i < w.g.ne; ++i) fprintf(stderr, " V %.9g %.9g", (double)w.g.vx[i], (double)w.g.vy[i]);
+      if (w.g.kind == 1) fprintf(stderr, " disc %.9g %.9g %.9g", (double)w.g.cx, (double)w.g.cy, (double)w.g.rad);
+      fprintf(stderr, "\n"); }
+  }
+#endif
+#endif
   if (lane == 0) {
     const CellGeom<Real>& g = w.g;
     const double x0 = w.xi0, x1 = w.xi1, k0d = (double)w.k0, c_ = w.cphi, s_ = w.sphi;
@@ -486,9 +759,9 @@ RDA_HD void cell_back_dr(const RobotGeom& rb, const CellWork<Real>& w, Real zeta
 template <typename Real>
 RDA_HD void cell_solve_dr(const RobotGeom& rb, int kind, int E, const float* A, const float* b, Real px, Real py,
                           Real cphi, Real sphi, Real dbar, Real zeta, Real xi0, Real xi1, Real ro2, Real theta,
-                          CellOut<Real>& out) {
+                          CellOut<Real>& out, bool searched_forms = true) {
   CellWork<Real> w;
-  cell_front_dr<Real>(rb, kind, E, A, b, px, py, cphi, sphi, dbar, zeta, xi0, xi1, ro2, w);
+  cell_front_dr<Real>(rb, kind, E, A, b, px, py, cphi, sphi, dbar, zeta, xi0, xi1, ro2, w, searched_forms);
   if (!w.have) {
     DiscSlowStore S;
     SeqCtx ctx;

@@ -683,7 +683,8 @@ __global__ void __launch_bounds__(128) k_cells_dr(DevPtrs d, RobotGeom rb, float
     if (live) {
       CellIn c = cell_load(d, idx);
       CellWork<float> w;
-      cell_front_dr<float>(rb, c.kind, d.E, c.A, c.bb, c.px, c.py, c.cp, c.sp, c.dbar, c.zeta, c.xi0, c.xi1, ro2, w);
+      // first pass: the closed forms of the inactive hinge only (the searched ones run per listed cell in k_cells_dr_mid)
+      cell_front_dr<float>(rb, c.kind, d.E, c.A, c.bb, c.px, c.py, c.cp, c.sp, c.dbar, c.zeta, c.xi0, c.xi1, ro2, w, false);
       if (w.have) {
         CellOut<float> out;
         cell_back_dr<float>(rb, w, c.zeta, theta, out);
@@ -741,22 +742,60 @@ __global__ void __launch_bounds__(64) k_cells_dr_slow(DevPtrs d, RobotGeom rb, f
   }
 }
 
+// Disc body, second pass: the searched closed forms (edge and point contacts, overlap cases; point contacts in float64) for the
+// cells the first pass listed, one thread per cell; what is left (0.01 % of the cells on the bench workload) goes to the
+// cooperative barrier pass through d.worklist.
+__global__ void __launch_bounds__(128) k_cells_dr_mid(DevPtrs d, RobotGeom rb, float ro2, float theta) {
+  const int count = d.wl_count[1];
+  const int lane = threadIdx.x & 31;
+  for (int base = blockIdx.x * blockDim.x; base < count; base += gridDim.x * blockDim.x) {
+    const int wi = base + threadIdx.x;
+    bool need = false;
+    int idx = 0;
+    if (wi < count) {
+      idx = d.worklist2[wi];
+      CellIn c = cell_load(d, idx);
+      CellWork<float> w;
+      cell_front_dr<float>(rb, c.kind, d.E, c.A, c.bb, c.px, c.py, c.cp, c.sp, c.dbar, c.zeta, c.xi0, c.xi1, ro2, w, true);
+      if (w.have) {
+        CellOut<float> out;
+        cell_back_dr<float>(rb, w, c.zeta, theta, out);
+        float hm2 = 0.f, dual = 0.f;
+        cell_store(d, c, out, &hm2, &dual);
+        atomicAdd(&d.resi_acc[2 * c.b], hm2);
+        atomicAdd(&d.resi_acc[2 * c.b + 1], dual);
+        atomicAdd(&d.counters[0], 1);
+      } else {
+        need = true;
+      }
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, need);
+    if (m) {
+      int leader = __ffs(m) - 1, pos = 0;
+      if (lane == leader) pos = atomicAdd(&d.wl_count[4], __popc(m));
+      pos = __shfl_sync(0xffffffffu, pos, leader);
+      if (need) d.worklist[pos + __popc(m & ((1u << lane) - 1))] = idx;
+    }
+  }
+}
+
 // one cell per WARP: the two-cone barrier iterations spread over the lanes, the problem in shared memory
 constexpr int DR_COOP_WARPS = 4;
 __global__ void __launch_bounds__(32 * DR_COOP_WARPS) k_cells_dr_slow_coop(DevPtrs d, RobotGeom rb, float ro2, float theta) {
   __shared__ DiscSlowStore store[DR_COOP_WARPS];
-  const int count = d.wl_count[1];
+  const int count = d.wl_count[4];          // what k_cells_dr_mid left, in d.worklist
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   DiscSlowStore& S = store[warp];
   GroupCtx<32> ctx;
   for (int wi = blockIdx.x * DR_COOP_WARPS + warp; wi < count; wi += gridDim.x * DR_COOP_WARPS) {
-    const long long idx = d.worklist2[wi];
+    const long long idx = d.worklist[wi];
     CellIn c;
     CellWork<float> w;
     w.have = false;
     if (lane == 0) {
       c = cell_load(d, idx);
-      cell_front_dr<float>(rb, c.kind, d.E, c.A, c.bb, c.px, c.py, c.cp, c.sp, c.dbar, c.zeta, c.xi0, c.xi1, ro2, w);
+      // geometry only: the closed forms have been tried by k_cells_dr_mid
+      cell_front_dr<float>(rb, c.kind, d.E, c.A, c.bb, c.px, c.py, c.cp, c.sp, c.dbar, c.zeta, c.xi0, c.xi1, ro2, w, false);
     }
     const int have = __shfl_sync(0xffffffffu, (int)w.have, 0);
     if (!have) {
@@ -1522,8 +1561,12 @@ static int step_lammuz_part(rda_handle* h, int b0, int nb, int part, cudaStream_
     if (h->rb.disc) {
       k_cells_dr<<<grid_for((long long)nb * h->N * h->T, 128), 128, 0, s>>>(d, h->rb, h->tun.ro2, theta);
       RDA_CUDA(cudaGetLastError());
-      if (h->dr_coop) k_cells_dr_slow_coop<<<148 * 16, 32 * DR_COOP_WARPS, 0, s>>>(d, h->rb, h->tun.ro2, theta);
-      else k_cells_dr_slow<<<148 * 16, 64, 0, s>>>(d, h->rb, h->tun.ro2, theta);
+      if (h->dr_coop) {
+        k_cells_dr_mid<<<148 * 8, 128, 0, s>>>(d, h->rb, h->tun.ro2, theta);
+        RDA_CUDA(cudaGetLastError());
+        h->launches += 1;
+        k_cells_dr_slow_coop<<<148 * 16, 32 * DR_COOP_WARPS, 0, s>>>(d, h->rb, h->tun.ro2, theta);
+      } else k_cells_dr_slow<<<148 * 16, 64, 0, s>>>(d, h->rb, h->tun.ro2, theta);
       RDA_CUDA(cudaGetLastError());
       h->launches += 2;
       k_finalize<<<(nb + 127) / 128, 128, 0, s>>>(d, h->rb, h->iter_threshold);

@@ -67,7 +67,7 @@ def cell_disc_robot(h, kind, A, b, p, phi, dbar, zeta, xi, ro2, theta=0.5, prec=
     """Cell of a DISC body (cone_type 'norm2', G = [[1,0],[0,1],[0,0]], h = (cx, cy, -r)): cell_disc_robot.cuh."""
     h = _f32(np.ravel(h)); A = _f32(A); b = _f32(np.ravel(b))
     out = np.zeros(28)
-    fn = getattr(lib(), 'shim_cell_dr_' + prec)
+    fn = getattr(lib(), 'shim_cell_dr_' + prec)      # prec 'barrier_d': searched closed forms off (float64)
     fn.restype = C.c_int
     rc = fn(_p(h), C.c_int(kind), C.c_int(A.shape[0]), _p(A), _p(b), C.c_double(p[0]), C.c_double(p[1]), C.c_double(phi),
             C.c_double(dbar), C.c_double(zeta), C.c_double(xi[0]), C.c_double(xi[1]), C.c_double(ro2), C.c_double(theta), _p(out))

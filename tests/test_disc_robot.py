@@ -55,7 +55,7 @@ def test_disc_robot_cell_matches_generic_oracle():
         o_ref = cell_objective(A, b, G_DISC, h, p, phi, dbar, zeta, xi, 1.0, ref['lam'], ref['mu'], ref['z'])
         # cone membership of the oracle's own answer (guards the restatement): |mu[0:2]| <= -mu[2]
         assert np.hypot(ref['mu'][0], ref['mu'][1]) <= -ref['mu'][2] + 1e-7
-        for prec, tol in (('d', 4e-5), ('f', 3e-4)):
+        for prec, tol in (('d', 4e-5), ('f', 3e-4), ('barrier_d', 4e-5)):
             kk = shim.cell_disc_robot(h, int(circ), A, b, p, phi, dbar, zeta, xi, 1.0, prec=prec)
             assert kk['path'] != 5
             paths[kk['path']] = paths.get(kk['path'], 0) + 1
@@ -63,12 +63,14 @@ def test_disc_robot_cell_matches_generic_oracle():
             np.testing.assert_allclose(kk['lam'], ref['lam'], atol=tol)
             np.testing.assert_allclose(kk['mu'], ref['mu'], atol=tol)
             assert abs(kk['z'] - ref['z']) < tol
-            if prec == 'd':
+            if prec != 'f':
                 # SLSQP is the less accurate of the two on active cells: the kernel's point must not be worse in the
                 # reference objective (:399-406)
                 o_k = cell_objective(A, b, G_DISC, h, p, phi, dbar, zeta, xi, 1.0, kk['lam'], kk['mu'], kk['z'])
                 assert o_k <= o_ref + 1e-8
-    assert paths.get(0, 0) > 6 and paths.get(3, 0) > 6 and paths.get(2, 0) > 3      # closed form, active, inactive-by-barrier
+    # plain inactive cells, searched closed forms (edge / point contacts: 1, overlap cases: 4), and — with the closed forms
+    # switched off ('barrier_d') — the two-cone programmes of both stages (2: max-margin stage, 3: active hinge)
+    assert paths.get(0, 0) > 10 and paths.get(1, 0) > 10 and paths.get(4, 0) >= 2 and paths.get(3, 0) > 6 and paths.get(2, 0) > 3, paths
 
 
 def test_disc_robot_oracle_shortcut_equals_generic():
