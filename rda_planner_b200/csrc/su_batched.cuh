@@ -706,7 +706,9 @@ __global__ void __launch_bounds__(128) ksb_reduce(SuBatch W, double Mrows) {
     sg = sg * sg * sg;
     W.sigma_mu[b] = fmin(sg, 1.0) * mu;
   } else {
-    W.alpha[b] = fmin(1.0, 0.995 * amax);
+    // fraction to the boundary as su_solve's (su_solver.cuh, RDA_SU_TAU_ADAPT)
+    const double tau_b = (RDA_SU_TAU_ADAPT) > 0 ? fmax(0.995, 1.0 - (double)(RDA_SU_TAU_ADAPT) * W.mu[b]) : 0.995;
+    W.alpha[b] = fmin(1.0, tau_b * amax);
   }
 }
 
