@@ -1,0 +1,44 @@
+"""CPU twin of tests/test_gpu_parity50.py: the g++ build of the kernel cores (oracle/cpu_port — the arithmetic of the CUDA path,
+float32 state, float64 su-QP) against the float64 oracle's per-iteration trace at the BENCHMARKED configuration
+(tests/golden/oracle_metric50.npz: 24 metric-row instances, T=30, N=20, 50 ADMM iterations, early stop off).  Guards the
+cores' parity without a GPU; same bounds as the GPU test: every instance inside the float32 tolerance through 8 iterations,
+the bulk of the distribution beyond (the ADMM map is not contractive on a few instances)."""
+import os
+
+import numpy as np
+
+from oracle import cpu_port
+from rda_planner_b200.rda_solver import pack_obstacles
+from rda_planner_b200.scenarios import rectangle_robot, make_instance
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+T, N, E = 30, 20, 4
+CHECK = [1, 2, 4, 8, 16, 32, 50]
+
+
+def test_cpu_build_of_the_cores_against_the_oracle_over_50_iterations():
+    z = np.load(os.path.join(HERE, 'golden', 'oracle_metric50.npz'))
+    B = len(z['seeds'])
+    car = rectangle_robot()
+    insts = [make_instance(int(sd), T=T, N=N, E=E, lateral=tuple(l)) for sd, l in zip(z['seeds'], z['lateral'])]
+    packs = [pack_obstacles(list(i['obstacles']), T, N, E) for i in insts]
+    st = lambda k: np.stack([i[k] for i in insts]).astype(np.float32)
+    for it in CHECK:
+        r = cpu_port.solve_batch(car, T, N, E, st('nom_s'), st('nom_u'), st('ref'),
+                                 np.array([i['ref_speed'] for i in insts], np.float32), np.stack([p[0] for p in packs]),
+                                 np.stack([p[1] for p in packs]), np.stack([p[2] for p in packs]),
+                                 np.array([p[3] for p in packs], np.int32), iter_num=it, iter_threshold=0.0)
+        assert int(r['cell_failures'][:, 0].sum()) == 0 and int(r['cell_failures'][:, 3].sum()) <= 1      # keep-previous exits / su cap
+        ds = np.abs(r['s'] - z['s'][:, it - 1]).reshape(B, -1).max(1)
+        du = np.abs(r['u'] - z['u'][:, it - 1]).reshape(B, -1).max(1)
+        rp = np.abs(r['resi_pri'] - z['resi_pri'][:, it - 1]) / (1 + z['resi_pri'][:, it - 1])
+        rd = np.abs(r['resi_dual'] - z['resi_dual'][:, it - 1]) / (1 + z['resi_dual'][:, it - 1])
+        print(f'it {it:2d}: |ds| med {np.median(ds):.1e} p75 {np.quantile(ds, .75):.1e} max {ds.max():.1e}   |du| med {np.median(du):.1e} '
+              f'max {du.max():.1e}   resi_pri med {np.median(rp):.1e} resi_dual med {np.median(rd):.1e}')
+        if it <= 8:
+            assert ds.max() < 1e-3 and du.max() < 5e-3, (it, ds.max(), du.max())
+            assert rp.max() < 2e-3 and rd.max() < 2e-3, (it, rp.max(), rd.max())
+        else:
+            assert np.median(ds) < 2e-3 and np.quantile(ds, .75) < 2e-2, (it, np.median(ds), np.quantile(ds, .75))
+            assert np.median(du) < 5e-3 and np.median(rp) < 2e-3 and np.median(rd) < 2e-3
+        assert np.all(np.isfinite(r['s'])) and np.all(np.isfinite(r['u']))
