@@ -220,9 +220,18 @@ __device__ __forceinline__ void su_instance(const DevPtrs& d, const SuParams& P,
 // ------------------------------------------------------------------------------------------------
 // K1: su-QP, one warp per instance.
 // ------------------------------------------------------------------------------------------------
+// Build-time experiment knobs (third session of round 2): RDA_SU_BSG = 1 keeps the box slacks / multipliers of the one-warp
+// variant in global memory ([c][t], coalesced) — 13.2 instead of 17.9 KB of shared memory per instance at the metric size;
+// RDA_SU_MINCTAS = n asks the compiler for n resident CTAs per SM (16 needs <= 128 registers).  Both off by default.
+#ifdef RDA_SU_MINCTAS
+#define RDA_SU_BOUNDS __launch_bounds__(32, RDA_SU_MINCTAS)
+#else
+#define RDA_SU_BOUNDS __launch_bounds__(32)
+#endif
 template <typename Real, int G>
-__global__ void __launch_bounds__(32) k_su(DevPtrs d, SuParams P, int smem_per_instance) {
+__global__ void RDA_SU_BOUNDS k_su(DevPtrs d, SuParams P, int smem_per_instance) {
   constexpr int LEVEL = G == 32 ? 0 : (G == 16 ? 1 : 2);      // workspace placement of sub-warp groups (su_work_layout)
+  constexpr bool BSG = G == 32 && RDA_SU_BSG != 0;
   extern __shared__ __align__(16) char smem[];
   constexpr int PER_WARP = 32 / G;
   const int grp = (threadIdx.x & 31) / G;
@@ -237,8 +246,8 @@ __global__ void __launch_bounds__(32) k_su(DevPtrs d, SuParams P, int smem_per_i
   // its stage, consecutive lanes read consecutive addresses.  With sub-warp groups (level > 0) the
   // Riccati gains / stage arrays live there too, so that shared memory does not limit the number of
   // resident instances.
-  su_work_layout<Real, Real, LEVEL>(T, N, &W, smem + (size_t)grp * smem_per_instance, false,
-                                    d.su_ws + (size_t)b * d.su_ws_stride);
+  su_work_layout<Real, Real, LEVEL, BSG>(T, N, &W, smem + (size_t)grp * smem_per_instance, false,
+                                         d.su_ws + (size_t)b * d.su_ws_stride);
   su_instance<Real, G>(d, P, b, W, ctx);
 }
 
@@ -1531,8 +1540,8 @@ static int step_su_part(rda_handle* h, int b0, int nb, int part, cudaStream_t s)
   if (G == 0) G = 32;
   const int per_warp = 32 / G;
   size_t smem1;
-  if (h->cfg.su_fp64) smem1 = G == 32 ? su_work_bytes<double, double, 0>(h->T, h->N, false) : (G == 16 ? su_work_bytes<double, double, 1>(h->T, h->N, false) : su_work_bytes<double, double, 2>(h->T, h->N, false));
-  else smem1 = G == 32 ? su_work_bytes<float, float, 0>(h->T, h->N, false) : (G == 16 ? su_work_bytes<float, float, 1>(h->T, h->N, false) : su_work_bytes<float, float, 2>(h->T, h->N, false));
+  if (h->cfg.su_fp64) smem1 = G == 32 ? su_work_bytes<double, double, 0, RDA_SU_BSG != 0>(h->T, h->N, false) : (G == 16 ? su_work_bytes<double, double, 1>(h->T, h->N, false) : su_work_bytes<double, double, 2>(h->T, h->N, false));
+  else smem1 = G == 32 ? su_work_bytes<float, float, 0, RDA_SU_BSG != 0>(h->T, h->N, false) : (G == 16 ? su_work_bytes<float, float, 1>(h->T, h->N, false) : su_work_bytes<float, float, 2>(h->T, h->N, false));
   if (smem1 * per_warp > 227 * 1024) return RDA_E_UNSUPPORTED;
   const int grid = (nb + per_warp - 1) / per_warp;
   size_t cta_smem = smem1 * per_warp;

@@ -31,6 +31,16 @@ namespace rda {
 #ifndef RDA_SU_TAU_ADAPT
 #define RDA_SU_TAU_ADAPT 0
 #endif
+// RDA_SU_BSG = 1 (build-time experiment, third session of round 2): the one-warp kernel keeps the box slacks / multipliers in
+// global memory, stored [c][t] so that the lanes (= stages) read consecutive addresses; default: [t][c] in shared memory.
+#ifndef RDA_SU_BSG
+#define RDA_SU_BSG 0
+#endif
+#if RDA_SU_BSG
+#define RDA_SU_BSI(T, t, c) ((c) * (T) + (t))
+#else
+#define RDA_SU_BSI(T, t, c) (10 * (t) + (c))
+#endif
 #ifndef RDA_SU_CH
 #define RDA_SU_CH 2      // hinges per chunk of the su-QP hinge loops (loads grouped ahead of the arithmetic)
 #endif
@@ -60,7 +70,7 @@ struct SuWork {
   float *hx, *hy, *hc;        // hinge rows: lam'A (2) and offset
   Slk *hs, *hnu;              // hinge slack / multiplier
   unsigned *hmask;            // T x ceil(N/32) words: hinges of stage t that take part in the interior point iteration
-  Slk *bs, *bnu;              // 10T box/rate slack / multiplier
+  Slk *bs, *bnu;              // 10T box/rate slack / multiplier, entry (t, c) at RDA_SU_BSI(T, t, c)
   Real *Wm;                   // 3T hinge Hessian of the position block after the elimination of d_t (xx, xy, yy)
   Real *Ed;                   // 3T elimination of d_t: (M_xd / Q_dd, M_yd / Q_dd, 1 / Q_dd)
   Real *g5q;                  // T   reduced-out gradient of d_t: g_d / Q_dd (d step = -(g5q + Ed . dp))
@@ -85,7 +95,9 @@ struct SuWork {
 // in `gbase`) are left out of `base` (each entry is touched only by the lane that owns its stage).
 // LEVEL is a compile-time constant so that every pointer keeps a single provenance (the compiler then
 // emits LDS / LDG instead of generic loads).  Returns the bytes of `base` used; *gbytes the bytes of `gbase`.
-template <typename Real, typename Slk = Real, int LEVEL = 0>
+// BSG (with LEVEL 0): only the box slacks / multipliers move to `gbase` — 4.8 KB less shared memory per instance at the
+// metric size (13.2 KB: 16 resident instances per SM instead of 12, if the registers allow it).
+template <typename Real, typename Slk = Real, int LEVEL = 0, bool BSG = false>
 RDA_HD size_t su_work_layout(int T, int N, SuWork<Real, Slk>* w, char* base, bool hinge_arrays = true,
                              char* gbase = nullptr, size_t* gbytes = nullptr) {
   size_t offs = 0, offg = 0;
@@ -115,7 +127,7 @@ RDA_HD size_t su_work_layout(int T, int N, SuWork<Real, Slk>* w, char* base, boo
   } else {
     RDA_TAKE_G(hs, N * T, Slk) RDA_TAKE_G(hnu, N * T, Slk)
   }
-  RDA_TAKE_L(1, bs, 10 * T, Slk) RDA_TAKE_L(1, bnu, 10 * T, Slk)
+  if (LEVEL >= 1 || BSG) { RDA_TAKE_G(bs, 10 * T, Slk) RDA_TAKE_G(bnu, 10 * T, Slk) } else { RDA_TAKE_S(bs, 10 * T, Slk) RDA_TAKE_S(bnu, 10 * T, Slk) }
   RDA_TAKE_L(2, Wm, 8 * T + 5, Real)                                  // (Wm, wb) | (dza, dva)
   if (w) { w->wb = w->Wm + 3 * T; w->dza = w->Wm; w->dva = w->Wm + 5 * (T + 1); }
   RDA_TAKE_L(2, Ed, 3 * T, Real) RDA_TAKE_L(2, g5q, T, Real)
@@ -131,9 +143,9 @@ RDA_HD size_t su_work_layout(int T, int N, SuWork<Real, Slk>* w, char* base, boo
 }
 
 // size-only query of su_work_layout
-template <typename Real, typename Slk = Real, int LEVEL = 0>
+template <typename Real, typename Slk = Real, int LEVEL = 0, bool BSG = false>
 RDA_HD size_t su_work_bytes(int T, int N, bool hinge_arrays = true, size_t* gbytes = nullptr) {
-  return su_work_layout<Real, Slk, LEVEL>(T, N, (SuWork<Real, Slk>*)nullptr, nullptr, hinge_arrays, nullptr, gbytes);
+  return su_work_layout<Real, Slk, LEVEL, BSG>(T, N, (SuWork<Real, Slk>*)nullptr, nullptr, hinge_arrays, nullptr, gbytes);
 }
 
 // Jacobians of the discrete model about (s, u): linear_ackermann_model :949-963,
@@ -400,8 +412,8 @@ RDA_HD int su_solve(const SuParams& P, SuWork<Real, Slk>& W, Ctx& ctx, const flo
     _Pragma("unroll 1") for (int c = 0; c < 10; ++c) {
       Row<Real> r = su_row<Real, Slk>(P, W, t, c);
       Real sv = r.live ? rmax(r.g, (Real)1e-2) : (Real)1;
-      W.bs[10 * t + c] = sv;
-      W.bnu[10 * t + c] = r.live ? mu0 / sv : (Real)0;
+      W.bs[RDA_SU_BSI(T, t, c)] = sv;
+      W.bnu[RDA_SU_BSI(T, t, c)] = r.live ? mu0 / sv : (Real)0;
       if (r.live) ++nrows;
     }
     if (acc) {
@@ -468,7 +480,7 @@ RDA_HD int su_solve(const SuParams& P, SuWork<Real, Slk>& W, Ctx& ctx, const flo
         _Pragma("unroll 1") for (int c = 0; c < 10; ++c) {
           Row<Real> r = su_row<Real, Slk>(P, W, t, c);
           if (!r.live) continue;
-          Real sv = W.bs[10 * t + c], nu = W.bnu[10 * t + c];
+          Real sv = W.bs[RDA_SU_BSI(T, t, c)], nu = W.bnu[RDA_SU_BSI(T, t, c)];
           Real res = r.g - sv;
           const Real isv = rcp_(sv);
           Real om = nu * isv;
@@ -575,7 +587,7 @@ RDA_HD int su_solve(const SuParams& P, SuWork<Real, Slk>& W, Ctx& ctx, const flo
         _Pragma("unroll 1") for (int c = 0; c < 10; ++c) {
           Row<Real> r = su_row<Real, Slk>(P, W, t, c);
           if (!r.live) continue;
-          Real sv = W.bs[10 * t + c], nu = W.bnu[10 * t + c];
+          Real sv = W.bs[RDA_SU_BSI(T, t, c)], nu = W.bnu[RDA_SU_BSI(T, t, c)];
           Real res = r.g - sv;
           Real dir = su_row_dir<Real>(r, dz + 5 * t, dv + 3 * t);
           Real ds = dir + res, dn;
@@ -657,7 +669,7 @@ RDA_HD int su_solve(const SuParams& P, SuWork<Real, Slk>& W, Ctx& ctx, const flo
           _Pragma("unroll 1") for (int c = 0; c < 10; ++c) {
             Row<Real> r = su_row<Real, Slk>(P, W, t, c);
             if (!r.live) continue;
-            Real sv = W.bs[10 * t + c], nu = W.bnu[10 * t + c];
+            Real sv = W.bs[RDA_SU_BSI(T, t, c)], nu = W.bnu[RDA_SU_BSI(T, t, c)];
             Real res = gsave[c] - sv;
             Real dir = su_row_dir<Real>(r, W.dz + 5 * t, W.dv + 3 * t);
             Real ds = dir + res;
@@ -666,8 +678,8 @@ RDA_HD int su_solve(const SuParams& P, SuWork<Real, Slk>& W, Ctx& ctx, const flo
             const Real isv = rcp_(sv), om = nu * isv;
             Real dna = -nu - om * dsa;
             Real dn = (sigma_mu - dsa * dna) * isv - nu - om * ds;
-            W.bs[10 * t + c] = sv + a * ds;
-            W.bnu[10 * t + c] = nu + a * dn;
+            W.bs[RDA_SU_BSI(T, t, c)] = sv + a * ds;
+            W.bnu[RDA_SU_BSI(T, t, c)] = nu + a * dn;
           }
           if (acc) {
             const Real dx = W.s[3 * t + 3] - W.pref[2 * t], dy = W.s[3 * t + 4] - W.pref[2 * t + 1], dd = W.d[t];
