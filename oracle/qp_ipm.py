@@ -88,6 +88,6 @@ def solve_qp(P, q, G, h, A=None, b=None, tol=1e-9, max_iter=80):
         s = s + a * ds
         lam = lam + a * dl
     merit, x, y, s, lam = best
-    if status != 'optimal' and merit < 1e3 * tol * scale:
+    if status != 'optimal' and merit < max(1e3 * tol, 1e-6) * scale:   # same acceptance whatever the requested tol
         status = 'optimal_inaccurate'      # accepted like cvxpy's OPTIMAL_INACCURATE (:696)
     return x, {'status': status, 'iters': it, 'merit': merit, 'ineq_dual': lam, 'eq_dual': y, 'slack': s}

@@ -6,6 +6,9 @@ gpurun_out/parity50_r02.json) and bounds it:
 
   * up to 8 iterations every instance stays inside the stated float32 tolerance (states 1e-3; controls 5e-3: the su-QP
     is nearly flat in some control directions — the oracle's own two solvers differ there by 3e-4);
+    (the trace was regenerated in the third session of round 2 with the oracle's su-QP solved to 1e-12 instead of 1e-9 — the
+    oracle had been the less accurate side; CPU build of the same cores against the new trace,
+    tests/test_parity50_cpu.py: states max 2.8e-4, controls max 7.8e-4 through 8 iterations; the bounds were left as they were);
   * beyond, the ADMM map is not contractive on a few instances (the float64 oracle itself moves by more
     than 1e-3 when its su-QP start is perturbed), so the bound is on the BULK of the distribution (median and the
     75th percentile) while the maximum is reported, not bounded.

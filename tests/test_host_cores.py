@@ -126,3 +126,41 @@ def test_pipeline_emulation_matches_oracle(seed, kind, dyn):
     assert abs(rd - io['resi_dual']) < 1e-3 * (1 + io['resi_dual'])
     assert abs(rp - io['resi_pri']) < 1e-3 * (1 + io['resi_pri'])
     assert 5 not in p.paths
+
+
+def test_su_core_is_closer_to_the_optimum_than_a_1e9_oracle_solve_at_metric_size():
+    """The su-QP is nearly flat in some control directions: an interior point solve that stops at a relative tolerance of
+    1e-9 (oracle/qp_ipm.py's default, the oracle's setting in rounds 1-2) is still 2e-3 (u) / 1.5e-4 (s) away from the
+    optimum there.  Measured against a 1e-13 solve of the same dense QP: the kernels' core (float64, 1e-9 on complementarity,
+    residuals AND step size) is 10-20 x closer than the 1e-9 oracle solve — the reason OracleRDA now solves to su_tol = 1e-12."""
+    T, N = 30, 20
+    car = rectangle_robot()
+    inst = make_instance(9003, T=T, N=N, E=4, lateral=(1.8, 6.0))
+    o = OracleRDA(T, car, max_edge_num=4, max_obs_num=N, iter_num=1, iter_threshold=0.0)
+    ref = [inst['ref'][:, t:t + 1] for t in range(T + 1)]
+    o.iterative_solve(inst['nom_s'], inst['nom_u'], ref, inst['ref_speed'], list(inst['obstacles']))
+    sols = {}
+    for name, tol in (('loose', 1e-9), ('default', o.su_tol), ('tight', 1e-13)):
+        o.su_tol = tol
+        s, u, d, info = o.su_prob_solve()
+        assert info['status'] in ('optimal', 'optimal_inaccurate')
+        sols[name] = (s, u)
+    P = shim.SuParams(T=T, N=N, dynamics=shim.DYN['acker'], accelerated=1, dt=0.1, L=3.0,
+                      umax=(shim.C.c_float * 2)(10, 1), ab=(shim.C.c_float * 2)(1.0, 0.05), ws=1, wu=1,
+                      slack_gain=8, dmin=0.1, dmax=1.0, ro1=200, ro2=1, max_iter=40)
+    pref = o.para_s[0:2, 1:]
+    hx, hy = o.para_obsA_lam[:, 1:, 0], o.para_obsA_lam[:, 1:, 1]
+    hc = np.zeros((N, T)); gx = np.zeros((N, T)); gy = np.zeros((N, T))
+    for n in range(N):
+        for t in range(T):
+            hc[n, t] = (o.para_obsA_lam[n, t + 1] @ pref[:, t] - o.para_obsb_lam[n, t + 1] - o.para_mu[n, :, t + 1] @ o.h
+                        - o.para_z[n, t] + o.para_zeta[n, t])
+            gx[n, t], gy[n, t] = o.para_mu[n, :, t + 1] @ o.G + o.para_xi[n, t + 1]
+    s_k, u_k, d_k, st, it = shim.su(P, o.para_s, o.para_u, o.ref_s, o.ref_speed, o.para_dis, hx, hy, hc, gx, gy, pref, prec='d')
+    assert st == 0
+    gap = lambda a, b: (np.abs(a[0] - b[0]).max(), np.abs(a[1] - b[1]).max())
+    core, loose, dflt = gap((s_k, u_k), sols['tight']), gap(sols['loose'], sols['tight']), gap(sols['default'], sols['tight'])
+    print('gap to the 1e-13 solve (s, u): core', core, ' 1e-9 oracle', loose, ' default oracle', dflt)
+    assert core[0] < 5e-5 and core[1] < 5e-4
+    assert dflt[0] < 1e-5 and dflt[1] < 1e-4
+    assert loose[0] > 3 * core[0] and loose[1] > 3 * core[1]
