@@ -36,7 +36,8 @@ def test_cpu_build_of_the_cores_against_the_oracle_over_50_iterations():
         print(f'it {it:2d}: |ds| med {np.median(ds):.1e} p75 {np.quantile(ds, .75):.1e} max {ds.max():.1e}   |du| med {np.median(du):.1e} '
               f'max {du.max():.1e}   resi_pri med {np.median(rp):.1e} resi_dual med {np.median(rd):.1e}')
         if it <= 8:
-            assert ds.max() < 1e-3 and du.max() < 5e-3, (it, ds.max(), du.max())
+            # measured: states max 2.8e-4, controls max 7.8e-4 (1e-3 / 5e-3 in the GPU test, whose bounds predate the 1e-12 oracle)
+            assert ds.max() < 6e-4 and du.max() < 2e-3, (it, ds.max(), du.max())
             assert rp.max() < 2e-3 and rd.max() < 2e-3, (it, rp.max(), rd.max())
         else:
             assert np.median(ds) < 2e-3 and np.quantile(ds, .75) < 2e-2, (it, np.median(ds), np.quantile(ds, .75))
