@@ -164,3 +164,27 @@ def test_su_core_is_closer_to_the_optimum_than_a_1e9_oracle_solve_at_metric_size
     assert core[0] < 5e-5 and core[1] < 5e-4
     assert dflt[0] < 1e-5 and dflt[1] < 1e-4
     assert loose[0] > 3 * core[0] and loose[1] > 3 * core[1]
+
+
+@pytest.mark.parametrize('dyn,N,seed', [('acker', 0, 7), ('acker', 0, 11), ('diff', 0, 11), ('omni', 0, 11), ('acker', 5, 11),
+                                        ('diff', 5, 11), ('omni', 5, 11)])
+def test_su_core_converges_on_random_problems(dyn, N, seed):
+    """Robustness guard of the interior point iteration (third session of round 2: a seemingly harmless change of the fraction
+    to the boundary made it CYCLE on a box-only problem, su_solver.cuh RDA_SU_TAU_ADAPT): 40 random problems per case,
+    without hinges (N = 0: only the control / rate boxes) and with hinges near activity — every solve converges, well below
+    the iteration cap, float64 and float32."""
+    from test_su_batched import _params, _inputs
+    T, nb = 12, 40
+    P = _params(T, N, dyn, 1)
+    cur_s, cur_u, ref_s, pref, coef, dis, vref = _inputs(nb, T, N, dyn, seed)       # seed 7 holds the problem that cycled
+    z = np.zeros((1, T), np.float32)
+    worst = 0
+    for b in range(nb):
+        hx, hy, hc, gx, gy = (coef[b, k] if N > 0 else z[:0] for k in range(5))
+        for prec in ('d', 'f'):
+            s, u, d, st, it = shim.su(P, cur_s[b].astype(float), cur_u[b].astype(float), ref_s[b].astype(float), float(vref[b]),
+                                      dis[b].astype(float), hx, hy, hc, gx, gy, pref[b].astype(float), prec=prec)
+            assert st == 0, (b, prec, st, it)
+            assert np.all(np.isfinite(s)) and np.all(np.isfinite(u))
+            worst = max(worst, it)
+    assert worst <= 30, worst
